@@ -1,0 +1,91 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference on CPU.
+
+Run in the authoring container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Each fixture stores the seeds/config needed to rebuild inputs with
+``oracle.nextdit_oracle.synthetic_*`` plus the reference's outputs, so the committed
+files stay small (outputs only).  Reference entry points exercised:
+``models.NextDiT(...)`` ctor + ``load_state_dict(strict=True)`` (pins the state-dict key
+names/shapes), ``forward_with_cfg`` (models/nextdit.py:838-885) in fp32 and under
+``torch.autocast("cpu", bf16)``, per-block outputs via forward hooks, and
+``transport.ODE(...).sample`` (transport.py:57-111) for euler and midpoint.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import nextdit_oracle as O  # noqa: E402
+from oracle.harness.ref_import import import_reference_mini  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+CASES = {
+    # name: (latent_hw, T, uncond_len, kwargs for forward_with_cfg, t value)
+    "tiny_prop": dict(hw=(16, 16), T=16, ul=8, t=0.25,
+                      kw=dict(cfg_scale=2.0, scale_factor=1.0, scale_watershed=1.0, base_seqlen=64, proportional_attn=True)),
+    "tiny_ntk": dict(hw=(16, 24), T=24, ul=8, t=0.6,
+                     kw=dict(cfg_scale=4.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=16, proportional_attn=True)),
+    "tiny_lin": dict(hw=(24, 16), T=16, ul=16, t=0.1,
+                     kw=dict(cfg_scale=1.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=None, proportional_attn=False)),
+}
+
+
+def build_ref(models, cfg: O.NextDiTConfig, W):
+    m = models.nextdit.NextDiT(patch_size=cfg.patch_size, in_channels=cfg.in_channels, dim=cfg.dim, n_layers=cfg.n_layers,
+                       n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=True, cap_feat_dim=cfg.cap_feat_dim,
+                       use_flash_attn=False)
+    m.load_state_dict({k: v.clone() for k, v in W.items()}, strict=True)
+    return m.eval()
+
+
+def main() -> None:
+    models, transport = import_reference_mini()
+    os.makedirs(OUT, exist_ok=True)
+    cfg = O.config_tiny(n_layers=2)
+    W = O.synthetic_weights(cfg, seed=0, dtype=torch.bfloat16)
+    torch.set_grad_enabled(False)
+
+    ref32 = build_ref(models, cfg, W).float()
+    ref16 = build_ref(models, cfg, W).to(torch.bfloat16)
+
+    for name, c in CASES.items():
+        z, cap, mask = O.synthetic_inputs(cfg, c["hw"], c["T"], c["ul"], seed=1)
+        t = torch.full((2,), c["t"], dtype=torch.float32)
+        taps = {}
+        hooks = [l.register_forward_hook(lambda mod, i, o, idx=idx: taps.__setitem__(f"block{idx}", o.clone()))
+                 for idx, l in enumerate(ref32.layers)]
+        out32 = ref32.forward_with_cfg(z.float(), t, cap.float(), mask, **c["kw"])
+        for h in hooks:
+            h.remove()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out16 = ref16.forward_with_cfg(z, t, cap, mask, **c["kw"])
+        fx = dict(case=name, cfg=dict(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads,
+                                      cap_feat_dim=cfg.cap_feat_dim),
+                  hw=c["hw"], T=c["T"], ul=c["ul"], t=c["t"], kw=c["kw"], weight_seed=0, input_seed=1,
+                  out_fp32=out32.clone(), out_autocast_cpu_bf16=out16.float().to(torch.bfloat16),
+                  taps={k: v.to(torch.bfloat16) for k, v in taps.items()})
+        torch.save(fx, os.path.join(OUT, f"fwd_{name}.pt"))
+        print(name, "out32 absmax", out32.abs().max().item(), "autocast diff", (out16.float() - out32).abs().max().item())
+
+    # trajectories through the reference's ODE class (fp32 state)
+    c = CASES["tiny_prop"]
+    z, cap, mask = O.synthetic_inputs(cfg, c["hw"], c["T"], c["ul"], seed=1)
+    for method, steps, shift in (("euler", 5, 1.0), ("midpoint", 4, 4.0)):
+        ode = transport.ODE(steps, method, shift)
+        traj = ode.sample(z.float(), ref32.forward_with_cfg, cap_feats=cap.float(), cap_mask=mask, **c["kw"])
+        fx = dict(method=method, num_steps=steps, time_shifting_factor=shift, hw=c["hw"], T=c["T"], ul=c["ul"], kw=c["kw"],
+                  weight_seed=0, input_seed=1, grid=ode.t.clone(), traj_fp32=traj.clone())
+        torch.save(fx, os.path.join(OUT, f"traj_{method}.pt"))
+        print(method, "traj", tuple(traj.shape), traj[-1].abs().max().item())
+
+
+if __name__ == "__main__":
+    main()
