@@ -1,0 +1,135 @@
+/* ndit.h - C ABI of the B200-native Next-DiT denoising engine (libndit_b200.so).
+ *
+ * The reference (Alpha-VLLM/Lumina-T2X) has no FFI: its boundary for this path is the Python module
+ * API.  Each entry point below names the reference interface it stands behind (paths relative to the
+ * reference root).  The Python mirror of that interface lives in lumina_t2x_b200/{models,transport} and
+ * reaches this library through ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions: plain C types only; every call returns 0 on success or a negative ndit_status; the
+ * message is available from ndit_last_error().  Never aborts.  A handle is bound to the CUDA device that
+ * was current at ndit_create(), is not re-entrant, and launches on the stream passed per call
+ * (a cudaStream_t cast to void*; NULL = legacy default stream).  "dev" pointers are device pointers owned
+ * by the caller; "host" pointers are host memory (pinned recommended).  bf16 = IEEE bfloat16.
+ */
+#ifndef NDIT_H_
+#define NDIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDIT_ABI_VERSION 1
+
+typedef struct ndit_engine* ndit_handle;
+
+typedef enum ndit_status {
+    NDIT_OK = 0,
+    NDIT_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+    NDIT_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+    NDIT_ERR_STATE = -3,     /* call order violated (weights not finalized, caption not set, ...) */
+    NDIT_ERR_NOMEM = -4
+} ndit_status;
+
+typedef enum ndit_dtype { NDIT_BF16 = 0, NDIT_F32 = 1 } ndit_dtype;
+typedef enum ndit_method { NDIT_EULER = 0, NDIT_MIDPOINT = 1 } ndit_method;
+
+/* Architecture of a NextDiT instance: the ctor arguments of
+ * lumina_next_t2i/models/model.py:665-741 (NextDiT.__init__) fixed by the factories at :994-999. */
+typedef struct ndit_config {
+    int32_t dim;            /* 2304 */
+    int32_t n_layers;       /* 24   */
+    int32_t n_heads;        /* 32   */
+    int32_t n_kv_heads;     /* 8 (GQA) or n_heads */
+    int32_t cap_feat_dim;   /* 2048 */
+    int32_t in_channels;    /* 4    */
+    int32_t patch_size;     /* 2    */
+    int32_t multiple_of;    /* 256  */
+    int32_t learn_sigma;    /* 1    */
+    float norm_eps;         /* 1e-5 */
+    int32_t max_tokens;     /* largest H/2*W/2 the workspace is sized for (e.g. 4096 for 1024x1024) */
+    int32_t max_cap_len;    /* largest caption length T (e.g. 256) */
+    int32_t max_batch;      /* rows of one forward_with_cfg call = 2 (cond + uncond) * samples; <= 4 */
+} ndit_config;
+
+/* Per-call arguments of NextDiT.forward_with_cfg (model.py:866-913) that are not tensors. */
+typedef struct ndit_step_params {
+    float cfg_scale;
+    float scale_factor;      /* time-aware RoPE scaling (model.py:944-952) */
+    float scale_watershed;
+    int32_t proportional_attn;
+    int32_t base_seqlen;     /* used when proportional_attn != 0 (model.py:373-376) */
+} ndit_step_params;
+
+/* --- lifecycle: models.NextDiT_2B_GQA_patch2(...) / .to("cuda") / del (sample.py:125-129) */
+int ndit_abi_version(void);
+int ndit_create(const ndit_config* cfg, ndit_handle* out);
+int ndit_destroy(ndit_handle h);
+const char* ndit_last_error(ndit_handle h);   /* h may be NULL: last error of a failed ndit_create */
+
+/* --- weights: nn.Module.load_state_dict(strict=True) (sample.py:135-142).  `key` is the reference
+ * state-dict key; the tensor is copied (bf16 or f32 source, row-major) into
+ * engine-owned, GEMM-ready storage.  ndit_finalize_weights fails if a key is missing (strict). */
+int ndit_set_weight(ndit_handle h, const char* key, const void* dev_ptr, const int64_t* shape, int32_t ndim,
+                    int32_t dtype, void* stream);
+int ndit_finalize_weights(ndit_handle h, void* stream);
+int64_t ndit_parameter_count(ndit_handle h);   /* NextDiT.parameter_count (model.py:965-982) */
+
+/* --- caption conditioning: the cap_feats / cap_mask kwargs of forward_with_cfg.  They are constant over
+ * an ODE solve, so the caption-side work (pooling + cap_embedder, model.py:847-850; attention_y_norm,
+ * wk_y/wv_y, ky_norm for all layers, :421-422,:602) is done once here.
+ * cap_feats_dev: bf16 [batch, T, cap_feat_dim]; cap_mask_dev: uint8 [batch, T] (non-zero = valid). */
+int ndit_set_caption(ndit_handle h, const void* cap_feats_dev, const uint8_t* cap_mask_dev, int32_t batch, int32_t T,
+                     void* stream);
+
+/* --- NextDiT.forward_with_cfg (model.py:866-913).  x_dev/out_dev: bf16 [batch, C, height, width] NCHW
+ * (latent size; batch = 2 * samples, second half of x ignored as in the reference); t is the (common)
+ * timestep.  Uses the caption set by ndit_set_caption (same batch). */
+int ndit_forward_cfg(ndit_handle h, const void* x_dev, float t, int32_t batch, int32_t height, int32_t width,
+                     const ndit_step_params* sp, void* out_dev, void* stream);
+
+/* --- transport.Sampler.sample_ode(...)(z, model.forward_with_cfg, **kw) (transport/transport.py:346-391,
+ * transport/integrators.py:79-116) with torchdiffeq's fixed-grid euler / midpoint.  t_grid_host: the
+ * n_grid time points (fp32, host).  z_dev: bf16 initial state [batch,C,height,width]; traj_dev: bf16
+ * [n_grid, batch, C, height, width] receiving every grid state (traj[0] = z), or NULL to keep only
+ * the final state, which is always written to final_dev (may alias z_dev). */
+int ndit_sample(ndit_handle h, const void* z_dev, int32_t batch, int32_t height, int32_t width,
+                const float* t_grid_host, int32_t n_grid, int32_t method, const ndit_step_params* sp,
+                void* traj_dev, void* final_dev, void* stream);
+
+/* Same solve with HOST buffers (the end-to-end entry point): copies z / caption host->device, runs
+ * ndit_set_caption + ndit_sample, copies the final latent device->host and synchronises the stream. */
+int ndit_sample_host(ndit_handle h, const void* z_host, const void* cap_feats_host, const uint8_t* cap_mask_host,
+                     int32_t batch, int32_t height, int32_t width, int32_t T, const float* t_grid_host, int32_t n_grid,
+                     int32_t method, const ndit_step_params* sp, void* final_host, void* stream);
+
+/* --- instrumentation */
+int64_t ndit_launch_count(ndit_handle h);          /* kernels launched by this handle so far */
+int ndit_set_option(ndit_handle h, const char* name, int32_t value);   /* "attn_ref" = 1: debug attention */
+
+/* --- single-operator entry points (parity tests and micro-benchmarks call the kernels through these) */
+/* C[M,N] = A[M,K] W[N,K]^T, bf16, fp32 accumulate.  swiglu != 0: W is [2F,K] block-interleaved
+ * (128 rows w1 | 128 rows w3) and C is [M,F] = silu(a)*b.  (F.linear call sites: model.py:358,438,502) */
+int ndit_op_gemm(const void* A_dev, const void* W_dev, void* C_dev, int32_t M, int32_t N, int32_t K, int32_t swiglu,
+                 void* stream);
+/* in place on qkv [M, (H+2Hkv)*hd]: q,k <- bf16(rope(LayerNorm(.))) (model.py:361-371); angles are built from
+ * (Hp, Wp, theta, linear_factor) like precompute_freqs_cis (:916-963). M = batch*Hp*Wp */
+int ndit_op_ln_rope(void* qkv_dev, const void* qw, const void* qb, const void* kw, const void* kb, int32_t batch,
+                    int32_t Hp, int32_t Wp, int32_t H, int32_t Hkv, int32_t hd, float theta, float linear_factor,
+                    void* stream);
+/* fused self + gated cross attention (model.py:373-434).  qkv [B*N,(H+2Hkv)*72] (q,k already normed+roped),
+ * kvy [B*T, 2*Hkv*72] (ky normed | vy), ymask uint8 [B,T], gate_tanh f32 [H]; out bf16 [B*N, H*72]. */
+int ndit_op_attention(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
+                      void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
+                      float scale_cross, int32_t use_ref, void* stream);
+/* X += tanh_g * RMS(o; w_post) (skipped if o NULL);  u = RMS(X; w_pre) * onepls   (model.py:597-610) */
+int ndit_op_resid_rms_mod(void* X_dev, const void* o_dev, const void* w_post, const float* tanh_g, const void* w_pre,
+                          const float* onepls, void* u_dev, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDIT_H_ */

@@ -1,0 +1,79 @@
+"""ctypes binding of libndit_b200.so (C ABI: include/ndit.h).  Fails loudly: there is no
+CPU or PyTorch fallback for the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libndit_b200.so")
+
+NDIT_BF16, NDIT_F32 = 0, 1
+NDIT_EULER, NDIT_MIDPOINT = 0, 1
+
+
+class NditConfig(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_layers", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32),
+                ("cap_feat_dim", C.c_int32), ("in_channels", C.c_int32), ("patch_size", C.c_int32),
+                ("multiple_of", C.c_int32), ("learn_sigma", C.c_int32), ("norm_eps", C.c_float),
+                ("max_tokens", C.c_int32), ("max_cap_len", C.c_int32), ("max_batch", C.c_int32)]
+
+
+class NditStepParams(C.Structure):
+    _fields_ = [("cfg_scale", C.c_float), ("scale_factor", C.c_float), ("scale_watershed", C.c_float),
+                ("proportional_attn", C.c_int32), ("base_seqlen", C.c_int32)]
+
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); every symbol declared in include/ndit.h
+SIGNATURES = {
+    "ndit_abi_version": (C.c_int, []),
+    "ndit_create": (C.c_int, [C.POINTER(NditConfig), C.POINTER(_vp)]),
+    "ndit_destroy": (C.c_int, [_vp]),
+    "ndit_last_error": (C.c_char_p, [_vp]),
+    "ndit_set_weight": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _i32, _vp]),
+    "ndit_finalize_weights": (C.c_int, [_vp, _vp]),
+    "ndit_parameter_count": (_i64, [_vp]),
+    "ndit_set_caption": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "ndit_forward_cfg": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),
+    "ndit_sample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_f32), _i32, _i32, C.POINTER(NditStepParams),
+                              _vp, _vp, _vp]),
+    "ndit_sample_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _i32, _i32,
+                                   C.POINTER(NditStepParams), _vp, _vp]),
+    "ndit_launch_count": (_i64, [_vp]),
+    "ndit_set_option": (C.c_int, [_vp, C.c_char_p, _i32]),
+    "ndit_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ndit_op_ln_rope": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
+    "ndit_op_attention": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
+    "ndit_op_resid_rms_mod": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library.  Raises if it has not been built (``__graft_entry__.build()`` or
+    ``python lumina_t2x_b200/build.py``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the B200 engine has no fallback path. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ndit_abi_version() != 1:
+        raise RuntimeError("libndit_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, handle=None) -> None:
+    if rc != 0:
+        msg = load().ndit_last_error(handle)
+        raise RuntimeError(f"ndit error {rc}: {msg.decode() if msg else '?'}")

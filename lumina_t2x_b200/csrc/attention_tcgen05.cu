@@ -1,0 +1,482 @@
+// Fused image self-attention + gated caption cross-attention for one Next-DiT block, head_dim 72.
+//
+// Replaces, in lumina_next_t2i/models/model.py: _upad_input/flash_attn_varlen_func/pad_input (:387-404),
+// the GQA repeat + masked SDPA over the caption tokens (:421-432), the tanh(gate) scale and add (:433-434).
+//
+//   out[b,n,h,:] = bf16( bf16(softmax(q k^T * s_self) v) + bf16(tanh(gate_h) * bf16(softmax(q ky^T / sqrt(hd) + mask) vy)) )
+//
+// Design (sm_100a, one CTA per (batch, head, 256 query rows), 320 threads, 1 CTA / SM):
+//   warps 0-3   softmax warpgroup for query tile A (rows 0..127): one thread per row (TMEM lane)
+//   warps 4-7   softmax warpgroup for query tile B (rows 128..255)
+//   warp  8     TMA producer: Q tiles once, then a ring of K / V^T stages (self blocks, then caption blocks)
+//   warp  9     MMA issuer:  S = Q K^T (tcgen05.mma 128x128x16, 5 k-steps: 4 from a 128B-swizzled
+//               [rows x 64] tile + 1 from a 32B-swizzled [rows x 16] tile, head_dim 72 zero-padded to 80 by
+//               TMA out-of-bounds fill), then O_j = P V (128x80x16, 8 k-steps, P from shared memory).
+// The two query tiles ping-pong on the tensor pipe: while warpgroup A does exp/row-sum on S_A the MMA warp
+// runs tile B's products.  Per block j the P.V partial product is written to TMEM with accumulate=0 and folded
+// into fp32 registers (o = o*alpha + O_j) one block later, so no TMEM read-modify-write is needed.
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464).
+#include <math.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ndit {
+
+constexpr int AT_HD = 72;
+constexpr int AT_HDP = 80;            // padded head dim (5 x 16)
+constexpr int AT_BQ = 128;            // rows per query tile
+constexpr int AT_BKV = 128;           // kv rows per block
+constexpr int AT_STAGES = 2;
+constexpr int AT_THREADS = 320;
+
+constexpr int AT_Q64_BYTES = AT_BQ * 128;        // 16 KB
+constexpr int AT_Q16_BYTES = AT_BQ * 32;         //  4 KB
+constexpr int AT_QTILE_BYTES = AT_Q64_BYTES + AT_Q16_BYTES;   // 20 KB
+constexpr int AT_KTILE_BYTES = AT_QTILE_BYTES;                // same shape as a Q tile
+constexpr int AT_VHALF_BYTES = AT_HDP * 128;     // 10 KB  (80 rows x 64 kv)
+constexpr int AT_VTILE_BYTES = 2 * AT_VHALF_BYTES;
+constexpr int AT_PHALF_BYTES = AT_BQ * 128;      // 16 KB
+constexpr int AT_PTILE_BYTES = 2 * AT_PHALF_BYTES;
+
+constexpr int AT_OFF_Q = 0;
+constexpr int AT_OFF_K = AT_OFF_Q + 2 * AT_QTILE_BYTES;
+constexpr int AT_OFF_V = AT_OFF_K + AT_STAGES * AT_KTILE_BYTES;
+constexpr int AT_OFF_P = AT_OFF_V + AT_STAGES * AT_VTILE_BYTES;
+constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_PTILE_BYTES;
+constexpr int AT_SMEM_BYTES = AT_OFF_BAR + 256 + 1024;
+
+constexpr uint32_t AT_TM_S = 0, AT_TM_O = 256;   // + X*128
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmQ16,
+                       const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
+                       const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmKy64,
+                       const __grid_constant__ CUtensorMap tmKy16, const __grid_constant__ CUtensorMap tmVyt,
+                       const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh, bf16* __restrict__ out,
+                       int N, int T, int H, int Hkv, float sl2_self, float sl2_cross) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = sbase + AT_OFF_BAR;
+    // barriers
+    auto q_full = [&](int x) { return bar0 + 8u * (0 + x); };
+    auto k_full = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto v_full = [&](int s) { return bar0 + 8u * (2 + AT_STAGES + s); };
+    auto kv_empty = [&](int s) { return bar0 + 8u * (2 + 2 * AT_STAGES + s); };
+    constexpr int BB = 2 + 3 * AT_STAGES;
+    auto s_full = [&](int x) { return bar0 + 8u * (BB + 0 + x); };
+    auto s_free = [&](int x) { return bar0 + 8u * (BB + 2 + x); };
+    auto p_full = [&](int x) { return bar0 + 8u * (BB + 4 + x); };
+    auto o_full = [&](int x) { return bar0 + 8u * (BB + 6 + x); };
+    auto o_free = [&](int x) { return bar0 + 8u * (BB + 8 + x); };
+    const uint32_t tmem_ptr_addr = bar0 + 8u * (BB + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (2 * AT_BQ);
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int g = h / (H / Hkv);
+    const int n_self = (N + AT_BKV - 1) / AT_BKV;
+    const int n_cross = (T + AT_BKV - 1) / AT_BKV;
+    const int n_total = n_self + n_cross;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmQ64); tma_prefetch_desc(&tmQ16); tma_prefetch_desc(&tmK64); tma_prefetch_desc(&tmK16);
+        tma_prefetch_desc(&tmVt); tma_prefetch_desc(&tmKy64); tma_prefetch_desc(&tmKy16); tma_prefetch_desc(&tmVyt);
+        for (int x = 0; x < 2; ++x) {
+            mbar_init(q_full(x), 1);
+            mbar_init(s_full(x), 1);
+            mbar_init(s_free(x), 4);
+            mbar_init(p_full(x), 4);
+            mbar_init(o_full(x), 1);
+            mbar_init(o_free(x), 4);
+        }
+        for (int s = 0; s < AT_STAGES; ++s) {
+            mbar_init(k_full(s), 1);
+            mbar_init(v_full(s), 1);
+            mbar_init(kv_empty(s), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        tmem_alloc(tmem_ptr_addr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp == 8) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            for (int x = 0; x < 2; ++x) {
+                const uint32_t dst = sbase + AT_OFF_Q + x * AT_QTILE_BYTES;
+                mbar_expect_tx(q_full(x), AT_QTILE_BYTES);
+                tma_load_3d(dst, &tmQ64, q_full(x), 0, h, b * N + q0 + x * AT_BQ);
+                tma_load_3d(dst + AT_Q64_BYTES, &tmQ16, q_full(x), 64, h, b * N + q0 + x * AT_BQ);
+            }
+        }
+        __syncwarp();
+        for (int jj = 0; jj < n_total; ++jj) {
+            const int s = jj % AT_STAGES;
+            mbar_wait(kv_empty(s), ((jj / AT_STAGES) & 1) ^ 1);
+            if (lane == 0) {
+                const uint32_t kd = sbase + AT_OFF_K + s * AT_KTILE_BYTES;
+                const uint32_t vd = sbase + AT_OFF_V + s * AT_VTILE_BYTES;
+                mbar_expect_tx(k_full(s), AT_KTILE_BYTES);
+                mbar_expect_tx(v_full(s), AT_VTILE_BYTES);
+                if (jj < n_self) {
+                    const int kv0 = jj * AT_BKV;
+                    tma_load_3d(kd, &tmK64, k_full(s), 0, g, b * N + kv0);
+                    tma_load_3d(kd + AT_Q64_BYTES, &tmK16, k_full(s), 64, g, b * N + kv0);
+                    tma_load_3d(vd, &tmVt, v_full(s), kv0, 0, b * Hkv + g);
+                    tma_load_3d(vd + AT_VHALF_BYTES, &tmVt, v_full(s), kv0 + 64, 0, b * Hkv + g);
+                } else {
+                    const int kv0 = (jj - n_self) * AT_BKV;
+                    tma_load_3d(kd, &tmKy64, k_full(s), 0, g, b * T + kv0);
+                    tma_load_3d(kd + AT_Q64_BYTES, &tmKy16, k_full(s), 64, g, b * T + kv0);
+                    tma_load_3d(vd, &tmVyt, v_full(s), kv0, 0, b * Hkv + g);
+                    tma_load_3d(vd + AT_VHALF_BYTES, &tmVyt, v_full(s), kv0 + 64, 0, b * Hkv + g);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 9) {
+        // ================================================================= MMA issuer
+        constexpr uint32_t idesc_qk = make_idesc_bf16(128, AT_BKV);
+        constexpr uint32_t idesc_pv = make_idesc_bf16(128, AT_HDP);
+        auto issue_qk = [&](int x, int jj) {
+            const int s = jj % AT_STAGES;
+            mbar_wait(k_full(s), (jj / AT_STAGES) & 1);
+            mbar_wait(s_free(x), (jj & 1) ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t qa = sbase + AT_OFF_Q + x * AT_QTILE_BYTES;
+                const uint32_t ka = sbase + AT_OFF_K + s * AT_KTILE_BYTES;
+                const uint64_t dq = make_smem_desc_kmajor(qa, 1024, UMMA_SW128);
+                const uint64_t dk = make_smem_desc_kmajor(ka, 1024, UMMA_SW128);
+                const uint32_t d = tmem_base + AT_TM_S + x * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+                const uint64_t dq16 = make_smem_desc_kmajor(qa + AT_Q64_BYTES, 256, UMMA_SW32);
+                const uint64_t dk16 = make_smem_desc_kmajor(ka + AT_Q64_BYTES, 256, UMMA_SW32);
+                umma_ss(d, dq16, dk16, idesc_qk, 1);
+                umma_commit(s_full(x));
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int x, int jj) {
+            const int s = jj % AT_STAGES;
+            mbar_wait(v_full(s), (jj / AT_STAGES) & 1);
+            mbar_wait(p_full(x), jj & 1);
+            mbar_wait(o_free(x), (jj & 1) ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t pa = sbase + AT_OFF_P + x * AT_PTILE_BYTES;
+                const uint32_t va = sbase + AT_OFF_V + s * AT_VTILE_BYTES;
+                const uint32_t d = tmem_base + AT_TM_O + x * 128;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t dp = make_smem_desc_kmajor(pa + (k >> 2) * AT_PHALF_BYTES, 1024, UMMA_SW128) + 2 * (k & 3);
+                    const uint64_t dv = make_smem_desc_kmajor(va + (k >> 2) * AT_VHALF_BYTES, 1024, UMMA_SW128) + 2 * (k & 3);
+                    umma_ss(d, dp, dv, idesc_pv, k != 0);
+                }
+                umma_commit(o_full(x));
+                if (x == 1) umma_commit(kv_empty(s));
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full(0), 0);
+        issue_qk(0, 0);
+        mbar_wait(q_full(1), 0);
+        issue_qk(1, 0);
+        for (int jj = 0; jj < n_total; ++jj) {
+            for (int x = 0; x < 2; ++x) {
+                issue_pv(x, jj);
+                if (jj + 1 < n_total) issue_qk(x, jj + 1);
+            }
+        }
+    } else {
+        // ================================================================= softmax warpgroups
+        const int x = warp >> 2;                 // query tile
+        const int qd = warp & 3;                 // TMEM lane quadrant
+        const int r = qd * 32 + lane;            // row inside the tile
+        const int qrow = q0 + x * AT_BQ + r;     // token index in this batch element
+        const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+        const uint32_t ts = tmem_base + lane_sel + AT_TM_S + x * 128;
+        const uint32_t to = tmem_base + lane_sel + AT_TM_O + x * 128;
+        const uint32_t pbase = sbase + AT_OFF_P + x * AT_PTILE_BYTES + r * 128;
+        const uint32_t rsw = static_cast<uint32_t>(r & 7);
+
+        float o[AT_HD];
+#pragma unroll
+        for (int i = 0; i < AT_HD; ++i) o[i] = 0.f;
+        uint32_t o_self[AT_HD / 2];
+#pragma unroll
+        for (int i = 0; i < AT_HD / 2; ++i) o_self[i] = 0u;
+        float m_run = -INFINITY, l_run = 0.f, l_self = 1.f, alpha_prev = 0.f;
+
+        auto consume_o = [&](int jj_prev, float alpha) {
+            mbar_wait(o_full(x), jj_prev & 1);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(to, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(v[i]);
+            tmem_ld_32x32b_x32(to + 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * alpha + __uint_as_float(v[i]);
+            uint32_t w[8];
+            tmem_ld_32x32b_x8(to + 64, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[64 + i] = o[64 + i] * alpha + __uint_as_float(w[i]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free(x));
+        };
+
+        for (int jj = 0; jj < n_total; ++jj) {
+            const bool cross = jj >= n_self;
+            if (jj == n_self) {                  // segment switch: new softmax statistics
+                l_self = l_run;
+                m_run = -INFINITY;
+                l_run = 0.f;
+            }
+            const float sl2 = cross ? sl2_cross : sl2_self;
+            // validity words for this block's 128 kv columns
+            uint32_t vw[4];
+            if (!cross) {
+                const int nvalid = N - jj * AT_BKV;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int rem = nvalid - c * 32;
+                    vw[c] = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+                }
+            } else {
+                const int t0 = (jj - n_self) * AT_BKV;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int t = t0 + c * 32 + lane;
+                    const bool ok = (t < T) && (ymask[b * T + t] != 0);
+                    vw[c] = __ballot_sync(0xffffffffu, ok);
+                }
+            }
+            const bool all_valid = (vw[0] & vw[1] & vw[2] & vw[3]) == 0xffffffffu;
+
+            mbar_wait(s_full(x), jj & 1);
+            tc_fence_after();
+            // ---- pass 1: row max
+            float mb = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(ts + c * 32, v);
+                tmem_ld_wait();
+                if (all_valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mb = fmaxf(mb, __uint_as_float(v[i]));
+                } else {
+                    const uint32_t w = vw[c];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if ((w >> i) & 1u) mb = fmaxf(mb, __uint_as_float(v[i]));
+                }
+            }
+            const float m_new = fmaxf(m_run, mb);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = ex2_approx((m_run - m_use) * sl2);
+            const float moff = m_use * sl2;
+            // ---- pass 2: p = exp2(s*sl2 - moff), row sum, P -> smem (bf16, K-major 128B swizzle)
+            float lb = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(ts + c * 32, v);
+                tmem_ld_wait();
+                float p[32];
+                const uint32_t w = all_valid ? 0xffffffffu : vw[c];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float e = ex2_approx(__uint_as_float(v[i]) * sl2 - moff);
+                    p[i] = ((w >> i) & 1u) ? e : 0.f;
+                    lb += p[i];
+                }
+                const uint32_t half = pbase + (c >> 1) * AT_PHALF_BYTES;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + ch);
+                    const uint32_t addr = half + ((chunk ^ rsw) << 4);
+                    const uint32_t a0 = pack_bf16(p[ch * 8 + 0], p[ch * 8 + 1]);
+                    const uint32_t a1 = pack_bf16(p[ch * 8 + 2], p[ch * 8 + 3]);
+                    const uint32_t a2 = pack_bf16(p[ch * 8 + 4], p[ch * 8 + 5]);
+                    const uint32_t a3 = pack_bf16(p[ch * 8 + 6], p[ch * 8 + 7]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3)
+                                 : "memory");
+                }
+            }
+            // S_x fully read -> free for the next Q K^T; P_x written -> visible to the tensor core
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(s_free(x));
+                mbar_arrive(p_full(x));
+            }
+            l_run = l_run * alpha + lb;
+            m_run = m_new;
+            // ---- fold the previous block's P.V partial product into the register accumulator
+            if (jj > 0) consume_o(jj - 1, alpha_prev);
+            alpha_prev = alpha;
+            if (jj == n_self) {
+                // the accumulator now holds the complete self-attention numerator
+                const float inv = 1.0f / l_self;
+#pragma unroll
+                for (int i = 0; i < AT_HD / 2; ++i) {
+                    o_self[i] = pack_bf16(o[2 * i] * inv, o[2 * i + 1] * inv);
+                    o[2 * i] = 0.f;
+                    o[2 * i + 1] = 0.f;
+                }
+                // alpha of this (first caption) block is 0 (m_run was -inf), so o restarts from O_j
+            }
+        }
+        consume_o(n_total - 1, alpha_prev);
+        // ---- epilogue: out = bf16(self + bf16(tanh(gate) * bf16(cross)))
+        if (qrow < N) {
+            const float gt = gate_tanh[h];
+            const float inv = 1.0f / l_run;
+            uint32_t res[AT_HD / 2];
+#pragma unroll
+            for (int i = 0; i < AT_HD / 2; ++i) {
+                const float2 sv = unpack_bf16(o_self[i]);
+                const float c0 = bf16_round(gt * bf16_round(o[2 * i] * inv));
+                const float c1 = bf16_round(gt * bf16_round(o[2 * i + 1] * inv));
+                res[i] = pack_bf16(sv.x + c0, sv.y + c1);
+            }
+            bf16* dst = out + (static_cast<size_t>(b) * N + qrow) * (static_cast<size_t>(H) * AT_HD) + h * AT_HD;
+#pragma unroll
+            for (int i = 0; i < AT_HD / 8; ++i)
+                *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             AT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (p.T <= 0 || p.N <= 0) return cudaErrorInvalidValue;
+    const float log2e = 1.4426950408889634f;
+    const dim3 grid((p.N + 2 * AT_BQ - 1) / (2 * AT_BQ), p.H, p.B);
+    attention_fused_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(
+        p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask, p.gate_tanh, p.out, p.N, p.T,
+        p.H, p.Hkv, p.scale_self * log2e, p.scale_cross * log2e);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Slow CUDA-core reference of the same fused op (debug only; selected with NDIT_ATTN=ref).
+// One block per (query row, head, batch); plain two-pass softmax in fp32.
+__global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, const bf16* __restrict__ kvy, int ld_kvy,
+                                     const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh,
+                                     bf16* __restrict__ out, int N, int T, int H, int Hkv, int hd, float scale_self,
+                                     float scale_cross) {
+    extern __shared__ float sh[];            // scores [max(N,T)] + q [hd] + red[32]
+    const int n = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int g = h / (H / Hkv);
+    const int L = N > T ? N : T;
+    float* sc = sh;
+    float* qv = sh + L;
+    float* red = qv + hd;
+    const bf16* qp = qkv + (static_cast<size_t>(b) * N + n) * ld_qkv + h * hd;
+    for (int d = threadIdx.x; d < hd; d += blockDim.x) qv[d] = __bfloat162float(qp[d]);
+    __syncthreads();
+    float result[2] = {0.f, 0.f};            // this thread owns output dims threadIdx.x (< hd) for both segments
+    for (int seg = 0; seg < 2; ++seg) {
+        const int len = seg == 0 ? N : T;
+        const float scale = seg == 0 ? scale_self : scale_cross;
+        float mx = -INFINITY;
+        for (int k = threadIdx.x; k < len; k += blockDim.x) {
+            const bf16* kp = seg == 0 ? qkv + (static_cast<size_t>(b) * N + k) * ld_qkv + H * hd + g * hd
+                                      : kvy + (static_cast<size_t>(b) * T + k) * ld_kvy + g * hd;
+            float s = 0.f;
+            for (int d = 0; d < hd; ++d) s += qv[d] * __bfloat162float(kp[d]);
+            s *= scale;
+            if (seg == 1 && ymask[b * T + k] == 0) s = -INFINITY;
+            sc[k] = s;
+            mx = fmaxf(mx, s);
+        }
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        mx = -INFINITY;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+        __syncthreads();
+        float sum = 0.f;
+        for (int k = threadIdx.x; k < len; k += blockDim.x) {
+            const float p = __expf(sc[k] - mx);
+            sum += p;
+            sc[k] = bf16_round(p);           // flash kernels feed bf16 probabilities to the P.V product
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        sum = 0.f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) sum += red[w];
+        __syncthreads();
+        if (threadIdx.x < hd) {
+            const int d = threadIdx.x;
+            float acc = 0.f;
+            for (int k = 0; k < len; ++k) {
+                const bf16* vp = seg == 0 ? qkv + (static_cast<size_t>(b) * N + k) * ld_qkv + (H + Hkv) * hd + g * hd
+                                          : kvy + (static_cast<size_t>(b) * T + k) * ld_kvy + Hkv * hd + g * hd;
+                acc += sc[k] * __bfloat162float(vp[d]);
+            }
+            result[seg] = bf16_round(acc / sum);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < hd) {
+        const float r = result[0] + bf16_round(gate_tanh[h] * result[1]);
+        out[(static_cast<size_t>(b) * N + n) * (static_cast<size_t>(H) * hd) + h * hd + threadIdx.x] = __float2bfloat16_rn(r);
+    }
+}
+
+cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_kvy, const uint8_t* ymask,
+                          const float* gate_tanh, bf16* out, int B, int N, int T, int H, int Hkv, int hd,
+                          float scale_self, float scale_cross, cudaStream_t stream) {
+    if (hd > 128) return cudaErrorInvalidValue;
+    const int L = N > T ? N : T;
+    const size_t sh = (L + hd + 32) * sizeof(float);
+    static size_t configured = 0;
+    if (sh > 48 * 1024 && sh > configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        if (e != cudaSuccess) return e;
+        configured = sh;
+    }
+    attention_ref_kernel<<<dim3(N, H, B), 128, sh, stream>>>(qkv, ld_qkv, kvy, ld_kvy, ymask, gate_tanh, out, N, T, H, Hkv,
+                                                           hd, scale_self, scale_cross);
+    return cudaGetLastError();
+}
+
+}  // namespace ndit

@@ -1,0 +1,690 @@
+// C-ABI engine (include/ndit.h): weight packing, workspace, the per-block kernel schedule of
+// NextDiT.forward_with_cfg and the fixed-grid ODE loop.  No torch types; plain CUDA runtime.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/ndit.h"
+#include "kernels.h"
+
+using namespace ndit;
+
+namespace {
+
+inline float host_bf16_round(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return x;   // NaN
+    const uint32_t lsb = (u >> 16) & 1u;
+    u += 0x7fffu + lsb;
+    u &= 0xffff0000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+inline float host_bf16_to_float(uint16_t h) {
+    uint32_t u = static_cast<uint32_t>(h) << 16;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+
+// dst[(r / blk) * dst_blk_stride + r % blk + dst_row0][c] = src[r][c]   (bf16 or f32 source)
+__global__ void place_rows_kernel(bf16* __restrict__ dst, size_t dst_ld, const void* __restrict__ src, int src_f32,
+                                  size_t rows, size_t cols, size_t blk, size_t dst_blk_stride, size_t dst_row0) {
+    const size_t total = rows * cols;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / cols, c = i % cols;
+        const size_t dr = (r / blk) * dst_blk_stride + (r % blk) + dst_row0;
+        const float v = src_f32 ? static_cast<const float*>(src)[i] : __bfloat162float(static_cast<const bf16*>(src)[i]);
+        dst[dr * dst_ld + c] = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void mask_to_u8_kernel(uint8_t* dst, const uint8_t* src, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] ? 1 : 0;
+}
+
+struct RopeSlot {
+    int Hp = 0, Wp = 0;
+    float theta = 0.f, lin = 0.f;
+    float2* tab = nullptr;
+};
+
+}  // namespace
+
+struct ndit_engine {
+    ndit_config cfg;
+    int D, L, H, Hkv, hd, F, C, cd, O, Wq;   // Wq = fused qkv width
+    int device = 0, num_sms = 148;
+    char err[512];
+    int64_t launches = 0;
+    int64_t n_params = 0;
+    bool finalized = false;
+    int attn_ref = 0;
+    std::set<std::string> seen;
+    std::vector<void*> allocs;
+
+    // weights
+    bf16 *Wx, *bx, *Wt0, *bt0, *Wt2, *bt2, *capln_w, *capln_b, *Wcap, *bcap, *Wada, *bada, *Wout, *bout, *pad_token;
+    bf16 *Wqkv, *Wo, *W13, *W2, *Wkvy;                       // [L][...]
+    bf16 *qn_w, *qn_b, *kn_w, *kn_b, *kyn_w, *kyn_b;         // [L][...]
+    bf16 *an1, *an2, *fn1, *fn2, *yn;                        // [L][...]
+    bf16* gate_raw;                                          // [L][H]
+    float* gate_tanh;                                        // [L][H]
+    // workspace
+    int Mmax, Tmax, Bmax, Tpad_max;
+    bf16 *X, *u, *qkv, *attn, *o, *hbuf, *vt;
+    bf16 *yhat, *kvy, *vyt;
+    uint8_t* ymask;
+    float *pool, *capemb, *tf, *h1, *sc, *mod, *tok;
+    bf16 *vel, *ystate, *ymid;
+    bf16 *stage_z, *stage_cap;
+    uint8_t* stage_mask;
+    RopeSlot rope[2];
+    int rope_next = 0;
+    // caption state
+    int cap_batch = 0, cap_T = 0;
+    // plans
+    int plan_M = 0, plan_B = 0, plan_N = 0, plan_T = 0;
+    std::vector<GemmPlan> p_qkv, p_wo, p_w13, p_w2;
+    std::vector<AttnPlan> p_attn;
+    bool attn_plans_valid = false;
+
+    int fail(int code, const char* fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, sizeof(err), fmt, ap);
+        va_end(ap);
+        return code;
+    }
+};
+
+static thread_local char g_create_err[512] = "";
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return h->fail(NDIT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKL(call)                                                                                             \
+    do {                                                                                                      \
+        CK(call);                                                                                             \
+        h->launches++;                                                                                        \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(ndit_engine* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) return h->fail(NDIT_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemset(q, 0, count * sizeof(T) + 256);
+    if (e != cudaSuccess) return h->fail(NDIT_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+#define ALLOC(ptr, count)                                \
+    do {                                                 \
+        int r_ = dev_alloc(h, &(h->ptr), (size_t)(count)); \
+        if (r_) return r_;                               \
+    } while (0)
+
+extern "C" int ndit_abi_version(void) { return NDIT_ABI_VERSION; }
+
+extern "C" const char* ndit_last_error(ndit_handle h) { return h ? h->err : g_create_err; }
+
+static int create_impl(ndit_engine* h) {
+    const ndit_config& c = h->cfg;
+    if (c.dim <= 0 || c.n_heads <= 0 || c.dim % c.n_heads != 0) return h->fail(NDIT_ERR_INVALID, "bad dim/n_heads");
+    h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
+    h->hd = c.dim / c.n_heads; h->C = c.cap_feat_dim; h->cd = c.dim < 1024 ? c.dim : 1024;
+    if (h->hd != 72) return h->fail(NDIT_ERR_INVALID, "this build supports head_dim 72 only (got %d)", h->hd);
+    if (c.patch_size != 2 || c.in_channels != 4) return h->fail(NDIT_ERR_INVALID, "patch_size 2 / in_channels 4 only");
+    if (h->H % h->Hkv != 0) return h->fail(NDIT_ERR_INVALID, "n_heads %% n_kv_heads != 0");
+    if (c.max_batch < 2 || c.max_batch > 4 || (c.max_batch & 1)) return h->fail(NDIT_ERR_INVALID, "max_batch must be 2 or 4");
+    if (h->C % 8 != 0 || h->D % 64 != 0) return h->fail(NDIT_ERR_INVALID, "dims must be multiples of 8/64");
+    int hidden = static_cast<int>(2 * (4 * c.dim) / 3);                 // model.py:441-503 FeedForward
+    h->F = c.multiple_of * ((hidden + c.multiple_of - 1) / c.multiple_of);
+    if (h->F % 128 != 0) return h->fail(NDIT_ERR_INVALID, "ffn dim must be a multiple of 128");
+    const int out_ch = c.learn_sigma ? 2 * c.in_channels : c.in_channels;
+    h->O = c.patch_size * c.patch_size * out_ch;
+    h->Wq = (h->H + 2 * h->Hkv) * h->hd;
+    CK(cudaGetDevice(&h->device));
+    CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    int cc_major = 0;
+    CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, h->device));
+    if (cc_major != 10) return h->fail(NDIT_ERR_INVALID, "needs an sm_100 device (compute capability %d.x found)", cc_major);
+
+    const size_t D = h->D, L = h->L, F = h->F, C = h->C, cd = h->cd, KV = (size_t)h->Hkv * h->hd;
+    ALLOC(Wx, D * 16); ALLOC(bx, D); ALLOC(Wt0, cd * 256); ALLOC(bt0, cd); ALLOC(Wt2, cd * cd); ALLOC(bt2, cd);
+    ALLOC(capln_w, C); ALLOC(capln_b, C); ALLOC(Wcap, cd * C); ALLOC(bcap, cd);
+    ALLOC(Wada, (L * 4 * D + D) * cd); ALLOC(bada, L * 4 * D + D);
+    ALLOC(Wout, (size_t)h->O * D); ALLOC(bout, h->O); ALLOC(pad_token, D);
+    ALLOC(Wqkv, L * h->Wq * D); ALLOC(Wo, L * D * D); ALLOC(W13, L * 2 * F * D); ALLOC(W2, L * D * F);
+    ALLOC(Wkvy, L * 2 * KV * C);
+    ALLOC(qn_w, L * D); ALLOC(qn_b, L * D); ALLOC(kn_w, L * KV); ALLOC(kn_b, L * KV); ALLOC(kyn_w, L * KV); ALLOC(kyn_b, L * KV);
+    ALLOC(an1, L * D); ALLOC(an2, L * D); ALLOC(fn1, L * D); ALLOC(fn2, L * D); ALLOC(yn, L * C);
+    ALLOC(gate_raw, L * h->H); ALLOC(gate_tanh, L * h->H);
+
+    h->Bmax = c.max_batch; h->Tmax = c.max_cap_len; h->Tpad_max = (c.max_cap_len + 7) / 8 * 8;
+    h->Mmax = c.max_batch * c.max_tokens;
+    const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
+    ALLOC(X, M * D); ALLOC(u, M * D); ALLOC(qkv, M * h->Wq); ALLOC(attn, M * D); ALLOC(o, M * D); ALLOC(hbuf, M * F);
+    ALLOC(vt, B * KV * c.max_tokens);
+    ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * KV * h->Tpad_max);
+    ALLOC(ymask, B * T); ALLOC(pool, B * C); ALLOC(capemb, B * cd); ALLOC(tf, B * 256); ALLOC(h1, B * cd); ALLOC(sc, B * cd);
+    ALLOC(mod, B * (L * 4 * D + D)); ALLOC(tok, M * h->O);
+    const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
+    ALLOC(vel, lat); ALLOC(ystate, lat); ALLOC(ymid, lat); ALLOC(stage_z, lat); ALLOC(stage_cap, B * T * C); ALLOC(stage_mask, B * T);
+    for (int i = 0; i < 2; ++i) {
+        int r = dev_alloc(h, &h->rope[i].tab, (size_t)c.max_tokens * (h->hd / 2));
+        if (r) return r;
+    }
+    // parameter inventory (NextDiT.parameter_count): everything in the state dict
+    h->n_params = (int64_t)(D * 16 + D + cd * 256 + cd + cd * cd + cd + 2 * C + cd * C + cd + D /*pad_token*/ +
+                            (size_t)h->O * D + h->O + D * cd + D) +
+                  (int64_t)L * (int64_t)(h->H + (size_t)h->Wq * D + 2 * KV * C + D * D + 2 * D + 4 * KV + 3 * F * D + 4 * D + C +
+                                         4 * D * cd + 4 * D);
+    return 0;
+}
+
+extern "C" int ndit_create(const ndit_config* cfg, ndit_handle* out) {
+    if (!cfg || !out) {
+        snprintf(g_create_err, sizeof(g_create_err), "ndit_create: null argument");
+        return NDIT_ERR_INVALID;
+    }
+    ndit_engine* h = new ndit_engine();
+    h->cfg = *cfg;
+    h->err[0] = 0;
+    int r = create_impl(h);
+    if (r) {
+        snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
+        for (void* p : h->allocs) cudaFree(p);
+        delete h;
+        *out = nullptr;
+        return r;
+    }
+    *out = h;
+    return NDIT_OK;
+}
+
+extern "C" int ndit_destroy(ndit_handle h) {
+    if (!h) return NDIT_OK;
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return NDIT_OK;
+}
+
+extern "C" int64_t ndit_parameter_count(ndit_handle h) { return h ? h->n_params : 0; }
+extern "C" int64_t ndit_launch_count(ndit_handle h) { return h ? h->launches : 0; }
+
+extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
+    if (!h || !name) return NDIT_ERR_INVALID;
+    if (!strcmp(name, "attn_ref")) { h->attn_ref = value; return NDIT_OK; }
+    return h->fail(NDIT_ERR_INVALID, "unknown option %s", name);
+}
+
+// ------------------------------------------------------------------------------------ weights
+
+static int place(ndit_engine* h, bf16* dst, size_t dst_ld, const void* src, int dtype, size_t rows, size_t cols,
+                 size_t blk, size_t blk_stride, size_t row0, cudaStream_t s) {
+    const size_t total = rows * cols;
+    const int grid = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+    place_rows_kernel<<<grid, 256, 0, s>>>(dst, dst_ld, src, dtype == NDIT_F32, rows, cols, blk ? blk : rows,
+                                           blk_stride, row0);
+    CKL(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, const int64_t* shape, int32_t ndim,
+                               int32_t dtype, void* stream) {
+    if (!h || !key || !src || !shape) return NDIT_ERR_INVALID;
+    if (dtype != NDIT_BF16 && dtype != NDIT_F32) return h->fail(NDIT_ERR_INVALID, "%s: dtype must be bf16 or f32", key);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t D = h->D, F = h->F, C = h->C, cd = h->cd, KV = (size_t)h->Hkv * h->hd, Wq = h->Wq;
+    const size_t r = ndim >= 1 ? (size_t)shape[0] : 1, c = ndim >= 2 ? (size_t)shape[1] : 1;
+    auto want = [&](size_t er, size_t ec) -> int {
+        const bool ok = (ec == 0) ? (ndim == 1 && r == er) : (ndim == 2 && r == er && c == ec);
+        if (!ok) return h->fail(NDIT_ERR_INVALID, "%s: shape mismatch (got [%zu,%zu] ndim %d, want [%zu,%zu])", key, r, c, ndim, er, ec);
+        return 0;
+    };
+#define VEC(name, dst, n)                                         \
+    if (!strcmp(key, name)) {                                     \
+        if (int e = want(n, 0)) return e;                         \
+        h->seen.insert(key);                                      \
+        return place(h, dst, 1, src, dtype, n, 1, 0, 0, 0, s);    \
+    }
+#define MAT(name, dst, rr, cc)                                    \
+    if (!strcmp(key, name)) {                                     \
+        if (int e = want(rr, cc)) return e;                       \
+        h->seen.insert(key);                                      \
+        return place(h, dst, cc, src, dtype, rr, cc, 0, 0, 0, s); \
+    }
+    VEC("pad_token", h->pad_token, D)
+    MAT("x_embedder.weight", h->Wx, D, 16) VEC("x_embedder.bias", h->bx, D)
+    MAT("t_embedder.mlp.0.weight", h->Wt0, cd, 256) VEC("t_embedder.mlp.0.bias", h->bt0, cd)
+    MAT("t_embedder.mlp.2.weight", h->Wt2, cd, cd) VEC("t_embedder.mlp.2.bias", h->bt2, cd)
+    VEC("cap_embedder.0.weight", h->capln_w, C) VEC("cap_embedder.0.bias", h->capln_b, C)
+    MAT("cap_embedder.1.weight", h->Wcap, cd, C) VEC("cap_embedder.1.bias", h->bcap, cd)
+    MAT("final_layer.linear.weight", h->Wout, (size_t)h->O, D) VEC("final_layer.linear.bias", h->bout, (size_t)h->O)
+    const size_t Lz = h->L;
+    MAT("final_layer.adaLN_modulation.1.weight", h->Wada + Lz * 4 * D * cd, D, cd)
+    VEC("final_layer.adaLN_modulation.1.bias", h->bada + Lz * 4 * D, D)
+#undef VEC
+#undef MAT
+    int li = -1, pos = 0;
+    if (sscanf(key, "layers.%d.%n", &li, &pos) >= 1 && pos > 0 && li >= 0 && li < h->L) {
+        const char* sub = key + pos;
+        const size_t l = li;
+        struct Ent { const char* name; bf16* dst; size_t dst_ld, rows, cols, blk, blk_stride, row0; };
+        const Ent ents[] = {
+            {"attention.wq.weight", h->Wqkv + l * Wq * D, D, D, D, 0, 0, 0},
+            {"attention.wk.weight", h->Wqkv + l * Wq * D, D, KV, D, 0, 0, D},
+            {"attention.wv.weight", h->Wqkv + l * Wq * D, D, KV, D, 0, 0, D + KV},
+            {"attention.wo.weight", h->Wo + l * D * D, D, D, D, 0, 0, 0},
+            {"attention.wk_y.weight", h->Wkvy + l * 2 * KV * C, C, KV, C, 0, 0, 0},
+            {"attention.wv_y.weight", h->Wkvy + l * 2 * KV * C, C, KV, C, 0, 0, KV},
+            // w1|w3 interleaved per 256-row block for the SwiGLU epilogue
+            {"feed_forward.w1.weight", h->W13 + l * 2 * F * D, D, F, D, 128, 256, 0},
+            {"feed_forward.w3.weight", h->W13 + l * 2 * F * D, D, F, D, 128, 256, 128},
+            {"feed_forward.w2.weight", h->W2 + l * D * F, F, D, F, 0, 0, 0},
+            {"adaLN_modulation.1.weight", h->Wada + l * 4 * D * cd, cd, 4 * D, cd, 0, 0, 0},
+        };
+        for (const Ent& e : ents) {
+            if (!strcmp(sub, e.name)) {
+                if (int er = want(e.rows, e.cols)) return er;
+                h->seen.insert(key);
+                return place(h, e.dst, e.dst_ld, src, dtype, e.rows, e.cols, e.blk, e.blk_stride, e.row0, s);
+            }
+        }
+        struct VEnt { const char* name; bf16* dst; size_t n; };
+        const VEnt vents[] = {
+            {"attention.gate", h->gate_raw + l * h->H, (size_t)h->H},
+            {"attention.q_norm.weight", h->qn_w + l * D, D}, {"attention.q_norm.bias", h->qn_b + l * D, D},
+            {"attention.k_norm.weight", h->kn_w + l * KV, KV}, {"attention.k_norm.bias", h->kn_b + l * KV, KV},
+            {"attention.ky_norm.weight", h->kyn_w + l * KV, KV}, {"attention.ky_norm.bias", h->kyn_b + l * KV, KV},
+            {"attention_norm1.weight", h->an1 + l * D, D}, {"attention_norm2.weight", h->an2 + l * D, D},
+            {"ffn_norm1.weight", h->fn1 + l * D, D}, {"ffn_norm2.weight", h->fn2 + l * D, D},
+            {"attention_y_norm.weight", h->yn + l * C, C},
+            {"adaLN_modulation.1.bias", h->bada + l * 4 * D, 4 * D},
+        };
+        for (const VEnt& e : vents) {
+            if (!strcmp(sub, e.name)) {
+                if (int er = want(e.n, 0)) return er;
+                h->seen.insert(key);
+                return place(h, e.dst, 1, src, dtype, e.n, 1, 0, 0, 0, s);
+            }
+        }
+    }
+    return h->fail(NDIT_ERR_INVALID, "unexpected state-dict key: %s", key);
+}
+
+static void expected_keys(const ndit_engine* h, std::vector<std::string>* out) {
+    const char* top[] = {"pad_token", "x_embedder.weight", "x_embedder.bias", "t_embedder.mlp.0.weight", "t_embedder.mlp.0.bias",
+                         "t_embedder.mlp.2.weight", "t_embedder.mlp.2.bias", "cap_embedder.0.weight", "cap_embedder.0.bias",
+                         "cap_embedder.1.weight", "cap_embedder.1.bias", "final_layer.linear.weight", "final_layer.linear.bias",
+                         "final_layer.adaLN_modulation.1.weight", "final_layer.adaLN_modulation.1.bias"};
+    for (const char* k : top) out->push_back(k);
+    const char* per[] = {"attention.gate", "attention.wq.weight", "attention.wk.weight", "attention.wv.weight", "attention.wk_y.weight",
+                         "attention.wv_y.weight", "attention.wo.weight", "attention.q_norm.weight", "attention.q_norm.bias",
+                         "attention.k_norm.weight", "attention.k_norm.bias", "attention.ky_norm.weight", "attention.ky_norm.bias",
+                         "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight", "attention_norm1.weight",
+                         "attention_norm2.weight", "ffn_norm1.weight", "ffn_norm2.weight", "attention_y_norm.weight",
+                         "adaLN_modulation.1.weight", "adaLN_modulation.1.bias"};
+    for (int l = 0; l < h->L; ++l)
+        for (const char* k : per) out->push_back("layers." + std::to_string(l) + "." + k);
+}
+
+extern "C" int ndit_finalize_weights(ndit_handle h, void* stream) {
+    if (!h) return NDIT_ERR_INVALID;
+    std::vector<std::string> keys;
+    expected_keys(h, &keys);
+    for (const std::string& k : keys)
+        if (!h->seen.count(k)) return h->fail(NDIT_ERR_STATE, "missing state-dict key (strict): %s", k.c_str());
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // tanh(gate) per head, bf16 in / bf16 out (model.py:433)
+    const size_t n = (size_t)h->L * h->H;
+    std::vector<uint16_t> raw(n);
+    std::vector<float> th(n);
+    CK(cudaMemcpyAsync(raw.data(), h->gate_raw, n * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < n; ++i) th[i] = host_bf16_round(tanhf(host_bf16_to_float(raw[i])));
+    CK(cudaMemcpyAsync(h->gate_tanh, th.data(), n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    h->finalized = true;
+    return NDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------ caption
+
+extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* mask, int32_t batch, int32_t T, void* stream) {
+    if (!h || !cap || !mask) return NDIT_ERR_INVALID;
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    if (batch < 1 || batch > h->Bmax || T < 1 || T > h->Tmax) return h->fail(NDIT_ERR_INVALID, "caption batch/T out of range (%d,%d)", batch, T);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t C = h->C, KV = (size_t)h->Hkv * h->hd, L = h->L;
+    const int M = batch * T;
+    const int Tpad = (T + 7) / 8 * 8;
+    mask_to_u8_kernel<<<(M + 255) / 256, 256, 0, s>>>(h->ymask, mask, M);
+    CKL(cudaGetLastError());
+    const bf16* capb = static_cast<const bf16*>(cap);
+    CKL(cond_prepare(0.f, capb, h->ymask, h->capln_w, h->capln_b, h->tf, h->pool, batch, T, (int)C, 1, s));
+    CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, batch, h->cd, (int)C, 0, POST_NONE, 0, 0, s));
+    CKL(rms_rows_layers(capb, h->yn, h->yhat, M, (int)C, (int)L, h->cfg.norm_eps, s));
+    const size_t ys = (size_t)M * C, ks = (size_t)M * 2 * KV;
+    for (size_t l = 0; l < L; ++l) {
+        GemmPlan p;
+        if (make_gemm_plan(&p, h->yhat + l * ys, (int)C, h->Wkvy + l * 2 * KV * C, h->kvy + l * ks, (int)(2 * KV), M,
+                           (int)(2 * KV), (int)C, EPI_STORE, h->num_sms))
+            return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
+        CKL(gemm_bf16_tn(p, s));
+    }
+    CKL(ln_rows(h->kvy, (int)(2 * KV), ks, h->kyn_w, h->kyn_b, KV, M, (int)KV, (int)L, s));
+    const size_t vs = (size_t)batch * KV * Tpad;
+    CK(cudaMemsetAsync(h->vyt, 0, L * vs * sizeof(bf16), s));
+    CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, batch, T, h->Hkv, h->hd, (int)L, s));
+    if (batch != h->cap_batch || T != h->cap_T) h->attn_plans_valid = false;
+    h->cap_batch = batch;
+    h->cap_T = T;
+    return NDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------ forward
+
+static int ensure_plans(ndit_engine* h, int batch, int N) {
+    const int M = batch * N;
+    const size_t D = h->D, F = h->F, L = h->L, Wq = h->Wq, KV = (size_t)h->Hkv * h->hd, C = h->C;
+    if (M != h->plan_M) {
+        h->p_qkv.resize(L); h->p_wo.resize(L); h->p_w13.resize(L); h->p_w2.resize(L);
+        for (size_t l = 0; l < L; ++l) {
+            int e = 0;
+            e |= make_gemm_plan(&h->p_qkv[l], h->u, (int)D, h->Wqkv + l * Wq * D, h->qkv, (int)Wq, M, (int)Wq, (int)D, EPI_STORE, h->num_sms);
+            e |= make_gemm_plan(&h->p_wo[l], h->attn, (int)D, h->Wo + l * D * D, h->o, (int)D, M, (int)D, (int)D, EPI_STORE, h->num_sms);
+            e |= make_gemm_plan(&h->p_w13[l], h->u, (int)D, h->W13 + l * 2 * F * D, h->hbuf, (int)F, M, (int)(2 * F), (int)D, EPI_SWIGLU, h->num_sms);
+            e |= make_gemm_plan(&h->p_w2[l], h->hbuf, (int)F, h->W2 + l * D * F, h->o, (int)D, M, (int)D, (int)F, EPI_STORE, h->num_sms);
+            if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
+        }
+        h->plan_M = M;
+        h->attn_plans_valid = false;
+    }
+    if (!h->attn_plans_valid || h->plan_B != batch || h->plan_N != N || h->plan_T != h->cap_T) {
+        const int T = h->cap_T, Tpad = (T + 7) / 8 * 8, hd = h->hd;
+        h->p_attn.resize(L);
+        const uint64_t rs = (uint64_t)Wq * 2;   // qkv row stride in bytes
+        for (size_t l = 0; l < L; ++l) {
+            AttnPlan& a = h->p_attn[l];
+            memset(&a, 0, sizeof(a));
+            int e = 0;
+            e |= make_tmap_3d(&a.tmQ64, h->qkv, hd, h->H, (uint64_t)M, hd * 2, rs, 64, 1, 128, 128);
+            e |= make_tmap_3d(&a.tmQ16, h->qkv, hd, h->H, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
+            e |= make_tmap_3d(&a.tmK64, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 64, 1, 128, 128);
+            e |= make_tmap_3d(&a.tmK16, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
+            e |= make_tmap_3d(&a.tmVt, h->vt, N, hd, (uint64_t)batch * h->Hkv, (uint64_t)N * 2, (uint64_t)N * hd * 2, 64, 80, 1, 128);
+            const bf16* kvy = h->kvy + l * (size_t)batch * T * 2 * KV;
+            const bf16* vyt = h->vyt + l * (size_t)batch * KV * Tpad;
+            e |= make_tmap_3d(&a.tmKy64, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 64, 1, 128, 128);
+            e |= make_tmap_3d(&a.tmKy16, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 16, 1, 128, 32);
+            e |= make_tmap_3d(&a.tmVyt, vyt, Tpad, hd, (uint64_t)batch * h->Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * hd * 2, 64, 80, 1, 128);
+            if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
+            a.ymask = h->ymask;
+            a.gate_tanh = h->gate_tanh + l * h->H;
+            a.out = h->attn;
+            a.B = batch; a.N = N; a.T = T; a.H = h->H; a.Hkv = h->Hkv;
+        }
+        (void)C;
+        h->plan_B = batch; h->plan_N = N; h->plan_T = h->cap_T;
+        h->attn_plans_valid = true;
+    }
+    return 0;
+}
+
+static int get_rope(ndit_engine* h, int Hp, int Wp, float theta, float lin, cudaStream_t s, const float2** out) {
+    for (int i = 0; i < 2; ++i) {
+        RopeSlot& r = h->rope[i];
+        if (r.Hp == Hp && r.Wp == Wp && r.theta == theta && r.lin == lin) { *out = r.tab; return 0; }
+    }
+    RopeSlot& r = h->rope[h->rope_next];
+    h->rope_next ^= 1;
+    CKL(rope_table(r.tab, Hp, Wp, h->hd, theta, lin, s));
+    r.Hp = Hp; r.Wp = Wp; r.theta = theta; r.lin = lin;
+    *out = r.tab;
+    return 0;
+}
+
+static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int Hh, int Ww, const ndit_step_params* sp,
+                        bf16* out, cudaStream_t s) {
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
+    if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
+    if ((Hh & 1) || (Ww & 1) || Hh <= 0 || Ww <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");
+    const int Hp = Hh / 2, Wp = Ww / 2, N = Hp * Wp, M = batch * N;
+    if (N > h->cfg.max_tokens) return h->fail(NDIT_ERR_INVALID, "%d tokens > max_tokens %d", N, h->cfg.max_tokens);
+    if (N % 8 != 0) return h->fail(NDIT_ERR_INVALID, "token count %d must be a multiple of 8", N);
+    if (Hp > 384 || Wp > 384) return h->fail(NDIT_ERR_INVALID, "rope table covers 384x384 patches (model.py:733)");
+    if (int e = ensure_plans(h, batch, N)) return e;
+    const int D = h->D, L = h->L, hd = h->hd;
+    const int mod_stride = L * 4 * D + D;
+    // time-aware RoPE scaling (model.py:944-952)
+    float lin, ntk;
+    if (t < sp->scale_watershed) { lin = sp->scale_factor; ntk = 1.0f; } else { lin = 1.0f; ntk = sp->scale_factor; }
+    const float theta = 10000.0f * ntk;
+    const float2* rope = nullptr;
+    if (int e = get_rope(h, Hp, Wp, theta, lin, s, &rope)) return e;
+    float scale_self;
+    if (sp->proportional_attn) {
+        if (sp->base_seqlen <= 1) return h->fail(NDIT_ERR_INVALID, "proportional_attn needs base_seqlen > 1");
+        scale_self = (float)sqrt(log((double)N) / log((double)sp->base_seqlen) / (double)hd);   // model.py:373-376
+    } else {
+        scale_self = (float)sqrt(1.0 / (double)hd);
+    }
+    const float scale_cross = (float)(1.0 / sqrt((double)hd));
+
+    CKL(patch_embed(x, h->Wx, h->bx, h->X, batch, batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
+    CKL(cond_prepare(t, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
+    CKL(gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, batch, h->cd, 256, 0, POST_SILU, 0, 0, s));
+    // sc = bf16(silu(c)), c = bf16(temb + cap_emb)
+    CKL(gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, s));
+    CKL(gemv_rows(h->sc, h->Wada, h->bada, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L, s));
+    CKL(resid_rms_mod(h->X, nullptr, nullptr, nullptr, h->an1, h->mod, h->u, M, N, D, mod_stride, h->cfg.norm_eps, s));
+    for (int l = 0; l < L; ++l) {
+        const float* ml = h->mod + (size_t)l * 4 * D;
+        CKL(gemm_bf16_tn(h->p_qkv[l], s));
+        CKL(ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
+                       h->kn_b + (size_t)l * h->Hkv * hd, rope, M, N, h->H, h->Hkv, hd, s));
+        if (h->attn_ref) {
+            CKL(attention_ref(h->qkv, h->Wq, h->kvy + (size_t)l * batch * h->cap_T * 2 * h->Hkv * hd, 2 * h->Hkv * hd, h->ymask,
+                              h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
+                              scale_cross, s));
+        } else {
+            CKL(transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, 1, s));
+            AttnPlan& a = h->p_attn[l];
+            a.scale_self = scale_self;
+            a.scale_cross = scale_cross;
+            CKL(attention_fused(a, s));
+        }
+        CKL(gemm_bf16_tn(h->p_wo[l], s));
+        CKL(resid_rms_mod(h->X, h->o, h->an2 + (size_t)l * D, ml + D, h->fn1 + (size_t)l * D, ml + 2 * D, h->u, M, N, D,
+                          mod_stride, h->cfg.norm_eps, s));
+        CKL(gemm_bf16_tn(h->p_w13[l], s));
+        CKL(gemm_bf16_tn(h->p_w2[l], s));
+        if (l + 1 < L) {
+            CKL(resid_rms_mod(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->an1 + (size_t)(l + 1) * D, ml + 4 * D, h->u, M, N,
+                              D, mod_stride, h->cfg.norm_eps, s));
+        } else {
+            CKL(final_layer(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->mod + (size_t)L * 4 * D, h->Wout, h->bout, h->tok, M,
+                            N, D, h->O, mod_stride, h->cfg.norm_eps, s));
+        }
+    }
+    CKL(unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, s));
+    return NDIT_OK;
+}
+
+extern "C" int ndit_forward_cfg(ndit_handle h, const void* x, float t, int32_t batch, int32_t height, int32_t width,
+                                const ndit_step_params* sp, void* out, void* stream) {
+    if (!h || !x || !sp || !out) return NDIT_ERR_INVALID;
+    return forward_impl(h, static_cast<const bf16*>(x), t, batch, height, width, sp, static_cast<bf16*>(out),
+                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ndit_sample(ndit_handle h, const void* z, int32_t batch, int32_t height, int32_t width, const float* grid,
+                           int32_t n_grid, int32_t method, const ndit_step_params* sp, void* traj, void* final_out,
+                           void* stream) {
+    if (!h || !z || !grid || !sp || !final_out) return NDIT_ERR_INVALID;
+    if (n_grid < 2) return h->fail(NDIT_ERR_INVALID, "need at least 2 grid points");
+    if (method != NDIT_EULER && method != NDIT_MIDPOINT) return h->fail(NDIT_ERR_INVALID, "method must be euler or midpoint");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
+    if (count > (size_t)h->Bmax * h->cfg.in_channels * h->cfg.max_tokens * 4) return h->fail(NDIT_ERR_INVALID, "latent too large");
+    bf16* y = h->ystate;
+    bf16* tr = static_cast<bf16*>(traj);
+    CK(cudaMemcpyAsync(y, z, count * 2, cudaMemcpyDeviceToDevice, s));
+    if (tr) CK(cudaMemcpyAsync(tr, z, count * 2, cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i + 1 < n_grid; ++i) {
+        const float t0 = grid[i], t1 = grid[i + 1];
+        const float dt = t1 - t0;
+        // torchdiffeq hands the model t cast to the state dtype (bf16)
+        if (method == NDIT_EULER) {
+            if (int e = forward_impl(h, y, host_bf16_round(t0), batch, height, width, sp, h->vel, s)) return e;
+            CKL(axpy_bf16(y, y, h->vel, dt, count, s));
+        } else {
+            const float half_dt = 0.5f * dt;
+            if (int e = forward_impl(h, y, host_bf16_round(t0), batch, height, width, sp, h->vel, s)) return e;
+            CKL(axpy_bf16(h->ymid, y, h->vel, half_dt, count, s));
+            if (int e = forward_impl(h, h->ymid, host_bf16_round(t0 + half_dt), batch, height, width, sp, h->vel, s)) return e;
+            CKL(axpy_bf16(y, y, h->vel, dt, count, s));
+        }
+        if (tr) CK(cudaMemcpyAsync(tr + (size_t)(i + 1) * count, y, count * 2, cudaMemcpyDeviceToDevice, s));
+    }
+    if (final_out != y) CK(cudaMemcpyAsync(final_out, y, count * 2, cudaMemcpyDeviceToDevice, s));
+    return NDIT_OK;
+}
+
+extern "C" int ndit_sample_host(ndit_handle h, const void* z_host, const void* cap_host, const uint8_t* mask_host,
+                                int32_t batch, int32_t height, int32_t width, int32_t T, const float* grid, int32_t n_grid,
+                                int32_t method, const ndit_step_params* sp, void* final_host, void* stream) {
+    if (!h || !z_host || !cap_host || !mask_host || !final_host) return NDIT_ERR_INVALID;
+    if (batch < 2 || batch > h->Bmax || T < 1 || T > h->Tmax) return h->fail(NDIT_ERR_INVALID, "batch/T out of range");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
+    if (count > (size_t)h->Bmax * h->cfg.in_channels * h->cfg.max_tokens * 4) return h->fail(NDIT_ERR_INVALID, "latent too large");
+    CK(cudaMemcpyAsync(h->stage_z, z_host, count * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->stage_cap, cap_host, (size_t)batch * T * h->C * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->stage_mask, mask_host, (size_t)batch * T, cudaMemcpyHostToDevice, s));
+    if (int e = ndit_set_caption(h, h->stage_cap, h->stage_mask, batch, T, stream)) return e;
+    if (int e = ndit_sample(h, h->stage_z, batch, height, width, grid, n_grid, method, sp, nullptr, h->stage_z, stream)) return e;
+    CK(cudaMemcpyAsync(final_host, h->stage_z, count * 2, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return NDIT_OK;
+}
+
+// ------------------------------------------------------------------------------------ single ops
+
+static thread_local char g_op_err[512] = "";
+static int op_fail(int code, const char* what, cudaError_t e) {
+    snprintf(g_create_err, sizeof(g_create_err), "%s: %s", what, e == cudaSuccess ? tmap_last_error() : cudaGetErrorString(e));
+    (void)g_op_err;
+    return code;
+}
+static int op_num_sms() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+extern "C" int ndit_op_gemm(const void* A, const void* W, void* C, int32_t M, int32_t N, int32_t K, int32_t swiglu, void* stream) {
+    GemmPlan p;
+    const int ldc = swiglu ? N / 2 : N;
+    if (make_gemm_plan(&p, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), static_cast<bf16*>(C), ldc, M, N, K,
+                       swiglu ? EPI_SWIGLU : EPI_STORE, op_num_sms()))
+        return op_fail(NDIT_ERR_CUDA, "ndit_op_gemm tensor map", cudaSuccess);
+    cudaError_t e = gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_gemm", e);
+}
+
+extern "C" int ndit_op_ln_rope(void* qkv, const void* qw, const void* qb, const void* kw, const void* kb, int32_t batch,
+                               int32_t Hp, int32_t Wp, int32_t H, int32_t Hkv, int32_t hd, float theta, float linear_factor,
+                               void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float2* tab = nullptr;
+    cudaError_t e = cudaMalloc(&tab, (size_t)Hp * Wp * (hd / 2) * sizeof(float2));
+    if (e != cudaSuccess) return op_fail(NDIT_ERR_NOMEM, "ndit_op_ln_rope", e);
+    e = rope_table(tab, Hp, Wp, hd, theta, linear_factor, s);
+    if (e == cudaSuccess)
+        e = ln_rope_qk(static_cast<bf16*>(qkv), (H + 2 * Hkv) * hd, static_cast<const bf16*>(qw), static_cast<const bf16*>(qb),
+                       static_cast<const bf16*>(kw), static_cast<const bf16*>(kb), tab, batch * Hp * Wp, Hp * Wp, H, Hkv, hd, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(tab);
+    if (e == cudaSuccess) e = e2;
+    return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_ln_rope", e);
+}
+
+extern "C" int ndit_op_attention(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
+                                 int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
+                                 int32_t use_ref, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int hd = 72;
+    const bf16* qkv = static_cast<const bf16*>(qkv_);
+    const bf16* kvy = static_cast<const bf16*>(kvy_);
+    const int Wq = (H + 2 * Hkv) * hd, KV = Hkv * hd;
+    if (use_ref) {
+        cudaError_t e = attention_ref(qkv, Wq, kvy, 2 * KV, ymask, gate_tanh, static_cast<bf16*>(out), B, N, T, H, Hkv, hd,
+                                      scale_self, scale_cross, s);
+        return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_attention(ref)", e);
+    }
+    if (N % 8 != 0) return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: N % 8 != 0", cudaErrorInvalidValue);
+    const int Tpad = (T + 7) / 8 * 8;
+    bf16 *vt = nullptr, *vyt = nullptr;
+    cudaError_t e = cudaMalloc(&vt, (size_t)B * KV * N * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&vyt, (size_t)B * KV * Tpad * 2);
+    if (e != cudaSuccess) return op_fail(NDIT_ERR_NOMEM, "ndit_op_attention", e);
+    cudaMemsetAsync(vyt, 0, (size_t)B * KV * Tpad * 2, s);
+    e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, N, 0, B, N, Hkv, hd, 1, s);
+    if (e == cudaSuccess) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, 1, s);
+    AttnPlan a;
+    memset(&a, 0, sizeof(a));
+    int te = 0;
+    const uint64_t rs = (uint64_t)Wq * 2, M = (uint64_t)B * N;
+    te |= make_tmap_3d(&a.tmQ64, qkv, hd, H, M, hd * 2, rs, 64, 1, 128, 128);
+    te |= make_tmap_3d(&a.tmQ16, qkv, hd, H, M, hd * 2, rs, 16, 1, 128, 32);
+    te |= make_tmap_3d(&a.tmK64, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, 128, 128);
+    te |= make_tmap_3d(&a.tmK16, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, 128, 32);
+    te |= make_tmap_3d(&a.tmVt, vt, N, hd, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * hd * 2, 64, 80, 1, 128);
+    te |= make_tmap_3d(&a.tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, 128, 128);
+    te |= make_tmap_3d(&a.tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, 128, 32);
+    te |= make_tmap_3d(&a.tmVyt, vyt, Tpad, hd, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * hd * 2, 64, 80, 1, 128);
+    int rc = NDIT_OK;
+    if (te) rc = op_fail(NDIT_ERR_CUDA, "ndit_op_attention tensor map", cudaSuccess);
+    if (!te && e == cudaSuccess) {
+        a.ymask = ymask; a.gate_tanh = gate_tanh; a.out = static_cast<bf16*>(out);
+        a.B = B; a.N = N; a.T = T; a.H = H; a.Hkv = Hkv; a.scale_self = scale_self; a.scale_cross = scale_cross;
+        e = attention_fused(a, s);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(vt);
+    cudaFree(vyt);
+    if (e == cudaSuccess) e = e2;
+    if (rc == NDIT_OK && e != cudaSuccess) rc = op_fail(NDIT_ERR_CUDA, "ndit_op_attention", e);
+    return rc;
+}
+
+extern "C" int ndit_op_resid_rms_mod(void* X, const void* o, const void* w_post, const float* tanh_g, const void* w_pre,
+                                     const float* onepls, void* u, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
+                                     void* stream) {
+    cudaError_t e = resid_rms_mod(static_cast<bf16*>(X), static_cast<const bf16*>(o), static_cast<const bf16*>(w_post), tanh_g,
+                                  static_cast<const bf16*>(w_pre), onepls, static_cast<bf16*>(u), M, rows_per_batch, D, D, eps,
+                                  static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_resid_rms_mod", e);
+}

@@ -1,0 +1,239 @@
+// bf16 GEMM  C[M,N] = A[M,K] * W[N,K]^T  (both operands K-major, fp32 accumulate in TMEM).
+//
+// Replaces the cuBLAS calls the reference reaches through F.linear at
+//   lumina_next_t2i/models/model.py:358 (wq|wk|wv), :438 (wo), :502 (w1, w3, w2), :421-422 (wk_y, wv_y).
+//
+// Design (sm_100a): persistent CTAs, one per SM; 192 threads:
+//   warp 0     TMA producer   (cp.async.bulk.tensor 128B-swizzled tiles -> smem ring)
+//   warp 1     MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction)
+//   warps 2-5  epilogue       (tcgen05.ld TMEM -> regs -> bf16 -> global)
+// Two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// EPI_SWIGLU: W rows are interleaved per 256-row block as [128 rows of w1 | 128 rows of w3]
+// and the epilogue writes silu(a)*b for the pair (FeedForward._forward_silu_gating, model.py:498-499),
+// rounding to bf16 where the reference materialises bf16 tensors.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ndit {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    bf16* __restrict__ C, int M, int N, int K, int ldc) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tempty_bar(as), aph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t da = make_smem_desc_kmajor(sa, 1024, UMMA_SW128);
+                    const uint64_t db = make_smem_desc_kmajor(sa + Cfg::A_BYTES, 1024, UMMA_SW128);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128B swizzle span: +2 in 16B units
+                        umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (kb == num_kb - 1) umma_commit(tfull_bar(as));
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            if (EPI == EPI_STORE) {
+                bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BN + c * 32;
+                    if (row < M) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (col0 + j * 8 < N) {  // N % 8 == 0
+                                uint4 o;
+                                o.x = pack_bf16(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+                                o.y = pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+                                o.z = pack_bf16(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+                                o.w = pack_bf16(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+                                *reinterpret_cast<uint4*>(crow + c * 32 + j * 8) = o;
+                            }
+                        }
+                    }
+                }
+            } else {
+                // SwiGLU: tile columns [0,BN/2) = w1 part, [BN/2,BN) = w3 part; output width N/2
+                constexpr int HN = BN / 2;
+                bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * HN;
+#pragma unroll 1
+                for (int c = 0; c < HN / 16; ++c) {
+                    uint32_t a[16], b[16];
+                    tmem_ld_32x32b_x16(taddr + c * 16, a);
+                    tmem_ld_32x32b_x16(taddr + HN + c * 16, b);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * HN + c * 16;
+                    if (row < M) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (col0 + j * 8 < N / 2) {
+                                float h[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float x1 = bf16_round(__uint_as_float(a[j * 8 + e]));
+                                    const float x3 = bf16_round(__uint_as_float(b[j * 8 + e]));
+                                    h[e] = bf16_round(silu_f(x1)) * x3;
+                                }
+                                uint4 o;
+                                o.x = pack_bf16(h[0], h[1]);
+                                o.y = pack_bf16(h[2], h[3]);
+                                o.z = pack_bf16(h[4], h[5]);
+                                o.w = pack_bf16(h[6], h[7]);
+                                *reinterpret_cast<uint4*>(crow + c * 16 + j * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+
+template <int BN, int EPI>
+static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, int M, int N, int K, int ldc,
+                               int num_sms, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_bf16_tn_kernel<BN, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
+    int grid = m_tiles * n_tiles;
+    if (grid > num_sms) grid = num_sms;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, C, M, N, K, ldc);
+    return cudaGetLastError();
+}
+
+cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
+    if (p.N % 8 != 0 || p.K % 8 != 0) return cudaErrorInvalidValue;
+    if (p.epi == EPI_SWIGLU) {
+        if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;
+        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    }
+    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+}
+
+}  // namespace ndit

@@ -1,0 +1,95 @@
+// Internal (C++) launch API of the sm_100a kernels.  The public boundary is include/ndit.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ndit {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- tensor maps (tensormap.cu)
+// bf16 2-D map over a row-major [rows, cols] matrix with row stride ld (elements):
+// box = box_rows x box_cols, swizzle = 128B (box_cols*2 must be 128) .
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+// bf16 3-D map: dims (d0 fastest, d1, d2) with byte strides s1, s2 (multiples of 16), box (b0,b1,b2).
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                 uint64_t s2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
+const char* tmap_last_error();
+
+// ---------------------------------------------------------------- GEMM (gemm_tcgen05.cu)
+enum { EPI_STORE = 0, EPI_SWIGLU = 1 };
+struct GemmPlan {
+    CUtensorMap tmA;  // A [M,K], box 128 x 64
+    CUtensorMap tmB;  // W [N,K], box bn  x 64
+    bf16* C;
+    int M, N, K, ldc;
+    int bn;   // 128 or 256
+    int epi;  // EPI_*
+    int num_sms;
+};
+cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream);
+// builds the maps of a plan (A: [M,K] ld=lda; W: [N,K] ld=K)
+int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int M, int N, int K, int epi,
+                   int num_sms);
+
+// ---------------------------------------------------------------- attention (attention_tcgen05.cu)
+struct AttnPlan {
+    CUtensorMap tmQ64, tmQ16;    // q  : dims (hd, H,   B*N) on the qkv buffer, boxes (64,1,128) / (16,1,128)
+    CUtensorMap tmK64, tmK16;    // k  : dims (hd, Hkv, B*N)
+    CUtensorMap tmVt;            // v^T: dims (N, hd, B*Hkv), box (64, 80, 1)
+    CUtensorMap tmKy64, tmKy16;  // ky : dims (hd, Hkv, B*T)
+    CUtensorMap tmVyt;           // vy^T: dims (Tpad, hd, B*Hkv), box (64, 80, 1)
+    const uint8_t* ymask;        // [B, T] bytes (0/1)
+    const float* gate_tanh;      // [H] bf16-rounded tanh(gate)
+    bf16* out;                   // [B*N, H*hd]
+    int B, N, T, H, Hkv;
+    float scale_self, scale_cross;
+};
+cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream);
+// slow CUDA-core reference of the same op (debug / NDIT_ATTN=ref); same inputs in plain layouts
+cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_kvy, const uint8_t* ymask,
+                          const float* gate_tanh, bf16* out, int B, int N, int T, int H, int Hkv, int hd,
+                          float scale_self, float scale_cross, cudaStream_t stream);
+
+// ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
+// X[token, :] = bf16(patch(x[b % n]) . Wx^T + bx)
+cudaError_t patch_embed(const bf16* x, const bf16* Wx, const bf16* bx, bf16* X, int B, int n_unique, int C, int Hh,
+                        int Ww, int D, cudaStream_t s);
+// tf[b, 0:256] = bf16(sinusoid(t)); pool[b, :] = bf16(LN(masked mean of cap[b]))  (fp32 storage)
+cudaError_t cond_prepare(float t, const bf16* cap, const uint8_t* mask, const bf16* ln_w, const bf16* ln_b, float* tf,
+                         float* pool, int B, int T, int C, int do_caption, cudaStream_t s);
+enum { POST_NONE = 0, POST_SILU = 1, POST_ADALN = 2 };
+// out[b,o] = post(bf16(sum_k in'[b,k] W[o,k] + bias[o]) (+ addend[b,o]));  in' = silu(in) if in_silu
+cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const float* addend, float* out, int B, int O,
+                      int K, int in_silu, int post, int adaln_D, int adaln_blocks, cudaStream_t s);
+// optional residual update  X += tanh_g * RMS(o; w_post)   then   u = RMS(X; w_pre) * onepls
+cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const float* tanh_g, const bf16* w_pre,
+                          const float* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
+                          cudaStream_t s);
+// residual update then LN(no affine, eps 1e-6) * onepls -> bf16 -> Linear(D->O)+bias -> out [M,O] (fp32 of bf16 values)
+cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const float* tanh_g, const float* onepls,
+                        const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
+                        int mod_stride, float eps, cudaStream_t s);
+// rope table [N][hd/2] (cos,sin)
+cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, cudaStream_t s);
+// in place on qkv [M, ld]: q = bf16(rope(LN(q))), k = bf16(rope(LN(k)))
+cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const bf16* kw, const bf16* kb,
+                       const float2* rope, int M, int N_tokens, int H, int Hkv, int hd, cudaStream_t s);
+// in place LayerNorm(width) + affine on rows of a [M, ld] matrix (no rope), layer-batched via blockIdx.y
+cudaError_t ln_rows(bf16* x, int ld, size_t layer_stride_x, const bf16* w, const bf16* b, size_t layer_stride_w,
+                    int M, int width, int layers, cudaStream_t s);
+// out[l][row,:] = RMS(y[row,:]; w[l]) for all layers
+cudaError_t rms_rows_layers(const bf16* y, const bf16* w, bf16* out, int M, int C, int layers, float eps, cudaStream_t s);
+// dst[(b*G + g)*hd + d][n] = src[(b*N + n)*ld + col0 + g*hd + d]   (v -> v^T), layers via blockIdx.z
+cudaError_t transpose_v(const bf16* src, int ld, int col0, size_t src_layer_stride, bf16* dst, int ld_dst,
+                        size_t dst_layer_stride, int B, int N, int G, int hd, int layers, cudaStream_t s);
+// unpatchify + learn_sigma slice + 3-channel CFG combine (+ optional fused Euler update)
+//   tok [2n*N, O] (fp32 of bf16 values) -> v [2n,4,Hh,Ww] bf16;  if y_inout: y = bf16(y + bf16(dt*v))
+cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale,
+                           cudaStream_t s);
+cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s);
+
+}  // namespace ndit

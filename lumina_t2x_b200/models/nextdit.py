@@ -1,0 +1,275 @@
+"""Drop-in mirror of the reference ``models.NextDiT`` for the sampling hot path.
+
+Same constructor arguments, factory names, state-dict keys/shapes and ``forward_with_cfg`` signature as
+``lumina_next_t2i/models/model.py:665-999`` (fairscale flavour) and
+``lumina_next_t2i_mini/models/nextdit.py:607-944``, so ``sample.py`` / ``demo.py`` keep working with only
+``sys.path`` changed.  The module only *holds* parameters (PyTorch owns them); all compute is done by
+libndit_b200.so through the C ABI in include/ndit.h.  There is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+class _Weight(nn.Module):
+    """Parameter holder for RMSNorm (reference: models/components.py:11-54)."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+def _linear(i: int, o: int, bias: bool, init: str = "xavier") -> nn.Linear:
+    m = nn.Linear(i, o, bias=bias)
+    if init == "xavier":
+        nn.init.xavier_uniform_(m.weight)
+    elif init == "zeros":
+        nn.init.zeros_(m.weight)
+    else:
+        nn.init.normal_(m.weight, std=0.02)
+    if bias:
+        nn.init.zeros_(m.bias)
+    return m
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, n_heads, n_kv_heads, qk_norm, y_dim):
+        super().__init__()
+        hd = dim // n_heads
+        kv = (n_kv_heads or n_heads) * hd
+        self.wq, self.wk, self.wv = _linear(dim, dim, False), _linear(dim, kv, False), _linear(dim, kv, False)
+        self.wk_y, self.wv_y = _linear(y_dim, kv, False), _linear(y_dim, kv, False)
+        self.gate = nn.Parameter(torch.zeros(n_heads))
+        self.wo = _linear(dim, dim, False)
+        if qk_norm:
+            self.q_norm, self.k_norm, self.ky_norm = nn.LayerNorm(dim), nn.LayerNorm(kv), nn.LayerNorm(kv)
+        else:
+            self.q_norm = self.k_norm = self.ky_norm = nn.Identity()
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.w1, self.w2, self.w3 = _linear(dim, hidden, False), _linear(hidden, dim, False), _linear(dim, hidden, False)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, n_heads, n_kv_heads, hidden, qk_norm, y_dim):
+        super().__init__()
+        self.attention = _Attention(dim, n_heads, n_kv_heads, qk_norm, y_dim)
+        self.feed_forward = _FeedForward(dim, hidden)
+        self.attention_norm1, self.ffn_norm1 = _Weight(dim), _Weight(dim)
+        self.attention_norm2, self.ffn_norm2 = _Weight(dim), _Weight(dim)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), _linear(min(dim, 1024), 4 * dim, True, "zeros"))
+        self.attention_y_norm = _Weight(y_dim)
+
+
+class _TimestepEmbedder(nn.Module):
+    def __init__(self, hidden, freq=256):
+        super().__init__()
+        self.mlp = nn.Sequential(_linear(freq, hidden, True, "normal"), nn.SiLU(), _linear(hidden, hidden, True, "normal"))
+
+
+class _FinalLayer(nn.Module):
+    def __init__(self, dim, patch_size, out_channels):
+        super().__init__()
+        self.linear = _linear(dim, patch_size * patch_size * out_channels, True, "zeros")
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), _linear(min(dim, 1024), dim, True, "zeros"))
+
+
+class NextDiT(nn.Module):
+    """B200 engine behind the reference ``NextDiT`` API (model.py:665-989)."""
+
+    def __init__(self, patch_size: int = 2, in_channels: int = 4, dim: int = 4096, n_layers: int = 32, n_heads: int = 32,
+                 n_kv_heads: Optional[int] = None, multiple_of: int = 256, ffn_dim_multiplier: Optional[float] = None,
+                 norm_eps: float = 1e-5, learn_sigma: bool = True, qk_norm: bool = False, cap_feat_dim: int = 5120,
+                 scale_factor: float = 1.0, use_flash_attn: bool = True,
+                 max_tokens: int = 4096, max_cap_len: int = 256, max_batch: int = 2) -> None:
+        super().__init__()
+        self.learn_sigma, self.in_channels, self.patch_size = learn_sigma, in_channels, patch_size
+        self.out_channels = in_channels * 2 if learn_sigma else in_channels
+        self.dim, self.n_heads, self.n_layers = dim, n_heads, n_layers
+        self.n_kv_heads = n_kv_heads or n_heads
+        self.cap_feat_dim, self.norm_eps, self.multiple_of = cap_feat_dim, norm_eps, multiple_of
+        self.qk_norm, self.scale_factor = qk_norm, scale_factor
+        hidden = int(2 * (4 * dim) / 3)
+        if ffn_dim_multiplier is not None:
+            hidden = int(ffn_dim_multiplier * hidden)
+        hidden = multiple_of * ((hidden + multiple_of - 1) // multiple_of)
+        self.ffn_dim = hidden
+        self._ffn_dim_multiplier = ffn_dim_multiplier
+        self.x_embedder = _linear(patch_size * patch_size * in_channels, dim, True)
+        self.t_embedder = _TimestepEmbedder(min(dim, 1024))
+        self.cap_embedder = nn.Sequential(nn.LayerNorm(cap_feat_dim), _linear(cap_feat_dim, min(dim, 1024), True, "zeros"))
+        self.layers = nn.ModuleList([_Block(dim, n_heads, n_kv_heads, hidden, qk_norm, cap_feat_dim) for _ in range(n_layers)])
+        self.final_layer = _FinalLayer(dim, patch_size, self.out_channels)
+        assert (dim // n_heads) % 4 == 0, "2d rope needs head dim to be divisible by 4"
+        self.pad_token = nn.Parameter(torch.empty(dim))
+        nn.init.normal_(self.pad_token, std=0.02)
+        # engine state (not part of the state dict)
+        self._limits = (max_tokens, max_cap_len, max_batch)
+        self._handle: Optional[C.c_void_p] = None
+        self._dirty = True
+        self._cap_key = None
+        self._cap_keepalive = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _apply(self, fn, *a, **k):           # .to() / .cuda() / .bfloat16() move the parameters
+        self._dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._dirty = True
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def mark_weights_changed(self) -> None:
+        """Call after modifying parameters in place; the engine re-packs them on the next forward."""
+        self._dirty = True
+
+    def _destroy(self):
+        if self._handle is not None:
+            _lib.load().ndit_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def reserve(self, max_tokens: Optional[int] = None, max_cap_len: Optional[int] = None, max_batch: Optional[int] = None):
+        """Resize the engine workspace limits (recreates the engine on the next call)."""
+        t, c, b = self._limits
+        self._limits = (max_tokens or t, max_cap_len or c, max_batch or b)
+        self._dirty = True
+
+    def _engine(self, device: torch.device):
+        lib = _lib.load()
+        if self._handle is not None and not self._dirty:
+            return lib, self._handle
+        if not self.qk_norm:
+            raise NotImplementedError("the B200 engine implements the qk_norm=True architecture (Lumina-Next-T2I)")
+        if self._ffn_dim_multiplier is not None:
+            raise NotImplementedError("ffn_dim_multiplier is not supported by the B200 engine")
+        if device.type != "cuda":
+            raise RuntimeError("NextDiT (B200 engine) needs its parameters on a CUDA device; there is no CPU path")
+        self._destroy()
+        cfg = _lib.NditConfig(self.dim, self.n_layers, self.n_heads, self.n_kv_heads, self.cap_feat_dim, self.in_channels,
+                              self.patch_size, self.multiple_of, int(self.learn_sigma), float(self.norm_eps), *self._limits)
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.ndit_create(C.byref(cfg), C.byref(h)), None)
+            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            for key, p in self.state_dict().items():
+                t = p.detach()
+                if t.device != device:
+                    raise RuntimeError(f"parameter {key} is on {t.device}, expected {device}")
+                if t.dtype == torch.bfloat16:
+                    dt = _lib.NDIT_BF16
+                elif t.dtype == torch.float32:
+                    dt = _lib.NDIT_F32
+                else:
+                    t, dt = t.float(), _lib.NDIT_F32
+                t = t.contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.ndit_set_weight(h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim(), dt, stream), h)
+            torch.cuda.current_stream(device).synchronize()   # temporaries above must outlive the copies
+            _lib.check(lib.ndit_finalize_weights(h, stream), h)
+        self._handle, self._dirty, self._cap_key = h, False, None
+        return lib, h
+
+    def _set_caption(self, lib, h, cap_feats: torch.Tensor, cap_mask: torch.Tensor, stream):
+        key = (cap_feats.data_ptr(), cap_feats._version, tuple(cap_feats.shape), cap_feats.dtype,
+               cap_mask.data_ptr(), cap_mask._version, tuple(cap_mask.shape))
+        if key == self._cap_key:
+            return
+        cap = cap_feats.detach().to(torch.bfloat16).contiguous()
+        mask = (cap_mask.detach() != 0).to(torch.uint8).contiguous()
+        B, T, Cd = cap.shape
+        if Cd != self.cap_feat_dim or tuple(mask.shape) != (B, T):
+            raise ValueError(f"cap_feats {tuple(cap.shape)} / cap_mask {tuple(mask.shape)} do not match cap_feat_dim {self.cap_feat_dim}")
+        _lib.check(lib.ndit_set_caption(h, C.c_void_p(cap.data_ptr()), C.c_void_p(mask.data_ptr()), B, T, stream), h)
+        self._cap_key = key
+        self._cap_keepalive = (cap_feats, cap_mask, cap, mask)   # keep the ids in the cache key alive
+
+    @staticmethod
+    def _step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn):
+        if proportional_attn:
+            assert base_seqlen is not None
+        return _lib.NditStepParams(float(cfg_scale), float(scale_factor), float(scale_watershed), int(bool(proportional_attn)),
+                                   int(base_seqlen) if base_seqlen is not None else 0)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x, t, cap_feats, cap_mask):
+        raise NotImplementedError("the B200 engine accelerates forward_with_cfg (the sampling path); "
+                                  "plain forward (training) is out of scope")
+
+    @torch.no_grad()
+    def forward_with_cfg(self, x, t, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0,
+                         base_seqlen: Optional[int] = None, proportional_attn: bool = False):
+        """model.py:866-913.  x [2n,C,H,W]; first half = cond, second half ignored on input."""
+        if not isinstance(x, torch.Tensor):
+            raise NotImplementedError("list-of-tensors (variable resolution) input is not supported by the B200 engine")
+        lib, h = self._engine(x.device)
+        with torch.cuda.device(x.device):
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._set_caption(lib, h, cap_feats, cap_mask, stream)
+            xb = x.detach().to(torch.bfloat16).contiguous()
+            out = torch.empty_like(xb)
+            tv = float(t[0].item()) if isinstance(t, torch.Tensor) else float(t)    # reference syncs here too (model.py:888)
+            sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
+            B, _, Hh, Ww = xb.shape
+            _lib.check(lib.ndit_forward_cfg(h, C.c_void_p(xb.data_ptr()), tv, B, Hh, Ww, C.byref(sp), C.c_void_p(out.data_ptr()), stream), h)
+        return out.to(x.dtype)
+
+    @torch.no_grad()
+    def sample_fixed_grid(self, z, t_grid, method: str, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0,
+                          base_seqlen: Optional[int] = None, proportional_attn: bool = False, return_trajectory: bool = True):
+        """Whole fixed-grid ODE solve inside the engine (used by transport.Sampler for euler / midpoint)."""
+        lib, h = self._engine(z.device)
+        with torch.cuda.device(z.device):
+            stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+            self._set_caption(lib, h, cap_feats, cap_mask, stream)
+            zb = z.detach().to(torch.bfloat16).contiguous()
+            grid = [float(v) for v in t_grid]
+            n = len(grid)
+            garr = (C.c_float * n)(*grid)
+            B, _, Hh, Ww = zb.shape
+            traj = torch.empty((n,) + tuple(zb.shape), dtype=torch.bfloat16, device=z.device) if return_trajectory else None
+            final = torch.empty_like(zb)
+            sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
+            m = {"euler": _lib.NDIT_EULER, "midpoint": _lib.NDIT_MIDPOINT}[method]
+            _lib.check(lib.ndit_sample(h, C.c_void_p(zb.data_ptr()), B, Hh, Ww, garr, n, m, C.byref(sp),
+                                       C.c_void_p(traj.data_ptr()) if traj is not None else None,
+                                       C.c_void_p(final.data_ptr()), stream), h)
+        return (traj if return_trajectory else final).to(z.dtype)
+
+    def parameter_count(self) -> int:
+        """model.py:965-982."""
+        return sum(p.numel() for p in self.parameters())
+
+    def launch_count(self) -> int:
+        return int(_lib.load().ndit_launch_count(self._handle)) if self._handle is not None else 0
+
+    def set_option(self, name: str, value: int) -> None:
+        lib, h = self._engine(next(self.parameters()).device)
+        _lib.check(lib.ndit_set_option(h, name.encode(), int(value)), h)
+
+    def get_fsdp_wrap_module_list(self):
+        return list(self.layers)
+
+
+def NextDiT_2B_patch2(**kwargs):
+    """model.py:994-995."""
+    return NextDiT(patch_size=2, dim=2304, n_layers=24, n_heads=32, **kwargs)
+
+
+def NextDiT_2B_GQA_patch2(**kwargs):
+    """model.py:998-999."""
+    return NextDiT(patch_size=2, dim=2304, n_layers=24, n_heads=32, n_kv_heads=8, **kwargs)

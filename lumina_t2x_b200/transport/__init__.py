@@ -1,0 +1,184 @@
+"""Drop-in mirror of the reference ``transport`` package for ODE sampling.
+
+Mirrors ``lumina_next_t2i/transport/__init__.py:4-66`` (create_transport), ``transport.py:221-391``
+(Sampler.sample_ode), ``integrators.py:79-116`` (the ``ode`` helper) and the mini flavour's
+``lumina_next_t2i_mini/transport.py:57-111`` (``ODE``).  Fixed-grid ``euler`` / ``midpoint`` solves whose model
+function is ``NextDiT.forward_with_cfg`` of the B200 engine run entirely inside libndit_b200.so
+(``ndit_sample``); any other model function is driven by the same fixed-grid loop in PyTorch.  Training
+losses, SDE sampling and likelihoods are out of scope.
+"""
+from __future__ import annotations
+
+import enum
+from typing import Callable, Optional
+
+import torch as th
+
+from ..models.nextdit import NextDiT
+
+__all__ = ["create_transport", "Sampler", "Transport", "ModelType", "PathType", "WeightType", "ODE"]
+
+
+class ModelType(enum.Enum):
+    NOISE = enum.auto()
+    SCORE = enum.auto()
+    VELOCITY = enum.auto()
+
+
+class PathType(enum.Enum):
+    LINEAR = enum.auto()
+    GVP = enum.auto()
+    VP = enum.auto()
+
+
+class WeightType(enum.Enum):
+    NONE = enum.auto()
+    VELOCITY = enum.auto()
+    LIKELIHOOD = enum.auto()
+
+
+class Transport:
+    def __init__(self, *, model_type, path_type, loss_type, train_eps, sample_eps, snr_type="uniform"):
+        self.model_type, self.path_type, self.loss_type = model_type, path_type, loss_type
+        self.train_eps, self.sample_eps, self.snr_type = train_eps, sample_eps, snr_type
+
+    def check_interval(self, train_eps, sample_eps, *, diffusion_form="SBDM", sde=False, reverse=False, eval=False,
+                       last_step_size=0.0):
+        """transport.py:67-93."""
+        t0, t1 = 0, 1
+        eps = train_eps if not eval else sample_eps
+        if self.path_type == PathType.VP:
+            t1 = 1 - eps if (not sde or last_step_size == 0) else 1 - last_step_size
+        elif self.model_type != ModelType.VELOCITY or sde:
+            t0 = eps if (diffusion_form == "SBDM" and sde) or self.model_type != ModelType.VELOCITY else 0
+            t1 = 1 - eps if (not sde or last_step_size == 0) else 1 - last_step_size
+        if reverse:
+            t0, t1 = 1 - t0, 1 - t1
+        return t0, t1
+
+    def training_losses(self, *a, **k):
+        raise NotImplementedError("training is out of scope for the B200 sampling engine")
+
+
+def create_transport(path_type="Linear", prediction="velocity", loss_weight=None, train_eps=None, sample_eps=None,
+                     snr_type="uniform") -> Transport:
+    """transport/__init__.py:4-66 (same defaults and eps selection, including its use of ``train_eps`` in the
+    ``sample_eps`` test)."""
+    model_type = {"noise": ModelType.NOISE, "score": ModelType.SCORE}.get(prediction, ModelType.VELOCITY)
+    loss_type = {"velocity": WeightType.VELOCITY, "likelihood": WeightType.LIKELIHOOD}.get(loss_weight, WeightType.NONE)
+    ptype = {"Linear": PathType.LINEAR, "GVP": PathType.GVP, "VP": PathType.VP}[path_type]
+    if ptype == PathType.VP:
+        train_eps, sample_eps = (1e-5 if train_eps is None else train_eps), (1e-3 if train_eps is None else sample_eps)
+    elif model_type != ModelType.VELOCITY:
+        train_eps, sample_eps = (1e-3 if train_eps is None else train_eps), (1e-3 if train_eps is None else sample_eps)
+    else:
+        train_eps = sample_eps = 0
+    return Transport(model_type=model_type, path_type=ptype, loss_type=loss_type, train_eps=train_eps,
+                     sample_eps=sample_eps, snr_type=snr_type)
+
+
+def _time_grid(t0, t1, num_steps, time_shifting_factor):
+    """integrators.py:97-99: ``num_steps`` grid POINTS (num_steps-1 integration steps)."""
+    t = th.linspace(t0, t1, num_steps)
+    if time_shifting_factor:
+        t = t / (t + time_shifting_factor - time_shifting_factor * t)
+    return t
+
+
+_ENGINE_KW = ("cap_feats", "cap_mask", "cfg_scale", "scale_factor", "scale_watershed", "base_seqlen", "proportional_attn")
+
+
+def _engine_of(model_fn) -> Optional[NextDiT]:
+    owner = getattr(model_fn, "__self__", None)
+    if isinstance(owner, NextDiT) and getattr(model_fn, "__func__", None) is NextDiT.forward_with_cfg:
+        return owner
+    return None
+
+
+def _fixed_grid_torch(fn: Callable, x: th.Tensor, t: th.Tensor, method: str) -> th.Tensor:
+    """torchdiffeq fixed-grid euler / midpoint / rk4 semantics for an arbitrary model function
+    (t is cast to the state dtype before the call, like torchdiffeq's _PerturbFunc)."""
+    sol, y = [x], x
+
+    def f(tt, yy):
+        return fn(tt.to(yy.dtype), yy)
+
+    for ta, tb in zip(t[:-1], t[1:]):
+        dt = tb - ta
+        if method == "euler":
+            dy = dt * f(ta, y)
+        elif method == "midpoint":
+            half = 0.5 * dt
+            dy = dt * f(ta + half, y + f(ta, y) * half)
+        elif method == "rk4":     # torchdiffeq's 3/8-rule rk4
+            k1 = f(ta, y)
+            k2 = f(ta + dt / 3, y + dt * k1 / 3)
+            k3 = f(ta + dt * 2 / 3, y + dt * (k2 - k1 / 3))
+            k4 = f(tb, y + dt * (k1 - k2 + k3))
+            dy = (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+        else:
+            raise NotImplementedError(
+                f"sampling_method={method!r}: the B200 transport implements the fixed-grid euler/midpoint/rk4 solvers; "
+                "adaptive solvers need torchdiffeq")
+        y = y + dy
+        sol.append(y)
+    return th.stack(sol, dim=0)
+
+
+def _solve(x, model_fn, t_grid, method, model_kwargs, wrap_drift=None):
+    eng = _engine_of(model_fn) if wrap_drift is None else None
+    if (eng is not None and method in ("euler", "midpoint") and isinstance(x, th.Tensor) and x.is_cuda
+            and set(model_kwargs) <= set(_ENGINE_KW) and {"cap_feats", "cap_mask", "cfg_scale"} <= set(model_kwargs)):
+        return eng.sample_fixed_grid(x, t_grid.tolist(), method, **model_kwargs)
+    device = x.device
+
+    def _fn(t, xx):
+        tv = th.ones(xx.size(0), device=device) * t
+        if wrap_drift is not None:
+            return wrap_drift(xx, tv, model_fn, **model_kwargs)
+        return model_fn(xx, tv, **model_kwargs)
+
+    return _fixed_grid_torch(_fn, x, t_grid.to(device), method)
+
+
+class Sampler:
+    """transport.py:221-391 (ODE part)."""
+
+    def __init__(self, transport: Transport):
+        self.transport = transport
+
+    def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False,
+                   time_shifting_factor=None):
+        tr = self.transport
+        t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, sde=False, eval=True, reverse=reverse, last_step_size=0.0)
+        velocity_linear = tr.model_type == ModelType.VELOCITY and not reverse
+        if not velocity_linear:
+            raise NotImplementedError("the B200 transport implements velocity-prediction forward-time ODE sampling "
+                                      "(the Lumina-Next configuration); score/noise parameterisations and reverse solves are out of scope")
+        assert t0 < t1, "ODE sampler has to be in forward time"
+        grid = _time_grid(t0, t1, num_steps, time_shifting_factor)
+
+        def _sample(x, model, **model_kwargs):
+            out = _solve(x, model, grid, sampling_method, model_kwargs)
+            assert out.shape[1:] == x.shape, "Output shape from ODE solver must match input shape"
+            return out
+
+        return _sample
+
+    def sample_sde(self, *a, **k):
+        raise NotImplementedError("SDE sampling is out of scope for the B200 engine (SURVEY.md 8f)")
+
+
+class ODE:
+    """lumina_next_t2i_mini/transport.py:57-111 (non-SD3 branch)."""
+
+    def __init__(self, num_steps, sampler_type="euler", time_shifting_factor=None, t0=0.0, t1=1.0, use_sd3=False, strength=1.0):
+        if use_sd3:
+            raise NotImplementedError("SD3 sampling is out of scope")
+        self.t = _time_grid(t0, t1, num_steps, time_shifting_factor)
+        if strength != 1.0:
+            self.t = self.t[int(num_steps * (1 - strength)):]
+        self.sampler_type = sampler_type
+
+    def sample(self, x, model, **model_kwargs):
+        return _solve(x, model, self.t, self.sampler_type, model_kwargs)

@@ -1,0 +1,159 @@
+"""GPU parity of the whole hot path through the drop-in Python API (-> C ABI -> sm_100a kernels) against
+the oracle and the committed golden fixtures (outputs of the unmodified reference, tests/golden/).
+
+Tolerances (relative L-inf = max|a-b| / max|ref|):
+  * engine vs oracle in "bf16" mode (same rounding points, fp32 accumulation order differs): 2e-2.
+    bf16 has 2^-8 = 3.9e-3 relative resolution; 24-layer error growth is bounded by the reference's own
+    bf16-vs-fp32 distance, which the fixtures record (about 1.3e-2 .. 1.5e-2 for the 2-layer tiny model).
+  * engine vs the reference's fp32 output: must be within 1.5x of the reference's own autocast-bf16 distance
+    to its fp32 output (the "noise floor" of SURVEY.md 7), plus 2e-3.
+The north-star's 1e-3 is not reachable by any bf16 pipeline, including the reference's own
+(see DESIGN.md "Parity").
+"""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import nextdit_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+
+
+def _build(cfg, W, **kw):
+    from lumina_t2x_b200 import models
+    m = models.NextDiT(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=True,
+                       cap_feat_dim=cfg.cap_feat_dim, **kw)
+    m.load_state_dict(W, strict=True)
+    return m.eval().to("cuda", dtype=torch.bfloat16)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = O.config_tiny(n_layers=2)
+    W = O.synthetic_weights(cfg, seed=0)
+    return cfg, W, _build(cfg, W, max_tokens=1024, max_cap_len=64)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fwd_*.pt"))), ids=os.path.basename)
+@pytest.mark.parametrize("attn", ["tcgen05", "refkernel"])
+def test_forward_with_cfg_vs_golden_and_oracle(tiny, path, attn):
+    cfg, W, m = tiny
+    fx = torch.load(path, map_location="cpu", weights_only=False)
+    z, cap, mask = O.synthetic_inputs(cfg, tuple(fx["hw"]), fx["T"], fx["ul"], seed=fx["input_seed"])
+    t = torch.full((2,), fx["t"])
+    m.set_option("attn_ref", 1 if attn == "refkernel" else 0)
+    out = m.forward_with_cfg(z.cuda(), t.cuda(), cap.cuda(), mask.cuda(), **fx["kw"]).float().cpu()
+    m.set_option("attn_ref", 0)
+    assert out.shape == z.shape and torch.isfinite(out).all()
+    orc = O.forward_with_cfg(cfg, W, z, t, cap, mask, precision="bf16", **fx["kw"])
+    ref32 = fx["out_fp32"]
+    floor = _rel(fx["out_autocast_cpu_bf16"], ref32)
+    assert _rel(out, orc) < 2e-2, (_rel(out, orc), floor)
+    assert _rel(out, ref32) < 1.5 * floor + 2e-3, (_rel(out, ref32), floor)
+    # CFG structure (model.py:904-913): guided channels identical for both rows
+    assert torch.equal(out[0, :3], out[1, :3])
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint"])
+def test_sampler_trajectory(tiny, method):
+    """transport.Sampler.sample_ode -> ndit_sample, against the oracle's bf16-state trajectory and the
+    reference's fp32 trajectory fixture."""
+    from lumina_t2x_b200 import transport
+    cfg, W, m = tiny
+    fx = torch.load(os.path.join(GOLD, f"traj_{method}.pt"), map_location="cpu", weights_only=False)
+    z, cap, mask = O.synthetic_inputs(cfg, tuple(fx["hw"]), fx["T"], fx["ul"], seed=fx["input_seed"])
+    tr = transport.create_transport("Linear", "velocity", None, None, None)
+    fn = transport.Sampler(tr).sample_ode(sampling_method=method, num_steps=fx["num_steps"], atol=1e-6, rtol=1e-3,
+                                          reverse=False, time_shifting_factor=fx["time_shifting_factor"])
+    traj = fn(z.cuda(), m.forward_with_cfg, cap_feats=cap.cuda(), cap_mask=mask.cuda(), **fx["kw"]).float().cpu()
+    assert traj.shape == fx["traj_fp32"].shape
+    assert torch.equal(traj[0], z.float())
+    orc = O.sample_ode(cfg, W, z, cap, mask, num_steps=fx["num_steps"], method=method,
+                       time_shifting_factor=fx["time_shifting_factor"], precision="bf16", **fx["kw"])
+    assert _rel(traj[-1], orc[-1]) < 3e-2, _rel(traj[-1], orc[-1])
+    assert _rel(traj[-1], fx["traj_fp32"][-1]) < 5e-2
+    # the generic (PyTorch-driven) loop over the same engine must agree with the fused loop bit for bit
+    traj2 = transport._fixed_grid_torch(
+        lambda t, x: m.forward_with_cfg(x, torch.ones(2, device="cuda") * t, cap.cuda(), mask.cuda(), **fx["kw"]),
+        z.cuda(), transport._time_grid(0, 1, fx["num_steps"], fx["time_shifting_factor"]).cuda(), method).float().cpu()
+    assert torch.equal(traj, traj2)
+
+
+def test_mini_ode_class_and_determinism(tiny):
+    from lumina_t2x_b200 import transport
+    cfg, W, m = tiny
+    z, cap, mask = O.synthetic_inputs(cfg, (32, 32), 24, 8, seed=4)
+    kw = dict(cfg_scale=2.0, scale_factor=1.0, scale_watershed=1.0, base_seqlen=64, proportional_attn=True)
+    a = transport.ODE(4, "euler", 1.0).sample(z.cuda(), m.forward_with_cfg, cap_feats=cap.cuda(), cap_mask=mask.cuda(), **kw)
+    b = transport.ODE(4, "euler", 1.0).sample(z.cuda(), m.forward_with_cfg, cap_feats=cap.cuda(), cap_mask=mask.cuda(), **kw)
+    assert a.shape == (4, 2, 4, 32, 32) and torch.equal(a, b)
+    orc = O.sample_ode(cfg, W, z, cap, mask, num_steps=4, method="euler", time_shifting_factor=1.0, precision="bf16", **kw)
+    assert _rel(a[-1].float().cpu(), orc[-1]) < 3e-2
+
+
+def test_strict_loading_and_errors():
+    from lumina_t2x_b200 import models
+    cfg = O.config_tiny(n_layers=1)
+    W = O.synthetic_weights(cfg, seed=0)
+    m = models.NextDiT(dim=cfg.dim, n_layers=1, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=True,
+                       cap_feat_dim=cfg.cap_feat_dim, max_tokens=256, max_cap_len=32)
+    bad = dict(W)
+    bad.pop("layers.0.attention.gate")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    m.load_state_dict(W, strict=True)
+    m = m.to("cuda", dtype=torch.bfloat16)
+    z, cap, mask = O.synthetic_inputs(cfg, (16, 16), 16, 8)
+    with pytest.raises(RuntimeError):           # more tokens than the workspace was sized for
+        m.forward_with_cfg(torch.zeros(2, 4, 64, 64, device="cuda", dtype=torch.bfloat16), torch.zeros(2, device="cuda"),
+                           cap.cuda(), mask.cuda(), 2.0)
+    out = m.forward_with_cfg(z.cuda(), torch.full((2,), 0.5, device="cuda"), cap.cuda(), mask.cuda(), 2.0)
+    assert torch.isfinite(out.float()).all()
+    assert m.launch_count() > 0
+
+
+def test_flagship_one_forward_properties():
+    """Config-2 shapes (2B GQA, 1024x1024 latent 128x128, T=128): one forward_with_cfg at full size.
+    The oracle needs ~1 min/forward on CPU, so full size is checked through size-independent properties:
+    determinism, CFG row structure, cfg_scale linearity of the guided channels, and agreement of the
+    tcgen05 attention with the CUDA-core reference attention kernel inside the same engine."""
+    from lumina_t2x_b200 import models
+    cfg = O.config_2b_gqa()
+    m = models.NextDiT_2B_GQA_patch2(qk_norm=True, cap_feat_dim=2048, max_tokens=4096, max_cap_len=128)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if p.dim() == 2:
+                std = (0.5 if "adaLN" in k else 1.0) / (p.shape[1] ** 0.5)
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+            elif k.endswith("gate"):
+                p.copy_(0.5 * torch.randn(p.shape, generator=g))
+            elif "norm" in k and k.endswith("weight") or k == "cap_embedder.0.weight":
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+    m = m.eval().to("cuda", dtype=torch.bfloat16)
+    z, cap, mask = O.synthetic_inputs(cfg, (128, 128), 128, 8, seed=1)
+    z, cap, mask = z.cuda(), cap.cuda(), mask.cuda()
+    t = torch.full((2,), 0.3, device="cuda")
+    kw = dict(scale_factor=1.0, scale_watershed=1.0, base_seqlen=4096, proportional_attn=True)
+    a = m.forward_with_cfg(z, t, cap, mask, 2.0, **kw)
+    b = m.forward_with_cfg(z, t, cap, mask, 2.0, **kw)
+    assert torch.isfinite(a.float()).all() and torch.equal(a, b)
+    assert torch.equal(a[0, :3], a[1, :3])
+    c1 = m.forward_with_cfg(z, t, cap, mask, 1.0, **kw).float()     # = cond (up to bf16 rounding of the combine)
+    c0 = m.forward_with_cfg(z, t, cap, mask, 0.0, **kw).float()     # = uncond
+    lin = c0[0, :3] + 2.0 * (c1[0, :3] - c0[0, :3])
+    assert _rel(a[0, :3], lin) < 2e-2
+    assert torch.equal(c1[0, 3], a[0, 3].float()) and torch.equal(c0[1, 3], a[1, 3].float())   # channel 3 is never guided
+    m.set_option("attn_ref", 1)
+    r = m.forward_with_cfg(z, t, cap, mask, 2.0, **kw)
+    m.set_option("attn_ref", 0)
+    assert _rel(a, r) < 2e-2, _rel(a, r)
