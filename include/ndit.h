@@ -107,7 +107,12 @@ int ndit_sample_host(ndit_handle h, const void* z_host, const void* cap_feats_ho
 
 /* --- instrumentation */
 int64_t ndit_launch_count(ndit_handle h);          /* kernels launched by this handle so far */
-int ndit_set_option(ndit_handle h, const char* name, int32_t value);   /* "attn_ref" = 1: debug attention */
+int ndit_set_option(ndit_handle h, const char* name, int32_t value);   /* "attn_ref" = 1: debug attention;
+                                                                          "profile" = 1: CUDA events around every launch */
+/* Sums the per-launch CUDA-event durations recorded since "profile" was switched on (or since the last read),
+ * per kernel class: 0 gemm_qkv, 1 gemm_wo, 2 gemm_w13(swiglu), 3 gemm_w2, 4 attention, 5 row-wise, 6 conditioning. */
+#define NDIT_PROFILE_CLASSES 7
+int ndit_profile_read(ndit_handle h, float* ms_out, int64_t* count_out, int32_t n_classes);
 
 /* --- single-operator entry points (parity tests and micro-benchmarks call the kernels through these) */
 /* C[M,N] = A[M,K] W[N,K]^T, bf16, fp32 accumulate.  swiglu != 0: W is [2F,K] block-interleaved

@@ -71,6 +71,10 @@ struct ndit_engine {
     int64_t n_params = 0;
     bool finalized = false;
     int attn_ref = 0;
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_class;       // class of event pair i (events 2i, 2i+1)
+    size_t ev_used = 0;
     std::set<std::string> seen;
     std::vector<void*> allocs;
 
@@ -121,6 +125,35 @@ static thread_local char g_create_err[512] = "";
     do {                                                                                                      \
         CK(call);                                                                                             \
         h->launches++;                                                                                        \
+    } while (0)
+
+// kernel classes for the optional per-launch CUDA-event profile (ndit_profile_read)
+enum { KC_GEMM_QKV = 0, KC_GEMM_WO, KC_GEMM_W13, KC_GEMM_W2, KC_ATTN, KC_ROWWISE, KC_COND, KC_COUNT };
+
+static int prof_begin(ndit_engine* h, int cls, cudaStream_t s) {
+    if (!h->profile) return 0;
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->ev_pool.push_back(e);
+        }
+    }
+    h->ev_class.push_back(cls);
+    CK(cudaEventRecord(h->ev_pool[h->ev_used], s));
+    return 0;
+}
+static int prof_end(ndit_engine* h, cudaStream_t s) {
+    if (!h->profile) return 0;
+    CK(cudaEventRecord(h->ev_pool[h->ev_used + 1], s));
+    h->ev_used += 2;
+    return 0;
+}
+#define PROF(cls, call)                                  \
+    do {                                                 \
+        if (int pe_ = prof_begin(h, cls, s)) return pe_; \
+        CKL(call);                                       \
+        if (int pe_ = prof_end(h, s)) return pe_;        \
     } while (0)
 
 template <typename T>
@@ -223,6 +256,7 @@ extern "C" int ndit_destroy(ndit_handle h) {
     if (!h) return NDIT_OK;
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return NDIT_OK;
 }
@@ -233,6 +267,12 @@ extern "C" int64_t ndit_launch_count(ndit_handle h) { return h ? h->launches : 0
 extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!h || !name) return NDIT_ERR_INVALID;
     if (!strcmp(name, "attn_ref")) { h->attn_ref = value; return NDIT_OK; }
+    if (!strcmp(name, "profile")) {
+        h->profile = value;
+        h->ev_used = 0;
+        h->ev_class.clear();
+        return NDIT_OK;
+    }
     return h->fail(NDIT_ERR_INVALID, "unknown option %s", name);
 }
 
@@ -491,43 +531,43 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     }
     const float scale_cross = (float)(1.0 / sqrt((double)hd));
 
-    CKL(patch_embed(x, h->Wx, h->bx, h->X, batch, batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
-    CKL(cond_prepare(t, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
-    CKL(gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, batch, h->cd, 256, 0, POST_SILU, 0, 0, s));
+    PROF(KC_ROWWISE, patch_embed(x, h->Wx, h->bx, h->X, batch, batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
+    PROF(KC_COND, cond_prepare(t, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
+    PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, batch, h->cd, 256, 0, POST_SILU, 0, 0, s));
     // sc = bf16(silu(c)), c = bf16(temb + cap_emb)
-    CKL(gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, s));
-    CKL(gemv_rows(h->sc, h->Wada, h->bada, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L, s));
-    CKL(resid_rms_mod(h->X, nullptr, nullptr, nullptr, h->an1, h->mod, h->u, M, N, D, mod_stride, h->cfg.norm_eps, s));
+    PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, s));
+    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L, s));
+    PROF(KC_ROWWISE, resid_rms_mod(h->X, nullptr, nullptr, nullptr, h->an1, h->mod, h->u, M, N, D, mod_stride, h->cfg.norm_eps, s));
     for (int l = 0; l < L; ++l) {
         const float* ml = h->mod + (size_t)l * 4 * D;
-        CKL(gemm_bf16_tn(h->p_qkv[l], s));
-        CKL(ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
+        PROF(KC_GEMM_QKV, gemm_bf16_tn(h->p_qkv[l], s));
+        PROF(KC_ROWWISE, ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
                        h->kn_b + (size_t)l * h->Hkv * hd, rope, M, N, h->H, h->Hkv, hd, s));
         if (h->attn_ref) {
-            CKL(attention_ref(h->qkv, h->Wq, h->kvy + (size_t)l * batch * h->cap_T * 2 * h->Hkv * hd, 2 * h->Hkv * hd, h->ymask,
+            PROF(KC_ATTN, attention_ref(h->qkv, h->Wq, h->kvy + (size_t)l * batch * h->cap_T * 2 * h->Hkv * hd, 2 * h->Hkv * hd, h->ymask,
                               h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
                               scale_cross, s));
         } else {
-            CKL(transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, 1, s));
+            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, 1, s));
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
-            CKL(attention_fused(a, s));
+            PROF(KC_ATTN, attention_fused(a, s));
         }
-        CKL(gemm_bf16_tn(h->p_wo[l], s));
-        CKL(resid_rms_mod(h->X, h->o, h->an2 + (size_t)l * D, ml + D, h->fn1 + (size_t)l * D, ml + 2 * D, h->u, M, N, D,
+        PROF(KC_GEMM_WO, gemm_bf16_tn(h->p_wo[l], s));
+        PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->an2 + (size_t)l * D, ml + D, h->fn1 + (size_t)l * D, ml + 2 * D, h->u, M, N, D,
                           mod_stride, h->cfg.norm_eps, s));
-        CKL(gemm_bf16_tn(h->p_w13[l], s));
-        CKL(gemm_bf16_tn(h->p_w2[l], s));
+        PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[l], s));
+        PROF(KC_GEMM_W2, gemm_bf16_tn(h->p_w2[l], s));
         if (l + 1 < L) {
-            CKL(resid_rms_mod(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->an1 + (size_t)(l + 1) * D, ml + 4 * D, h->u, M, N,
+            PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->an1 + (size_t)(l + 1) * D, ml + 4 * D, h->u, M, N,
                               D, mod_stride, h->cfg.norm_eps, s));
         } else {
-            CKL(final_layer(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->mod + (size_t)L * 4 * D, h->Wout, h->bout, h->tok, M,
+            PROF(KC_ROWWISE, final_layer(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->mod + (size_t)L * 4 * D, h->Wout, h->bout, h->tok, M,
                             N, D, h->O, mod_stride, h->cfg.norm_eps, s));
         }
     }
-    CKL(unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, s));
+    PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, s));
     return NDIT_OK;
 }
 
@@ -554,16 +594,18 @@ extern "C" int ndit_sample(ndit_handle h, const void* z, int32_t batch, int32_t 
     for (int i = 0; i + 1 < n_grid; ++i) {
         const float t0 = grid[i], t1 = grid[i + 1];
         const float dt = t1 - t0;
-        // torchdiffeq hands the model t cast to the state dtype (bf16)
+        // torchdiffeq semantics with a bf16 state: the model sees t cast to the state dtype, and the 0-dim
+        // fp32 tensors dt / dt/2 are cast to bf16 by type promotion when multiplied with the bf16 velocity.
+        const float dt_b = host_bf16_round(dt);
         if (method == NDIT_EULER) {
             if (int e = forward_impl(h, y, host_bf16_round(t0), batch, height, width, sp, h->vel, s)) return e;
-            CKL(axpy_bf16(y, y, h->vel, dt, count, s));
+            CKL(axpy_bf16(y, y, h->vel, dt_b, count, s));
         } else {
             const float half_dt = 0.5f * dt;
             if (int e = forward_impl(h, y, host_bf16_round(t0), batch, height, width, sp, h->vel, s)) return e;
-            CKL(axpy_bf16(h->ymid, y, h->vel, half_dt, count, s));
+            CKL(axpy_bf16(h->ymid, y, h->vel, host_bf16_round(half_dt), count, s));
             if (int e = forward_impl(h, h->ymid, host_bf16_round(t0 + half_dt), batch, height, width, sp, h->vel, s)) return e;
-            CKL(axpy_bf16(y, y, h->vel, dt, count, s));
+            CKL(axpy_bf16(y, y, h->vel, dt_b, count, s));
         }
         if (tr) CK(cudaMemcpyAsync(tr + (size_t)(i + 1) * count, y, count * 2, cudaMemcpyDeviceToDevice, s));
     }
@@ -586,6 +628,21 @@ extern "C" int ndit_sample_host(ndit_handle h, const void* z_host, const void* c
     if (int e = ndit_sample(h, h->stage_z, batch, height, width, grid, n_grid, method, sp, nullptr, h->stage_z, stream)) return e;
     CK(cudaMemcpyAsync(final_host, h->stage_z, count * 2, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return NDIT_OK;
+}
+
+extern "C" int ndit_profile_read(ndit_handle h, float* ms_out, int64_t* count_out, int32_t n_classes) {
+    if (!h || !ms_out || !count_out) return NDIT_ERR_INVALID;
+    for (int i = 0; i < n_classes; ++i) { ms_out[i] = 0.f; count_out[i] = 0; }
+    CK(cudaDeviceSynchronize());
+    for (size_t i = 0; i < h->ev_class.size() && 2 * i + 1 < h->ev_used; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+        const int c = h->ev_class[i];
+        if (c < n_classes) { ms_out[c] += ms; count_out[c] += 1; }
+    }
+    h->ev_used = 0;
+    h->ev_class.clear();
     return NDIT_OK;
 }
 

@@ -86,6 +86,17 @@ def main() -> None:
         torch.save(fx, os.path.join(OUT, f"traj_{method}.pt"))
         print(method, "traj", tuple(traj.shape), traj[-1].abs().max().item())
 
+    # stepping semantics with a bf16 state and a toy velocity (pins the t / dt dtype handling of the solver glue)
+    def toy(x, t, **kw):
+        return (torch.sin(3.0 * x.float()) * (1.0 + t.float().view(-1, 1, 1, 1))).to(x.dtype)
+
+    zb = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(7)).to(torch.bfloat16)
+    for method, steps, shift in (("euler", 7, 4.0), ("midpoint", 6, 4.0)):
+        traj = transport.ODE(steps, method, shift).sample(zb, toy)
+        torch.save(dict(method=method, num_steps=steps, time_shifting_factor=shift, z=zb, traj_bf16=traj),
+                   os.path.join(OUT, f"toy_{method}_bf16.pt"))
+        print("toy", method, traj.dtype, tuple(traj.shape))
+
 
 if __name__ == "__main__":
     main()

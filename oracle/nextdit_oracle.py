@@ -166,11 +166,15 @@ def apply_rope(x: Tensor, ang: Tensor) -> Tensor:
 def _sdpa(p: _Prec, q: Tensor, k: Tensor, v: Tensor, scale: float, mask: Optional[Tensor]) -> Tensor:
     """softmax(q k^T * scale + mask) v with bf16 q/k/v, fp32 softmax, bf16 output.
     q [B,H,N,hd], k/v [B,H,T,hd]; mask [B,T] bool or None."""
+    if not p.bf16:
+        # fp32 mode: the same fused CPU kernel the reference's non-flash branch calls (nextdit.py:358-373)
+        am = None if mask is None else mask[:, None, None, :].expand(-1, q.shape[1], q.shape[2], -1)
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=am, scale=scale)
     s = torch.matmul(q, k.transpose(-1, -2)) * scale
     if mask is not None:
         s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
     a = torch.softmax(s, dim=-1)
-    return p.r(torch.matmul(a, v))
+    return p.r(torch.matmul(p.r(a), v))       # flash kernels round P to bf16 before P.V
 
 
 # --------------------------------------------------------------------------- model
@@ -325,12 +329,14 @@ def sample_ode(cfg: NextDiTConfig, W: Dict[str, Tensor], z: Tensor, cap_feats: T
                num_steps: int, method: str = "euler", time_shifting_factor: Optional[float] = None,
                cfg_scale: float = 4.0, scale_factor: float = 1.0, scale_watershed: float = 1.0,
                base_seqlen: Optional[int] = None, proportional_attn: bool = False,
-               precision: str = "fp32", max_calls: Optional[int] = None) -> Tensor:
+               precision: str = "fp32", max_calls: Optional[int] = None, velocity_fn=None,
+               cpu_mul_scalar_quirk: bool = False) -> Tensor:
     """ODE.sample (transport.py:87-111) with torchdiffeq's fixed-grid euler / midpoint.
 
     torchdiffeq (0.2.x ``_PerturbFunc.forward``) casts the time handed to the model to the
-    state dtype, so in "bf16" mode the model sees bf16-rounded t; ``dt`` stays fp32 and the
-    state update ``y + dt*f`` rounds to the state dtype after each op.
+    state dtype, so in "bf16" mode the model sees bf16-rounded t; the step ``dt`` (a 0-dim fp32 tensor) is
+    cast to the state dtype by type promotion when multiplied with the bf16 velocity, and the state update
+    ``y + dt*f`` rounds to the state dtype after each op.
     Returns [num_steps, *z.shape] (all grid states), like odeint."""
     p = _Prec(precision)
     grid = time_grid(num_steps, time_shifting_factor)
@@ -343,6 +349,8 @@ def sample_ode(cfg: NextDiTConfig, W: Dict[str, Tensor], z: Tensor, cap_feats: T
         calls += 1
         tm = p.r(tt.float())                                   # t.to(y.dtype)
         tv = torch.ones(yy.shape[0]) * tm
+        if velocity_fn is not None:              # test hook: pin the stepping semantics with a toy model
+            return p.r(velocity_fn(yy, tv))
         return forward_with_cfg(cfg, W, yy, tv, cap_feats, cap_mask, cfg_scale, scale_factor, scale_watershed,
                                 base_seqlen, proportional_attn, precision)
 
@@ -350,12 +358,18 @@ def sample_ode(cfg: NextDiTConfig, W: Dict[str, Tensor], z: Tensor, cap_feats: T
         if max_calls is not None and calls >= max_calls:
             break
         dt = tb - ta
+        # torchdiffeq multiplies by the 0-dim *tensor* dt; with a bf16 state PyTorch's type promotion casts that
+        # tensor to bf16 before the multiply, so the step size itself is bf16-rounded (identity in fp32 mode).
         if method == "euler":
-            y = p.r(y + p.r(dt * f(ta, y)))
+            y = p.r(y + p.r(p.r(dt) * f(ta, y)))
         elif method == "midpoint":
             half_dt = 0.5 * dt
-            ymid = p.r(y + p.r(f(ta, y) * half_dt))
-            y = p.r(y + p.r(dt * f(ta + half_dt, ymid)))
+            # `f0 * half_dt` (tensor * 0-dim tensor): on CUDA both operands are cast to bf16; ATen's CPU mul kernel
+            # instead keeps the fp32 scalar when it is the SECOND operand (BinaryOpsKernel.cpp mul_kernel), which
+            # is what the CPU-generated fixture tests/golden/toy_midpoint_bf16.pt contains.
+            hd_ = half_dt if cpu_mul_scalar_quirk else p.r(half_dt)
+            ymid = p.r(y + p.r(f(ta, y) * hd_))
+            y = p.r(y + p.r(p.r(dt) * f(ta + half_dt, ymid)))
         else:
             raise ValueError(f"oracle supports euler/midpoint, got {method}")
         sols.append(y)
