@@ -129,9 +129,14 @@ int ndit_op_ln_rope(void* qkv_dev, const void* qw, const void* qb, const void* k
 int ndit_op_attention(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                       void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
                       float scale_cross, int32_t use_ref, void* stream);
-/* X += tanh_g * RMS(o; w_post) (skipped if o NULL);  u = RMS(X; w_pre) * onepls   (model.py:597-610) */
-int ndit_op_resid_rms_mod(void* X_dev, const void* o_dev, const void* w_post, const float* tanh_g, const void* w_pre,
-                          const float* onepls, void* u_dev, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
+/* same op, launched `iters` times after a warm-up; *ms_out = average device time per launch (CUDA events) */
+int ndit_op_attention_bench(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
+                            void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
+                            float scale_cross, int32_t iters, float* ms_out, void* stream);
+/* X += tanh_g * RMS(o; w_post) (skipped if o NULL);  u = RMS(X; w_pre) * onepls   (model.py:597-610);
+ * tanh_g / onepls: bf16 [M / rows_per_batch, D] */
+int ndit_op_resid_rms_mod(void* X_dev, const void* o_dev, const void* w_post, const void* tanh_g, const void* w_pre,
+                          const void* onepls, void* u_dev, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
                           void* stream);
 
 #ifdef __cplusplus

@@ -29,9 +29,11 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defs: str = "") -> str:
+    """variant/defs: experimental builds (extra -D flags) go to build_<variant>/ and libndit_b200_<variant>.so."""
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + variant if variant else ""))
+    lib_path = LIB if not variant else os.path.join(HERE, f"libndit_b200_{variant}.so")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "ndit.h"))
@@ -44,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+        extra = (defs or os.environ.get("NDIT_NVCC_DEFS", "")).split()     # e.g. "-DAT_TIMING -DAT_POLY_PER8=0"
+        r = subprocess.run([nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o], capture_output=True, text=True)
         return s, r
 
     with ThreadPoolExecutor(max_workers=4) as ex:
@@ -56,13 +59,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             with open(os.path.join(objdir, os.path.basename(s) + ".ptxas.log"), "w") as f:
                 f.write(r.stdout + r.stderr)
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
-        r = subprocess.run([nvcc, "-shared", "-o", LIB, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"] + objs,
+    if force or jobs or _stale(lib_path, objs):
+        r = subprocess.run([nvcc, "-shared", "-o", lib_path, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"] + objs,
                            capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -90,7 +90,8 @@ struct ndit_engine {
     bf16 *X, *u, *qkv, *attn, *o, *hbuf, *vt;
     bf16 *yhat, *kvy, *vyt;
     uint8_t* ymask;
-    float *pool, *capemb, *tf, *h1, *sc, *mod, *tok;
+    float *pool, *capemb, *tf, *h1, *sc, *tok;
+    bf16* mod;
     bf16 *vel, *ystate, *ymid;
     bf16 *stage_z, *stage_cap;
     uint8_t* stage_mask;
@@ -103,6 +104,7 @@ struct ndit_engine {
     std::vector<GemmPlan> p_qkv, p_wo, p_w13, p_w2;
     std::vector<AttnPlan> p_attn;
     bool attn_plans_valid = false;
+    bool vt_ones_valid = false;
 
     int fail(int code, const char* fmt, ...) {
         va_list ap;
@@ -214,8 +216,8 @@ static int create_impl(ndit_engine* h) {
     h->Mmax = c.max_batch * c.max_tokens;
     const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
     ALLOC(X, M * D); ALLOC(u, M * D); ALLOC(qkv, M * h->Wq); ALLOC(attn, M * D); ALLOC(o, M * D); ALLOC(hbuf, M * F);
-    ALLOC(vt, B * KV * c.max_tokens);
-    ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * KV * h->Tpad_max);
+    ALLOC(vt, B * h->Hkv * ATTN_VROWS * c.max_tokens);
+    ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * h->Hkv * ATTN_VROWS * h->Tpad_max);
     ALLOC(ymask, B * T); ALLOC(pool, B * C); ALLOC(capemb, B * cd); ALLOC(tf, B * 256); ALLOC(h1, B * cd); ALLOC(sc, B * cd);
     ALLOC(mod, B * (L * 4 * D + D)); ALLOC(tok, M * h->O);
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
@@ -421,7 +423,7 @@ extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* m
     CKL(cudaGetLastError());
     const bf16* capb = static_cast<const bf16*>(cap);
     CKL(cond_prepare(0.f, capb, h->ymask, h->capln_w, h->capln_b, h->tf, h->pool, batch, T, (int)C, 1, s));
-    CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, batch, h->cd, (int)C, 0, POST_NONE, 0, 0, s));
+    CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, nullptr, batch, h->cd, (int)C, 0, POST_NONE, 0, 0, s));
     CKL(rms_rows_layers(capb, h->yn, h->yhat, M, (int)C, (int)L, h->cfg.norm_eps, s));
     const size_t ys = (size_t)M * C, ks = (size_t)M * 2 * KV;
     for (size_t l = 0; l < L; ++l) {
@@ -432,9 +434,10 @@ extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* m
         CKL(gemm_bf16_tn(p, s));
     }
     CKL(ln_rows(h->kvy, (int)(2 * KV), ks, h->kyn_w, h->kyn_b, KV, M, (int)KV, (int)L, s));
-    const size_t vs = (size_t)batch * KV * Tpad;
+    const size_t vs = (size_t)batch * h->Hkv * ATTN_VROWS * Tpad;
     CK(cudaMemsetAsync(h->vyt, 0, L * vs * sizeof(bf16), s));
-    CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, batch, T, h->Hkv, h->hd, (int)L, s));
+    CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, batch, T, h->Hkv, h->hd, ATTN_VROWS, (int)L, s));
+    CKL(fill_ones_row(h->vyt, Tpad, vs, batch * h->Hkv, Tpad, h->hd, ATTN_VROWS, (int)L, s));
     if (batch != h->cap_batch || T != h->cap_T) h->attn_plans_valid = false;
     h->cap_batch = batch;
     h->cap_T = T;
@@ -471,12 +474,12 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
             e |= make_tmap_3d(&a.tmQ16, h->qkv, hd, h->H, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
             e |= make_tmap_3d(&a.tmK64, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 64, 1, 128, 128);
             e |= make_tmap_3d(&a.tmK16, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
-            e |= make_tmap_3d(&a.tmVt, h->vt, N, hd, (uint64_t)batch * h->Hkv, (uint64_t)N * 2, (uint64_t)N * hd * 2, 64, 80, 1, 128);
+            e |= make_tmap_3d(&a.tmVt, h->vt, N, ATTN_VROWS, (uint64_t)batch * h->Hkv, (uint64_t)N * 2, (uint64_t)N * ATTN_VROWS * 2, 64, 80, 1, 128);
             const bf16* kvy = h->kvy + l * (size_t)batch * T * 2 * KV;
-            const bf16* vyt = h->vyt + l * (size_t)batch * KV * Tpad;
+            const bf16* vyt = h->vyt + l * (size_t)batch * h->Hkv * ATTN_VROWS * Tpad;
             e |= make_tmap_3d(&a.tmKy64, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 64, 1, 128, 128);
             e |= make_tmap_3d(&a.tmKy16, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 16, 1, 128, 32);
-            e |= make_tmap_3d(&a.tmVyt, vyt, Tpad, hd, (uint64_t)batch * h->Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * hd * 2, 64, 80, 1, 128);
+            e |= make_tmap_3d(&a.tmVyt, vyt, Tpad, ATTN_VROWS, (uint64_t)batch * h->Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * ATTN_VROWS * 2, 64, 80, 1, 128);
             if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
             a.ymask = h->ymask;
             a.gate_tanh = h->gate_tanh + l * h->H;
@@ -486,6 +489,7 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
         (void)C;
         h->plan_B = batch; h->plan_N = N; h->plan_T = h->cap_T;
         h->attn_plans_valid = true;
+        h->vt_ones_valid = false;       // V^T layout depends on (batch, N): rewrite its all-ones row
     }
     return 0;
 }
@@ -515,6 +519,11 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     if (Hp > 384 || Wp > 384) return h->fail(NDIT_ERR_INVALID, "rope table covers 384x384 patches (model.py:733)");
     if (int e = ensure_plans(h, batch, N)) return e;
     const int D = h->D, L = h->L, hd = h->hd;
+    if (!h->vt_ones_valid) {
+        CK(cudaMemsetAsync(h->vt, 0, (size_t)batch * h->Hkv * ATTN_VROWS * N * sizeof(bf16), s));
+        CKL(fill_ones_row(h->vt, N, 0, batch * h->Hkv, N, hd, ATTN_VROWS, 1, s));
+        h->vt_ones_valid = true;
+    }
     const int mod_stride = L * 4 * D + D;
     // time-aware RoPE scaling (model.py:944-952)
     float lin, ntk;
@@ -533,13 +542,13 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
 
     PROF(KC_ROWWISE, patch_embed(x, h->Wx, h->bx, h->X, batch, batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
     PROF(KC_COND, cond_prepare(t, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
-    PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, batch, h->cd, 256, 0, POST_SILU, 0, 0, s));
+    PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, nullptr, batch, h->cd, 256, 0, POST_SILU, 0, 0, s));
     // sc = bf16(silu(c)), c = bf16(temb + cap_emb)
-    PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, s));
-    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L, s));
+    PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, nullptr, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, s));
+    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L, s));
     PROF(KC_ROWWISE, resid_rms_mod(h->X, nullptr, nullptr, nullptr, h->an1, h->mod, h->u, M, N, D, mod_stride, h->cfg.norm_eps, s));
     for (int l = 0; l < L; ++l) {
-        const float* ml = h->mod + (size_t)l * 4 * D;
+        const bf16* ml = h->mod + (size_t)l * 4 * D;
         PROF(KC_GEMM_QKV, gemm_bf16_tn(h->p_qkv[l], s));
         PROF(KC_ROWWISE, ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
                        h->kn_b + (size_t)l * h->Hkv * hd, rope, M, N, h->H, h->Hkv, hd, s));
@@ -548,7 +557,7 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                               h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
                               scale_cross, s));
         } else {
-            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, 1, s));
+            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, ATTN_VROWS, 1, s));
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
@@ -688,9 +697,9 @@ extern "C" int ndit_op_ln_rope(void* qkv, const void* qw, const void* qb, const 
     return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_ln_rope", e);
 }
 
-extern "C" int ndit_op_attention(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
-                                 int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
-                                 int32_t use_ref, void* stream) {
+static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
+                             int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
+                             int32_t use_ref, void* stream, int bench_iters, float* bench_ms) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int hd = 72;
     const bf16* qkv = static_cast<const bf16*>(qkv_);
@@ -704,12 +713,16 @@ extern "C" int ndit_op_attention(const void* qkv_, const void* kvy_, const uint8
     if (N % 8 != 0) return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: N % 8 != 0", cudaErrorInvalidValue);
     const int Tpad = (T + 7) / 8 * 8;
     bf16 *vt = nullptr, *vyt = nullptr;
-    cudaError_t e = cudaMalloc(&vt, (size_t)B * KV * N * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&vyt, (size_t)B * KV * Tpad * 2);
+    const size_t vt_elems = (size_t)B * Hkv * ATTN_VROWS * N, vyt_elems = (size_t)B * Hkv * ATTN_VROWS * Tpad;
+    cudaError_t e = cudaMalloc(&vt, vt_elems * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&vyt, vyt_elems * 2);
     if (e != cudaSuccess) return op_fail(NDIT_ERR_NOMEM, "ndit_op_attention", e);
-    cudaMemsetAsync(vyt, 0, (size_t)B * KV * Tpad * 2, s);
-    e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, N, 0, B, N, Hkv, hd, 1, s);
-    if (e == cudaSuccess) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, 1, s);
+    cudaMemsetAsync(vt, 0, vt_elems * 2, s);
+    cudaMemsetAsync(vyt, 0, vyt_elems * 2, s);
+    e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, N, 0, B, N, Hkv, hd, ATTN_VROWS, 1, s);
+    if (e == cudaSuccess) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, ATTN_VROWS, 1, s);
+    if (e == cudaSuccess) e = fill_ones_row(vt, N, 0, B * Hkv, N, hd, ATTN_VROWS, 1, s);
+    if (e == cudaSuccess) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, ATTN_VROWS, 1, s);
     AttnPlan a;
     memset(&a, 0, sizeof(a));
     int te = 0;
@@ -718,16 +731,31 @@ extern "C" int ndit_op_attention(const void* qkv_, const void* kvy_, const uint8
     te |= make_tmap_3d(&a.tmQ16, qkv, hd, H, M, hd * 2, rs, 16, 1, 128, 32);
     te |= make_tmap_3d(&a.tmK64, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, 128, 128);
     te |= make_tmap_3d(&a.tmK16, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, 128, 32);
-    te |= make_tmap_3d(&a.tmVt, vt, N, hd, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * hd * 2, 64, 80, 1, 128);
+    te |= make_tmap_3d(&a.tmVt, vt, N, ATTN_VROWS, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * ATTN_VROWS * 2, 64, 80, 1, 128);
     te |= make_tmap_3d(&a.tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, 128, 128);
     te |= make_tmap_3d(&a.tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, 128, 32);
-    te |= make_tmap_3d(&a.tmVyt, vyt, Tpad, hd, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * hd * 2, 64, 80, 1, 128);
+    te |= make_tmap_3d(&a.tmVyt, vyt, Tpad, ATTN_VROWS, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * ATTN_VROWS * 2, 64, 80, 1, 128);
     int rc = NDIT_OK;
     if (te) rc = op_fail(NDIT_ERR_CUDA, "ndit_op_attention tensor map", cudaSuccess);
     if (!te && e == cudaSuccess) {
         a.ymask = ymask; a.gate_tanh = gate_tanh; a.out = static_cast<bf16*>(out);
         a.B = B; a.N = N; a.T = T; a.H = H; a.Hkv = Hkv; a.scale_self = scale_self; a.scale_cross = scale_cross;
         e = attention_fused(a, s);
+        if (bench_iters > 0 && bench_ms && e == cudaSuccess) {      // micro-benchmark: average of `bench_iters` launches
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = attention_fused(a, s);
+            cudaEventRecord(e0, s);
+            for (int i = 0; i < bench_iters && e == cudaSuccess; ++i) e = attention_fused(a, s);
+            cudaEventRecord(e1, s);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            *bench_ms = ms / bench_iters;
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
     }
     cudaError_t e2 = cudaStreamSynchronize(s);
     cudaFree(vt);
@@ -737,11 +765,25 @@ extern "C" int ndit_op_attention(const void* qkv_, const void* kvy_, const uint8
     return rc;
 }
 
-extern "C" int ndit_op_resid_rms_mod(void* X, const void* o, const void* w_post, const float* tanh_g, const void* w_pre,
-                                     const float* onepls, void* u, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
+extern "C" int ndit_op_attention(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
+                                 int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
+                                 int32_t use_ref, void* stream) {
+    return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, use_ref, stream, 0, nullptr);
+}
+
+extern "C" int ndit_op_attention_bench(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
+                                       int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
+                                       int32_t iters, float* ms_out, void* stream) {
+    if (iters <= 0 || !ms_out) return NDIT_ERR_INVALID;
+    return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, 0, stream, iters, ms_out);
+}
+
+extern "C" int ndit_op_resid_rms_mod(void* X, const void* o, const void* w_post, const void* tanh_g, const void* w_pre,
+                                     const void* onepls, void* u, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
                                      void* stream) {
-    cudaError_t e = resid_rms_mod(static_cast<bf16*>(X), static_cast<const bf16*>(o), static_cast<const bf16*>(w_post), tanh_g,
-                                  static_cast<const bf16*>(w_pre), onepls, static_cast<bf16*>(u), M, rows_per_batch, D, D, eps,
+    cudaError_t e = resid_rms_mod(static_cast<bf16*>(X), static_cast<const bf16*>(o), static_cast<const bf16*>(w_post),
+                                  static_cast<const bf16*>(tanh_g), static_cast<const bf16*>(w_pre),
+                                  static_cast<const bf16*>(onepls), static_cast<bf16*>(u), M, rows_per_batch, D, D, eps,
                                   static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_resid_rms_mod", e);
 }

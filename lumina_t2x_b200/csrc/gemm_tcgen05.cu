@@ -52,6 +52,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int n_tiles = (N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    // Tile order: all full-width tiles first (m-major), then the ragged last-N tiles.  With N = 3456 (fused
+    // q|k|v) the 64 half-empty tiles land at the end of the persistent round-robin instead of costing a whole wave.
+    const int n_full = N / BN;
+    const int full_tiles = m_tiles * n_full;
+    auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+        if (tile < full_tiles) { m_blk = tile / n_full; n_blk = tile - m_blk * n_full; }
+        else { m_blk = tile - full_tiles; n_blk = n_full; }
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -81,7 +89,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 if (lane == 0) {
@@ -96,11 +105,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            // a ragged last-N tile only multiplies the columns that exist (UMMA N is a multiple of 16)
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            const int n_rem = N - n_blk * BN;
+            const uint32_t idesc = make_idesc_bf16(GEMM_BM, n_rem >= BN ? BN : ((n_rem + 15) & ~15));
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tempty_bar(as), aph ^ 1);
@@ -130,7 +143,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tfull_bar(as), aph);

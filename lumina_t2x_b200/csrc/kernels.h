@@ -39,9 +39,9 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
 struct AttnPlan {
     CUtensorMap tmQ64, tmQ16;    // q  : dims (hd, H,   B*N) on the qkv buffer, boxes (64,1,128) / (16,1,128)
     CUtensorMap tmK64, tmK16;    // k  : dims (hd, Hkv, B*N)
-    CUtensorMap tmVt;            // v^T: dims (N, hd, B*Hkv), box (64, 80, 1)
+    CUtensorMap tmVt;            // v^T: dims (N, 80, B*Hkv), box (64, 80, 1); row 72 = ones
     CUtensorMap tmKy64, tmKy16;  // ky : dims (hd, Hkv, B*T)
-    CUtensorMap tmVyt;           // vy^T: dims (Tpad, hd, B*Hkv), box (64, 80, 1)
+    CUtensorMap tmVyt;           // vy^T: dims (Tpad, 80, B*Hkv), box (64, 80, 1); row 72 = ones
     const uint8_t* ymask;        // [B, T] bytes (0/1)
     const float* gate_tanh;      // [H] bf16-rounded tanh(gate)
     bf16* out;                   // [B*N, H*hd]
@@ -63,14 +63,15 @@ cudaError_t cond_prepare(float t, const bf16* cap, const uint8_t* mask, const bf
                          float* pool, int B, int T, int C, int do_caption, cudaStream_t s);
 enum { POST_NONE = 0, POST_SILU = 1, POST_ADALN = 2 };
 // out[b,o] = post(bf16(sum_k in'[b,k] W[o,k] + bias[o]) (+ addend[b,o]));  in' = silu(in) if in_silu
-cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const float* addend, float* out, int B, int O,
-                      int K, int in_silu, int post, int adaln_D, int adaln_blocks, cudaStream_t s);
+// result goes to out_b (bf16) when non-null, else to out (fp32 storage of bf16 values)
+cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const float* addend, float* out, bf16* out_b,
+                      int B, int O, int K, int in_silu, int post, int adaln_D, int adaln_blocks, cudaStream_t s);
 // optional residual update  X += tanh_g * RMS(o; w_post)   then   u = RMS(X; w_pre) * onepls
-cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const float* tanh_g, const bf16* w_pre,
-                          const float* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
+cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* w_pre,
+                          const bf16* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
                           cudaStream_t s);
 // residual update then LN(no affine, eps 1e-6) * onepls -> bf16 -> Linear(D->O)+bias -> out [M,O] (fp32 of bf16 values)
-cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const float* tanh_g, const float* onepls,
+cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
                         const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
                         int mod_stride, float eps, cudaStream_t s);
 // rope table [N][hd/2] (cos,sin)
@@ -83,9 +84,13 @@ cudaError_t ln_rows(bf16* x, int ld, size_t layer_stride_x, const bf16* w, const
                     int M, int width, int layers, cudaStream_t s);
 // out[l][row,:] = RMS(y[row,:]; w[l]) for all layers
 cudaError_t rms_rows_layers(const bf16* y, const bf16* w, bf16* out, int M, int C, int layers, float eps, cudaStream_t s);
-// dst[(b*G + g)*hd + d][n] = src[(b*N + n)*ld + col0 + g*hd + d]   (v -> v^T), layers via blockIdx.z
+// dst[(b*G + g)*grows + d][n] = src[(b*N + n)*ld + col0 + g*hd + d]   (v -> v^T), layers via blockIdx.z
 cudaError_t transpose_v(const bf16* src, int ld, int col0, size_t src_layer_stride, bf16* dst, int ld_dst,
-                        size_t dst_layer_stride, int B, int N, int G, int hd, int layers, cudaStream_t s);
+                        size_t dst_layer_stride, int B, int N, int G, int hd, int grows, int layers, cudaStream_t s);
+// dst[group*grows + hd][0:n_cols] = 1  (the all-ones row of V^T: column hd of P.V becomes the softmax row sum)
+cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int groups, int n_cols, int hd, int grows,
+                          int layers, cudaStream_t s);
+constexpr int ATTN_VROWS = 80;   // rows per (batch, kv head) group in the V^T buffers
 // unpatchify + learn_sigma slice + 3-channel CFG combine (+ optional fused Euler update)
 //   tok [2n*N, O] (fp32 of bf16 values) -> v [2n,4,Hh,Ww] bf16;  if y_inout: y = bf16(y + bf16(dt*v))
 cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale,

@@ -38,11 +38,27 @@ __device__ __forceinline__ void store8(bf16* p, const float* f) {
 // Gated residual update + pre-norm + modulate.  NV = ceil(D / 256) vectors per lane.
 //   if (o)  X = bf16(X + bf16(tanh_g * bf16(bf16(rmsnorm(o)) * w_post)))
 //   u = bf16(bf16(bf16(rmsnorm(X)) * w_pre) * onepls)
+// Rows stay packed (bf16) in registers between the passes so two 256-thread CTAs fit per SM.
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    return u;
+}
+
+__device__ __forceinline__ bf162 as_bf162(uint32_t u) { return *reinterpret_cast<bf162*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(bf162 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// bf16 x bf16 -> bf16 and bf16 + bf16 -> bf16 are done with the native packed instructions (HMUL2.BF16 / HADD2.BF16:
+// exact product or sum, one rounding) - the same result PyTorch produces by computing in fp32 and rounding.
 template <int NV>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2)
 resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
-                     const float* __restrict__ tanh_g, const bf16* __restrict__ w_pre,
-                     const float* __restrict__ onepls, bf16* __restrict__ u, int M, int rows_per_batch, int D,
+                     const bf16* __restrict__ tanh_g, const bf16* __restrict__ w_pre,
+                     const bf16* __restrict__ onepls, bf16* __restrict__ u, int M, int rows_per_batch, int D,
                      int mod_stride, float eps) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -50,76 +66,105 @@ resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf1
     const int nvec = D >> 3;
     const int b = row / rows_per_batch;
     const size_t off = static_cast<size_t>(row) * D;
-    float x[NV][8];
+    uint4 xv[NV];
+    float ss2 = 0.f;      // sum of squares of the (updated) residual row
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int v = lane + i * 32;
-        if (v < nvec) load8(X + off + v * 8, x[i]);
+        if (v < nvec) xv[i] = *reinterpret_cast<const uint4*>(X + off + v * 8);
     }
     if (o != nullptr) {
-        float ov[NV][8];
+        uint4 ov[NV];
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int v = lane + i * 32;
-            if (v < nvec) {
-                load8(o + off + v * 8, ov[i]);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) ss += ov[i][e] * ov[i][e];
-            }
+            if (v < nvec) ov[i] = *reinterpret_cast<const uint4*>(o + off + v * 8);
         }
-        const float rinv = rsqrtf(warp_sum(ss) / D + eps);
-        const float* tg = tanh_g + static_cast<size_t>(b) * mod_stride;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int v = lane + i * 32;
             if (v < nvec) {
-                float w[8];
-                load8(w_post + v * 8, w);
-                const float4 g0 = *reinterpret_cast<const float4*>(tg + v * 8);
-                const float4 g1 = *reinterpret_cast<const float4*>(tg + v * 8 + 4);
-                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const uint32_t w4[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float n = bf16_round(bf16_round(ov[i][e] * rinv) * w[e]);
-                    x[i][e] = bf16_round(x[i][e] + bf16_round(g[e] * n));
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16(w4[j]);
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
                 }
-                store8(X + off + v * 8, x[i]);
+            }
+        }
+        const float rinv = rsqrtf(warp_sum(ss) / D + eps);
+        const bf16* tg = tanh_g + static_cast<size_t>(b) * mod_stride;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + i * 32;
+            if (v < nvec) {
+                const uint4 wq = *reinterpret_cast<const uint4*>(w_post + v * 8);
+                const uint4 gq = *reinterpret_cast<const uint4*>(tg + v * 8);
+                const uint32_t o4[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
+                const uint32_t w4[4] = {wq.x, wq.y, wq.z, wq.w};
+                const uint32_t g4[4] = {gq.x, gq.y, gq.z, gq.w};
+                uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 of = unpack_bf16(o4[j]);
+                    const bf162 n2 = __floats2bfloat162_rn(of.x * rinv, of.y * rinv);
+                    const bf162 r2 = __hmul2_rn(n2, as_bf162(w4[j]));
+                    const bf162 p2 = __hmul2_rn(as_bf162(g4[j]), r2);
+                    const bf162 x2 = __hadd2_rn(as_bf162(x4[j]), p2);
+                    x4[j] = as_u32(x2);
+                    const float2 xf = __bfloat1622float2(x2);
+                    ss2 = fmaf(xf.x, xf.x, ss2);
+                    ss2 = fmaf(xf.y, xf.y, ss2);
+                }
+                xv[i] = make_uint4(x4[0], x4[1], x4[2], x4[3]);
+                *reinterpret_cast<uint4*>(X + off + v * 8) = xv[i];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + i * 32;
+            if (v < nvec) {
+                const uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16(x4[j]);
+                    ss2 = fmaf(f.x, f.x, ss2);
+                    ss2 = fmaf(f.y, f.y, ss2);
+                }
             }
         }
     }
     if (u == nullptr) return;
-    float ss = 0.f;
+    const float rinv = rsqrtf(warp_sum(ss2) / D + eps);
+    const bf16* op = onepls + static_cast<size_t>(b) * mod_stride;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
+            const uint4 wq = *reinterpret_cast<const uint4*>(w_pre + v * 8);
+            const uint4 sq = *reinterpret_cast<const uint4*>(op + v * 8);
+            const uint32_t w4[4] = {wq.x, wq.y, wq.z, wq.w};
+            const uint32_t s4[4] = {sq.x, sq.y, sq.z, sq.w};
+            const uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+            uint32_t r4[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ss += x[i][e] * x[i][e];
-        }
-    }
-    const float rinv = rsqrtf(warp_sum(ss) / D + eps);
-    const float* op = onepls + static_cast<size_t>(b) * mod_stride;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int v = lane + i * 32;
-        if (v < nvec) {
-            float w[8], r[8];
-            load8(w_pre + v * 8, w);
-            const float4 s0 = *reinterpret_cast<const float4*>(op + v * 8);
-            const float4 s1 = *reinterpret_cast<const float4*>(op + v * 8 + 4);
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) r[e] = bf16_round(bf16_round(x[i][e] * rinv) * w[e]) * sc[e];
-            store8(u + off + v * 8, r);
+            for (int j = 0; j < 4; ++j) {
+                const float2 xf = unpack_bf16(x4[j]);
+                const bf162 n2 = __floats2bfloat162_rn(xf.x * rinv, xf.y * rinv);
+                r4[j] = as_u32(__hmul2_rn(__hmul2_rn(n2, as_bf162(w4[j])), as_bf162(s4[j])));
+            }
+            *reinterpret_cast<uint4*>(u + off + v * 8) = make_uint4(r4[0], r4[1], r4[2], r4[3]);
         }
     }
 }
 
-cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const float* tanh_g, const bf16* w_pre,
-                          const float* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
+cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* w_pre,
+                          const bf16* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
                           cudaStream_t s) {
-    if (D % 8 != 0 || D > MAX_VEC * 256 || mod_stride % 4 != 0) return cudaErrorInvalidValue;
+    if (D % 8 != 0 || D > MAX_VEC * 256 || mod_stride % 8 != 0) return cudaErrorInvalidValue;
     const int nv = (D / 8 + 31) / 32;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
 #define LAUNCH(NVV)                                                                                             \
@@ -137,7 +182,7 @@ cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const floa
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
-                   const float* __restrict__ tanh_g, const float* __restrict__ onepls, const bf16* __restrict__ Wout,
+                   const bf16* __restrict__ tanh_g, const bf16* __restrict__ onepls, const bf16* __restrict__ Wout,
                    const bf16* __restrict__ bout, float* __restrict__ out, int M, int rows_per_batch, int D, int O,
                    int mod_stride, float eps_rms) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -169,17 +214,18 @@ final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const
             }
         }
         const float rinv = rsqrtf(warp_sum(ss) / D + eps_rms);
-        const float* tg = tanh_g + static_cast<size_t>(b) * mod_stride;
+        const bf16* tg = tanh_g + static_cast<size_t>(b) * mod_stride;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int v = lane + i * 32;
             if (v < nvec) {
-                float w[8];
+                float w[8], g[8];
                 load8(w_post + v * 8, w);
+                load8(tg + v * 8, g);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float n = bf16_round(bf16_round(ov[i][e] * rinv) * w[e]);
-                    x[i][e] = bf16_round(x[i][e] + bf16_round(tg[v * 8 + e] * n));
+                    x[i][e] = bf16_round(x[i][e] + bf16_round(g[e] * n));
                 }
             }
         }
@@ -204,13 +250,15 @@ final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const
         }
     }
     const float rstd = rsqrtf(warp_sum(sq) / D + 1e-6f);
-    const float* op = onepls + static_cast<size_t>(b) * mod_stride;
+    const bf16* op = onepls + static_cast<size_t>(b) * mod_stride;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
+            float sc[8];
+            load8(op + v * 8, sc);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[i][e] = bf16_round((x[i][e] - mean) * rstd * op[v * 8 + e]);
+            for (int e = 0; e < 8; ++e) x[i][e] = bf16_round((x[i][e] - mean) * rstd * sc[e]);
         }
     }
     for (int oc = 0; oc < O; ++oc) {
@@ -230,7 +278,7 @@ final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const
     }
 }
 
-cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const float* tanh_g, const float* onepls,
+cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
                         const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
                         int mod_stride, float eps, cudaStream_t s) {
     if (D % 8 != 0 || D > MAX_VEC * 256) return cudaErrorInvalidValue;
@@ -343,56 +391,97 @@ cudaError_t cond_prepare(float t, const bf16* cap, const uint8_t* mask, const bf
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small-batch Linear: one warp per output feature, B <= 4 input rows share each weight row.
+// Small-batch Linear (B <= 4 rows share every weight row): HBM-bound on the weight matrix.  The input rows are
+// staged once per block in shared memory; each warp streams GEMV_RPW weight rows at a time with 16-byte loads.
 constexpr int GEMV_MAXB = 4;
+constexpr int GEMV_RPW = 4;                   // output rows per warp (independent loads in flight)
+template <int NB>
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const float* __restrict__ in, const bf16* __restrict__ W, const bf16* __restrict__ bias,
-                 const float* __restrict__ addend, float* __restrict__ out, int B, int O, int K, int in_silu, int post,
-                 int adaln_D, int adaln_blocks) {
-    const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (o >= O) return;
+                 const float* __restrict__ addend, float* __restrict__ out, bf16* __restrict__ out_b, int O, int K,
+                 int in_silu, int post, int adaln_D, int adaln_blocks) {
+    extern __shared__ float xin[];            // [NB][K]
+    for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
+        float v = in[i];
+        if (in_silu) v = bf16_round(silu_f(v));
+        xin[i] = v;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    float acc[GEMV_MAXB] = {0.f, 0.f, 0.f, 0.f};
+    const int o0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GEMV_RPW;
+    if (o0 >= O) return;
+    float acc[GEMV_RPW][NB];
+#pragma unroll
+    for (int r = 0; r < GEMV_RPW; ++r)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
     for (int k = lane * 8; k < K; k += 256) {
-        float w[8];
-        load8(W + static_cast<size_t>(o) * K + k, w);
+        uint4 wq[GEMV_RPW];
 #pragma unroll
-        for (int b = 0; b < GEMV_MAXB; ++b) {
-            if (b < B) {
+        for (int r = 0; r < GEMV_RPW; ++r) {
+            const int o = o0 + r < O ? o0 + r : O - 1;
+            wq[r] = *reinterpret_cast<const uint4*>(W + static_cast<size_t>(o) * K + k);
+        }
+        float x[NB][8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float xv = in[static_cast<size_t>(b) * K + k + e];
-                    if (in_silu) xv = bf16_round(silu_f(xv));
-                    acc[b] += xv * w[e];
-                }
-            }
+        for (int b = 0; b < NB; ++b) {
+            const float4 a = *reinterpret_cast<const float4*>(xin + b * K + k);
+            const float4 c = *reinterpret_cast<const float4*>(xin + b * K + k + 4);
+            x[b][0] = a.x; x[b][1] = a.y; x[b][2] = a.z; x[b][3] = a.w; x[b][4] = c.x; x[b][5] = c.y; x[b][6] = c.z; x[b][7] = c.w;
+        }
+#pragma unroll
+        for (int r = 0; r < GEMV_RPW; ++r) {
+            float w[8];
+            unpack8(wq[r], w);
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[r][b] = fmaf(x[b][e], w[e], acc[r][b]);
         }
     }
 #pragma unroll
-    for (int b = 0; b < GEMV_MAXB; ++b) acc[b] = warp_sum(acc[b]);
+    for (int r = 0; r < GEMV_RPW; ++r)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
     if (lane == 0) {
-        const float bv = bias ? __bfloat162float(bias[o]) : 0.f;
-        for (int b = 0; b < B; ++b) {
-            float y = bf16_round(acc[b] + bv);
-            if (addend) y = bf16_round(y + addend[static_cast<size_t>(b) * O + o]);
-            if (post == POST_SILU) y = bf16_round(silu_f(y));
-            else if (post == POST_ADALN) {
-                // per layer chunks [scale_msa | gate_msa | scale_mlp | gate_mlp] (model.py:595), then the
-                // final layer's scale: scale -> bf16(1+scale); gate -> bf16(tanh(gate))
-                const int chunk = o / adaln_D;
-                const bool is_gate = (chunk < adaln_blocks * 4) && (chunk & 1);
-                y = is_gate ? bf16_round(tanhf(y)) : bf16_round(1.0f + y);
+#pragma unroll
+        for (int r = 0; r < GEMV_RPW; ++r) {
+            const int o = o0 + r;
+            if (o >= O) break;
+            const float bv = bias ? __bfloat162float(bias[o]) : 0.f;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float y = bf16_round(acc[r][b] + bv);
+                if (addend) y = bf16_round(y + addend[static_cast<size_t>(b) * O + o]);
+                if (post == POST_SILU) y = bf16_round(silu_f(y));
+                else if (post == POST_ADALN) {
+                    // per layer chunks [scale_msa | gate_msa | scale_mlp | gate_mlp] (model.py:595), then the
+                    // final layer's scale: scale -> bf16(1+scale); gate -> bf16(tanh(gate))
+                    const int chunk = o / adaln_D;
+                    const bool is_gate = (chunk < adaln_blocks * 4) && (chunk & 1);
+                    y = is_gate ? bf16_round(tanhf(y)) : bf16_round(1.0f + y);
+                }
+                if (out_b) out_b[static_cast<size_t>(b) * O + o] = __float2bfloat16_rn(y);   // y is bf16-representable
+                else out[static_cast<size_t>(b) * O + o] = y;
             }
-            out[static_cast<size_t>(b) * O + o] = y;
         }
     }
 }
 
-cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const float* addend, float* out, int B, int O,
-                      int K, int in_silu, int post, int adaln_D, int adaln_blocks, cudaStream_t s) {
-    if (B > GEMV_MAXB || K % 8 != 0) return cudaErrorInvalidValue;
-    gemv_rows_kernel<<<(O + 7) / 8, 256, 0, s>>>(in, W, bias, addend, out, B, O, K, in_silu, post, adaln_D,
-                                                 adaln_blocks);
+cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const float* addend, float* out, bf16* out_b,
+                      int B, int O, int K, int in_silu, int post, int adaln_D, int adaln_blocks, cudaStream_t s) {
+    if (B < 1 || B > GEMV_MAXB || K % 8 != 0 || static_cast<size_t>(B) * K * sizeof(float) > 48 * 1024) return cudaErrorInvalidValue;
+    const int grid = (O + 8 * GEMV_RPW - 1) / (8 * GEMV_RPW);
+    const size_t sh = static_cast<size_t>(B) * K * sizeof(float);
+#define LAUNCH(NBB) \
+    gemv_rows_kernel<NBB><<<grid, 256, sh, s>>>(in, W, bias, addend, out, out_b, O, K, in_silu, post, adaln_D, adaln_blocks)
+    switch (B) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 3: LAUNCH(3); break;
+        default: LAUNCH(4); break;
+    }
+#undef LAUNCH
     return cudaGetLastError();
 }
 
@@ -567,32 +656,60 @@ cudaError_t rms_rows_layers(const bf16* y, const bf16* w, bf16* out, int M, int 
 
 // ---------------------------------------------------------------------------------------------
 // v -> v^T (head-dim major) so the P.V product reads a K-major B operand.  32x32 smem tiles.
-__global__ void transpose_v_kernel(const bf16* __restrict__ src, int ld, int col0, size_t sls, bf16* __restrict__ dst,
-                                   int ld_dst, size_t dls, int N, int G, int hd) {
-    __shared__ bf16 tile[32][33];
+// Each (batch, kv-head) group owns `grows` (>= hd) rows of the destination; row `hd` is the all-ones row that makes
+// the tensor core produce the softmax row sum (fill_ones_row), rows above it stay zero.
+__global__ void __launch_bounds__(256)
+transpose_v_kernel(const bf16* __restrict__ src, int ld, int col0, size_t sls, bf16* __restrict__ dst, int ld_dst,
+                   size_t dls, int N, int G, int hd, int grows) {
+    // one block = 64 tokens of one (batch, kv head): 16-byte loads along head_dim, token PAIRS packed into 32-bit words
+    // in shared memory (pitch 33 words), 128-byte coalesced stores along the token axis.
+    __shared__ uint32_t tile[128 * 33];
     const int l = blockIdx.z;
     const int bg = blockIdx.y;                 // b * G + g
     const int b = bg / G, g = bg % G;
-    const int tiles_d = (hd + 31) / 32;
-    const int n0 = (blockIdx.x / tiles_d) * 32, d0 = (blockIdx.x % tiles_d) * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    for (int r = ty; r < 32; r += 8) {
-        const int n = n0 + r, d = d0 + tx;
-        bf16 v = __float2bfloat16(0.f);
-        if (n < N && d < hd) v = src[l * sls + (static_cast<size_t>(b) * N + n) * ld + col0 + g * hd + d];
-        tile[r][tx] = v;
+    const int n0 = blockIdx.x * 64;
+    const int nvec = hd >> 3;                  // 16-byte vectors per token row
+    const bf16* sp = src + l * sls + static_cast<size_t>(b) * N * ld + col0 + g * hd;
+    for (int idx = threadIdx.x; idx < 32 * nvec; idx += blockDim.x) {
+        const int p = idx / nvec, dv = idx % nvec;
+        const int t0 = n0 + 2 * p;
+        uint4 a = make_uint4(0, 0, 0, 0), c = a;
+        if (t0 < N) a = *reinterpret_cast<const uint4*>(sp + static_cast<size_t>(t0) * ld + dv * 8);
+        if (t0 + 1 < N) c = *reinterpret_cast<const uint4*>(sp + static_cast<size_t>(t0 + 1) * ld + dv * 8);
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tile[(dv * 8 + 2 * j) * 33 + p] = (av[j] & 0xffffu) | (cv[j] << 16);
+            tile[(dv * 8 + 2 * j + 1) * 33 + p] = (av[j] >> 16) | (cv[j] & 0xffff0000u);
+        }
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int d = d0 + r, n = n0 + tx;
-        if (d < hd && n < N) dst[l * dls + (static_cast<size_t>(bg) * hd + d) * ld_dst + n] = tile[tx][r];
+    const int lane = threadIdx.x & 31;
+    const int n = n0 + 2 * lane;
+    if (n < N) {    // token pair (n, n+1); for odd N the last pair spills one zero into the row padding
+        for (int d = threadIdx.x >> 5; d < hd; d += blockDim.x >> 5)
+            *reinterpret_cast<uint32_t*>(dst + l * dls + (static_cast<size_t>(bg) * grows + d) * ld_dst + n) = tile[d * 33 + lane];
     }
 }
 
 cudaError_t transpose_v(const bf16* src, int ld, int col0, size_t src_layer_stride, bf16* dst, int ld_dst,
-                        size_t dst_layer_stride, int B, int N, int G, int hd, int layers, cudaStream_t s) {
-    const dim3 grid(((N + 31) / 32) * ((hd + 31) / 32), B * G, layers);
-    transpose_v_kernel<<<grid, 256, 0, s>>>(src, ld, col0, src_layer_stride, dst, ld_dst, dst_layer_stride, N, G, hd);
+                        size_t dst_layer_stride, int B, int N, int G, int hd, int grows, int layers, cudaStream_t s) {
+    if (hd % 8 != 0 || hd > 128 || (ld_dst & 1) || ld_dst < ((N + 1) & ~1) || (ld & 7) || (col0 & 7)) return cudaErrorInvalidValue;
+    const dim3 grid((N + 63) / 64, B * G, layers);
+    transpose_v_kernel<<<grid, 256, 0, s>>>(src, ld, col0, src_layer_stride, dst, ld_dst, dst_layer_stride, N, G, hd, grows);
+    return cudaGetLastError();
+}
+
+__global__ void fill_ones_row_kernel(bf16* __restrict__ dst, int ld_dst, size_t dls, int n_cols, int hd, int grows) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_cols) return;
+    dst[blockIdx.z * dls + (static_cast<size_t>(blockIdx.y) * grows + hd) * ld_dst + n] = __float2bfloat16(1.0f);
+}
+
+cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int groups, int n_cols, int hd, int grows, int layers,
+                          cudaStream_t s) {
+    const dim3 grid((n_cols + 255) / 256, groups, layers);
+    fill_ones_row_kernel<<<grid, 256, 0, s>>>(dst, ld_dst, dst_layer_stride, n_cols, hd, grows);
     return cudaGetLastError();
 }
 

@@ -195,8 +195,9 @@ def test_resid_rms_mod(lib, M, rows, D, with_o):
     o = torch.randn(M, D, device="cuda", generator=g).to(torch.bfloat16)
     w_post = (1 + 0.1 * torch.randn(D, device="cuda", generator=g)).to(torch.bfloat16)
     w_pre = (1 + 0.1 * torch.randn(D, device="cuda", generator=g)).to(torch.bfloat16)
-    tanh_g = torch.tanh(torch.randn(Bn, D, device="cuda", generator=g)).to(torch.bfloat16).float().contiguous()
-    onepls = (1 + 0.3 * torch.randn(Bn, D, device="cuda", generator=g)).to(torch.bfloat16).float().contiguous()
+    tanh_g_b = torch.tanh(torch.randn(Bn, D, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    onepls_b = (1 + 0.3 * torch.randn(Bn, D, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    tanh_g, onepls = tanh_g_b.float(), onepls_b.float()
     p = O._Prec("bf16")
     Xr = X.float()
     if with_o:
@@ -205,7 +206,7 @@ def test_resid_rms_mod(lib, M, rows, D, with_o):
     ur = p.r(O.rms_norm(p, Xr, w_pre, 1e-5) * onepls.repeat_interleave(rows, 0))
     Xg = X.clone()
     u = torch.full((M, D), float("nan"), device="cuda", dtype=torch.bfloat16)
-    rc = lib.ndit_op_resid_rms_mod(ptr(Xg), ptr(o) if with_o else None, ptr(w_post), ptr(tanh_g), ptr(w_pre), ptr(onepls),
+    rc = lib.ndit_op_resid_rms_mod(ptr(Xg), ptr(o) if with_o else None, ptr(w_post), ptr(tanh_g_b), ptr(w_pre), ptr(onepls_b),
                                    ptr(u), M, rows, D, 1e-5, None)
     torch.cuda.synchronize()
     assert rc == 0, lib.ndit_last_error(None)

@@ -1,0 +1,43 @@
+"""Attention micro-benchmark over build variants (config-2 shape: B=2, N=4096, T=128, H=32, Hkv=8).
+usage: python tools/attn_bench.py <lib.so> [<lib.so> ...]   (run on the GPU box)"""
+import ctypes as C
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+B, N, T, H, Hkv, hd = 2, 4096, 128, 32, 8, 72
+g = torch.Generator(device="cuda").manual_seed(0)
+qkv = torch.randn(B * N, (H + 2 * Hkv) * hd, device="cuda", generator=g).to(torch.bfloat16)
+kvy = torch.randn(B * T, 2 * Hkv * hd, device="cuda", generator=g).to(torch.bfloat16)
+ymask = torch.zeros(B, T, dtype=torch.uint8, device="cuda")
+ymask[0, :] = 1
+ymask[1, :8] = 1
+gate = torch.tanh(0.5 * torch.randn(H, device="cuda", generator=g)).to(torch.bfloat16).float()
+out = torch.empty(B * N, H * hd, device="cuda", dtype=torch.bfloat16)
+ss, sc = math.sqrt(math.log(N, 4096) / hd), 1 / math.sqrt(hd)
+flops = 4 * B * N * N * H * hd + 4 * B * N * T * H * hd
+ref = None
+for path in sys.argv[1:]:
+    lib = C.CDLL(os.path.abspath(path))
+    ms = C.c_float(0)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    f = lib.ndit_op_attention_bench
+    f.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_float, C.c_float, C.c_int32, C.POINTER(C.c_float), C.c_void_p]
+    rc = f(p(qkv), p(kvy), p(ymask), p(gate), p(out), B, N, T, H, Hkv, ss, sc, 20, C.byref(ms), None)
+    torch.cuda.synchronize()
+    if ref is None:
+        ref = out.clone()
+    diff = (out.float() - ref.float()).abs().max().item()
+    print(f"{os.path.basename(path):40s} rc={rc} {ms.value * 1e3:8.1f} us  {flops / ms.value / 1e9:7.1f} TFLOP/s  maxdiff_vs_first={diff:.4f}", flush=True)
+    if hasattr(lib, "ndit_debug_attn_timing"):
+        buf = (C.c_longlong * (2 * 64 * 8))()
+        lib.ndit_debug_attn_timing(buf)
+        t = torch.tensor(list(buf), dtype=torch.float64).view(2, 64, 8)
+        names = ["wait_S", "ldS+free", "max+rescale", "wait_Pfree", "exp+stP", "fence+arrive"]
+        for x in range(2):
+            d = (t[x, 4:30, 1:7] - t[x, 4:30, 0:6])
+            per_block = (t[x, 5:31, 0] - t[x, 4:30, 0]).mean().item()
+            print(f"   tile {x}: cycles/block {per_block:7.0f} | " + "  ".join(f"{n} {v:6.0f}" for n, v in zip(names, d.mean(0).tolist())), flush=True)
