@@ -119,6 +119,10 @@ int ndit_profile_read(ndit_handle h, float* ms_out, int64_t* count_out, int32_t 
  * (128 rows w1 | 128 rows w3) and C is [M,F] = silu(a)*b.  (F.linear call sites: model.py:358,438,502) */
 int ndit_op_gemm(const void* A_dev, const void* W_dev, void* C_dev, int32_t M, int32_t N, int32_t K, int32_t swiglu,
                  void* stream);
+/* micro-benchmark of the same GEMM: `iters` launches after a warm-up, *ms_out = average device time per launch.
+ * allow_pair = 0 forces the single-CTA kernel.  Returns 1 if the CTA-pair kernel ran, 0 if the single-CTA one, < 0 on error. */
+int ndit_op_gemm_bench(const void* A_dev, const void* W_dev, void* C_dev, int32_t M, int32_t N, int32_t K, int32_t swiglu,
+                       int32_t allow_pair, int32_t iters, float* ms_out, void* stream);
 /* in place on qkv [M, (H+2Hkv)*hd]: q,k <- bf16(rope(LayerNorm(.))) (model.py:361-371); angles are built from
  * (Hp, Wp, theta, linear_factor) like precompute_freqs_cis (:916-963). M = batch*Hp*Wp */
 int ndit_op_ln_rope(void* qkv_dev, const void* qw, const void* qb, const void* kw, const void* kb, int32_t batch,

@@ -45,6 +45,7 @@ SIGNATURES = {
     "ndit_set_option": (C.c_int, [_vp, C.c_char_p, _i32]),
     "ndit_profile_read": (C.c_int, [_vp, C.POINTER(_f32), C.POINTER(_i64), _i32]),
     "ndit_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ndit_op_gemm_bench": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp]),
     "ndit_op_ln_rope": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
     "ndit_op_attention": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
     "ndit_op_attention_bench": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32,

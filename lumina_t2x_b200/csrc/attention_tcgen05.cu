@@ -52,6 +52,9 @@ constexpr int AT_SMEM_BYTES = AT_OFF_BAR + 256 + 1024;
 static_assert(AT_SMEM_BYTES <= 227 * 1024, "attention smem budget");
 
 constexpr uint32_t AT_TM_S = 0, AT_TM_O = 256;   // + X*128
+#ifndef AT_EXP_MODE
+#define AT_EXP_MODE 0
+#endif
 #ifndef AT_EXP_LAG
 #define AT_EXP_LAG 1                                 // software-pipeline distance (groups of 8 exponentials)
 #endif
@@ -64,6 +67,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// P is converted fp32 -> bf16 by TRUNCATION (one PRMT on the ALU pipe per pair) instead of cvt.rn (F2FP, which shares
+// the XU pipe with MUFU.EX2 and costs ~2.7 cycles per pair there).  The row sum comes from the same truncated
+// values (all-ones row of V^T), so the -2^-9 mean bias of truncation cancels in O / l; the remaining error has the
+// same variance as round-to-nearest.
+__device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
 }
 
 // Volatile variants: ptxas keeps volatile asm statements in source order.  The exp loop below uses them to software-
@@ -126,6 +137,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     auto o_full = [&](int x) { return bar0 + 8u * (BB + 6 + x); };   // O_x += P_x V finished (P_x smem reusable)
     const uint32_t stagger_bar = bar0 + 8u * (BB + 8);                // tile B starts ~half a softmax period after tile A
     const uint32_t tmem_ptr_addr = bar0 + 8u * (BB + 9);
+    auto xu_token = [&](int tile, int quad) { return bar0 + 8u * (BB + 10 + tile * 4 + quad); };   // exp-phase ping-pong
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (2 * AT_BQ);
@@ -151,6 +163,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             mbar_init(kv_empty(s), 2);
         }
         mbar_init(stagger_bar, 4);
+        for (int i = 0; i < 8; ++i) mbar_init(xu_token(i >> 2, i & 3), 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -388,11 +401,39 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(stagger_bar);
             }
+#if AT_EXP_MODE == 0
+            if (jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);   // P_x smem reusable: P_x(jj-1) V has completed
+#endif
+#ifdef AT_XU_TOKEN
+            // The two softmax warps that share an SM sub-partition (same quadrant of tile A / tile B) take turns in
+            // the MUFU-heavy phase: one runs its exponentials at the full XU rate while the other does everything else.
+            if (x == 0) { if (jj > 0) mbar_wait(xu_token(0, qd), (jj - 1) & 1); }
+            else mbar_wait(xu_token(1, qd), jj & 1);
+#endif
             AT_STAMP(4);
             // ---- p = exp2(s*sl2 - moff), row sum, P -> smem (bf16, K-major 128B swizzle)
             // The row sum is not accumulated here: row 72 of V^T is all ones, so the tensor core adds sum_kv P into
             // column 72 of O_x (fp32, consistent with the bf16 P it multiplies).
             if (all_valid) {
+#if AT_EXP_MODE == 0
+                // compiler-scheduled variant
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float pe[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float xs = fmaf(__uint_as_float(sreg[c * 32 + i]), sl2, -moff);
+                        pe[i] = ((i & 7) >= 8 - AT_POLY_PER8) ? exp2_poly(xs) : ex2_approx(xs);
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const uint32_t addr = pbase + (c >> 1) * AT_PHALF_BYTES + ((static_cast<uint32_t>((c & 1) * 4 + ch) ^ rsw) << 4);
+                        const uint32_t a0 = pack_bf16_trunc(pe[ch * 8 + 0], pe[ch * 8 + 1]), a1 = pack_bf16_trunc(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+                        const uint32_t a2 = pack_bf16_trunc(pe[ch * 8 + 4], pe[ch * 8 + 5]), a3 = pack_bf16_trunc(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+                    }
+                }
+#else
                 // branch-free, hand-pipelined fast path.  Stage c: 32 FFMA + 32 MUFU.EX2 for columns [32c, 32c+32),
                 // interleaved (8 MUFU : 4 F2FP : 1 STS) with packing/storing the results of stage c-1.
                 auto store_group = [&](int c, int ch) {   // 8 probabilities of chunk c -> one 16-byte swizzled store
@@ -406,23 +447,6 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                     const uint32_t a3 = pack_bf16_v(__uint_as_float(sreg[b0 + 6]), __uint_as_float(sreg[b0 + 7]));
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
                 };
-#ifdef AT_EXP_AUTO
-                // compiler-scheduled variant (kept for A/B measurements)
-                if (jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float pe[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) pe[i] = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + i]), sl2, -moff));
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const uint32_t addr = pbase + (c >> 1) * AT_PHALF_BYTES + ((static_cast<uint32_t>((c & 1) * 4 + ch) ^ rsw) << 4);
-                        const uint32_t a0 = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]), a1 = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-                        const uint32_t a2 = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]), a3 = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
-                    }
-                }
-#else
                 // group = 8 columns (one 16-byte store).  MUFU results of group g are packed AT_EXP_LAG groups later.
 #pragma unroll
                 for (int i = 0; i < 128; ++i) sreg[i] = __float_as_uint(fmaf(__uint_as_float(sreg[i]), sl2, -moff));
@@ -441,7 +465,9 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 }
 #endif
             } else {
+#if AT_EXP_MODE != 0
                 if (jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);
+#endif
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t half = pbase + (c >> 1) * AT_PHALF_BYTES;
@@ -459,6 +485,10 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                     }
                 }
             }
+#ifdef AT_XU_TOKEN
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xu_token(1 - x, qd));
+#endif
             AT_STAMP(5);
             // P_x written (and O_x rescaled) -> visible to the tensor core
             tc_fence_before();

@@ -680,6 +680,33 @@ extern "C" int ndit_op_gemm(const void* A, const void* W, void* C, int32_t M, in
     return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_gemm", e);
 }
 
+extern "C" int ndit_op_gemm_bench(const void* A, const void* W, void* C, int32_t M, int32_t N, int32_t K, int32_t swiglu,
+                                  int32_t allow_pair, int32_t iters, float* ms_out, void* stream) {
+    if (iters <= 0 || !ms_out) return NDIT_ERR_INVALID;
+    GemmPlan p;
+    const int ldc = swiglu ? N / 2 : N;
+    if (make_gemm_plan(&p, static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), static_cast<bf16*>(C), ldc, M, N, K,
+                       swiglu ? EPI_SWIGLU : EPI_STORE, op_num_sms(), allow_pair))
+        return op_fail(NDIT_ERR_CUDA, "ndit_op_gemm_bench tensor map", cudaSuccess);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = gemm_bf16_tn(p, s);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters && e == cudaSuccess; ++i) e = gemm_bf16_tn(p, s);
+    cudaEventRecord(e1, s);
+    cudaError_t e2 = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e == cudaSuccess) e = e2;
+    return e == cudaSuccess ? (p.pair ? 1 : NDIT_OK) : op_fail(NDIT_ERR_CUDA, "ndit_op_gemm_bench", e);
+}
+
 extern "C" int ndit_op_ln_rope(void* qkv, const void* qw, const void* qb, const void* kw, const void* kb, int32_t batch,
                                int32_t Hp, int32_t Wp, int32_t H, int32_t Hkv, int32_t hd, float theta, float linear_factor,
                                void* stream) {

@@ -220,6 +220,219 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+
+// ================================================================================================
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per pair of SMs.  Each CTA loads its own
+// 128 rows of A and HALF of the W tile (128 of the 256 rows), so per-SM shared-memory fill and
+// operand-read traffic per flop is halved against the single-CTA kernel; the leader CTA issues one
+// tcgen05.mma (M=256) that drives both tensor cores, each accumulating its 128 rows in its own TMEM.
+// Used when M % 256 == 0 (the four block GEMMs at full size).
+struct Gemm2Cfg {
+    static constexpr int A_BYTES = 128 * GEMM_BK * 2;      // this CTA's A rows
+    static constexpr int B_BYTES = 128 * GEMM_BK * 2;      // this CTA's half of the W tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB
+    static constexpr int STAGES = 6;
+    static constexpr int BN = 256;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     bf16* __restrict__ C, int M, int N, int K, int ldc) {
+    using Cfg = Gemm2Cfg;
+    constexpr int BN = Cfg::BN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };                         // leader's copy is the live one
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };          // per CTA (commit multicast)
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };      // per CTA (commit multicast)
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); }; // leader's copy, 8 arrivals
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    const int m_tiles = M / 256;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    const int n_full = N / BN;
+    const int full_tiles = m_tiles * n_full;
+    auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+        if (tile < full_tiles) { m_blk = tile / n_full; n_blk = tile - m_blk * n_full; }
+        else { m_blk = tile - full_tiles; n_blk = n_full; }
+    };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_ptr_addr, Cfg::TMEM_COLS);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();              // barriers of both CTAs initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land on this barrier
+                    tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * 256 + rank * 128);
+                    tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN + rank * 128);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                int m_blk, n_blk;
+                tile_coords(tile, m_blk, n_blk);
+                constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+                const int as = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(tempty_bar(as), aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint64_t da = make_smem_desc_kmajor(sa, 1024, UMMA_SW128);
+                        const uint64_t db = make_smem_desc_kmajor(sa + Cfg::A_BYTES, 1024, UMMA_SW128);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit_pair(empty_bar(stage));
+                        if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as));
+                    }
+                    __syncwarp();
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+        const int q = warp & 3;
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            if (EPI == EPI_STORE) {
+                bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = n_blk * BN + c * 32;
+                    if (col0 >= N) break;
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (col0 + j * 8 < N) {
+                            uint4 o;
+                            o.x = pack_bf16(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+                            o.y = pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+                            o.z = pack_bf16(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+                            o.w = pack_bf16(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+                            *reinterpret_cast<uint4*>(crow + c * 32 + j * 8) = o;
+                        }
+                    }
+                }
+            } else {
+                constexpr int HN = BN / 2;
+                bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * HN;
+#pragma unroll 1
+                for (int c = 0; c < HN / 16; ++c) {
+                    uint32_t a[16], b[16];
+                    tmem_ld_32x32b_x16(taddr + c * 16, a);
+                    tmem_ld_32x32b_x16(taddr + HN + c * 16, b);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float h[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float x1 = bf16_round(__uint_as_float(a[j * 8 + e]));
+                            const float x3 = bf16_round(__uint_as_float(b[j * 8 + e]));
+                            h[e] = bf16_round(silu_f(x1)) * x3;
+                        }
+                        uint4 o;
+                        o.x = pack_bf16(h[0], h[1]); o.y = pack_bf16(h[2], h[3]);
+                        o.z = pack_bf16(h[4], h[5]); o.w = pack_bf16(h[6], h[7]);
+                        *reinterpret_cast<uint4*>(crow + c * 16 + j * 8) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);   // the leader's MMA warp owns the accumulator hand-off
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();              // no CTA of the pair may exit (or free TMEM) while its peer can still touch it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int EPI>
+static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, int M, int N, int K, int ldc,
+                                int num_sms, cudaStream_t stream) {
+    auto kern = gemm2_bf16_tn_kernel<EPI>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = (M / 256) * ((N + 255) / 256);
+    int pairs = num_sms / 2;
+    if (pairs > tiles) pairs = tiles;
+    kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, C, M, N, K, ldc);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------- host side
 
 template <int BN, int EPI>
@@ -242,6 +455,14 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
 
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     if (p.N % 8 != 0 || p.K % 8 != 0) return cudaErrorInvalidValue;
+    if (p.pair) {
+        if (p.M % 256 != 0) return cudaErrorInvalidValue;
+        if (p.epi == EPI_SWIGLU) {
+            if (p.N % 256 != 0) return cudaErrorInvalidValue;
+            return launch_gemm2<EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        }
+        return launch_gemm2<EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    }
     if (p.epi == EPI_SWIGLU) {
         if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;
         return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);

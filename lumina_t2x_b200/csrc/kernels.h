@@ -27,13 +27,14 @@ struct GemmPlan {
     bf16* C;
     int M, N, K, ldc;
     int bn;   // 128 or 256
+    int pair; // 1: CTA-pair kernel (cta_group::2, 256x256 tiles; W box is 128 rows)
     int epi;  // EPI_*
     int num_sms;
 };
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream);
 // builds the maps of a plan (A: [M,K] ld=lda; W: [N,K] ld=K)
 int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int M, int N, int K, int epi,
-                   int num_sms);
+                   int num_sms, int allow_pair = 1);
 
 // ---------------------------------------------------------------- attention (attention_tcgen05.cu)
 struct AttnPlan {

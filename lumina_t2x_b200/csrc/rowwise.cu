@@ -513,9 +513,19 @@ cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float l
 // q/k LayerNorm over ALL heads jointly + 2-D RoPE, in place on the fused qkv GEMM output.
 // One warp per token row.  seg 0 = q (width H*hd), seg 1 = k (width Hkv*hd).
 template <int NV>
+__device__ __forceinline__ void ln_segment_load(const bf16* __restrict__ p, int width, int lane, uint4* raw) {
+    const int nvec = width >> 3;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) raw[i] = *reinterpret_cast<const uint4*>(p + v * 8);
+    }
+}
+
+template <int NV>
 __device__ __forceinline__ void ln_rope_segment(bf16* __restrict__ p, int width, const bf16* __restrict__ w,
                                                 const bf16* __restrict__ bsh, const float2* __restrict__ rp, int hd,
-                                                int lane) {
+                                                int lane, const uint4* raw) {
     const int nvec = width >> 3;
     float x[NV][8];
     float sum = 0.f;
@@ -523,7 +533,7 @@ __device__ __forceinline__ void ln_rope_segment(bf16* __restrict__ p, int width,
     for (int i = 0; i < NV; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
-            load8(p + v * 8, x[i]);
+            unpack8(raw[i], x[i]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) sum += x[i][e];
         }
@@ -578,8 +588,11 @@ ln_rope_qk_kernel(bf16* __restrict__ qkv, int ld, const bf16* __restrict__ qw, c
     const int lane = threadIdx.x & 31;
     bf16* p = qkv + static_cast<size_t>(row) * ld;
     const float2* rp = rope + static_cast<size_t>(row % N_tokens) * (hd >> 1);
-    ln_rope_segment<NVQ>(p, H * hd, qw, qb, rp, hd, lane);
-    ln_rope_segment<NVK>(p + H * hd, Hkv * hd, kw, kb, rp, hd, lane);
+    uint4 rq[NVQ], rk[NVK];          // both segments' loads are in flight before any math starts
+    ln_segment_load<NVQ>(p, H * hd, lane, rq);
+    ln_segment_load<NVK>(p + H * hd, Hkv * hd, lane, rk);
+    ln_rope_segment<NVQ>(p, H * hd, qw, qb, rp, hd, lane, rq);
+    ln_rope_segment<NVK>(p + H * hd, Hkv * hd, kw, kb, rp, hd, lane, rk);
 }
 
 cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const bf16* kw, const bf16* kb,
@@ -600,8 +613,10 @@ ln_rows_kernel(bf16* __restrict__ x, int ld, size_t lsx, const bf16* __restrict_
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int l = blockIdx.y;
-    ln_rope_segment<9>(x + l * lsx + static_cast<size_t>(row) * ld, width, w + l * lsw, b + l * lsw, nullptr, 8,
-                       threadIdx.x & 31);
+    uint4 raw[9];
+    bf16* xp = x + l * lsx + static_cast<size_t>(row) * ld;
+    ln_segment_load<9>(xp, width, threadIdx.x & 31, raw);
+    ln_rope_segment<9>(xp, width, w + l * lsw, b + l * lsw, nullptr, 8, threadIdx.x & 31, raw);
 }
 
 cudaError_t ln_rows(bf16* x, int ld, size_t layer_stride_x, const bf16* w, const bf16* b, size_t layer_stride_w, int M,

@@ -2,6 +2,7 @@
 // cudaGetDriverEntryPoint so the shared library links only against the (static) CUDA runtime and
 // loads on a machine without libcuda (the CPU-side "does the C-ABI load" test).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -73,7 +74,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 }
 
 int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int M, int N, int K, int epi,
-                   int num_sms) {
+                   int num_sms, int allow_pair) {
     memset(p, 0, sizeof(*p));
     p->C = C; p->M = M; p->N = N; p->K = K; p->ldc = ldc; p->epi = epi; p->num_sms = num_sms;
     // BN = 256 keeps the per-flop shared-memory operand traffic under the 128 B/clk/SM port limit
@@ -83,8 +84,12 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
     int bn = 256;
     if (epi != EPI_SWIGLU && m_tiles * ((N + 255) / 256) < num_sms) bn = 128;
     p->bn = bn;
+    // CTA-pair kernel for the large GEMMs: 256x256 tiles, each CTA loads 128 rows of A and 128 rows of W
+    static const int pair_env = getenv("NDIT_GEMM_PAIR") ? atoi(getenv("NDIT_GEMM_PAIR")) : 1;
+    // (N must be a multiple of 256: a narrower last tile would need a different split of W between the two CTAs)
+    p->pair = (allow_pair && pair_env && M % 256 == 0 && N % 256 == 0 && (M / 256) * (N / 256) >= num_sms / 2) ? 1 : 0;
     if (make_tmap_2d(&p->tmA, A, M, K, lda, 128, 64, 128)) return -1;
-    if (make_tmap_2d(&p->tmB, W, N, K, K, bn, 64, 128)) return -1;
+    if (make_tmap_2d(&p->tmB, W, N, K, K, p->pair ? 128 : bn, 64, 128)) return -1;
     return 0;
 }
 

@@ -45,6 +45,8 @@ def _diag(out, ref, tile=(128, 64)):
 GEMM_SHAPES = [
     (128, 128, 64), (128, 256, 64), (128, 256, 256), (256, 512, 576), (512, 864, 576), (300, 1096, 584),
     (2048, 3456, 2304), (1024, 2304, 6144), (64, 1152, 256),
+    # large enough for the CTA-pair (cta_group::2) kernel: M % 256 == 0, N % 256 == 0, >= 74 tiles of 256x256
+    (4096, 2304, 2304), (8192, 2304, 6144), (2560, 2048, 192),
 ]
 
 
@@ -77,7 +79,8 @@ def test_gemm_identity_layout(lib):
     assert torch.equal(Cc, A[:, :N]), _diag(Cc, A[:, :N])
 
 
-@pytest.mark.parametrize("M,F,K", [(128, 128, 64), (256, 512, 576), (1024, 6144, 2304), (200, 1536, 576)])
+@pytest.mark.parametrize("M,F,K", [(128, 128, 64), (256, 512, 576), (1024, 6144, 2304), (200, 1536, 576),
+                                   (8192, 6144, 2304)])
 def test_gemm_swiglu(lib, M, F, K):
     g = torch.Generator(device="cuda").manual_seed(M + F + K)
     A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)

@@ -41,3 +41,5 @@ for path in sys.argv[1:]:
             d = (t[x, 4:30, 1:7] - t[x, 4:30, 0:6])
             per_block = (t[x, 5:31, 0] - t[x, 4:30, 0]).mean().item()
             print(f"   tile {x}: cycles/block {per_block:7.0f} | " + "  ".join(f"{n} {v:6.0f}" for n, v in zip(names, d.mean(0).tolist())), flush=True)
+        off = (t[1, 4:30, 4] - t[0, 4:30, 4])
+        print(f"   exp-phase start offset tile1-tile0 (same block index): mean {off.mean().item():7.0f}  min {off.min().item():7.0f}  max {off.max().item():7.0f}", flush=True)
