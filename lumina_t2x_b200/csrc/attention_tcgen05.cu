@@ -21,6 +21,7 @@
 // V^T carries an all-ones row (index 72) so column 72 of O is the softmax row sum, accumulated by the tensor core.
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464).
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -48,10 +49,14 @@ constexpr int AT_OFF_K = AT_OFF_Q + 2 * AT_QTILE_BYTES;
 constexpr int AT_OFF_V = AT_OFF_K + AT_STAGES * AT_KTILE_BYTES;
 constexpr int AT_OFF_P = AT_OFF_V + AT_STAGES * AT_VTILE_BYTES;
 constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_PTILE_BYTES;
-constexpr int AT_SMEM_BYTES = AT_OFF_BAR + 256 + 1024;
+constexpr int AT_OFF_MX = AT_OFF_BAR + 256;                      // SPLIT=2: bf16 half-row maxima [tile][half][row]
+constexpr int AT_SMEM_BYTES = AT_OFF_MX + 1024 + 1024;
 static_assert(AT_SMEM_BYTES <= 227 * 1024, "attention smem budget");
 
 constexpr uint32_t AT_TM_S = 0, AT_TM_O = 256;   // + X*128
+#ifndef AT_DEFAULT_SPLIT
+#define AT_DEFAULT_SPLIT 1
+#endif
 #ifndef AT_EXP_MODE
 #define AT_EXP_MODE 0
 #endif
@@ -115,7 +120,11 @@ __device__ long long g_at_timing[2][64][8];
 #define AT_STAMP(k)
 #endif
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+// SPLIT = 1: one softmax thread per query row (384 threads).  SPLIT = 2: two threads per row, 64 columns each
+// (640 threads): four softmax warps per SM sub-partition instead of two, so the MUFU / TMEM / shared-memory latencies
+// of one warp are covered by the others.
+template <int SPLIT>
+__global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
 attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmQ16,
                        const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
                        const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmKy64,
@@ -153,8 +162,8 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
         for (int x = 0; x < 2; ++x) {
             mbar_init(q_full(x), 1);
             mbar_init(s_full(x), 1);
-            mbar_init(s_free(x), 4);
-            mbar_init(p_full(x), 4);
+            mbar_init(s_free(x), 4 * SPLIT);
+            mbar_init(p_full(x), 4 * SPLIT);
             mbar_init(o_full(x), 1);
         }
         for (int s = 0; s < AT_STAGES; ++s) {
@@ -162,7 +171,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             mbar_init(v_full(s), 1);
             mbar_init(kv_empty(s), 2);
         }
-        mbar_init(stagger_bar, 4);
+        mbar_init(stagger_bar, 4 * SPLIT);
         for (int i = 0; i < 8; ++i) mbar_init(xu_token(i >> 2, i & 3), 1);
         fence_mbar_init();
     }
@@ -177,7 +186,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
     if (warp < 4) {
-        setmaxnreg_dec<56>();
+        if constexpr (SPLIT == 1) setmaxnreg_dec<56>(); else setmaxnreg_dec<40>();
         if (warp == 0) {
             // ================================================================= TMA producer
             if (lane == 0) {
@@ -271,8 +280,191 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 issue_pv(jj);
             }
         }
+    } else if constexpr (SPLIT == 2) {
+        // ================================================================= softmax, two threads per row
+        // warps 4-7: tile A columns 0-63, 8-11: tile A columns 64-127, 12-15 / 16-19: tile B.  A thread owns row
+        // r = 32*(warp%4)+lane (its TMEM lane) and half `hf` of the 128 kv columns of every block, i.e. exactly one of
+        // the two 64-column halves of the P tile; the two halves of a row agree on the exponent reference through a
+        // 2-byte exchange in shared memory + a 256-thread named barrier.
+        setmaxnreg_inc<112>();
+        const int sw = warp - 4;
+        const int x = sw >> 3;                   // query tile
+        const int hf = (sw >> 2) & 1;            // column half
+        const int qd = warp & 3;                 // TMEM lane quadrant
+        const int r = qd * 32 + lane;
+        const int qrow = q0 + x * AT_BQ + r;
+        const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+        const uint32_t ts = tmem_base + lane_sel + AT_TM_S + x * 128 + hf * 64;
+        const uint32_t to = tmem_base + lane_sel + AT_TM_O + x * 128;
+        const uint32_t pbase = sbase + AT_OFF_P + x * AT_PTILE_BYTES + hf * AT_PHALF_BYTES + r * 128;
+        const uint32_t rsw = static_cast<uint32_t>(r & 7);
+        const uint32_t mx_own = sbase + AT_OFF_MX + ((x * 2 + hf) * 128 + r) * 2;
+        const uint32_t mx_peer = sbase + AT_OFF_MX + ((x * 2 + (1 - hf)) * 128 + r) * 2;
+        // output columns: half 0 owns [0,40), half 1 owns [40,72) (TMEM column offsets stay multiples of 8)
+        const int ocol0 = hf ? 40 : 0;
+
+        uint32_t o_self[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) o_self[i] = 0u;
+        float m_ref = -INFINITY;
+
+        // bf16(O[:, own columns] / rowsum) as packed words; the row sum is column 72 (all-ones row of V^T)
+        auto read_o_scaled = [&](uint32_t* dst, bool combine, float gt) {
+            uint32_t v[32], w[8], l8[8];
+            tmem_ld_32x32b_x8(to + 72, l8);
+            tmem_ld_32x32b_x32(to + ocol0, v);
+            if (hf == 0) tmem_ld_32x32b_x8(to + 32, w);
+            tmem_ld_wait();
+            const float inv = 1.0f / __uint_as_float(l8[0]);
+#pragma unroll
+            for (int i = 0; i < 20; ++i) {
+                if (i >= 16 && hf != 0) break;
+                const float a = __uint_as_float(i < 16 ? v[2 * i] : w[2 * (i - 16)]) * inv;
+                const float c = __uint_as_float(i < 16 ? v[2 * i + 1] : w[2 * (i - 16) + 1]) * inv;
+                if (!combine) dst[i] = pack_bf16(a, c);
+                else {
+                    const float2 sv = unpack_bf16(dst[i]);
+                    dst[i] = pack_bf16(sv.x + bf16_round(gt * bf16_round(a)), sv.y + bf16_round(gt * bf16_round(c)));
+                }
+            }
+        };
+
+#ifndef AT_NO_STAGGER
+        if (x == 1) mbar_wait(stagger_bar, 0);
+#endif
+        for (int jj = 0; jj < n_total; ++jj) {
+            const bool cross = jj >= n_self;
+            const bool first = (jj == 0) || (jj == n_self);
+            if (jj == n_self) {
+                mbar_wait(o_full(x), (jj - 1) & 1);
+                tc_fence_after();
+                read_o_scaled(o_self, false, 0.f);
+                m_ref = -INFINITY;
+            }
+            const float sl2 = cross ? sl2_cross : sl2_self;
+            // validity words of this thread's 64 columns
+            uint32_t vw[2];
+            if (!cross) {
+                const int nvalid = N - jj * AT_BKV - hf * 64;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int rem = nvalid - c * 32;
+                    vw[c] = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+                }
+            } else {
+                const int t0 = (jj - n_self) * AT_BKV + hf * 64;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int t = t0 + c * 32 + lane;
+                    const bool ok = (t < T) && (ymask[b * T + t] != 0);
+                    vw[c] = __ballot_sync(0xffffffffu, ok);
+                }
+            }
+            const bool all_valid = (vw[0] & vw[1]) == 0xffffffffu;
+
+            mbar_wait(s_full(x), jj & 1);
+            tc_fence_after();
+            uint32_t sreg[64];
+            tmem_ld_32x32b_x32(ts, sreg);
+            tmem_ld_32x32b_x32(ts + 32, sreg + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free(x));
+
+            // ---- half-row max, exchanged with the thread that owns the other 64 columns of this row
+            float mb;
+            if (all_valid) {
+                float m0 = __uint_as_float(sreg[0]), m1 = __uint_as_float(sreg[1]), m2 = __uint_as_float(sreg[2]), m3 = __uint_as_float(sreg[3]);
+#pragma unroll
+                for (int i = 4; i < 64; i += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(sreg[i]));
+                    m1 = fmaxf(m1, __uint_as_float(sreg[i + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(sreg[i + 2]));
+                    m3 = fmaxf(m3, __uint_as_float(sreg[i + 3]));
+                }
+                mb = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            } else {
+                mb = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    if (!((vw[i >> 5] >> (i & 31)) & 1u)) sreg[i] = 0xff800000u;   // -inf
+                    mb = fmaxf(mb, __uint_as_float(sreg[i]));
+                }
+            }
+            // both halves must use the SAME reference: exchange bf16-rounded maxima and combine the rounded values
+            const uint32_t mb16 = __float_as_uint(bf16_round(mb)) >> 16;
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(mx_own), "h"(static_cast<uint16_t>(mb16)) : "memory");
+            named_bar_sync(1 + x, 256);
+            uint16_t pb16;
+            asm volatile("ld.shared.b16 %0, [%1];" : "=h"(pb16) : "r"(mx_peer) : "memory");
+            named_bar_sync(1 + x, 256);          // the slot may be overwritten by the next block only after both reads
+            mb = fmaxf(__uint_as_float(mb16 << 16), __uint_as_float(static_cast<uint32_t>(pb16) << 16));
+            const float m_new = fmaxf(m_ref, mb);
+            if (first) {
+                m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+            } else {
+                const bool need = (m_new - m_ref) * sl2 > AT_RESCALE_LOG2;
+                if (__any_sync(0xffffffffu, need)) {       // same rows, same values in both halves -> same decision
+                    const float alpha = ex2_approx((m_ref - m_new) * sl2);
+                    mbar_wait(o_full(x), (jj - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t tb = to + hf * 40;      // this half rescales 40 of the 80 accumulator columns
+                    uint32_t v[16], w[16], u8[8];
+                    tmem_ld_32x32b_x16(tb, v);
+                    tmem_ld_32x32b_x16(tb + 16, w);
+                    tmem_ld_32x32b_x8(tb + 32, u8);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) u8[i] = __float_as_uint(__uint_as_float(u8[i]) * alpha);
+                    tmem_st_32x32b_x16(tb, v);
+                    tmem_st_32x32b_x16(tb + 16, w);
+                    tmem_st_32x32b_x8(tb + 32, u8);
+                    tmem_st_wait();
+                    m_ref = m_new;
+                }
+            }
+            const float moff = m_ref * sl2;
+            if (jj == 0 && x == 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stagger_bar);
+            }
+            if (jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);   // P_x smem reusable: P_x(jj-1) V has completed
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float pe[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pe[i] = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + i]), sl2, -moff));   // -inf -> 0
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    const uint32_t addr = pbase + ((static_cast<uint32_t>(c * 4 + ch) ^ rsw) << 4);
+                    const uint32_t a0 = pack_bf16_trunc(pe[ch * 8 + 0], pe[ch * 8 + 1]), a1 = pack_bf16_trunc(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+                    const uint32_t a2 = pack_bf16_trunc(pe[ch * 8 + 4], pe[ch * 8 + 5]), a3 = pack_bf16_trunc(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(x));
+        }
+        // ---- epilogue: out = bf16(self + bf16(tanh(gate) * bf16(cross))), 36 columns per thread
+        mbar_wait(o_full(x), (n_total - 1) & 1);
+        tc_fence_after();
+        read_o_scaled(o_self, true, gate_tanh[h]);
+        if (qrow < N) {
+            bf16* dst = out + (static_cast<size_t>(b) * N + qrow) * (static_cast<size_t>(H) * AT_HD) + h * AT_HD + ocol0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+                if (i < 4 || hf == 0) *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(o_self[4 * i], o_self[4 * i + 1], o_self[4 * i + 2], o_self[4 * i + 3]);
+        }
     } else {
-        // ================================================================= softmax warpgroups
+        // ================================================================= softmax warpgroups (one thread per row)
         setmaxnreg_inc<208>();
         const int x = (warp >> 2) - 1;           // query tile
         const int qd = warp & 3;                 // TMEM lane quadrant
@@ -552,21 +744,27 @@ extern "C" int ndit_debug_attn_timing(long long* out) {   // [2][64][8] clock64 
 }
 #endif
 
-cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
+template <int SPLIT>
+static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
+    auto kern = attention_fused_kernel<SPLIT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             AT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (p.T <= 0 || p.N <= 0) return cudaErrorInvalidValue;
     const float log2e = 1.4426950408889634f;
     const dim3 grid((p.N + 2 * AT_BQ - 1) / (2 * AT_BQ), p.H, p.B);
-    attention_fused_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(
-        p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask, p.gate_tanh, p.out, p.N, p.T,
-        p.H, p.Hkv, p.scale_self * log2e, p.scale_cross * log2e);
+    kern<<<grid, 128 + 256 * SPLIT, AT_SMEM_BYTES, stream>>>(p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt,
+                                                            p.ymask, p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv,
+                                                            p.scale_self * log2e, p.scale_cross * log2e);
     return cudaGetLastError();
+}
+
+cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
+    if (p.T <= 0 || p.N <= 0) return cudaErrorInvalidValue;
+    static const int split = getenv("NDIT_ATTN_SPLIT") ? atoi(getenv("NDIT_ATTN_SPLIT")) : AT_DEFAULT_SPLIT;
+    return split == 2 ? launch_attention<2>(p, stream) : launch_attention<1>(p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -227,22 +227,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // operand-read traffic per flop is halved against the single-CTA kernel; the leader CTA issues one
 // tcgen05.mma (M=256) that drives both tensor cores, each accumulating its 128 rows in its own TMEM.
 // Used when M % 256 == 0 (the four block GEMMs at full size).
+template <int BN_>
 struct Gemm2Cfg {
-    static constexpr int A_BYTES = 128 * GEMM_BK * 2;      // this CTA's A rows
-    static constexpr int B_BYTES = 128 * GEMM_BK * 2;      // this CTA's half of the W tile
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB
+    static constexpr int BN = BN_;                           // 256, or 192 when N is a multiple of 192 only (fused q|k|v)
+    static constexpr int A_BYTES = 128 * GEMM_BK * 2;        // this CTA's A rows
+    static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the W tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB / 28 KB
     static constexpr int STAGES = 6;
-    static constexpr int BN = 256;
-    static constexpr int TMEM_COLS = 512;
+    static constexpr int TMEM_COLS = 512;                    // accumulator stages at columns 0 and 256
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int EPI>
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      bf16* __restrict__ C, int M, int N, int K, int ldc) {
-    using Cfg = Gemm2Cfg;
-    constexpr int BN = Cfg::BN;
+    using Cfg = Gemm2Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -305,7 +305,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land on this barrier
                     tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * 256 + rank * 128);
-                    tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN + rank * 128);
+                    tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN + rank * (BN / 2));
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -325,7 +325,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(tempty_bar(as), aph ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
+                const uint32_t tmem_d = tmem_base + as * 256;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -355,7 +355,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
             const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
             if (EPI == EPI_STORE) {
                 bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * BN;
 #pragma unroll 1
@@ -416,20 +416,20 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-template <int EPI>
+template <int BN, int EPI>
 static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, int M, int N, int K, int ldc,
                                 int num_sms, cudaStream_t stream) {
-    auto kern = gemm2_bf16_tn_kernel<EPI>;
+    auto kern = gemm2_bf16_tn_kernel<BN, EPI>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int tiles = (M / 256) * ((N + 255) / 256);
+    const int tiles = (M / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, C, M, N, K, ldc);
+    kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, C, M, N, K, ldc);
     return cudaGetLastError();
 }
 
@@ -456,12 +456,13 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     if (p.N % 8 != 0 || p.K % 8 != 0) return cudaErrorInvalidValue;
     if (p.pair) {
-        if (p.M % 256 != 0) return cudaErrorInvalidValue;
+        if (p.M % 256 != 0 || p.N % p.bn != 0) return cudaErrorInvalidValue;
         if (p.epi == EPI_SWIGLU) {
-            if (p.N % 256 != 0) return cudaErrorInvalidValue;
-            return launch_gemm2<EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+            if (p.bn != 256) return cudaErrorInvalidValue;
+            return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
         }
-        return launch_gemm2<EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
     }
     if (p.epi == EPI_SWIGLU) {
         if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;

@@ -86,10 +86,14 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
     p->bn = bn;
     // CTA-pair kernel for the large GEMMs: 256x256 tiles, each CTA loads 128 rows of A and 128 rows of W
     static const int pair_env = getenv("NDIT_GEMM_PAIR") ? atoi(getenv("NDIT_GEMM_PAIR")) : 1;
-    // (N must be a multiple of 256: a narrower last tile would need a different split of W between the two CTAs)
-    p->pair = (allow_pair && pair_env && M % 256 == 0 && N % 256 == 0 && (M / 256) * (N / 256) >= num_sms / 2) ? 1 : 0;
+    // (N must be a multiple of the tile width: 256, or 192 for the fused q|k|v projection, N = 3456 = 18 x 192)
+    p->pair = 0;
+    if (allow_pair && pair_env && M % 256 == 0) {
+        const int pbn = (N % 256 == 0) ? 256 : ((N % 192 == 0 && epi != EPI_SWIGLU) ? 192 : 0);
+        if (pbn && (M / 256) * (N / pbn) >= num_sms / 2) { p->pair = 1; p->bn = pbn; }
+    }
     if (make_tmap_2d(&p->tmA, A, M, K, lda, 128, 64, 128)) return -1;
-    if (make_tmap_2d(&p->tmB, W, N, K, K, p->pair ? 128 : bn, 64, 128)) return -1;
+    if (make_tmap_2d(&p->tmB, W, N, K, K, p->pair ? p->bn / 2 : bn, 64, 128)) return -1;
     return 0;
 }
 
