@@ -62,6 +62,16 @@ def peaks():
     return dict(bf16=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_summarize.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))["gemm_w13_swiglu_pair"]
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -299,7 +309,7 @@ def run_engine(args, rank, local_rank, world):
         "frac_of_bf16_peak_whole_path": total_tf * lat_per_s / world / pk["bf16"],
         "roofline": {"kernel": "gemm_bf16_tn_kernel (tcgen05, all four projections of the block)", "bound": "tensor",
                      "achieved": gemm_tflops, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["bf16"],
-                     "traffic": None, "peak_source": pk["src"], "launches_timed": gemm_launches,
+                     "traffic": ncu_traffic(), "peak_source": pk["src"], "launches_timed": gemm_launches,
                      "share_of_step": gemm_ms / prof_total if prof_total else None},
         "kernels": {**prof, "attention_tflops": attn_tflops, "attention_frac_of_peak": attn_tflops / pk["bf16"]},
     }

@@ -286,7 +286,9 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
         // r = 32*(warp%4)+lane (its TMEM lane) and half `hf` of the 128 kv columns of every block, i.e. exactly one of
         // the two 64-column halves of the P tile; the two halves of a row agree on the exponent reference through a
         // 2-byte exchange in shared memory + a 256-thread named barrier.
-        setmaxnreg_inc<112>();
+        // register budget: the CTA can only re-distribute what it was launched with (640 threads x 96 = 61440):
+        // 128 x 40 + 512 x 104 = 58368.  (Asking for more than the pool makes setmaxnreg.inc wait forever.)
+        setmaxnreg_inc<104>();
         const int sw = warp - 4;
         const int x = sw >> 3;                   // query tile
         const int hf = (sw >> 2) & 1;            // column half

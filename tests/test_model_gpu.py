@@ -157,3 +157,40 @@ def test_flagship_one_forward_properties():
     r = m.forward_with_cfg(z, t, cap, mask, 2.0, **kw)
     m.set_option("attn_ref", 0)
     assert _rel(a, r) < 2e-2, _rel(a, r)
+
+
+def test_config3_resolution_extrapolation_2048():
+    """BASELINE config 3 shapes: 2048x2048 image = latent 256x256 = 16384 tokens per row, time-aware scaled RoPE
+    (scale_factor 2, watershed 0.3) and proportional attention with base_seqlen 4096, on a 2-layer model with the 2B
+    widths (full depth only repeats the same kernels).  Both RoPE branches are exercised (t below / above the
+    watershed); the tcgen05 attention must agree with the CUDA-core reference attention on the same engine."""
+    from lumina_t2x_b200 import models
+    m = models.NextDiT(patch_size=2, dim=2304, n_layers=2, n_heads=32, n_kv_heads=8, qk_norm=True, cap_feat_dim=2048,
+                       max_tokens=16384, max_cap_len=128)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if p.dim() == 2:
+                p.copy_(torch.randn(p.shape, generator=g) * ((0.5 if "adaLN" in k else 1.0) / p.shape[1] ** 0.5))
+            elif k.endswith("gate"):
+                p.copy_(0.5 * torch.randn(p.shape, generator=g))
+            elif "norm" in k and k.endswith("weight") or k == "cap_embedder.0.weight":
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+    m = m.eval().to("cuda", dtype=torch.bfloat16)
+    cfg = O.NextDiTConfig(n_layers=2)
+    z, cap, mask = O.synthetic_inputs(cfg, (256, 256), 128, 8, seed=3)
+    z, cap, mask = z.cuda(), cap.cuda(), mask.cuda()
+    kw = dict(scale_factor=2.0, scale_watershed=0.3, base_seqlen=4096, proportional_attn=True)
+    outs = {}
+    for tval in (0.1, 0.8):
+        t = torch.full((2,), tval, device="cuda")
+        a = m.forward_with_cfg(z, t, cap, mask, 4.0, **kw)
+        m.set_option("attn_ref", 1)
+        r = m.forward_with_cfg(z, t, cap, mask, 4.0, **kw)
+        m.set_option("attn_ref", 0)
+        assert a.shape == z.shape and torch.isfinite(a.float()).all()
+        assert _rel(a, r) < 2e-2, (tval, _rel(a, r))
+        outs[tval] = a
+    assert not torch.equal(outs[0.1], outs[0.8])

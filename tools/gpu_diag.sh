@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv > gpurun_o
 run() {  # name, timeout, pytest args...
   local name=$1; local to=$2; shift 2
   echo "=== $name" | tee -a gpurun_out/summary.txt
-  timeout $to python -m pytest -x -q -m gpu "$@" > gpurun_out/$name.log 2>&1
+  timeout -k 5 $to python -m pytest -x -q -m gpu "$@" > gpurun_out/$name.log 2>&1
   local rc=$?
   echo "rc=$rc $(tail -n 1 gpurun_out/$name.log)" | tee -a gpurun_out/summary.txt
   if [ $rc -ne 0 ]; then grep -E "^E |Error|error" gpurun_out/$name.log | head -20 | tee -a gpurun_out/summary.txt; fi
@@ -14,12 +14,12 @@ run() {  # name, timeout, pytest args...
 : > gpurun_out/summary.txt
 for g in "$@"; do
   case $g in
-    gemm)   run gemm_id 120 tests/test_ops_gpu.py -k "identity"; run gemm 300 tests/test_ops_gpu.py -k "gemm_store"; run swiglu 300 tests/test_ops_gpu.py -k "swiglu";;
-    rows)   run lnrope 200 tests/test_ops_gpu.py -k "ln_rope"; run resid 200 tests/test_ops_gpu.py -k "resid";;
-    attnref) run attnref 300 tests/test_ops_gpu.py -k "attention and refkernel";;
-    attn)   run attn 300 tests/test_ops_gpu.py -k "attention and tcgen05";;
-    model)  run model 900 tests/test_model_gpu.py;;
-    all)    run all 1800 tests;;
+    gemm)   run gemm_id 60 tests/test_ops_gpu.py -k "identity"; run gemm 120 tests/test_ops_gpu.py -k "gemm_store"; run swiglu 120 tests/test_ops_gpu.py -k "swiglu";;
+    rows)   run lnrope 90 tests/test_ops_gpu.py -k "ln_rope"; run resid 90 tests/test_ops_gpu.py -k "resid";;
+    attnref) run attnref 120 tests/test_ops_gpu.py -k "attention and refkernel";;
+    attn)   run attn 90 tests/test_ops_gpu.py -k "attention and tcgen05";;
+    model)  run model 600 tests/test_model_gpu.py;;
+    all)    run all 1200 tests;;
   esac
 done
 cat gpurun_out/summary.txt
