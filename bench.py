@@ -64,10 +64,11 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_summarize.py); None if absent."""
+    `ncu --set full` capture of one gemm2_bf16_tn_kernel launch (the wo projection, 8192x2304x2304: 86 MB algorithmic,
+    profiles/r01_ncu_gemm2_pair_full.txt -> profiles/ncu_traffic.json via tools/ncu_summarize.py); None if absent."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p))["gemm_w13_swiglu_pair"]
+        return json.load(open(p))["gemm_first_pair"]
     except Exception:
         return None
 

@@ -29,6 +29,17 @@ def main():
             if k in d:
                 f.write(f"{k} = {d[k][0]} {d[k][1]}\n")
     print(open(out).read())
+    if len(sys.argv) > 4:      # <traffic.json> <key>: record DRAM bytes per launch for bench.py's roofline.traffic
+        import json
+        import os
+        tj, key = sys.argv[4], sys.argv[5]
+        def to_bytes(k):
+            v, u = d[k]
+            return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        cur = json.load(open(tj)) if os.path.exists(tj) else {}
+        cur[key] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+        json.dump(cur, open(tj, "w"), indent=1)
+        print("traffic", key, cur[key])
 
 
 if __name__ == "__main__":
