@@ -194,7 +194,18 @@ def run_engine(args, rank, local_rank, world):
     torch.cuda.set_device(device)
     if dist_on:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL may print its version banner on stdout when the communicator is created: keep stdout clean for the
+        # single JSON line by pointing fd 1 at stderr until the first collective has run.
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     m = build_flagship(device)
     lib, h = m._engine(device)
     stream = torch.cuda.current_stream(device)

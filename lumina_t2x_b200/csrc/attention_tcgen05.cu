@@ -1,25 +1,33 @@
-// Fused image self-attention + gated caption cross-attention for one Next-DiT block, head_dim 72.
+// Fused image self-attention (+ optional gated caption cross-attention) for one Next-DiT block; head_dim 72 or 48.
 //
 // Replaces, in lumina_next_t2i/models/model.py: _upad_input/flash_attn_varlen_func/pad_input (:387-404),
-// the GQA repeat + masked SDPA over the caption tokens (:421-432), the tanh(gate) scale and add (:433-434).
+// the GQA repeat + masked SDPA over the caption tokens (:421-432), the tanh(gate) scale and add (:433-434);
+// and the dense flash_attn_func of the class-conditional Next-DiT (Next-DiT-ImageNet/models/models.py:389), T = 0.
 //
 //   out[b,n,h,:] = bf16( bf16(softmax(q k^T * s_self) v) + bf16(tanh(gate_h) * bf16(softmax(q ky^T / sqrt(hd) + mask) vy)) )
 //
 // Design (sm_100a, one CTA per (batch, head, 256 query rows), 384 threads, 1 CTA / SM):
 //   warp  0     TMA producer: Q tiles once, then a 3-stage ring of K / V^T tiles (self blocks, then caption blocks)
-//   warps 1,2   MMA issuers (one per query tile):  S = Q K^T (tcgen05.mma 128x128x16, 5 k-steps: 4 from a 128B-swizzled
-//               [rows x 64] tile + 1 from a 32B-swizzled [rows x 16] tile, head_dim 72 zero-padded to 80 by
-//               TMA out-of-bounds fill), then O += P V (128x80x16, 8 k-steps, P from shared memory).
+//   warps 1,2   MMA issuers (one per 128-row query tile):  S = Q K^T (tcgen05.mma 128x128x16; for head_dim 72: 4 k-steps
+//               from a 128B-swizzled [rows x 64] tile + 1 from a 32B-swizzled [rows x 16] tile, the zero padding 72 -> 80
+//               comes from TMA out-of-bounds fill; for head_dim 48: 3 k-steps), then O += P V (128 x HDP x 16, 8 k-steps,
+//               P from shared memory).  One issuer per tile with plain blocking waits, so the two tiles are free to run
+//               half a softmax period apart (tile B is started late on purpose).
 //   warps 4-7   softmax warpgroup for query tile A (rows 0..127): one thread per row (TMEM lane)
 //   warps 8-11  softmax warpgroup for query tile B (rows 128..255)
-// Registers are re-balanced with setmaxnreg (control warps 56, softmax warps 208) so a softmax thread keeps its
-// whole 128-column row of S in registers (one TMEM read pass) and S_x is handed back to the tensor core before
-// the exponentials start: Q K^T of the next block overlaps the softmax of the current one.  O accumulates in
-// TMEM across blocks; it is rescaled in place (tcgen05.ld / st) only when a row maximum grows by more than
-// 2^8 (lazy rescale: a stale reference maximum is exact after the final division by the row sum).
-// The two query tiles ping-pong on the tensor pipe.
-// V^T carries an all-ones row (index 72) so column 72 of O is the softmax row sum, accumulated by the tensor core.
-// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464).
+// Registers are re-balanced with setmaxnreg (control warps 56, softmax warps 208: 128*56 + 256*208 must stay within
+// the 384*168 the CTA was launched with - asking for more makes setmaxnreg.inc wait forever) so a softmax thread keeps
+// its whole 128-column row of S in registers (one TMEM read pass) and S_x is handed back to the tensor core before the
+// exponentials start: Q K^T of the next block overlaps the softmax of the current one.  O accumulates in TMEM across
+// blocks; it is rescaled in place (tcgen05.ld / st) only when a row maximum grows by more than 2^8 (lazy rescale: a
+// stale reference maximum is exact after the final division by the row sum).  V^T carries an all-ones row (index HD),
+// so column HD of O is the softmax row sum, accumulated by the tensor core from the same bf16 P it multiplies with V.
+// P is converted to bf16 by truncation (one PRMT per pair; cvt.rn shares the XU pipe with MUFU.EX2); the -2^-9 mean
+// bias cancels in O / rowsum.
+// Measured alternatives that were slower and are not kept (profiles/r01_attention_microbench_phase_timing.txt):
+// polynomial exp2 on the FMA pipe for 1/8..3/8 of the columns, hand-pipelined MUFU/pack ordering with volatile asm,
+// two softmax threads per row (640-thread CTA), an explicit XU token between the two tiles.
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,256+HDP) O_B [384,384+HDP).
 #include <math.h>
 #include <stdlib.h>
 
@@ -28,18 +36,17 @@
 
 namespace ndit {
 
-constexpr int AT_HD = 72;
-constexpr int AT_HDP = 80;            // padded head dim (5 x 16)
 constexpr int AT_BQ = 128;            // rows per query tile
 constexpr int AT_BKV = 128;           // kv rows per block
 constexpr int AT_STAGES = 3;
 constexpr int AT_THREADS = 384;       // warps 0-3 control (TMA, MMA tile A, MMA tile B, idle), 4-7 softmax A, 8-11 softmax B
 
-constexpr int AT_Q64_BYTES = AT_BQ * 128;        // 16 KB
-constexpr int AT_Q16_BYTES = AT_BQ * 32;         //  4 KB
+// shared-memory layout, sized for head_dim 72 (head_dim 48 uses a prefix of each region)
+constexpr int AT_Q64_BYTES = AT_BQ * 128;        // 16 KB  [rows x 64] bf16, 128B swizzle
+constexpr int AT_Q16_BYTES = AT_BQ * 32;         //  4 KB  [rows x 16] bf16, 32B swizzle (head_dim 72 only)
 constexpr int AT_QTILE_BYTES = AT_Q64_BYTES + AT_Q16_BYTES;   // 20 KB
-constexpr int AT_KTILE_BYTES = AT_QTILE_BYTES;                // same shape as a Q tile
-constexpr int AT_VHALF_BYTES = AT_HDP * 128;     // 10 KB  (80 rows x 64 kv)
+constexpr int AT_KTILE_BYTES = AT_QTILE_BYTES;
+constexpr int AT_VHALF_BYTES = 80 * 128;         // 10 KB  (up to 80 V^T rows x 64 kv)
 constexpr int AT_VTILE_BYTES = 2 * AT_VHALF_BYTES;
 constexpr int AT_PHALF_BYTES = AT_BQ * 128;      // 16 KB
 constexpr int AT_PTILE_BYTES = 2 * AT_PHALF_BYTES;
@@ -49,64 +56,29 @@ constexpr int AT_OFF_K = AT_OFF_Q + 2 * AT_QTILE_BYTES;
 constexpr int AT_OFF_V = AT_OFF_K + AT_STAGES * AT_KTILE_BYTES;
 constexpr int AT_OFF_P = AT_OFF_V + AT_STAGES * AT_VTILE_BYTES;
 constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_PTILE_BYTES;
-constexpr int AT_OFF_MX = AT_OFF_BAR + 256;                      // SPLIT=2: bf16 half-row maxima [tile][half][row]
-constexpr int AT_SMEM_BYTES = AT_OFF_MX + 1024 + 1024;
+constexpr int AT_SMEM_BYTES = AT_OFF_BAR + 256 + 1024;
 static_assert(AT_SMEM_BYTES <= 227 * 1024, "attention smem budget");
 
 constexpr uint32_t AT_TM_S = 0, AT_TM_O = 256;   // + X*128
-#ifndef AT_DEFAULT_SPLIT
-#define AT_DEFAULT_SPLIT 1
-#endif
-#ifndef AT_EXP_MODE
-#define AT_EXP_MODE 0
-#endif
-#ifndef AT_EXP_LAG
-#define AT_EXP_LAG 1                                 // software-pipeline distance (groups of 8 exponentials)
-#endif
-#ifndef AT_POLY_PER8
-#define AT_POLY_PER8 0                                // exponentials per 8 evaluated by polynomial on the FMA pipe
-#endif
 constexpr float AT_RESCALE_LOG2 = 8.0f;          // lazy rescale: keep a stale reference max while exp2 args stay <= 8
+
+template <int HD>
+struct AttnDims {
+    static_assert(HD == 72 || HD == 48, "head_dim 72 (Lumina-Next-T2I 2B / Next-DiT 2B) or 48 (Next-DiT 600M)");
+    static constexpr int NK64 = HD >= 64 ? 4 : HD / 16;     // Q K^T k-steps from the 64-wide chunk
+    static constexpr bool HAS16 = HD == 72;                 // + one k-step from the 16-wide chunk (elements 64..79)
+    static constexpr int HDP = attn_vrows(HD);              // P V width = V^T rows: head_dim + ones row, padded to 16
+    static constexpr int QK_TX = AT_Q64_BYTES + (HAS16 ? AT_Q16_BYTES : 0);
+    static constexpr int V_TX = 2 * HDP * 128;
+};
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
-// P is converted fp32 -> bf16 by TRUNCATION (one PRMT on the ALU pipe per pair) instead of cvt.rn (F2FP, which shares
-// the XU pipe with MUFU.EX2 and costs ~2.7 cycles per pair there).  The row sum comes from the same truncated
-// values (all-ones row of V^T), so the -2^-9 mean bias of truncation cancels in O / l; the remaining error has the
-// same variance as round-to-nearest.
 __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
     return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
-}
-
-// Volatile variants: ptxas keeps volatile asm statements in source order.  The exp loop below uses them to software-
-// pipeline by hand (pack/store chunk c-1 while the MUFU results of chunk c are still in flight); left to itself
-// the scheduler places each F2FP right behind the two MUFU.EX2 that feed it and stalls ~20 cycles per pair.
-__device__ __forceinline__ float ex2_approx_v(float x) {
-    float y;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ uint32_t pack_bf16_v(float lo, float hi) {
-    uint32_t r;
-    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-
-// 2^x on the FMA/ALU pipes (Cody-Waite: round-to-nearest split + degree-3 minimax on [-0.5, 0.5], relative error
-// 8e-5, i.e. 50x below bf16 resolution).  A quarter of the exponentials go through this path so the MUFU (XU)
-// pipe, 16 ex2/clk/SM, stops being the bound of the softmax.
-__device__ __forceinline__ float exp2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = x + 12582912.0f;           // 1.5 * 2^23: integer part lands in the low mantissa bits
-    const float f = x - (t - 12582912.0f);     // [-0.5, 0.5]
-    float p = fmaf(f, 0.05519810691475868f, 0.24267712235450745f);
-    p = fmaf(p, f, 0.6932618021965027f);
-    p = fmaf(p, f, 0.9999227523803711f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 #ifdef AT_TIMING
@@ -120,21 +92,19 @@ __device__ long long g_at_timing[2][64][8];
 #define AT_STAMP(k)
 #endif
 
-// SPLIT = 1: one softmax thread per query row (384 threads).  SPLIT = 2: two threads per row, 64 columns each
-// (640 threads): four softmax warps per SM sub-partition instead of two, so the MUFU / TMEM / shared-memory latencies
-// of one warp are covered by the others.
-template <int SPLIT>
-__global__ void __launch_bounds__(128 + 256 * SPLIT, 1)
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmQ16,
                        const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
                        const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmKy64,
                        const __grid_constant__ CUtensorMap tmKy16, const __grid_constant__ CUtensorMap tmVyt,
                        const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh, bf16* __restrict__ out,
                        int N, int T, int H, int Hkv, float sl2_self, float sl2_cross) {
+    using Dm = AttnDims<HD>;
+    constexpr int HDP = Dm::HDP;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = sbase + AT_OFF_BAR;
-    // barriers
     auto q_full = [&](int x) { return bar0 + 8u * (0 + x); };
     auto k_full = [&](int s) { return bar0 + 8u * (2 + s); };
     auto v_full = [&](int s) { return bar0 + 8u * (2 + AT_STAGES + s); };
@@ -146,24 +116,24 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     auto o_full = [&](int x) { return bar0 + 8u * (BB + 6 + x); };   // O_x += P_x V finished (P_x smem reusable)
     const uint32_t stagger_bar = bar0 + 8u * (BB + 8);                // tile B starts ~half a softmax period after tile A
     const uint32_t tmem_ptr_addr = bar0 + 8u * (BB + 9);
-    auto xu_token = [&](int tile, int quad) { return bar0 + 8u * (BB + 10 + tile * 4 + quad); };   // exp-phase ping-pong
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (2 * AT_BQ);
     const int h = blockIdx.y, b = blockIdx.z;
     const int g = h / (H / Hkv);
     const int n_self = (N + AT_BKV - 1) / AT_BKV;
-    const int n_cross = (T + AT_BKV - 1) / AT_BKV;
+    const int n_cross = (T + AT_BKV - 1) / AT_BKV;      // 0 for the class-conditional model
     const int n_total = n_self + n_cross;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ64); tma_prefetch_desc(&tmQ16); tma_prefetch_desc(&tmK64); tma_prefetch_desc(&tmK16);
-        tma_prefetch_desc(&tmVt); tma_prefetch_desc(&tmKy64); tma_prefetch_desc(&tmKy16); tma_prefetch_desc(&tmVyt);
+        tma_prefetch_desc(&tmQ64); tma_prefetch_desc(&tmK64); tma_prefetch_desc(&tmVt);
+        if (Dm::HAS16) { tma_prefetch_desc(&tmQ16); tma_prefetch_desc(&tmK16); }
+        if (n_cross > 0) { tma_prefetch_desc(&tmKy64); tma_prefetch_desc(&tmVyt); if (Dm::HAS16) tma_prefetch_desc(&tmKy16); }
         for (int x = 0; x < 2; ++x) {
             mbar_init(q_full(x), 1);
             mbar_init(s_full(x), 1);
-            mbar_init(s_free(x), 4 * SPLIT);
-            mbar_init(p_full(x), 4 * SPLIT);
+            mbar_init(s_free(x), 4);
+            mbar_init(p_full(x), 4);
             mbar_init(o_full(x), 1);
         }
         for (int s = 0; s < AT_STAGES; ++s) {
@@ -171,8 +141,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             mbar_init(v_full(s), 1);
             mbar_init(kv_empty(s), 2);
         }
-        mbar_init(stagger_bar, 4 * SPLIT);
-        for (int i = 0; i < 8; ++i) mbar_init(xu_token(i >> 2, i & 3), 1);
+        mbar_init(stagger_bar, 4);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -186,15 +155,15 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
     if (warp < 4) {
-        if constexpr (SPLIT == 1) setmaxnreg_dec<56>(); else setmaxnreg_dec<40>();
+        setmaxnreg_dec<56>();
         if (warp == 0) {
             // ================================================================= TMA producer
             if (lane == 0) {
                 for (int x = 0; x < 2; ++x) {
                     const uint32_t dst = sbase + AT_OFF_Q + x * AT_QTILE_BYTES;
-                    mbar_expect_tx(q_full(x), AT_QTILE_BYTES);
+                    mbar_expect_tx(q_full(x), Dm::QK_TX);
                     tma_load_3d(dst, &tmQ64, q_full(x), 0, h, b * N + q0 + x * AT_BQ);
-                    tma_load_3d(dst + AT_Q64_BYTES, &tmQ16, q_full(x), 64, h, b * N + q0 + x * AT_BQ);
+                    if (Dm::HAS16) tma_load_3d(dst + AT_Q64_BYTES, &tmQ16, q_full(x), 64, h, b * N + q0 + x * AT_BQ);
                 }
             }
             __syncwarp();
@@ -205,18 +174,18 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 if (lane == 0) {
                     const uint32_t kd = sbase + AT_OFF_K + s * AT_KTILE_BYTES;
                     const uint32_t vd = sbase + AT_OFF_V + s * AT_VTILE_BYTES;
-                    mbar_expect_tx(k_full(s), AT_KTILE_BYTES);
-                    mbar_expect_tx(v_full(s), AT_VTILE_BYTES);
+                    mbar_expect_tx(k_full(s), Dm::QK_TX);
+                    mbar_expect_tx(v_full(s), Dm::V_TX);
                     if (jj < n_self) {
                         const int kv0 = jj * AT_BKV;
                         tma_load_3d(kd, &tmK64, k_full(s), 0, g, b * N + kv0);
-                        tma_load_3d(kd + AT_Q64_BYTES, &tmK16, k_full(s), 64, g, b * N + kv0);
+                        if (Dm::HAS16) tma_load_3d(kd + AT_Q64_BYTES, &tmK16, k_full(s), 64, g, b * N + kv0);
                         tma_load_3d(vd, &tmVt, v_full(s), kv0, 0, b * Hkv + g);
                         tma_load_3d(vd + AT_VHALF_BYTES, &tmVt, v_full(s), kv0 + 64, 0, b * Hkv + g);
                     } else {
                         const int kv0 = (jj - n_self) * AT_BKV;
                         tma_load_3d(kd, &tmKy64, k_full(s), 0, g, b * T + kv0);
-                        tma_load_3d(kd + AT_Q64_BYTES, &tmKy16, k_full(s), 64, g, b * T + kv0);
+                        if (Dm::HAS16) tma_load_3d(kd + AT_Q64_BYTES, &tmKy16, k_full(s), 64, g, b * T + kv0);
                         tma_load_3d(vd, &tmVyt, v_full(s), kv0, 0, b * Hkv + g);
                         tma_load_3d(vd + AT_VHALF_BYTES, &tmVyt, v_full(s), kv0 + 64, 0, b * Hkv + g);
                     }
@@ -225,12 +194,10 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 if (++s == AT_STAGES) { s = 0; ph ^= 1; }
             }
         } else if (warp == 1 || warp == 2) {
-            // ================================================================= MMA issuers: warp 1 -> query tile A, warp 2 -> tile B
-            // (one issuing warp per tile, each with simple blocking waits: the two tiles run half a softmax period
-            //  apart and must not be serialised by a shared in-order issue loop)
+            // ================================================================= MMA issuers: warp 1 -> tile A, warp 2 -> tile B
             const int x = warp - 1;
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, AT_BKV);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, AT_HDP);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, HDP);
             auto issue_qk = [&](int jj) {
                 const int s = jj % AT_STAGES;
                 mbar_wait(k_full(s), (jj / AT_STAGES) & 1);
@@ -243,10 +210,12 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                     const uint64_t dk = make_smem_desc_kmajor(ka, 1024, UMMA_SW128);
                     const uint32_t d = tmem_base + AT_TM_S + x * 128;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-                    const uint64_t dq16 = make_smem_desc_kmajor(qa + AT_Q64_BYTES, 256, UMMA_SW32);
-                    const uint64_t dk16 = make_smem_desc_kmajor(ka + AT_Q64_BYTES, 256, UMMA_SW32);
-                    umma_ss(d, dq16, dk16, idesc_qk, 1);
+                    for (int k = 0; k < Dm::NK64; ++k) umma_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+                    if (Dm::HAS16) {
+                        const uint64_t dq16 = make_smem_desc_kmajor(qa + AT_Q64_BYTES, 256, UMMA_SW32);
+                        const uint64_t dk16 = make_smem_desc_kmajor(ka + AT_Q64_BYTES, 256, UMMA_SW32);
+                        umma_ss(d, dq16, dk16, idesc_qk, 1);
+                    }
                     umma_commit(s_full(x));
                 }
                 __syncwarp();
@@ -280,191 +249,6 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 issue_pv(jj);
             }
         }
-    } else if constexpr (SPLIT == 2) {
-        // ================================================================= softmax, two threads per row
-        // warps 4-7: tile A columns 0-63, 8-11: tile A columns 64-127, 12-15 / 16-19: tile B.  A thread owns row
-        // r = 32*(warp%4)+lane (its TMEM lane) and half `hf` of the 128 kv columns of every block, i.e. exactly one of
-        // the two 64-column halves of the P tile; the two halves of a row agree on the exponent reference through a
-        // 2-byte exchange in shared memory + a 256-thread named barrier.
-        // register budget: the CTA can only re-distribute what it was launched with (640 threads x 96 = 61440):
-        // 128 x 40 + 512 x 104 = 58368.  (Asking for more than the pool makes setmaxnreg.inc wait forever.)
-        setmaxnreg_inc<104>();
-        const int sw = warp - 4;
-        const int x = sw >> 3;                   // query tile
-        const int hf = (sw >> 2) & 1;            // column half
-        const int qd = warp & 3;                 // TMEM lane quadrant
-        const int r = qd * 32 + lane;
-        const int qrow = q0 + x * AT_BQ + r;
-        const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-        const uint32_t ts = tmem_base + lane_sel + AT_TM_S + x * 128 + hf * 64;
-        const uint32_t to = tmem_base + lane_sel + AT_TM_O + x * 128;
-        const uint32_t pbase = sbase + AT_OFF_P + x * AT_PTILE_BYTES + hf * AT_PHALF_BYTES + r * 128;
-        const uint32_t rsw = static_cast<uint32_t>(r & 7);
-        const uint32_t mx_own = sbase + AT_OFF_MX + ((x * 2 + hf) * 128 + r) * 2;
-        const uint32_t mx_peer = sbase + AT_OFF_MX + ((x * 2 + (1 - hf)) * 128 + r) * 2;
-        // output columns: half 0 owns [0,40), half 1 owns [40,72) (TMEM column offsets stay multiples of 8)
-        const int ocol0 = hf ? 40 : 0;
-
-        uint32_t o_self[20];
-#pragma unroll
-        for (int i = 0; i < 20; ++i) o_self[i] = 0u;
-        float m_ref = -INFINITY;
-
-        // bf16(O[:, own columns] / rowsum) as packed words; the row sum is column 72 (all-ones row of V^T)
-        auto read_o_scaled = [&](uint32_t* dst, bool combine, float gt) {
-            uint32_t v[32], w[8], l8[8];
-            tmem_ld_32x32b_x8(to + 72, l8);
-            tmem_ld_32x32b_x32(to + ocol0, v);
-            if (hf == 0) tmem_ld_32x32b_x8(to + 32, w);
-            tmem_ld_wait();
-            const float inv = 1.0f / __uint_as_float(l8[0]);
-#pragma unroll
-            for (int i = 0; i < 20; ++i) {
-                if (i >= 16 && hf != 0) break;
-                const float a = __uint_as_float(i < 16 ? v[2 * i] : w[2 * (i - 16)]) * inv;
-                const float c = __uint_as_float(i < 16 ? v[2 * i + 1] : w[2 * (i - 16) + 1]) * inv;
-                if (!combine) dst[i] = pack_bf16(a, c);
-                else {
-                    const float2 sv = unpack_bf16(dst[i]);
-                    dst[i] = pack_bf16(sv.x + bf16_round(gt * bf16_round(a)), sv.y + bf16_round(gt * bf16_round(c)));
-                }
-            }
-        };
-
-#ifndef AT_NO_STAGGER
-        if (x == 1) mbar_wait(stagger_bar, 0);
-#endif
-        for (int jj = 0; jj < n_total; ++jj) {
-            const bool cross = jj >= n_self;
-            const bool first = (jj == 0) || (jj == n_self);
-            if (jj == n_self) {
-                mbar_wait(o_full(x), (jj - 1) & 1);
-                tc_fence_after();
-                read_o_scaled(o_self, false, 0.f);
-                m_ref = -INFINITY;
-            }
-            const float sl2 = cross ? sl2_cross : sl2_self;
-            // validity words of this thread's 64 columns
-            uint32_t vw[2];
-            if (!cross) {
-                const int nvalid = N - jj * AT_BKV - hf * 64;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int rem = nvalid - c * 32;
-                    vw[c] = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-                }
-            } else {
-                const int t0 = (jj - n_self) * AT_BKV + hf * 64;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int t = t0 + c * 32 + lane;
-                    const bool ok = (t < T) && (ymask[b * T + t] != 0);
-                    vw[c] = __ballot_sync(0xffffffffu, ok);
-                }
-            }
-            const bool all_valid = (vw[0] & vw[1]) == 0xffffffffu;
-
-            mbar_wait(s_full(x), jj & 1);
-            tc_fence_after();
-            uint32_t sreg[64];
-            tmem_ld_32x32b_x32(ts, sreg);
-            tmem_ld_32x32b_x32(ts + 32, sreg + 32);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free(x));
-
-            // ---- half-row max, exchanged with the thread that owns the other 64 columns of this row
-            float mb;
-            if (all_valid) {
-                float m0 = __uint_as_float(sreg[0]), m1 = __uint_as_float(sreg[1]), m2 = __uint_as_float(sreg[2]), m3 = __uint_as_float(sreg[3]);
-#pragma unroll
-                for (int i = 4; i < 64; i += 4) {
-                    m0 = fmaxf(m0, __uint_as_float(sreg[i]));
-                    m1 = fmaxf(m1, __uint_as_float(sreg[i + 1]));
-                    m2 = fmaxf(m2, __uint_as_float(sreg[i + 2]));
-                    m3 = fmaxf(m3, __uint_as_float(sreg[i + 3]));
-                }
-                mb = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-            } else {
-                mb = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    if (!((vw[i >> 5] >> (i & 31)) & 1u)) sreg[i] = 0xff800000u;   // -inf
-                    mb = fmaxf(mb, __uint_as_float(sreg[i]));
-                }
-            }
-            // both halves must use the SAME reference: exchange bf16-rounded maxima and combine the rounded values
-            const uint32_t mb16 = __float_as_uint(bf16_round(mb)) >> 16;
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(mx_own), "h"(static_cast<uint16_t>(mb16)) : "memory");
-            named_bar_sync(1 + x, 256);
-            uint16_t pb16;
-            asm volatile("ld.shared.b16 %0, [%1];" : "=h"(pb16) : "r"(mx_peer) : "memory");
-            named_bar_sync(1 + x, 256);          // the slot may be overwritten by the next block only after both reads
-            mb = fmaxf(__uint_as_float(mb16 << 16), __uint_as_float(static_cast<uint32_t>(pb16) << 16));
-            const float m_new = fmaxf(m_ref, mb);
-            if (first) {
-                m_ref = (m_new == -INFINITY) ? 0.f : m_new;
-            } else {
-                const bool need = (m_new - m_ref) * sl2 > AT_RESCALE_LOG2;
-                if (__any_sync(0xffffffffu, need)) {       // same rows, same values in both halves -> same decision
-                    const float alpha = ex2_approx((m_ref - m_new) * sl2);
-                    mbar_wait(o_full(x), (jj - 1) & 1);
-                    tc_fence_after();
-                    const uint32_t tb = to + hf * 40;      // this half rescales 40 of the 80 accumulator columns
-                    uint32_t v[16], w[16], u8[8];
-                    tmem_ld_32x32b_x16(tb, v);
-                    tmem_ld_32x32b_x16(tb + 16, w);
-                    tmem_ld_32x32b_x8(tb + 32, u8);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        w[i] = __float_as_uint(__uint_as_float(w[i]) * alpha);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) u8[i] = __float_as_uint(__uint_as_float(u8[i]) * alpha);
-                    tmem_st_32x32b_x16(tb, v);
-                    tmem_st_32x32b_x16(tb + 16, w);
-                    tmem_st_32x32b_x8(tb + 32, u8);
-                    tmem_st_wait();
-                    m_ref = m_new;
-                }
-            }
-            const float moff = m_ref * sl2;
-            if (jj == 0 && x == 0) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(stagger_bar);
-            }
-            if (jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);   // P_x smem reusable: P_x(jj-1) V has completed
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float pe[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pe[i] = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + i]), sl2, -moff));   // -inf -> 0
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    const uint32_t addr = pbase + ((static_cast<uint32_t>(c * 4 + ch) ^ rsw) << 4);
-                    const uint32_t a0 = pack_bf16_trunc(pe[ch * 8 + 0], pe[ch * 8 + 1]), a1 = pack_bf16_trunc(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-                    const uint32_t a2 = pack_bf16_trunc(pe[ch * 8 + 4], pe[ch * 8 + 5]), a3 = pack_bf16_trunc(pe[ch * 8 + 6], pe[ch * 8 + 7]);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full(x));
-        }
-        // ---- epilogue: out = bf16(self + bf16(tanh(gate) * bf16(cross))), 36 columns per thread
-        mbar_wait(o_full(x), (n_total - 1) & 1);
-        tc_fence_after();
-        read_o_scaled(o_self, true, gate_tanh[h]);
-        if (qrow < N) {
-            bf16* dst = out + (static_cast<size_t>(b) * N + qrow) * (static_cast<size_t>(H) * AT_HD) + h * AT_HD + ocol0;
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-                if (i < 4 || hf == 0) *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(o_self[4 * i], o_self[4 * i + 1], o_self[4 * i + 2], o_self[4 * i + 3]);
-        }
     } else {
         // ================================================================= softmax warpgroups (one thread per row)
         setmaxnreg_inc<208>();
@@ -478,10 +262,33 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
         const uint32_t pbase = sbase + AT_OFF_P + x * AT_PTILE_BYTES + r * 128;
         const uint32_t rsw = static_cast<uint32_t>(r & 7);
 
-        uint32_t o_self[AT_HD / 2];
+        uint32_t o_self[HD / 2];
 #pragma unroll
-        for (int i = 0; i < AT_HD / 2; ++i) o_self[i] = 0u;
+        for (int i = 0; i < HD / 2; ++i) o_self[i] = 0u;
         float m_ref = -INFINITY;
+
+        // O_x[:, 0:HD] / rowsum (column HD) -> packed bf16.  combine: dst = bf16(dst + bf16(gt * bf16(value)))
+        auto read_o = [&](uint32_t* dst, bool combine, float gt) {
+            uint32_t l8[8];
+            tmem_ld_32x32b_x8(to + HD, l8);       // HD is a multiple of 8
+            tmem_ld_wait();
+            const float inv = 1.0f / __uint_as_float(l8[0]);
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                uint32_t v[8];
+                tmem_ld_32x32b_x8(to + c * 8, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float a = __uint_as_float(v[2 * i]) * inv, cc = __uint_as_float(v[2 * i + 1]) * inv;
+                    if (!combine) dst[c * 4 + i] = pack_bf16(a, cc);
+                    else {
+                        const float2 sv = unpack_bf16(dst[c * 4 + i]);
+                        dst[c * 4 + i] = pack_bf16(sv.x + bf16_round(gt * bf16_round(a)), sv.y + bf16_round(gt * bf16_round(cc)));
+                    }
+                }
+            }
+        };
 
 #ifndef AT_NO_STAGGER
         if (x == 1) mbar_wait(stagger_bar, 0);   // anti-phase the two tiles: one is in its exp phase while the other is not
@@ -493,20 +300,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 // ---- segment switch: O_x holds the complete self-attention numerator -> bf16(O / l) into registers
                 mbar_wait(o_full(x), (jj - 1) & 1);
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld_32x32b_x16(to + 64, v);          // columns 64..71 and the row sum (ones column, 72)
-                tmem_ld_wait();
-                const float inv = 1.0f / __uint_as_float(v[8]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) o_self[32 + i] = pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv);
-                tmem_ld_32x32b_x32(to, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o_self[i] = pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv);
-                tmem_ld_32x32b_x32(to + 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o_self[16 + i] = pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv);
+                read_o(o_self, false, 0.f);
                 m_ref = -INFINITY;
             }
             const float sl2 = cross ? sl2_cross : sl2_self;
@@ -573,11 +367,11 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
                 const bool need = (m_new - m_ref) * sl2 > AT_RESCALE_LOG2;
                 if (__any_sync(0xffffffffu, need)) {
-                    const float alpha = ex2_approx((m_ref - m_new) * sl2);   // scales O and the row sum (column 72)
+                    const float alpha = ex2_approx((m_ref - m_new) * sl2);   // scales O and the row sum (column HD)
                     mbar_wait(o_full(x), (jj - 1) & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < AT_HDP / 16; ++c) {
+                    for (int c = 0; c < HDP / 16; ++c) {
                         uint32_t v[16];
                         tmem_ld_32x32b_x16(to + c * 16, v);
                         tmem_ld_wait();
@@ -595,94 +389,23 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(stagger_bar);
             }
-#if AT_EXP_MODE == 0
             if (jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);   // P_x smem reusable: P_x(jj-1) V has completed
-#endif
-#ifdef AT_XU_TOKEN
-            // The two softmax warps that share an SM sub-partition (same quadrant of tile A / tile B) take turns in
-            // the MUFU-heavy phase: one runs its exponentials at the full XU rate while the other does everything else.
-            if (x == 0) { if (jj > 0) mbar_wait(xu_token(0, qd), (jj - 1) & 1); }
-            else mbar_wait(xu_token(1, qd), jj & 1);
-#endif
             AT_STAMP(4);
-            // ---- p = exp2(s*sl2 - moff), row sum, P -> smem (bf16, K-major 128B swizzle)
-            // The row sum is not accumulated here: row 72 of V^T is all ones, so the tensor core adds sum_kv P into
-            // column 72 of O_x (fp32, consistent with the bf16 P it multiplies).
-            if (all_valid) {
-#if AT_EXP_MODE == 0
-                // compiler-scheduled variant
+            // ---- p = exp2(s*sl2 - moff) -> P_x in smem (bf16, K-major 128B swizzle).  Masked entries hold -inf -> 0.
+            // The row sum is not accumulated here (all-ones row of V^T, see the header).
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float pe[32];
+            for (int c = 0; c < 4; ++c) {
+                float pe[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float xs = fmaf(__uint_as_float(sreg[c * 32 + i]), sl2, -moff);
-                        pe[i] = ((i & 7) >= 8 - AT_POLY_PER8) ? exp2_poly(xs) : ex2_approx(xs);
-                    }
+                for (int i = 0; i < 32; ++i) pe[i] = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + i]), sl2, -moff));
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const uint32_t addr = pbase + (c >> 1) * AT_PHALF_BYTES + ((static_cast<uint32_t>((c & 1) * 4 + ch) ^ rsw) << 4);
-                        const uint32_t a0 = pack_bf16_trunc(pe[ch * 8 + 0], pe[ch * 8 + 1]), a1 = pack_bf16_trunc(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-                        const uint32_t a2 = pack_bf16_trunc(pe[ch * 8 + 4], pe[ch * 8 + 5]), a3 = pack_bf16_trunc(pe[ch * 8 + 6], pe[ch * 8 + 7]);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
-                    }
-                }
-#else
-                // branch-free, hand-pipelined fast path.  Stage c: 32 FFMA + 32 MUFU.EX2 for columns [32c, 32c+32),
-                // interleaved (8 MUFU : 4 F2FP : 1 STS) with packing/storing the results of stage c-1.
-                auto store_group = [&](int c, int ch) {   // 8 probabilities of chunk c -> one 16-byte swizzled store
-                    const uint32_t half = pbase + (c >> 1) * AT_PHALF_BYTES;
-                    const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + ch);
-                    const uint32_t addr = half + ((chunk ^ rsw) << 4);
-                    const int b0 = c * 32 + ch * 8;
-                    const uint32_t a0 = pack_bf16_v(__uint_as_float(sreg[b0 + 0]), __uint_as_float(sreg[b0 + 1]));
-                    const uint32_t a1 = pack_bf16_v(__uint_as_float(sreg[b0 + 2]), __uint_as_float(sreg[b0 + 3]));
-                    const uint32_t a2 = pack_bf16_v(__uint_as_float(sreg[b0 + 4]), __uint_as_float(sreg[b0 + 5]));
-                    const uint32_t a3 = pack_bf16_v(__uint_as_float(sreg[b0 + 6]), __uint_as_float(sreg[b0 + 7]));
+                for (int ch = 0; ch < 4; ++ch) {
+                    const uint32_t addr = pbase + (c >> 1) * AT_PHALF_BYTES + ((static_cast<uint32_t>((c & 1) * 4 + ch) ^ rsw) << 4);
+                    const uint32_t a0 = pack_bf16_trunc(pe[ch * 8 + 0], pe[ch * 8 + 1]), a1 = pack_bf16_trunc(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+                    const uint32_t a2 = pack_bf16_trunc(pe[ch * 8 + 4], pe[ch * 8 + 5]), a3 = pack_bf16_trunc(pe[ch * 8 + 6], pe[ch * 8 + 7]);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
-                };
-                // group = 8 columns (one 16-byte store).  MUFU results of group g are packed AT_EXP_LAG groups later.
-#pragma unroll
-                for (int i = 0; i < 128; ++i) sreg[i] = __float_as_uint(fmaf(__uint_as_float(sreg[i]), sl2, -moff));
-#pragma unroll
-                for (int gq = 0; gq < 16 + AT_EXP_LAG; ++gq) {
-                    if (gq < 16) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int i = gq * 8 + e;
-                            sreg[i] = __float_as_uint((e >= 8 - AT_POLY_PER8) ? exp2_poly(__uint_as_float(sreg[i]))
-                                                                              : ex2_approx_v(__uint_as_float(sreg[i])));
-                        }
-                    }
-                    if (gq == AT_EXP_LAG && jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);   // P_x smem reusable: P_x(jj-1) V done
-                    if (gq >= AT_EXP_LAG) store_group((gq - AT_EXP_LAG) >> 2, (gq - AT_EXP_LAG) & 3);
-                }
-#endif
-            } else {
-#if AT_EXP_MODE != 0
-                if (jj > 0) mbar_wait(o_full(x), (jj - 1) & 1);
-#endif
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t half = pbase + (c >> 1) * AT_PHALF_BYTES;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        float pe[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)   // masked entries hold -inf -> exp2 = 0
-                            pe[e] = ex2_approx(fmaf(__uint_as_float(sreg[c * 32 + ch * 8 + e]), sl2, -moff));
-                        const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + ch);
-                        const uint32_t addr = half + ((chunk ^ rsw) << 4);
-                        const uint32_t a0 = pack_bf16(pe[0], pe[1]), a1 = pack_bf16(pe[2], pe[3]);
-                        const uint32_t a2 = pack_bf16(pe[4], pe[5]), a3 = pack_bf16(pe[6], pe[7]);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
-                    }
                 }
             }
-#ifdef AT_XU_TOKEN
-            __syncwarp();
-            if (lane == 0) mbar_arrive(xu_token(1 - x, qd));
-#endif
             AT_STAMP(5);
             // P_x written (and O_x rescaled) -> visible to the tensor core
             tc_fence_before();
@@ -691,44 +414,16 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             if (lane == 0) mbar_arrive(p_full(x));
             AT_STAMP(6);
         }
-        // ---- epilogue: out = bf16(self + bf16(tanh(gate) * bf16(cross)))
+        // ---- epilogue: out = bf16(self + bf16(tanh(gate) * bf16(cross)))   (no caption segment: out = bf16(self))
         mbar_wait(o_full(x), (n_total - 1) & 1);
         tc_fence_after();
-        {
-            const float gt = gate_tanh[h];
-            uint32_t res[AT_HD / 2];
-            uint32_t v[32];
-            tmem_ld_32x32b_x16(to + 64, v);
-            tmem_ld_wait();
-            const float inv = 1.0f / __uint_as_float(v[8]);
+        if (n_cross > 0) read_o(o_self, true, gate_tanh[h]);
+        else read_o(o_self, false, 0.f);
+        if (qrow < N) {
+            bf16* dst = out + (static_cast<size_t>(b) * N + qrow) * (static_cast<size_t>(H) * HD) + h * HD;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 sv = unpack_bf16(o_self[32 + i]);
-                res[32 + i] = pack_bf16(sv.x + bf16_round(gt * bf16_round(__uint_as_float(v[2 * i]) * inv)),
-                                        sv.y + bf16_round(gt * bf16_round(__uint_as_float(v[2 * i + 1]) * inv)));
-            }
-            tmem_ld_32x32b_x32(to, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float2 sv = unpack_bf16(o_self[i]);
-                res[i] = pack_bf16(sv.x + bf16_round(gt * bf16_round(__uint_as_float(v[2 * i]) * inv)),
-                                   sv.y + bf16_round(gt * bf16_round(__uint_as_float(v[2 * i + 1]) * inv)));
-            }
-            tmem_ld_32x32b_x32(to + 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float2 sv = unpack_bf16(o_self[16 + i]);
-                res[16 + i] = pack_bf16(sv.x + bf16_round(gt * bf16_round(__uint_as_float(v[2 * i]) * inv)),
-                                        sv.y + bf16_round(gt * bf16_round(__uint_as_float(v[2 * i + 1]) * inv)));
-            }
-            if (qrow < N) {
-                bf16* dst = out + (static_cast<size_t>(b) * N + qrow) * (static_cast<size_t>(H) * AT_HD) + h * AT_HD;
-#pragma unroll
-                for (int i = 0; i < AT_HD / 8; ++i)
-                    *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(res[4 * i], res[4 * i + 1], res[4 * i + 2], res[4 * i + 3]);
-            }
+            for (int i = 0; i < HD / 8; ++i)
+                *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(o_self[4 * i], o_self[4 * i + 1], o_self[4 * i + 2], o_self[4 * i + 3]);
         }
     }
 
@@ -746,9 +441,9 @@ extern "C" int ndit_debug_attn_timing(long long* out) {   // [2][64][8] clock64 
 }
 #endif
 
-template <int SPLIT>
+template <int HD>
 static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
-    auto kern = attention_fused_kernel<SPLIT>;
+    auto kern = attention_fused_kernel<HD>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
@@ -757,16 +452,17 @@ static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
     }
     const float log2e = 1.4426950408889634f;
     const dim3 grid((p.N + 2 * AT_BQ - 1) / (2 * AT_BQ), p.H, p.B);
-    kern<<<grid, 128 + 256 * SPLIT, AT_SMEM_BYTES, stream>>>(p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt,
-                                                            p.ymask, p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv,
-                                                            p.scale_self * log2e, p.scale_cross * log2e);
+    kern<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask,
+                                                      p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv, p.scale_self * log2e,
+                                                      p.scale_cross * log2e);
     return cudaGetLastError();
 }
 
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
-    if (p.T <= 0 || p.N <= 0) return cudaErrorInvalidValue;
-    static const int split = getenv("NDIT_ATTN_SPLIT") ? atoi(getenv("NDIT_ATTN_SPLIT")) : AT_DEFAULT_SPLIT;
-    return split == 2 ? launch_attention<2>(p, stream) : launch_attention<1>(p, stream);
+    if (p.T < 0 || p.N <= 0) return cudaErrorInvalidValue;
+    if (p.hd == 72) return launch_attention<72>(p, stream);
+    if (p.hd == 48) return launch_attention<48>(p, stream);
+    return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -789,6 +485,7 @@ __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, c
     float result[2] = {0.f, 0.f};            // this thread owns output dims threadIdx.x (< hd) for both segments
     for (int seg = 0; seg < 2; ++seg) {
         const int len = seg == 0 ? N : T;
+        if (len == 0) continue;              // no caption segment (uniform for the whole block)
         const float scale = seg == 0 ? scale_self : scale_cross;
         float mx = -INFINITY;
         for (int k = threadIdx.x; k < len; k += blockDim.x) {

@@ -216,8 +216,8 @@ static int create_impl(ndit_engine* h) {
     h->Mmax = c.max_batch * c.max_tokens;
     const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
     ALLOC(X, M * D); ALLOC(u, M * D); ALLOC(qkv, M * h->Wq); ALLOC(attn, M * D); ALLOC(o, M * D); ALLOC(hbuf, M * F);
-    ALLOC(vt, B * h->Hkv * ATTN_VROWS * c.max_tokens);
-    ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * h->Hkv * ATTN_VROWS * h->Tpad_max);
+    ALLOC(vt, B * h->Hkv * h->vrows * c.max_tokens);
+    ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
     ALLOC(ymask, B * T); ALLOC(pool, B * C); ALLOC(capemb, B * cd); ALLOC(tf, B * 256); ALLOC(h1, B * cd); ALLOC(sc, B * cd);
     ALLOC(mod, B * (L * 4 * D + D)); ALLOC(tok, M * h->O);
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
@@ -434,10 +434,10 @@ extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* m
         CKL(gemm_bf16_tn(p, s));
     }
     CKL(ln_rows(h->kvy, (int)(2 * KV), ks, h->kyn_w, h->kyn_b, KV, M, (int)KV, (int)L, s));
-    const size_t vs = (size_t)batch * h->Hkv * ATTN_VROWS * Tpad;
+    const size_t vs = (size_t)batch * h->Hkv * h->vrows * Tpad;
     CK(cudaMemsetAsync(h->vyt, 0, L * vs * sizeof(bf16), s));
-    CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, batch, T, h->Hkv, h->hd, ATTN_VROWS, (int)L, s));
-    CKL(fill_ones_row(h->vyt, Tpad, vs, batch * h->Hkv, Tpad, h->hd, ATTN_VROWS, (int)L, s));
+    CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, batch, T, h->Hkv, h->hd, h->vrows, (int)L, s));
+    CKL(fill_ones_row(h->vyt, Tpad, vs, batch * h->Hkv, Tpad, h->hd, h->vrows, (int)L, s));
     if (batch != h->cap_batch || T != h->cap_T) h->attn_plans_valid = false;
     h->cap_batch = batch;
     h->cap_T = T;
@@ -474,12 +474,12 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
             e |= make_tmap_3d(&a.tmQ16, h->qkv, hd, h->H, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
             e |= make_tmap_3d(&a.tmK64, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 64, 1, 128, 128);
             e |= make_tmap_3d(&a.tmK16, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
-            e |= make_tmap_3d(&a.tmVt, h->vt, N, ATTN_VROWS, (uint64_t)batch * h->Hkv, (uint64_t)N * 2, (uint64_t)N * ATTN_VROWS * 2, 64, 80, 1, 128);
+            e |= make_tmap_3d(&a.tmVt, h->vt, N, h->vrows, (uint64_t)batch * h->Hkv, (uint64_t)N * 2, (uint64_t)N * h->vrows * 2, 64, 80, 1, 128);
             const bf16* kvy = h->kvy + l * (size_t)batch * T * 2 * KV;
-            const bf16* vyt = h->vyt + l * (size_t)batch * h->Hkv * ATTN_VROWS * Tpad;
+            const bf16* vyt = h->vyt + l * (size_t)batch * h->Hkv * h->vrows * Tpad;
             e |= make_tmap_3d(&a.tmKy64, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 64, 1, 128, 128);
             e |= make_tmap_3d(&a.tmKy16, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 16, 1, 128, 32);
-            e |= make_tmap_3d(&a.tmVyt, vyt, Tpad, ATTN_VROWS, (uint64_t)batch * h->Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * ATTN_VROWS * 2, 64, 80, 1, 128);
+            e |= make_tmap_3d(&a.tmVyt, vyt, Tpad, h->vrows, (uint64_t)batch * h->Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * h->vrows * 2, 64, 80, 1, 128);
             if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
             a.ymask = h->ymask;
             a.gate_tanh = h->gate_tanh + l * h->H;
@@ -520,8 +520,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     if (int e = ensure_plans(h, batch, N)) return e;
     const int D = h->D, L = h->L, hd = h->hd;
     if (!h->vt_ones_valid) {
-        CK(cudaMemsetAsync(h->vt, 0, (size_t)batch * h->Hkv * ATTN_VROWS * N * sizeof(bf16), s));
-        CKL(fill_ones_row(h->vt, N, 0, batch * h->Hkv, N, hd, ATTN_VROWS, 1, s));
+        CK(cudaMemsetAsync(h->vt, 0, (size_t)batch * h->Hkv * h->vrows * N * sizeof(bf16), s));
+        CKL(fill_ones_row(h->vt, N, 0, batch * h->Hkv, N, hd, h->vrows, 1, s));
         h->vt_ones_valid = true;
     }
     const int mod_stride = L * 4 * D + D;
@@ -557,7 +557,7 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                               h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
                               scale_cross, s));
         } else {
-            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, ATTN_VROWS, 1, s));
+            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, h->vrows, 1, s));
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
@@ -726,9 +726,10 @@ extern "C" int ndit_op_ln_rope(void* qkv, const void* qw, const void* qb, const 
 
 static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
                              int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
-                             int32_t use_ref, void* stream, int bench_iters, float* bench_ms) {
+                             int32_t use_ref, void* stream, int bench_iters, float* bench_ms, int hd) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int hd = 72;
+    if (hd != 72 && hd != 48) return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: head_dim must be 72 or 48", cudaErrorInvalidValue);
+    const int vrows = attn_vrows(hd);
     const bf16* qkv = static_cast<const bf16*>(qkv_);
     const bf16* kvy = static_cast<const bf16*>(kvy_);
     const int Wq = (H + 2 * Hkv) * hd, KV = Hkv * hd;
@@ -740,16 +741,16 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
     if (N % 8 != 0) return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: N % 8 != 0", cudaErrorInvalidValue);
     const int Tpad = (T + 7) / 8 * 8;
     bf16 *vt = nullptr, *vyt = nullptr;
-    const size_t vt_elems = (size_t)B * Hkv * ATTN_VROWS * N, vyt_elems = (size_t)B * Hkv * ATTN_VROWS * Tpad;
+    const size_t vt_elems = (size_t)B * Hkv * vrows * N, vyt_elems = (size_t)B * Hkv * vrows * Tpad;
     cudaError_t e = cudaMalloc(&vt, vt_elems * 2);
     if (e == cudaSuccess) e = cudaMalloc(&vyt, vyt_elems * 2);
     if (e != cudaSuccess) return op_fail(NDIT_ERR_NOMEM, "ndit_op_attention", e);
     cudaMemsetAsync(vt, 0, vt_elems * 2, s);
     cudaMemsetAsync(vyt, 0, vyt_elems * 2, s);
-    e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, N, 0, B, N, Hkv, hd, ATTN_VROWS, 1, s);
-    if (e == cudaSuccess) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, ATTN_VROWS, 1, s);
-    if (e == cudaSuccess) e = fill_ones_row(vt, N, 0, B * Hkv, N, hd, ATTN_VROWS, 1, s);
-    if (e == cudaSuccess) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, ATTN_VROWS, 1, s);
+    e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, N, 0, B, N, Hkv, hd, vrows, 1, s);
+    if (e == cudaSuccess) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, vrows, 1, s);
+    if (e == cudaSuccess) e = fill_ones_row(vt, N, 0, B * Hkv, N, hd, vrows, 1, s);
+    if (e == cudaSuccess) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, vrows, 1, s);
     AttnPlan a;
     memset(&a, 0, sizeof(a));
     int te = 0;
@@ -758,15 +759,15 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
     te |= make_tmap_3d(&a.tmQ16, qkv, hd, H, M, hd * 2, rs, 16, 1, 128, 32);
     te |= make_tmap_3d(&a.tmK64, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, 128, 128);
     te |= make_tmap_3d(&a.tmK16, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, 128, 32);
-    te |= make_tmap_3d(&a.tmVt, vt, N, ATTN_VROWS, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * ATTN_VROWS * 2, 64, 80, 1, 128);
+    te |= make_tmap_3d(&a.tmVt, vt, N, vrows, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * vrows * 2, 64, 80, 1, 128);
     te |= make_tmap_3d(&a.tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, 128, 128);
     te |= make_tmap_3d(&a.tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, 128, 32);
-    te |= make_tmap_3d(&a.tmVyt, vyt, Tpad, ATTN_VROWS, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * ATTN_VROWS * 2, 64, 80, 1, 128);
+    te |= make_tmap_3d(&a.tmVyt, vyt, Tpad, vrows, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * vrows * 2, 64, 80, 1, 128);
     int rc = NDIT_OK;
     if (te) rc = op_fail(NDIT_ERR_CUDA, "ndit_op_attention tensor map", cudaSuccess);
     if (!te && e == cudaSuccess) {
         a.ymask = ymask; a.gate_tanh = gate_tanh; a.out = static_cast<bf16*>(out);
-        a.B = B; a.N = N; a.T = T; a.H = H; a.Hkv = Hkv; a.scale_self = scale_self; a.scale_cross = scale_cross;
+        a.B = B; a.N = N; a.T = T; a.H = H; a.Hkv = Hkv; a.hd = hd; a.scale_self = scale_self; a.scale_cross = scale_cross;
         e = attention_fused(a, s);
         if (bench_iters > 0 && bench_ms && e == cudaSuccess) {      // micro-benchmark: average of `bench_iters` launches
             cudaEvent_t e0, e1;

@@ -46,7 +46,7 @@ struct AttnPlan {
     const uint8_t* ymask;        // [B, T] bytes (0/1)
     const float* gate_tanh;      // [H] bf16-rounded tanh(gate)
     bf16* out;                   // [B*N, H*hd]
-    int B, N, T, H, Hkv;
+    int B, N, T, H, Hkv, hd;     // T = 0: no caption segment (class-conditional model); hd = 72 or 48
     float scale_self, scale_cross;
 };
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream);
@@ -91,7 +91,8 @@ cudaError_t transpose_v(const bf16* src, int ld, int col0, size_t src_layer_stri
 // dst[group*grows + hd][0:n_cols] = 1  (the all-ones row of V^T: column hd of P.V becomes the softmax row sum)
 cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int groups, int n_cols, int hd, int grows,
                           int layers, cudaStream_t s);
-constexpr int ATTN_VROWS = 80;   // rows per (batch, kv head) group in the V^T buffers
+// rows per (batch, kv head) group in the V^T buffers: head_dim data rows + the all-ones row, padded to a multiple of 16
+__host__ __device__ constexpr int attn_vrows(int hd) { return (hd + 1 + 15) / 16 * 16; }
 // unpatchify + learn_sigma slice + 3-channel CFG combine (+ optional fused Euler update)
 //   tok [2n*N, O] (fp32 of bf16 values) -> v [2n,4,Hh,Ww] bf16;  if y_inout: y = bf16(y + bf16(dt*v))
 cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale,
