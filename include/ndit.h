@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NDIT_ABI_VERSION 1
+#define NDIT_ABI_VERSION 2
 
 typedef struct ndit_engine* ndit_handle;
 
@@ -52,6 +52,11 @@ typedef struct ndit_config {
     int32_t max_tokens;     /* largest H/2*W/2 the workspace is sized for (e.g. 4096 for 1024x1024) */
     int32_t max_cap_len;    /* largest caption length T (e.g. 256) */
     int32_t max_batch;      /* rows of one forward_with_cfg call = 2 (cond + uncond) * samples; <= 4 */
+    int32_t num_classes;    /* 0: caption-conditioned Lumina-Next-T2I NextDiT (above).  > 0: class-conditional Next-DiT
+                             * (Next-DiT-ImageNet/models/models.py:836-1056 DiT_Llama + TransformerBlockSandwichNorm2):
+                             * label embedding table [num_classes + 1, min(dim,1024)] instead of the caption path, no
+                             * cross-attention, weight-free pre-norms, final layer with shift + scale; cap_feat_dim and
+                             * max_cap_len are ignored.  head_dim = dim / n_heads must be 72 or 48 in both cases. */
 } ndit_config;
 
 /* Per-call arguments of NextDiT.forward_with_cfg (model.py:866-913) that are not tensors. */
@@ -61,6 +66,8 @@ typedef struct ndit_step_params {
     float scale_watershed;
     int32_t proportional_attn;
     int32_t base_seqlen;     /* used when proportional_attn != 0 (model.py:373-376) */
+    float ntk_factor;        /* class-conditional model only: DiT_Llama.forward_with_cfg(rope_scaling_factor=scale_factor,
+                              * ntk_factor=...) (models.py:946-1012); 0 is treated as 1 */
 } ndit_step_params;
 
 /* --- lifecycle: models.NextDiT_2B_GQA_patch2(...) / .to("cuda") / del (sample.py:125-129) */
@@ -83,6 +90,10 @@ int64_t ndit_parameter_count(ndit_handle h);   /* NextDiT.parameter_count (model
  * cap_feats_dev: bf16 [batch, T, cap_feat_dim]; cap_mask_dev: uint8 [batch, T] (non-zero = valid). */
 int ndit_set_caption(ndit_handle h, const void* cap_feats_dev, const uint8_t* cap_mask_dev, int32_t batch, int32_t T,
                      void* stream);
+
+/* --- class-conditional model: the `y` argument of DiT_Llama.forward_with_cfg (models.py:946): labels_dev int64 [batch]
+ * (second half = the null class num_classes for CFG).  Replaces ndit_set_caption for num_classes > 0. */
+int ndit_set_labels(ndit_handle h, const int64_t* labels_dev, int32_t batch, void* stream);
 
 /* --- NextDiT.forward_with_cfg (model.py:866-913).  x_dev/out_dev: bf16 [batch, C, height, width] NCHW
  * (latent size; batch = 2 * samples, second half of x ignored as in the reference); t is the (common)
@@ -133,6 +144,10 @@ int ndit_op_ln_rope(void* qkv_dev, const void* qw, const void* qb, const void* k
 int ndit_op_attention(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                       void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
                       float scale_cross, int32_t use_ref, void* stream);
+/* general form: head_dim hd = 72 or 48; T = 0 (kvy/ymask/gate may be NULL) = no caption segment */
+int ndit_op_attention_hd(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
+                         void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, int32_t hd, float scale_self,
+                         float scale_cross, int32_t use_ref, void* stream);
 /* same op, launched `iters` times after a warm-up; *ms_out = average device time per launch (CUDA events) */
 int ndit_op_attention_bench(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                             void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,

@@ -16,12 +16,13 @@ class NditConfig(C.Structure):
     _fields_ = [("dim", C.c_int32), ("n_layers", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32),
                 ("cap_feat_dim", C.c_int32), ("in_channels", C.c_int32), ("patch_size", C.c_int32),
                 ("multiple_of", C.c_int32), ("learn_sigma", C.c_int32), ("norm_eps", C.c_float),
-                ("max_tokens", C.c_int32), ("max_cap_len", C.c_int32), ("max_batch", C.c_int32)]
+                ("max_tokens", C.c_int32), ("max_cap_len", C.c_int32), ("max_batch", C.c_int32),
+                ("num_classes", C.c_int32)]
 
 
 class NditStepParams(C.Structure):
     _fields_ = [("cfg_scale", C.c_float), ("scale_factor", C.c_float), ("scale_watershed", C.c_float),
-                ("proportional_attn", C.c_int32), ("base_seqlen", C.c_int32)]
+                ("proportional_attn", C.c_int32), ("base_seqlen", C.c_int32), ("ntk_factor", C.c_float)]
 
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -36,6 +37,7 @@ SIGNATURES = {
     "ndit_finalize_weights": (C.c_int, [_vp, _vp]),
     "ndit_parameter_count": (_i64, [_vp]),
     "ndit_set_caption": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "ndit_set_labels": (C.c_int, [_vp, _vp, _i32, _vp]),
     "ndit_forward_cfg": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),
     "ndit_sample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_f32), _i32, _i32, C.POINTER(NditStepParams),
                               _vp, _vp, _vp]),
@@ -48,6 +50,7 @@ SIGNATURES = {
     "ndit_op_gemm_bench": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp]),
     "ndit_op_ln_rope": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
     "ndit_op_attention": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
+    "ndit_op_attention_hd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
     "ndit_op_attention_bench": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32,
                                           C.POINTER(_f32), _vp]),
     "ndit_op_resid_rms_mod": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
@@ -71,7 +74,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ndit_abi_version() != 1:
+    if lib.ndit_abi_version() != 2:
         raise RuntimeError("libndit_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -65,6 +65,10 @@ struct RopeSlot {
 struct ndit_engine {
     ndit_config cfg;
     int D, L, H, Hkv, hd, F, C, cd, O, Wq;   // Wq = fused qkv width
+    int vrows = 80;                          // V^T rows per (batch, kv head): head_dim + ones row, padded to 16
+    bool cls = false;                        // class-conditional variant (DiT_Llama): labels instead of captions
+    int FD = 1;                              // final-layer adaLN chunks: 1 (scale) or 2 (shift, scale)
+    bf16* Yemb = nullptr;                    // [num_classes + 1, cd] label embedding table
     int device = 0, num_sms = 148;
     char err[512];
     int64_t launches = 0;
@@ -183,8 +187,11 @@ static int create_impl(ndit_engine* h) {
     const ndit_config& c = h->cfg;
     if (c.dim <= 0 || c.n_heads <= 0 || c.dim % c.n_heads != 0) return h->fail(NDIT_ERR_INVALID, "bad dim/n_heads");
     h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
-    h->hd = c.dim / c.n_heads; h->C = c.cap_feat_dim; h->cd = c.dim < 1024 ? c.dim : 1024;
-    if (h->hd != 72) return h->fail(NDIT_ERR_INVALID, "this build supports head_dim 72 only (got %d)", h->hd);
+    h->cls = c.num_classes > 0;
+    h->FD = h->cls ? 2 : 1;
+    h->hd = c.dim / c.n_heads; h->C = h->cls ? 0 : c.cap_feat_dim; h->cd = c.dim < 1024 ? c.dim : 1024;
+    if (h->hd != 72 && h->hd != 48) return h->fail(NDIT_ERR_INVALID, "head_dim must be 72 or 48 (got %d)", h->hd);
+    h->vrows = attn_vrows(h->hd);
     if (c.patch_size != 2 || c.in_channels != 4) return h->fail(NDIT_ERR_INVALID, "patch_size 2 / in_channels 4 only");
     if (h->H % h->Hkv != 0) return h->fail(NDIT_ERR_INVALID, "n_heads %% n_kv_heads != 0");
     if (c.max_batch < 2 || c.max_batch > 4 || (c.max_batch & 1)) return h->fail(NDIT_ERR_INVALID, "max_batch must be 2 or 4");
@@ -204,7 +211,8 @@ static int create_impl(ndit_engine* h) {
     const size_t D = h->D, L = h->L, F = h->F, C = h->C, cd = h->cd, KV = (size_t)h->Hkv * h->hd;
     ALLOC(Wx, D * 16); ALLOC(bx, D); ALLOC(Wt0, cd * 256); ALLOC(bt0, cd); ALLOC(Wt2, cd * cd); ALLOC(bt2, cd);
     ALLOC(capln_w, C); ALLOC(capln_b, C); ALLOC(Wcap, cd * C); ALLOC(bcap, cd);
-    ALLOC(Wada, (L * 4 * D + D) * cd); ALLOC(bada, L * 4 * D + D);
+    ALLOC(Wada, (L * 4 * D + h->FD * D) * cd); ALLOC(bada, L * 4 * D + h->FD * D);
+    if (h->cls) ALLOC(Yemb, ((size_t)c.num_classes + 1) * cd);
     ALLOC(Wout, (size_t)h->O * D); ALLOC(bout, h->O); ALLOC(pad_token, D);
     ALLOC(Wqkv, L * h->Wq * D); ALLOC(Wo, L * D * D); ALLOC(W13, L * 2 * F * D); ALLOC(W2, L * D * F);
     ALLOC(Wkvy, L * 2 * KV * C);
@@ -212,25 +220,26 @@ static int create_impl(ndit_engine* h) {
     ALLOC(an1, L * D); ALLOC(an2, L * D); ALLOC(fn1, L * D); ALLOC(fn2, L * D); ALLOC(yn, L * C);
     ALLOC(gate_raw, L * h->H); ALLOC(gate_tanh, L * h->H);
 
-    h->Bmax = c.max_batch; h->Tmax = c.max_cap_len; h->Tpad_max = (c.max_cap_len + 7) / 8 * 8;
+    h->Bmax = c.max_batch; h->Tmax = h->cls ? 0 : c.max_cap_len; h->Tpad_max = (h->Tmax + 7) / 8 * 8;
     h->Mmax = c.max_batch * c.max_tokens;
     const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
     ALLOC(X, M * D); ALLOC(u, M * D); ALLOC(qkv, M * h->Wq); ALLOC(attn, M * D); ALLOC(o, M * D); ALLOC(hbuf, M * F);
     ALLOC(vt, B * h->Hkv * h->vrows * c.max_tokens);
     ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
     ALLOC(ymask, B * T); ALLOC(pool, B * C); ALLOC(capemb, B * cd); ALLOC(tf, B * 256); ALLOC(h1, B * cd); ALLOC(sc, B * cd);
-    ALLOC(mod, B * (L * 4 * D + D)); ALLOC(tok, M * h->O);
+    ALLOC(mod, B * (L * 4 * D + h->FD * D)); ALLOC(tok, M * h->O);
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
     ALLOC(vel, lat); ALLOC(ystate, lat); ALLOC(ymid, lat); ALLOC(stage_z, lat); ALLOC(stage_cap, B * T * C); ALLOC(stage_mask, B * T);
     for (int i = 0; i < 2; ++i) {
         int r = dev_alloc(h, &h->rope[i].tab, (size_t)c.max_tokens * (h->hd / 2));
         if (r) return r;
     }
-    // parameter inventory (NextDiT.parameter_count): everything in the state dict
-    h->n_params = (int64_t)(D * 16 + D + cd * 256 + cd + cd * cd + cd + 2 * C + cd * C + cd + D /*pad_token*/ +
-                            (size_t)h->O * D + h->O + D * cd + D) +
-                  (int64_t)L * (int64_t)(h->H + (size_t)h->Wq * D + 2 * KV * C + D * D + 2 * D + 4 * KV + 3 * F * D + 4 * D + C +
-                                         4 * D * cd + 4 * D);
+    if (h->cls) {
+        // weight-free pre-norms (PFRMSNorm, models.py:76-117) = RMSNorm with unit weight
+        std::vector<uint16_t> ones(L * D, 0x3F80);
+        CK(cudaMemcpy(h->an1, ones.data(), ones.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->fn1, ones.data(), ones.size() * 2, cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -281,8 +290,9 @@ extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
 // ------------------------------------------------------------------------------------ weights
 
 static int place(ndit_engine* h, bf16* dst, size_t dst_ld, const void* src, int dtype, size_t rows, size_t cols,
-                 size_t blk, size_t blk_stride, size_t row0, cudaStream_t s) {
+                 size_t blk, size_t blk_stride, size_t row0, cudaStream_t s, bool fresh = true) {
     const size_t total = rows * cols;
+    if (fresh) h->n_params += (int64_t)total;     // NextDiT.parameter_count: every state-dict tensor once
     const int grid = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
     place_rows_kernel<<<grid, 256, 0, s>>>(dst, dst_ld, src, dtype == NDIT_F32, rows, cols, blk ? blk : rows,
                                            blk_stride, row0);
@@ -305,25 +315,30 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
 #define VEC(name, dst, n)                                         \
     if (!strcmp(key, name)) {                                     \
         if (int e = want(n, 0)) return e;                         \
-        h->seen.insert(key);                                      \
-        return place(h, dst, 1, src, dtype, n, 1, 0, 0, 0, s);    \
+        const bool fresh_ = h->seen.insert(key).second;           \
+        return place(h, dst, 1, src, dtype, n, 1, 0, 0, 0, s, fresh_); \
     }
 #define MAT(name, dst, rr, cc)                                    \
     if (!strcmp(key, name)) {                                     \
         if (int e = want(rr, cc)) return e;                       \
-        h->seen.insert(key);                                      \
-        return place(h, dst, cc, src, dtype, rr, cc, 0, 0, 0, s); \
+        const bool fresh_ = h->seen.insert(key).second;           \
+        return place(h, dst, cc, src, dtype, rr, cc, 0, 0, 0, s, fresh_); \
     }
-    VEC("pad_token", h->pad_token, D)
+    if (!h->cls) { VEC("pad_token", h->pad_token, D) }
     MAT("x_embedder.weight", h->Wx, D, 16) VEC("x_embedder.bias", h->bx, D)
     MAT("t_embedder.mlp.0.weight", h->Wt0, cd, 256) VEC("t_embedder.mlp.0.bias", h->bt0, cd)
     MAT("t_embedder.mlp.2.weight", h->Wt2, cd, cd) VEC("t_embedder.mlp.2.bias", h->bt2, cd)
-    VEC("cap_embedder.0.weight", h->capln_w, C) VEC("cap_embedder.0.bias", h->capln_b, C)
-    MAT("cap_embedder.1.weight", h->Wcap, cd, C) VEC("cap_embedder.1.bias", h->bcap, cd)
+    if (!h->cls) {
+        VEC("cap_embedder.0.weight", h->capln_w, C) VEC("cap_embedder.0.bias", h->capln_b, C)
+        MAT("cap_embedder.1.weight", h->Wcap, cd, C) VEC("cap_embedder.1.bias", h->bcap, cd)
+    } else {
+        MAT("y_embedder.embedding_table.weight", h->Yemb, (size_t)h->cfg.num_classes + 1, cd)
+    }
     MAT("final_layer.linear.weight", h->Wout, (size_t)h->O, D) VEC("final_layer.linear.bias", h->bout, (size_t)h->O)
     const size_t Lz = h->L;
-    MAT("final_layer.adaLN_modulation.1.weight", h->Wada + Lz * 4 * D * cd, D, cd)
-    VEC("final_layer.adaLN_modulation.1.bias", h->bada + Lz * 4 * D, D)
+    // T2I: [scale]; class-conditional: [shift | scale] (models.py:829-833)
+    MAT("final_layer.adaLN_modulation.1.weight", h->Wada + Lz * 4 * D * cd, (size_t)h->FD * D, cd)
+    VEC("final_layer.adaLN_modulation.1.bias", h->bada + Lz * 4 * D, (size_t)h->FD * D)
 #undef VEC
 #undef MAT
     int li = -1, pos = 0;
@@ -345,10 +360,11 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
             {"adaLN_modulation.1.weight", h->Wada + l * 4 * D * cd, cd, 4 * D, cd, 0, 0, 0},
         };
         for (const Ent& e : ents) {
+            if (h->cls && (!strcmp(e.name, "attention.wk_y.weight") || !strcmp(e.name, "attention.wv_y.weight"))) continue;
             if (!strcmp(sub, e.name)) {
                 if (int er = want(e.rows, e.cols)) return er;
-                h->seen.insert(key);
-                return place(h, e.dst, e.dst_ld, src, dtype, e.rows, e.cols, e.blk, e.blk_stride, e.row0, s);
+                const bool fresh = h->seen.insert(key).second;
+                return place(h, e.dst, e.dst_ld, src, dtype, e.rows, e.cols, e.blk, e.blk_stride, e.row0, s, fresh);
             }
         }
         struct VEnt { const char* name; bf16* dst; size_t n; };
@@ -362,11 +378,29 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
             {"attention_y_norm.weight", h->yn + l * C, C},
             {"adaLN_modulation.1.bias", h->bada + l * 4 * D, 4 * D},
         };
+        // class-conditional block (TransformerBlockSandwichNorm2, models.py:692-796): post-norms are called
+        // attention_norm / ffn_norm, the pre-norms carry no weight, there is no caption branch
+        const VEnt cls_vents[] = {
+            {"attention.q_norm.weight", h->qn_w + l * D, D}, {"attention.q_norm.bias", h->qn_b + l * D, D},
+            {"attention.k_norm.weight", h->kn_w + l * KV, KV}, {"attention.k_norm.bias", h->kn_b + l * KV, KV},
+            {"attention_norm.weight", h->an2 + l * D, D}, {"ffn_norm.weight", h->fn2 + l * D, D},
+            {"adaLN_modulation.1.bias", h->bada + l * 4 * D, 4 * D},
+        };
+        if (h->cls) {
+            for (const VEnt& e : cls_vents) {
+                if (!strcmp(sub, e.name)) {
+                    if (int er = want(e.n, 0)) return er;
+                    const bool fresh = h->seen.insert(key).second;
+                    return place(h, e.dst, 1, src, dtype, e.n, 1, 0, 0, 0, s, fresh);
+                }
+            }
+            return h->fail(NDIT_ERR_INVALID, "unexpected state-dict key: %s", key);
+        }
         for (const VEnt& e : vents) {
             if (!strcmp(sub, e.name)) {
                 if (int er = want(e.n, 0)) return er;
-                h->seen.insert(key);
-                return place(h, e.dst, 1, src, dtype, e.n, 1, 0, 0, 0, s);
+                const bool fresh = h->seen.insert(key).second;
+                return place(h, e.dst, 1, src, dtype, e.n, 1, 0, 0, 0, s, fresh);
             }
         }
     }
@@ -374,19 +408,27 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
 }
 
 static void expected_keys(const ndit_engine* h, std::vector<std::string>* out) {
-    const char* top[] = {"pad_token", "x_embedder.weight", "x_embedder.bias", "t_embedder.mlp.0.weight", "t_embedder.mlp.0.bias",
-                         "t_embedder.mlp.2.weight", "t_embedder.mlp.2.bias", "cap_embedder.0.weight", "cap_embedder.0.bias",
-                         "cap_embedder.1.weight", "cap_embedder.1.bias", "final_layer.linear.weight", "final_layer.linear.bias",
-                         "final_layer.adaLN_modulation.1.weight", "final_layer.adaLN_modulation.1.bias"};
-    for (const char* k : top) out->push_back(k);
-    const char* per[] = {"attention.gate", "attention.wq.weight", "attention.wk.weight", "attention.wv.weight", "attention.wk_y.weight",
-                         "attention.wv_y.weight", "attention.wo.weight", "attention.q_norm.weight", "attention.q_norm.bias",
-                         "attention.k_norm.weight", "attention.k_norm.bias", "attention.ky_norm.weight", "attention.ky_norm.bias",
-                         "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight", "attention_norm1.weight",
-                         "attention_norm2.weight", "ffn_norm1.weight", "ffn_norm2.weight", "attention_y_norm.weight",
+    const char* common[] = {"x_embedder.weight", "x_embedder.bias", "t_embedder.mlp.0.weight", "t_embedder.mlp.0.bias",
+                            "t_embedder.mlp.2.weight", "t_embedder.mlp.2.bias", "final_layer.linear.weight", "final_layer.linear.bias",
+                            "final_layer.adaLN_modulation.1.weight", "final_layer.adaLN_modulation.1.bias"};
+    for (const char* k : common) out->push_back(k);
+    const char* t2i_top[] = {"pad_token", "cap_embedder.0.weight", "cap_embedder.0.bias", "cap_embedder.1.weight", "cap_embedder.1.bias"};
+    if (h->cls) out->push_back("y_embedder.embedding_table.weight");
+    else for (const char* k : t2i_top) out->push_back(k);
+    const char* per[] = {"attention.wq.weight", "attention.wk.weight", "attention.wv.weight", "attention.wo.weight",
+                         "attention.q_norm.weight", "attention.q_norm.bias", "attention.k_norm.weight", "attention.k_norm.bias",
+                         "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight",
                          "adaLN_modulation.1.weight", "adaLN_modulation.1.bias"};
-    for (int l = 0; l < h->L; ++l)
-        for (const char* k : per) out->push_back("layers." + std::to_string(l) + "." + k);
+    const char* per_t2i[] = {"attention.gate", "attention.wk_y.weight", "attention.wv_y.weight", "attention.ky_norm.weight",
+                             "attention.ky_norm.bias", "attention_norm1.weight", "attention_norm2.weight", "ffn_norm1.weight",
+                             "ffn_norm2.weight", "attention_y_norm.weight"};
+    const char* per_cls[] = {"attention_norm.weight", "ffn_norm.weight"};
+    for (int l = 0; l < h->L; ++l) {
+        const std::string pre = "layers." + std::to_string(l) + ".";
+        for (const char* k : per) out->push_back(pre + k);
+        if (h->cls) for (const char* k : per_cls) out->push_back(pre + k);
+        else for (const char* k : per_t2i) out->push_back(pre + k);
+    }
 }
 
 extern "C" int ndit_finalize_weights(ndit_handle h, void* stream) {
@@ -396,6 +438,10 @@ extern "C" int ndit_finalize_weights(ndit_handle h, void* stream) {
     for (const std::string& k : keys)
         if (!h->seen.count(k)) return h->fail(NDIT_ERR_STATE, "missing state-dict key (strict): %s", k.c_str());
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (h->cls) {
+        h->finalized = true;
+        return NDIT_OK;
+    }
     // tanh(gate) per head, bf16 in / bf16 out (model.py:433)
     const size_t n = (size_t)h->L * h->H;
     std::vector<uint16_t> raw(n);
@@ -413,6 +459,7 @@ extern "C" int ndit_finalize_weights(ndit_handle h, void* stream) {
 
 extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* mask, int32_t batch, int32_t T, void* stream) {
     if (!h || !cap || !mask) return NDIT_ERR_INVALID;
+    if (h->cls) return h->fail(NDIT_ERR_STATE, "ndit_set_caption: this engine is class-conditional (use ndit_set_labels)");
     if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
     if (batch < 1 || batch > h->Bmax || T < 1 || T > h->Tmax) return h->fail(NDIT_ERR_INVALID, "caption batch/T out of range (%d,%d)", batch, T);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -444,7 +491,44 @@ extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* m
     return NDIT_OK;
 }
 
+extern "C" int ndit_set_labels(ndit_handle h, const int64_t* labels, int32_t batch, void* stream) {
+    if (!h || !labels) return NDIT_ERR_INVALID;
+    if (!h->cls) return h->fail(NDIT_ERR_STATE, "ndit_set_labels: this engine is caption-conditioned (num_classes == 0)");
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    if (batch < 1 || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "label batch out of range (%d)", batch);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CKL(gather_label_rows(h->Yemb, reinterpret_cast<const long long*>(labels), h->capemb, batch, h->cfg.num_classes + 1, h->cd, s));
+    if (batch != h->cap_batch) h->attn_plans_valid = false;
+    h->cap_batch = batch;
+    h->cap_T = 0;
+    return NDIT_OK;
+}
+
 // ------------------------------------------------------------------------------------ forward
+
+// Tensor maps of the fused attention kernel.  q/k are read straight from the fused qkv buffer [B*N, Wq] through 3-D maps
+// (head_dim, head, token); the 64-wide box covers elements [0,64) (head_dim 48: 48..63 are out-of-bounds zeros), the
+// 16-wide box elements [64,80) of head_dim 72.  V^T buffers are [group][vrows][tokens].
+static int build_attn_maps(AttnPlan* a, const bf16* qkv, int Wq, const bf16* vt, const bf16* kvy, const bf16* vyt, int B, int N,
+                           int T, int H, int Hkv, int hd) {
+    const int vrows = attn_vrows(hd), KV = Hkv * hd, Tpad = (T + 7) / 8 * 8;
+    const uint64_t rs = (uint64_t)Wq * 2, M = (uint64_t)B * N;
+    int e = 0;
+    e |= make_tmap_3d(&a->tmQ64, qkv, hd, H, M, hd * 2, rs, 64, 1, 128, 128);
+    e |= make_tmap_3d(&a->tmK64, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, 128, 128);
+    e |= make_tmap_3d(&a->tmVt, vt, N, vrows, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * vrows * 2, 64, vrows, 1, 128);
+    if (hd > 64) {
+        e |= make_tmap_3d(&a->tmQ16, qkv, hd, H, M, hd * 2, rs, 16, 1, 128, 32);
+        e |= make_tmap_3d(&a->tmK16, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, 128, 32);
+    }
+    if (T > 0) {
+        e |= make_tmap_3d(&a->tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, 128, 128);
+        if (hd > 64) e |= make_tmap_3d(&a->tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, 128, 32);
+        e |= make_tmap_3d(&a->tmVyt, vyt, Tpad, vrows, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * vrows * 2, 64, vrows, 1, 128);
+    }
+    a->B = B; a->N = N; a->T = T; a->H = H; a->Hkv = Hkv; a->hd = hd;
+    return e;
+}
 
 static int ensure_plans(ndit_engine* h, int batch, int N) {
     const int M = batch * N;
@@ -463,29 +547,20 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
         h->attn_plans_valid = false;
     }
     if (!h->attn_plans_valid || h->plan_B != batch || h->plan_N != N || h->plan_T != h->cap_T) {
-        const int T = h->cap_T, Tpad = (T + 7) / 8 * 8, hd = h->hd;
+        const int T = h->cap_T, Tpad = (T + 7) / 8 * 8;
         h->p_attn.resize(L);
-        const uint64_t rs = (uint64_t)Wq * 2;   // qkv row stride in bytes
         for (size_t l = 0; l < L; ++l) {
             AttnPlan& a = h->p_attn[l];
             memset(&a, 0, sizeof(a));
-            int e = 0;
-            e |= make_tmap_3d(&a.tmQ64, h->qkv, hd, h->H, (uint64_t)M, hd * 2, rs, 64, 1, 128, 128);
-            e |= make_tmap_3d(&a.tmQ16, h->qkv, hd, h->H, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
-            e |= make_tmap_3d(&a.tmK64, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 64, 1, 128, 128);
-            e |= make_tmap_3d(&a.tmK16, h->qkv + D, hd, h->Hkv, (uint64_t)M, hd * 2, rs, 16, 1, 128, 32);
-            e |= make_tmap_3d(&a.tmVt, h->vt, N, h->vrows, (uint64_t)batch * h->Hkv, (uint64_t)N * 2, (uint64_t)N * h->vrows * 2, 64, 80, 1, 128);
             const bf16* kvy = h->kvy + l * (size_t)batch * T * 2 * KV;
             const bf16* vyt = h->vyt + l * (size_t)batch * h->Hkv * h->vrows * Tpad;
-            e |= make_tmap_3d(&a.tmKy64, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 64, 1, 128, 128);
-            e |= make_tmap_3d(&a.tmKy16, kvy, hd, h->Hkv, (uint64_t)batch * T, hd * 2, 2 * KV * 2, 16, 1, 128, 32);
-            e |= make_tmap_3d(&a.tmVyt, vyt, Tpad, h->vrows, (uint64_t)batch * h->Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * h->vrows * 2, 64, 80, 1, 128);
-            if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
+            if (build_attn_maps(&a, h->qkv, (int)Wq, h->vt, kvy, vyt, batch, N, T, h->H, h->Hkv, h->hd))
+                return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
             a.ymask = h->ymask;
             a.gate_tanh = h->gate_tanh + l * h->H;
             a.out = h->attn;
-            a.B = batch; a.N = N; a.T = T; a.H = h->H; a.Hkv = h->Hkv;
         }
+        (void)D;
         (void)C;
         h->plan_B = batch; h->plan_N = N; h->plan_T = h->cap_T;
         h->attn_plans_valid = true;
@@ -524,10 +599,16 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
         CKL(fill_ones_row(h->vt, N, 0, batch * h->Hkv, N, hd, h->vrows, 1, s));
         h->vt_ones_valid = true;
     }
-    const int mod_stride = L * 4 * D + D;
-    // time-aware RoPE scaling (model.py:944-952)
+    const int mod_stride = L * 4 * D + h->FD * D;
     float lin, ntk;
-    if (t < sp->scale_watershed) { lin = sp->scale_factor; ntk = 1.0f; } else { lin = 1.0f; ntk = sp->scale_factor; }
+    if (h->cls) {   // DiT_Llama.precompute_freqs_cis(rope_scaling_factor, ntk_factor) (models.py:977-1012)
+        lin = sp->scale_factor > 0.f ? sp->scale_factor : 1.0f;
+        ntk = sp->ntk_factor > 0.f ? sp->ntk_factor : 1.0f;
+    } else if (t < sp->scale_watershed) {   // time-aware RoPE scaling (model.py:944-952)
+        lin = sp->scale_factor; ntk = 1.0f;
+    } else {
+        lin = 1.0f; ntk = sp->scale_factor;
+    }
     const float theta = 10000.0f * ntk;
     const float2* rope = nullptr;
     if (int e = get_rope(h, Hp, Wp, theta, lin, s, &rope)) return e;
@@ -545,7 +626,7 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, nullptr, batch, h->cd, 256, 0, POST_SILU, 0, 0, s));
     // sc = bf16(silu(c)), c = bf16(temb + cap_emb)
     PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, nullptr, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, s));
-    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L, s));
+    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, h->cls ? -L : L, s));
     PROF(KC_ROWWISE, resid_rms_mod(h->X, nullptr, nullptr, nullptr, h->an1, h->mod, h->u, M, N, D, mod_stride, h->cfg.norm_eps, s));
     for (int l = 0; l < L; ++l) {
         const bf16* ml = h->mod + (size_t)l * 4 * D;
@@ -572,8 +653,10 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->an1 + (size_t)(l + 1) * D, ml + 4 * D, h->u, M, N,
                               D, mod_stride, h->cfg.norm_eps, s));
         } else {
-            PROF(KC_ROWWISE, final_layer(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->mod + (size_t)L * 4 * D, h->Wout, h->bout, h->tok, M,
-                            N, D, h->O, mod_stride, h->cfg.norm_eps, s));
+            // final adaLN: T2I [scale]; class-conditional [shift | scale]
+            const bf16* fin = h->mod + (size_t)L * 4 * D;
+            PROF(KC_ROWWISE, final_layer(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->cls ? fin + D : fin, h->cls ? fin : nullptr,
+                                         h->Wout, h->bout, h->tok, M, N, D, h->O, mod_stride, h->cfg.norm_eps, s));
         }
     }
     PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, s));
@@ -626,6 +709,7 @@ extern "C" int ndit_sample_host(ndit_handle h, const void* z_host, const void* c
                                 int32_t batch, int32_t height, int32_t width, int32_t T, const float* grid, int32_t n_grid,
                                 int32_t method, const ndit_step_params* sp, void* final_host, void* stream) {
     if (!h || !z_host || !cap_host || !mask_host || !final_host) return NDIT_ERR_INVALID;
+    if (h->cls) return h->fail(NDIT_ERR_INVALID, "ndit_sample_host is the text-conditioned entry point; class-conditional engines use ndit_set_labels + ndit_sample");
     if (batch < 2 || batch > h->Bmax || T < 1 || T > h->Tmax) return h->fail(NDIT_ERR_INVALID, "batch/T out of range");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
@@ -743,31 +827,22 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
     bf16 *vt = nullptr, *vyt = nullptr;
     const size_t vt_elems = (size_t)B * Hkv * vrows * N, vyt_elems = (size_t)B * Hkv * vrows * Tpad;
     cudaError_t e = cudaMalloc(&vt, vt_elems * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&vyt, vyt_elems * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&vyt, vyt_elems * 2 + 256);
     if (e != cudaSuccess) return op_fail(NDIT_ERR_NOMEM, "ndit_op_attention", e);
     cudaMemsetAsync(vt, 0, vt_elems * 2, s);
     cudaMemsetAsync(vyt, 0, vyt_elems * 2, s);
     e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, N, 0, B, N, Hkv, hd, vrows, 1, s);
-    if (e == cudaSuccess) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, vrows, 1, s);
+    if (e == cudaSuccess && T > 0) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, vrows, 1, s);
     if (e == cudaSuccess) e = fill_ones_row(vt, N, 0, B * Hkv, N, hd, vrows, 1, s);
-    if (e == cudaSuccess) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, vrows, 1, s);
+    if (e == cudaSuccess && T > 0) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, vrows, 1, s);
     AttnPlan a;
     memset(&a, 0, sizeof(a));
-    int te = 0;
-    const uint64_t rs = (uint64_t)Wq * 2, M = (uint64_t)B * N;
-    te |= make_tmap_3d(&a.tmQ64, qkv, hd, H, M, hd * 2, rs, 64, 1, 128, 128);
-    te |= make_tmap_3d(&a.tmQ16, qkv, hd, H, M, hd * 2, rs, 16, 1, 128, 32);
-    te |= make_tmap_3d(&a.tmK64, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, 128, 128);
-    te |= make_tmap_3d(&a.tmK16, qkv + H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, 128, 32);
-    te |= make_tmap_3d(&a.tmVt, vt, N, vrows, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * vrows * 2, 64, 80, 1, 128);
-    te |= make_tmap_3d(&a.tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, 128, 128);
-    te |= make_tmap_3d(&a.tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, 128, 32);
-    te |= make_tmap_3d(&a.tmVyt, vyt, Tpad, vrows, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * vrows * 2, 64, 80, 1, 128);
+    const int te = build_attn_maps(&a, qkv, Wq, vt, kvy, vyt, B, N, T, H, Hkv, hd);
     int rc = NDIT_OK;
     if (te) rc = op_fail(NDIT_ERR_CUDA, "ndit_op_attention tensor map", cudaSuccess);
     if (!te && e == cudaSuccess) {
         a.ymask = ymask; a.gate_tanh = gate_tanh; a.out = static_cast<bf16*>(out);
-        a.B = B; a.N = N; a.T = T; a.H = H; a.Hkv = Hkv; a.hd = hd; a.scale_self = scale_self; a.scale_cross = scale_cross;
+        a.scale_self = scale_self; a.scale_cross = scale_cross;
         e = attention_fused(a, s);
         if (bench_iters > 0 && bench_ms && e == cudaSuccess) {      // micro-benchmark: average of `bench_iters` launches
             cudaEvent_t e0, e1;
@@ -796,14 +871,20 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
 extern "C" int ndit_op_attention(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
                                  int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
                                  int32_t use_ref, void* stream) {
-    return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, use_ref, stream, 0, nullptr);
+    return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, use_ref, stream, 0, nullptr, 72);
+}
+
+extern "C" int ndit_op_attention_hd(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
+                                    int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, int32_t hd, float scale_self,
+                                    float scale_cross, int32_t use_ref, void* stream) {
+    return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, use_ref, stream, 0, nullptr, hd);
 }
 
 extern "C" int ndit_op_attention_bench(const void* qkv_, const void* kvy_, const uint8_t* ymask, const float* gate_tanh, void* out,
                                        int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
                                        int32_t iters, float* ms_out, void* stream) {
     if (iters <= 0 || !ms_out) return NDIT_ERR_INVALID;
-    return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, 0, stream, iters, ms_out);
+    return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, 0, stream, iters, ms_out, 72);
 }
 
 extern "C" int ndit_op_resid_rms_mod(void* X, const void* o, const void* w_post, const void* tanh_g, const void* w_pre,

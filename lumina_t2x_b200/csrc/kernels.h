@@ -72,9 +72,11 @@ cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16
                           const bf16* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
                           cudaStream_t s);
 // residual update then LN(no affine, eps 1e-6) * onepls -> bf16 -> Linear(D->O)+bias -> out [M,O] (fp32 of bf16 values)
+// (shift: optional additive term of the final modulate, class-conditional model)
 cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
-                        const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
+                        const bf16* shift, const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
                         int mod_stride, float eps, cudaStream_t s);
+cudaError_t gather_label_rows(const bf16* table, const long long* labels, float* out, int B, int n_rows, int width, cudaStream_t s);
 // rope table [N][hd/2] (cos,sin)
 cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, cudaStream_t s);
 // in place on qkv [M, ld]: q = bf16(rope(LN(q))), k = bf16(rope(LN(k)))

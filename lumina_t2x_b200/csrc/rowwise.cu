@@ -182,7 +182,8 @@ cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
-                   const bf16* __restrict__ tanh_g, const bf16* __restrict__ onepls, const bf16* __restrict__ Wout,
+                   const bf16* __restrict__ tanh_g, const bf16* __restrict__ onepls, const bf16* __restrict__ shift,
+                   const bf16* __restrict__ Wout,
                    const bf16* __restrict__ bout, float* __restrict__ out, int M, int rows_per_batch, int D, int O,
                    int mod_stride, float eps_rms) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -255,10 +256,11 @@ final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const
     for (int i = 0; i < NV; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
-            float sc[8];
+            float sc[8], sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             load8(op + v * 8, sc);
+            if (shift != nullptr) load8(shift + static_cast<size_t>(b) * mod_stride + v * 8, sh);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[i][e] = bf16_round((x[i][e] - mean) * rstd * sc[e]);
+            for (int e = 0; e < 8; ++e) x[i][e] = bf16_round((x[i][e] - mean) * rstd * sc[e] + sh[e]);
         }
     }
     for (int oc = 0; oc < O; ++oc) {
@@ -279,18 +281,33 @@ final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const
 }
 
 cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
-                        const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
+                        const bf16* shift, const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
                         int mod_stride, float eps, cudaStream_t s) {
     if (D % 8 != 0 || D > MAX_VEC * 256) return cudaErrorInvalidValue;
     const int nv = (D / 8 + 31) / 32;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
 #define LAUNCH(NVV)                                                                                              \
-    final_layer_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, onepls, Wout, bout, out, M,             \
+    final_layer_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, onepls, shift, Wout, bout, out, M,      \
                                                    rows_per_batch, D, O, mod_stride, eps)
     if (nv <= 3) LAUNCH(3);
     else if (nv <= 9) LAUNCH(9);
     else LAUNCH(MAX_VEC);
 #undef LAUNCH
+    return cudaGetLastError();
+}
+
+// y_embedder lookup (models.py:216-225): out[b, :] = table[label[b], :]  (fp32 storage of bf16 values)
+__global__ void gather_label_rows_kernel(const bf16* __restrict__ table, const long long* __restrict__ labels,
+                                         float* __restrict__ out, int n_rows, int width) {
+    const int b = blockIdx.x;
+    long long lab = labels[b];
+    if (lab < 0) lab = 0;
+    if (lab >= n_rows) lab = n_rows - 1;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) out[static_cast<size_t>(b) * width + c] = __bfloat162float(table[lab * width + c]);
+}
+
+cudaError_t gather_label_rows(const bf16* table, const long long* labels, float* out, int B, int n_rows, int width, cudaStream_t s) {
+    gather_label_rows_kernel<<<B, 256, 0, s>>>(table, labels, out, n_rows, width);
     return cudaGetLastError();
 }
 
@@ -457,9 +474,12 @@ gemv_rows_kernel(const float* __restrict__ in, const bf16* __restrict__ W, const
                 else if (post == POST_ADALN) {
                     // per layer chunks [scale_msa | gate_msa | scale_mlp | gate_mlp] (model.py:595), then the
                     // final layer's scale: scale -> bf16(1+scale); gate -> bf16(tanh(gate))
+                    // adaln_blocks < 0: the final layer has [shift | scale] (class-conditional model), shift stays raw
+                    const int nb = adaln_blocks < 0 ? -adaln_blocks : adaln_blocks;
                     const int chunk = o / adaln_D;
-                    const bool is_gate = (chunk < adaln_blocks * 4) && (chunk & 1);
-                    y = is_gate ? bf16_round(tanhf(y)) : bf16_round(1.0f + y);
+                    const bool is_gate = (chunk < nb * 4) && (chunk & 1);
+                    const bool is_shift = adaln_blocks < 0 && chunk == nb * 4;
+                    if (!is_shift) y = is_gate ? bf16_round(tanhf(y)) : bf16_round(1.0f + y);
                 }
                 if (out_b) out_b[static_cast<size_t>(b) * O + o] = __float2bfloat16_rn(y);   // y is bf16-representable
                 else out[static_cast<size_t>(b) * O + o] = y;

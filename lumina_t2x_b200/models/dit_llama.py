@@ -1,0 +1,147 @@
+"""Drop-in mirror of the reference's class-conditional Next-DiT (``Next-DiT-ImageNet/models/models.py:836-1056``,
+``DiT_Llama`` with ``TransformerBlockSandwichNorm2`` blocks) on the same B200 engine: same constructor
+arguments, factory names, state-dict keys and ``forward_with_cfg(x, t, y, cfg_scale, rope_scaling_factor,
+ntk_factor)`` signature as used by ``Next-DiT-ImageNet/sample.py:168-186``.  head_dim must be 72 or 48
+(the 600M and 2B factories); the 3B / 7B factories (head_dim 96 / 128) are not supported by the attention kernel yet."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .nextdit import EngineModule, _FeedForward, _TimestepEmbedder, _Weight, _linear
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, n_heads, n_kv_heads, qk_norm):
+        super().__init__()
+        kv = (n_kv_heads or n_heads) * (dim // n_heads)
+        self.wq, self.wk, self.wv, self.wo = _linear(dim, dim, False), _linear(dim, kv, False), _linear(dim, kv, False), _linear(dim, dim, False)
+        if qk_norm:
+            self.q_norm, self.k_norm = nn.LayerNorm(dim), nn.LayerNorm(kv)
+        else:
+            self.q_norm = self.k_norm = nn.Identity()
+
+
+class _Block(nn.Module):
+    """TransformerBlockSandwichNorm2 (models.py:692-796): the pre-norms (PFRMSNorm) carry no parameters."""
+
+    def __init__(self, dim, n_heads, n_kv_heads, hidden, qk_norm):
+        super().__init__()
+        self.attention = _Attention(dim, n_heads, n_kv_heads, qk_norm)
+        self.feed_forward = _FeedForward(dim, hidden)
+        self.attention_norm, self.ffn_norm = _Weight(dim), _Weight(dim)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), _linear(min(dim, 1024), 4 * dim, True, "zeros"))
+
+
+class _LabelEmbedder(nn.Module):
+    def __init__(self, num_classes, hidden, dropout_prob):
+        super().__init__()
+        self.embedding_table = nn.Embedding(num_classes + int(dropout_prob > 0), hidden)
+        nn.init.normal_(self.embedding_table.weight, std=0.02)
+        self.num_classes, self.dropout_prob = num_classes, dropout_prob
+
+
+class _FinalLayer(nn.Module):
+    def __init__(self, dim, patch_size, out_channels):
+        super().__init__()
+        self.linear = _linear(dim, patch_size * patch_size * out_channels, True, "zeros")
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), _linear(min(dim, 1024), 2 * dim, True, "zeros"))
+
+
+class DiT_Llama(EngineModule):
+    def __init__(self, input_size: int = 32, patch_size: int = 2, in_channels: int = 4, dim: int = 4096, n_layers: int = 32,
+                 n_heads: int = 32, n_kv_heads: Optional[int] = None, multiple_of: int = 256,
+                 ffn_dim_multiplier: Optional[float] = None, norm_eps: float = 1e-5, class_dropout_prob: float = 0.1,
+                 num_classes: int = 1000, learn_sigma: bool = True, qk_norm: bool = False,
+                 max_tokens: Optional[int] = None, max_batch: int = 2) -> None:
+        super().__init__()
+        self.learn_sigma, self.in_channels, self.input_size, self.patch_size = learn_sigma, in_channels, input_size, patch_size
+        self.out_channels = in_channels * 2 if learn_sigma else in_channels
+        self.dim, self.n_heads, self.n_layers = dim, n_heads, n_layers
+        self.n_kv_heads = n_kv_heads or n_heads
+        self.norm_eps, self.multiple_of, self.qk_norm, self.num_classes = norm_eps, multiple_of, qk_norm, num_classes
+        self._ffn_dim_multiplier, self._class_dropout_prob = ffn_dim_multiplier, class_dropout_prob
+        hidden = int(2 * (4 * dim) / 3)
+        if ffn_dim_multiplier is not None:
+            hidden = int(ffn_dim_multiplier * hidden)
+        hidden = multiple_of * ((hidden + multiple_of - 1) // multiple_of)
+        self.x_embedder = _linear(patch_size * patch_size * in_channels, dim, True)
+        self.t_embedder = _TimestepEmbedder(min(dim, 1024))
+        self.y_embedder = _LabelEmbedder(num_classes, min(dim, 1024), class_dropout_prob)
+        self.layers = nn.ModuleList([_Block(dim, n_heads, n_kv_heads, hidden, qk_norm) for _ in range(n_layers)])
+        self.final_layer = _FinalLayer(dim, patch_size, self.out_channels)
+        assert (dim // n_heads) % 4 == 0, "2d rope needs head dim to be divisible by 4"
+        self._init_engine_state(max_tokens or max(256, (input_size // patch_size) ** 2), 0, max_batch)
+        self._label_key = None
+
+    def _check_supported(self) -> None:
+        if not self.qk_norm:
+            raise NotImplementedError("the B200 engine implements the qk_norm=True architecture")
+        if self._ffn_dim_multiplier is not None:
+            raise NotImplementedError("ffn_dim_multiplier is not supported by the B200 engine")
+        if self._class_dropout_prob <= 0:
+            raise NotImplementedError("the B200 engine expects the CFG null-class row (class_dropout_prob > 0)")
+        if self.dim // self.n_heads not in (48, 72):
+            raise NotImplementedError("the B200 attention kernel supports head_dim 48 and 72 (600M / 2B factories)")
+
+    def _ndit_config(self):
+        return _lib.NditConfig(self.dim, self.n_layers, self.n_heads, self.n_kv_heads, 0, self.in_channels, self.patch_size,
+                               self.multiple_of, int(self.learn_sigma), float(self.norm_eps), self._limits[0], 0, self._limits[2],
+                               self.num_classes)
+
+    def _set_labels(self, lib, h, y: torch.Tensor, stream):
+        key = (y.data_ptr(), y._version, tuple(y.shape), y.dtype)
+        if key == self._label_key:
+            return
+        yl = y.detach().to(torch.int64).contiguous()
+        _lib.check(lib.ndit_set_labels(h, C.c_void_p(yl.data_ptr()), yl.numel(), stream), h)
+        self._label_key, self._cap_keepalive = key, (y, yl)
+
+    def _engine(self, device):
+        fresh = self._handle is None or self._dirty
+        lib, h = super()._engine(device)
+        if fresh:
+            self._label_key = None
+        return lib, h
+
+    @staticmethod
+    def _step_params(cfg_scale, rope_scaling_factor, ntk_factor):
+        if rope_scaling_factor is not None or ntk_factor is not None:
+            assert rope_scaling_factor is not None and ntk_factor is not None       # models.py:952-953
+        return _lib.NditStepParams(float(cfg_scale), float(rope_scaling_factor or 1.0), 1.0, 0, 0, float(ntk_factor or 1.0))
+
+    def forward(self, x, t, y):
+        raise NotImplementedError("the B200 engine accelerates forward_with_cfg (the sampling path); training forward is out of scope")
+
+    @torch.no_grad()
+    def forward_with_cfg(self, x, t, y, cfg_scale, rope_scaling_factor=None, ntk_factor=None):
+        """models.py:946-974.  x [2n,C,H,W] (first half cond, second half ignored on input); y [2n] labels."""
+        lib, h = self._engine(x.device)
+        with torch.cuda.device(x.device):
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._set_labels(lib, h, y, stream)
+            return self._run_forward(lib, h, x, t, self._step_params(cfg_scale, rope_scaling_factor, ntk_factor))
+
+    @torch.no_grad()
+    def sample_fixed_grid(self, z, t_grid, method: str, y, cfg_scale, rope_scaling_factor=None, ntk_factor=None,
+                          return_trajectory: bool = True):
+        lib, h = self._engine(z.device)
+        with torch.cuda.device(z.device):
+            stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+            self._set_labels(lib, h, y, stream)
+            return self._run_sample(lib, h, z, t_grid, method, self._step_params(cfg_scale, rope_scaling_factor, ntk_factor),
+                                    return_trajectory)
+
+
+def DiT_Llama_600M_patch2(**kwargs):
+    """models.py:1042-1043."""
+    return DiT_Llama(patch_size=2, dim=1536, n_layers=16, n_heads=32, **kwargs)
+
+
+def DiT_Llama_2B_patch2(**kwargs):
+    """models.py:1046-1047."""
+    return DiT_Llama(patch_size=2, dim=2304, n_layers=24, n_heads=32, **kwargs)

@@ -83,7 +83,123 @@ class _FinalLayer(nn.Module):
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), _linear(min(dim, 1024), dim, True, "zeros"))
 
 
-class NextDiT(nn.Module):
+class EngineModule(nn.Module):
+    """Parameter holder whose compute lives in libndit_b200.so: owns the engine handle, re-packs the weights
+    after load_state_dict / .to(), and offers the option / instrumentation hooks shared by the model mirrors."""
+
+    def _init_engine_state(self, max_tokens: int, max_cap_len: int, max_batch: int) -> None:
+        self._limits = (max_tokens, max_cap_len, max_batch)
+        self._handle: Optional[C.c_void_p] = None
+        self._dirty = True
+        self._cap_key = None
+        self._cap_keepalive = None
+
+    def _ndit_config(self) -> "_lib.NditConfig":          # pragma: no cover - provided by the subclasses
+        raise NotImplementedError
+
+    def _check_supported(self) -> None:
+        pass
+
+    def _apply(self, fn, *a, **k):           # .to() / .cuda() / .bfloat16() move the parameters
+        self._dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._dirty = True
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def mark_weights_changed(self) -> None:
+        """Call after modifying parameters in place; the engine re-packs them on the next forward."""
+        self._dirty = True
+
+    def _destroy(self):
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().ndit_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def reserve(self, max_tokens: Optional[int] = None, max_cap_len: Optional[int] = None, max_batch: Optional[int] = None):
+        """Resize the engine workspace limits (recreates the engine on the next call)."""
+        t, c, b = self._limits
+        self._limits = (max_tokens or t, max_cap_len or c, max_batch or b)
+        self._dirty = True
+
+    def _engine(self, device: torch.device):
+        lib = _lib.load()
+        if self._handle is not None and not self._dirty:
+            return lib, self._handle
+        self._check_supported()
+        if device.type != "cuda":
+            raise RuntimeError(f"{type(self).__name__} (B200 engine) needs its parameters on a CUDA device; there is no CPU path")
+        self._destroy()
+        cfg = self._ndit_config()
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.ndit_create(C.byref(cfg), C.byref(h)), None)
+            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            for key, p in self.state_dict().items():
+                t = p.detach()
+                if t.device != device:
+                    raise RuntimeError(f"parameter {key} is on {t.device}, expected {device}")
+                if t.dtype == torch.bfloat16:
+                    dt = _lib.NDIT_BF16
+                elif t.dtype == torch.float32:
+                    dt = _lib.NDIT_F32
+                else:
+                    t, dt = t.float(), _lib.NDIT_F32
+                t = t.contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                _lib.check(lib.ndit_set_weight(h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim(), dt, stream), h)
+            torch.cuda.current_stream(device).synchronize()   # temporaries above must outlive the copies
+            _lib.check(lib.ndit_finalize_weights(h, stream), h)
+        self._handle, self._dirty, self._cap_key = h, False, None
+        return lib, h
+
+    def parameter_count(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+    def launch_count(self) -> int:
+        return int(_lib.load().ndit_launch_count(self._handle)) if self._handle is not None else 0
+
+    def set_option(self, name: str, value: int) -> None:
+        lib, h = self._engine(next(self.parameters()).device)
+        _lib.check(lib.ndit_set_option(h, name.encode(), int(value)), h)
+
+    def get_fsdp_wrap_module_list(self):
+        return list(self.layers)
+
+    @torch.no_grad()
+    def _run_forward(self, lib, h, x, t, sp):
+        xb = x.detach().to(torch.bfloat16).contiguous()
+        out = torch.empty_like(xb)
+        tv = float(t[0].item()) if isinstance(t, torch.Tensor) else float(t)    # the reference syncs here too (model.py:888)
+        B, _, Hh, Ww = xb.shape
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib.ndit_forward_cfg(h, C.c_void_p(xb.data_ptr()), tv, B, Hh, Ww, C.byref(sp), C.c_void_p(out.data_ptr()), stream), h)
+        return out.to(x.dtype)
+
+    @torch.no_grad()
+    def _run_sample(self, lib, h, z, t_grid, method, sp, return_trajectory):
+        zb = z.detach().to(torch.bfloat16).contiguous()
+        grid = [float(v) for v in t_grid]
+        n = len(grid)
+        garr = (C.c_float * n)(*grid)
+        B, _, Hh, Ww = zb.shape
+        traj = torch.empty((n,) + tuple(zb.shape), dtype=torch.bfloat16, device=z.device) if return_trajectory else None
+        final = torch.empty_like(zb)
+        m = {"euler": _lib.NDIT_EULER, "midpoint": _lib.NDIT_MIDPOINT}[method]
+        stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+        _lib.check(lib.ndit_sample(h, C.c_void_p(zb.data_ptr()), B, Hh, Ww, garr, n, m, C.byref(sp),
+                                   C.c_void_p(traj.data_ptr()) if traj is not None else None, C.c_void_p(final.data_ptr()), stream), h)
+        return (traj if return_trajectory else final).to(z.dtype)
+
+
+class NextDiT(EngineModule):
     """B200 engine behind the reference ``NextDiT`` API (model.py:665-989)."""
 
     def __init__(self, patch_size: int = 2, in_channels: int = 4, dim: int = 4096, n_layers: int = 32, n_heads: int = 32,
@@ -112,77 +228,18 @@ class NextDiT(nn.Module):
         assert (dim // n_heads) % 4 == 0, "2d rope needs head dim to be divisible by 4"
         self.pad_token = nn.Parameter(torch.empty(dim))
         nn.init.normal_(self.pad_token, std=0.02)
-        # engine state (not part of the state dict)
-        self._limits = (max_tokens, max_cap_len, max_batch)
-        self._handle: Optional[C.c_void_p] = None
-        self._dirty = True
-        self._cap_key = None
-        self._cap_keepalive = None
+        self._init_engine_state(max_tokens, max_cap_len, max_batch)
 
     # ------------------------------------------------------------------ engine plumbing
-    def _apply(self, fn, *a, **k):           # .to() / .cuda() / .bfloat16() move the parameters
-        self._dirty = True
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        self._dirty = True
-        return super().load_state_dict(state_dict, strict=strict, **kw)
-
-    def mark_weights_changed(self) -> None:
-        """Call after modifying parameters in place; the engine re-packs them on the next forward."""
-        self._dirty = True
-
-    def _destroy(self):
-        if self._handle is not None:
-            _lib.load().ndit_destroy(self._handle)
-            self._handle = None
-
-    def __del__(self):
-        try:
-            self._destroy()
-        except Exception:
-            pass
-
-    def reserve(self, max_tokens: Optional[int] = None, max_cap_len: Optional[int] = None, max_batch: Optional[int] = None):
-        """Resize the engine workspace limits (recreates the engine on the next call)."""
-        t, c, b = self._limits
-        self._limits = (max_tokens or t, max_cap_len or c, max_batch or b)
-        self._dirty = True
-
-    def _engine(self, device: torch.device):
-        lib = _lib.load()
-        if self._handle is not None and not self._dirty:
-            return lib, self._handle
+    def _check_supported(self) -> None:
         if not self.qk_norm:
             raise NotImplementedError("the B200 engine implements the qk_norm=True architecture (Lumina-Next-T2I)")
         if self._ffn_dim_multiplier is not None:
             raise NotImplementedError("ffn_dim_multiplier is not supported by the B200 engine")
-        if device.type != "cuda":
-            raise RuntimeError("NextDiT (B200 engine) needs its parameters on a CUDA device; there is no CPU path")
-        self._destroy()
-        cfg = _lib.NditConfig(self.dim, self.n_layers, self.n_heads, self.n_kv_heads, self.cap_feat_dim, self.in_channels,
-                              self.patch_size, self.multiple_of, int(self.learn_sigma), float(self.norm_eps), *self._limits)
-        h = C.c_void_p()
-        with torch.cuda.device(device):
-            _lib.check(lib.ndit_create(C.byref(cfg), C.byref(h)), None)
-            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-            for key, p in self.state_dict().items():
-                t = p.detach()
-                if t.device != device:
-                    raise RuntimeError(f"parameter {key} is on {t.device}, expected {device}")
-                if t.dtype == torch.bfloat16:
-                    dt = _lib.NDIT_BF16
-                elif t.dtype == torch.float32:
-                    dt = _lib.NDIT_F32
-                else:
-                    t, dt = t.float(), _lib.NDIT_F32
-                t = t.contiguous()
-                shape = (C.c_int64 * t.dim())(*t.shape)
-                _lib.check(lib.ndit_set_weight(h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim(), dt, stream), h)
-            torch.cuda.current_stream(device).synchronize()   # temporaries above must outlive the copies
-            _lib.check(lib.ndit_finalize_weights(h, stream), h)
-        self._handle, self._dirty, self._cap_key = h, False, None
-        return lib, h
+
+    def _ndit_config(self):
+        return _lib.NditConfig(self.dim, self.n_layers, self.n_heads, self.n_kv_heads, self.cap_feat_dim, self.in_channels,
+                               self.patch_size, self.multiple_of, int(self.learn_sigma), float(self.norm_eps), *self._limits, 0)
 
     def _set_caption(self, lib, h, cap_feats: torch.Tensor, cap_mask: torch.Tensor, stream):
         key = (cap_feats.data_ptr(), cap_feats._version, tuple(cap_feats.shape), cap_feats.dtype,
@@ -220,13 +277,8 @@ class NextDiT(nn.Module):
         with torch.cuda.device(x.device):
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
-            xb = x.detach().to(torch.bfloat16).contiguous()
-            out = torch.empty_like(xb)
-            tv = float(t[0].item()) if isinstance(t, torch.Tensor) else float(t)    # reference syncs here too (model.py:888)
             sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
-            B, _, Hh, Ww = xb.shape
-            _lib.check(lib.ndit_forward_cfg(h, C.c_void_p(xb.data_ptr()), tv, B, Hh, Ww, C.byref(sp), C.c_void_p(out.data_ptr()), stream), h)
-        return out.to(x.dtype)
+            return self._run_forward(lib, h, x, t, sp)
 
     @torch.no_grad()
     def sample_fixed_grid(self, z, t_grid, method: str, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0,
@@ -236,33 +288,8 @@ class NextDiT(nn.Module):
         with torch.cuda.device(z.device):
             stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
-            zb = z.detach().to(torch.bfloat16).contiguous()
-            grid = [float(v) for v in t_grid]
-            n = len(grid)
-            garr = (C.c_float * n)(*grid)
-            B, _, Hh, Ww = zb.shape
-            traj = torch.empty((n,) + tuple(zb.shape), dtype=torch.bfloat16, device=z.device) if return_trajectory else None
-            final = torch.empty_like(zb)
             sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
-            m = {"euler": _lib.NDIT_EULER, "midpoint": _lib.NDIT_MIDPOINT}[method]
-            _lib.check(lib.ndit_sample(h, C.c_void_p(zb.data_ptr()), B, Hh, Ww, garr, n, m, C.byref(sp),
-                                       C.c_void_p(traj.data_ptr()) if traj is not None else None,
-                                       C.c_void_p(final.data_ptr()), stream), h)
-        return (traj if return_trajectory else final).to(z.dtype)
-
-    def parameter_count(self) -> int:
-        """model.py:965-982."""
-        return sum(p.numel() for p in self.parameters())
-
-    def launch_count(self) -> int:
-        return int(_lib.load().ndit_launch_count(self._handle)) if self._handle is not None else 0
-
-    def set_option(self, name: str, value: int) -> None:
-        lib, h = self._engine(next(self.parameters()).device)
-        _lib.check(lib.ndit_set_option(h, name.encode(), int(value)), h)
-
-    def get_fsdp_wrap_module_list(self):
-        return list(self.layers)
+            return self._run_sample(lib, h, z, t_grid, method, sp, return_trajectory)
 
 
 def NextDiT_2B_patch2(**kwargs):

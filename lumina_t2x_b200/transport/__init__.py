@@ -14,6 +14,7 @@ from typing import Callable, Optional
 
 import torch as th
 
+from ..models.dit_llama import DiT_Llama
 from ..models.nextdit import NextDiT
 
 __all__ = ["create_transport", "Sampler", "Transport", "ModelType", "PathType", "WeightType", "ODE"]
@@ -85,13 +86,19 @@ def _time_grid(t0, t1, num_steps, time_shifting_factor):
     return t
 
 
-_ENGINE_KW = ("cap_feats", "cap_mask", "cfg_scale", "scale_factor", "scale_watershed", "base_seqlen", "proportional_attn")
+# kwargs the fused in-engine solve understands, and the ones it needs, per model mirror
+_ENGINE_KW = {
+    NextDiT: (("cap_feats", "cap_mask", "cfg_scale", "scale_factor", "scale_watershed", "base_seqlen", "proportional_attn"),
+              ("cap_feats", "cap_mask", "cfg_scale")),
+    DiT_Llama: (("y", "cfg_scale", "rope_scaling_factor", "ntk_factor"), ("y", "cfg_scale")),
+}
 
 
-def _engine_of(model_fn) -> Optional[NextDiT]:
+def _engine_of(model_fn):
     owner = getattr(model_fn, "__self__", None)
-    if isinstance(owner, NextDiT) and getattr(model_fn, "__func__", None) is NextDiT.forward_with_cfg:
-        return owner
+    for cls in _ENGINE_KW:
+        if isinstance(owner, cls) and getattr(model_fn, "__func__", None) is cls.forward_with_cfg:
+            return owner
     return None
 
 
@@ -127,9 +134,10 @@ def _fixed_grid_torch(fn: Callable, x: th.Tensor, t: th.Tensor, method: str) -> 
 
 def _solve(x, model_fn, t_grid, method, model_kwargs, wrap_drift=None):
     eng = _engine_of(model_fn) if wrap_drift is None else None
-    if (eng is not None and method in ("euler", "midpoint") and isinstance(x, th.Tensor) and x.is_cuda
-            and set(model_kwargs) <= set(_ENGINE_KW) and {"cap_feats", "cap_mask", "cfg_scale"} <= set(model_kwargs)):
-        return eng.sample_fixed_grid(x, t_grid.tolist(), method, **model_kwargs)
+    if eng is not None and method in ("euler", "midpoint") and isinstance(x, th.Tensor) and x.is_cuda:
+        allowed, required = _ENGINE_KW[type(eng)]
+        if set(model_kwargs) <= set(allowed) and set(required) <= set(model_kwargs):
+            return eng.sample_fixed_grid(x, t_grid.tolist(), method, **model_kwargs)
     device = x.device
 
     def _fn(t, xx):

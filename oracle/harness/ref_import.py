@@ -58,6 +58,65 @@ def install_shims() -> None:
         torch.Tensor.cuda = lambda self, *a, **k: self  # type: ignore[assignment]
 
 
+def _install_fairscale_stub() -> None:
+    """fairscale (unpinned third-party dependency, requirements.txt:2) at model-parallel world size 1:
+    Column/RowParallelLinear(in, out, bias, init_method=...) == nn.Linear with init_method(weight) and a zero bias,
+    ParallelEmbedding == nn.Embedding, fs_init.get_model_parallel_world_size() == 1."""
+    if "fairscale" in sys.modules:
+        return
+    import torch.nn as nn
+
+    class _PLinear(nn.Linear):
+        def __init__(self, in_features, out_features, bias=True, gather_output=True, input_is_parallel=False, init_method=None, **kw):
+            super().__init__(in_features, out_features, bias=bias)
+            if init_method is not None:
+                init_method(self.weight)
+            if bias:
+                nn.init.zeros_(self.bias)
+
+    class _PEmbedding(nn.Embedding):
+        def __init__(self, num_embeddings, embedding_dim, init_method=None, **kw):
+            super().__init__(num_embeddings, embedding_dim)
+            if init_method is not None:
+                init_method(self.weight)
+
+    fs = types.ModuleType("fairscale")
+    nnm = types.ModuleType("fairscale.nn")
+    mp = types.ModuleType("fairscale.nn.model_parallel")
+    init = types.ModuleType("fairscale.nn.model_parallel.initialize")
+    layers = types.ModuleType("fairscale.nn.model_parallel.layers")
+    init.get_model_parallel_world_size = lambda: 1
+    init.get_model_parallel_rank = lambda: 0
+    init.get_model_parallel_src_rank = lambda: 0
+    init.get_model_parallel_group = lambda: None
+    layers.ColumnParallelLinear = _PLinear
+    layers.RowParallelLinear = _PLinear
+    layers.ParallelEmbedding = _PEmbedding
+    mp.initialize, mp.layers = init, layers
+    nnm.model_parallel = mp
+    fs.nn = nnm
+    for name, mod in (("fairscale", fs), ("fairscale.nn", nnm), ("fairscale.nn.model_parallel", mp),
+                      ("fairscale.nn.model_parallel.initialize", init), ("fairscale.nn.model_parallel.layers", layers)):
+        sys.modules[name] = mod
+
+
+def import_reference_imagenet():
+    """Returns the unmodified Next-DiT-ImageNet ``models.models`` module (class-conditional DiT_Llama)."""
+    import importlib.util
+    import os
+    os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")      # @torch.compile on the SiLU gate cannot build on this CPU box
+    install_shims()
+    _install_fairscale_stub()
+    path = REF_ROOT + "/Next-DiT-ImageNet/models/models.py"
+    spec = importlib.util.spec_from_file_location("ref_imagenet_models", path)
+    mod = importlib.util.module_from_spec(spec)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    return mod
+
+
 def import_reference_mini():
     """Returns (models_module, transport_module) of lumina_next_t2i_mini, unmodified."""
     install_shims()

@@ -23,7 +23,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle import nextdit_oracle as O  # noqa: E402
-from oracle.harness.ref_import import import_reference_mini  # noqa: E402
+from oracle import dit_llama_oracle as DL  # noqa: E402
+from oracle.harness.ref_import import import_reference_imagenet, import_reference_mini  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
@@ -96,6 +97,38 @@ def main() -> None:
         torch.save(dict(method=method, num_steps=steps, time_shifting_factor=shift, z=zb, traj_bf16=traj),
                    os.path.join(OUT, f"toy_{method}_bf16.pt"))
         print("toy", method, traj.dtype, tuple(traj.shape))
+
+    make_imagenet()
+
+
+def make_imagenet() -> None:
+    """Class-conditional Next-DiT (BASELINE config 1 / SURVEY 8a14): unmodified Next-DiT-ImageNet/models/models.py (fp32,
+    CPU, fairscale at world size 1).  Fixtures: two tiny models (head_dim 48 and 72, default and scaled RoPE) and the
+    config-1 case itself - DiT_Llama_600M_patch2, 256x256 image = latent 32x32, label 207, one forward_with_cfg."""
+    ref = import_reference_imagenet()
+    torch.set_grad_enabled(False)
+    cases = {
+        "imagenet_tiny48": dict(cfg=DL.config_tiny48(), hw=(16, 16), labels=(3, 7), t=0.35, cfg_scale=3.0, rope=None),
+        "imagenet_tiny72_rope": dict(cfg=DL.config_tiny72(), hw=(16, 24), labels=(1,), t=0.8, cfg_scale=1.5, rope=(2.0, 1.5)),
+        "imagenet_600m_config1": dict(cfg=DL.config_600m(), hw=(32, 32), labels=(207,), t=0.0, cfg_scale=4.0, rope=None),
+    }
+    for name, c in cases.items():
+        cfg = c["cfg"]
+        W = DL.synthetic_weights(cfg, seed=0)
+        m = ref.DiT_Llama(input_size=c["hw"][0], patch_size=2, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                          num_classes=cfg.num_classes, qk_norm=True)
+        m.load_state_dict({k: v.float() for k, v in W.items()}, strict=True)
+        m = m.eval().float()
+        z, y = DL.synthetic_inputs(cfg, c["hw"], c["labels"], seed=1)
+        t = torch.full((len(z),), c["t"])
+        kw = {} if c["rope"] is None else dict(rope_scaling_factor=c["rope"][0], ntk_factor=c["rope"][1])
+        out = m.forward_with_cfg(z.float(), t, y, c["cfg_scale"], **kw)
+        fx = dict(case=name, cfg=dict(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, num_classes=cfg.num_classes),
+                  hw=c["hw"], labels=c["labels"], t=c["t"], cfg_scale=c["cfg_scale"], rope=c["rope"], weight_seed=0, input_seed=1,
+                  out_fp32=out.clone())
+        torch.save(fx, os.path.join(OUT, f"{name}.pt"))
+        print(name, tuple(out.shape), "absmax", out.abs().max().item())
+        del m, W
 
 
 if __name__ == "__main__":

@@ -25,7 +25,7 @@ def test_cabi_loads_and_exports_header_symbols():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ndit_abi_version() == 1
+    assert lib.ndit_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
@@ -52,6 +52,19 @@ def test_state_dict_keys_match_reference_inventory():
     assert have == want
     assert m.parameter_count() == sum(int(torch.tensor(s).prod()) for s in want.values())
     assert hasattr(models, "NextDiT_2B_GQA_patch2") and hasattr(models, "NextDiT_2B_patch2")
+
+
+def test_class_conditional_state_dict_keys_match_reference_inventory():
+    from lumina_t2x_b200 import models
+    from oracle import dit_llama_oracle as DL
+    cfg = DL.config_tiny48()
+    m = models.DiT_Llama(input_size=16, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, num_classes=cfg.num_classes, qk_norm=True)
+    want = DL.state_dict_shapes(cfg)         # pinned against the reference by make_golden.make_imagenet (strict load)
+    have = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert have == want
+    assert hasattr(models, "DiT_Llama_600M_patch2") and hasattr(models, "DiT_Llama_2B_patch2")
+    with pytest.raises(RuntimeError):        # no GPU / no CUDA library -> loud failure, never a CPU fallback
+        m.forward_with_cfg(torch.zeros(2, 4, 16, 16), torch.zeros(2), torch.tensor([1, cfg.num_classes]), 2.0)
 
 
 def test_create_transport_and_grid_semantics():
