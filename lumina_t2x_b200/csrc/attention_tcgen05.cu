@@ -529,7 +529,7 @@ __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, c
         __syncthreads();
     }
     if (threadIdx.x < hd) {
-        const float r = result[0] + bf16_round(gate_tanh[h] * result[1]);
+        const float r = T > 0 ? result[0] + bf16_round(gate_tanh[h] * result[1]) : result[0];
         out[(static_cast<size_t>(b) * N + n) * (static_cast<size_t>(H) * hd) + h * hd + threadIdx.x] = __float2bfloat16_rn(r);
     }
 }

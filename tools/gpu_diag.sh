@@ -18,6 +18,8 @@ for g in "$@"; do
     rows)   run lnrope 90 tests/test_ops_gpu.py -k "ln_rope"; run resid 90 tests/test_ops_gpu.py -k "resid";;
     attnref) run attnref 120 tests/test_ops_gpu.py -k "attention and refkernel";;
     attn)   run attn 90 tests/test_ops_gpu.py -k "attention and tcgen05";;
+    attn48) run attn48ref 120 tests/test_imagenet_gpu.py -k "head_dim_48 and refkernel"; run attn48 120 tests/test_imagenet_gpu.py -k "head_dim_48 and tcgen05";;
+    imagenet) run imagenet_ref 300 tests/test_imagenet_gpu.py -k "forward_with_cfg and refkernel"; run imagenet 300 tests/test_imagenet_gpu.py -k "forward_with_cfg and tcgen05"; run imagenet_traj 120 tests/test_imagenet_gpu.py -k "sampler";;
     model)  run model 600 tests/test_model_gpu.py;;
     all)    run all 1200 tests;;
   esac
