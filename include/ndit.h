@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NDIT_ABI_VERSION 2
+#define NDIT_ABI_VERSION 3
 
 typedef struct ndit_engine* ndit_handle;
 
@@ -56,7 +56,13 @@ typedef struct ndit_config {
                              * (Next-DiT-ImageNet/models/models.py:836-1056 DiT_Llama + TransformerBlockSandwichNorm2):
                              * label embedding table [num_classes + 1, min(dim,1024)] instead of the caption path, no
                              * cross-attention, weight-free pre-norms, final layer with shift + scale; cap_feat_dim and
-                             * max_cap_len are ignored.  head_dim = dim / n_heads must be 72 or 48 in both cases. */
+                             * max_cap_len are ignored. */
+    int32_t flag_dit;       /* != 0 (with num_classes == 0): the Flag-DiT of Lumina-T2I, lumina_t2i/models/model.py:661-991
+                             * (DiT_Llama; DiT_Llama_5B_patch2 :989-990): caption-conditioned like NextDiT but with a 6-chunk
+                             * adaLN (shift, scale, plain gate) :596-609, one weighted RMSNorm per sub-block and no post-norms,
+                             * a 1-D RoPE over the token index :925-960, a learned [eol] token closing each row of patches
+                             * :779-785 (max_tokens counts them: H/2 * (W/2 + 1)) and shift + scale in the final layer
+                             * :655-656.  head_dim = dim / n_heads must be 72, 48 or 96 in all variants. */
 } ndit_config;
 
 /* Per-call arguments of NextDiT.forward_with_cfg (model.py:866-913) that are not tensors. */
@@ -66,8 +72,8 @@ typedef struct ndit_step_params {
     float scale_watershed;
     int32_t proportional_attn;
     int32_t base_seqlen;     /* used when proportional_attn != 0 (model.py:373-376) */
-    float ntk_factor;        /* class-conditional model only: DiT_Llama.forward_with_cfg(rope_scaling_factor=scale_factor,
-                              * ntk_factor=...) (models.py:946-1012); 0 is treated as 1 */
+    float ntk_factor;        /* class-conditional model and Flag-DiT: DiT_Llama.forward_with_cfg(rope_scaling_factor=scale_factor,
+                              * ntk_factor=...) (models.py:946-1012; lumina_t2i model.py:868-899); 0 is treated as 1 */
 } ndit_step_params;
 
 /* --- lifecycle: models.NextDiT_2B_GQA_patch2(...) / .to("cuda") / del (sample.py:125-129) */
@@ -135,16 +141,18 @@ int ndit_op_gemm(const void* A_dev, const void* W_dev, void* C_dev, int32_t M, i
 int ndit_op_gemm_bench(const void* A_dev, const void* W_dev, void* C_dev, int32_t M, int32_t N, int32_t K, int32_t swiglu,
                        int32_t allow_pair, int32_t iters, float* ms_out, void* stream);
 /* in place on qkv [M, (H+2Hkv)*hd]: q,k <- bf16(rope(LayerNorm(.))) (model.py:361-371); angles are built from
- * (Hp, Wp, theta, linear_factor) like precompute_freqs_cis (:916-963). M = batch*Hp*Wp */
+ * (Hp, Wp, theta, linear_factor) like precompute_freqs_cis (:916-963). M = batch*Hp*Wp.
+ * one_d != 0: the 1-D table of Flag-DiT over Hp*Wp token positions (lumina_t2i model.py:925-960), linear_factor = rope
+ * scaling factor */
 int ndit_op_ln_rope(void* qkv_dev, const void* qw, const void* qb, const void* kw, const void* kb, int32_t batch,
                     int32_t Hp, int32_t Wp, int32_t H, int32_t Hkv, int32_t hd, float theta, float linear_factor,
-                    void* stream);
+                    int32_t one_d, void* stream);
 /* fused self + gated cross attention (model.py:373-434).  qkv [B*N,(H+2Hkv)*72] (q,k already normed+roped),
  * kvy [B*T, 2*Hkv*72] (ky normed | vy), ymask uint8 [B,T], gate_tanh f32 [H]; out bf16 [B*N, H*72]. */
 int ndit_op_attention(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                       void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
                       float scale_cross, int32_t use_ref, void* stream);
-/* general form: head_dim hd = 72 or 48; T = 0 (kvy/ymask/gate may be NULL) = no caption segment */
+/* general form: head_dim hd = 72, 48 or 96; T = 0 (kvy/ymask/gate may be NULL) = no caption segment */
 int ndit_op_attention_hd(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                          void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, int32_t hd, float scale_self,
                          float scale_cross, int32_t use_ref, void* stream);
@@ -152,11 +160,12 @@ int ndit_op_attention_hd(const void* qkv_dev, const void* kvy_dev, const uint8_t
 int ndit_op_attention_bench(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                             void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
                             float scale_cross, int32_t iters, float* ms_out, void* stream);
-/* X += tanh_g * RMS(o; w_post) (skipped if o NULL);  u = RMS(X; w_pre) * onepls   (model.py:597-610);
- * tanh_g / onepls: bf16 [M / rows_per_batch, D] */
+/* X += tanh_g * RMS(o; w_post) (skipped if o NULL; w_post NULL: X += tanh_g * o, Flag-DiT);
+ * u = RMS(X; w_pre) * onepls (+ shift if not NULL)   (model.py:597-610; lumina_t2i model.py:596-609);
+ * tanh_g / onepls / shift: bf16 [M / rows_per_batch, D] */
 int ndit_op_resid_rms_mod(void* X_dev, const void* o_dev, const void* w_post, const void* tanh_g, const void* w_pre,
-                          const void* onepls, void* u_dev, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
-                          void* stream);
+                          const void* onepls, const void* shift, void* u_dev, int32_t M, int32_t rows_per_batch, int32_t D,
+                          float eps, void* stream);
 
 #ifdef __cplusplus
 }

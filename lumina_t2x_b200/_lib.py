@@ -17,7 +17,7 @@ class NditConfig(C.Structure):
                 ("cap_feat_dim", C.c_int32), ("in_channels", C.c_int32), ("patch_size", C.c_int32),
                 ("multiple_of", C.c_int32), ("learn_sigma", C.c_int32), ("norm_eps", C.c_float),
                 ("max_tokens", C.c_int32), ("max_cap_len", C.c_int32), ("max_batch", C.c_int32),
-                ("num_classes", C.c_int32)]
+                ("num_classes", C.c_int32), ("flag_dit", C.c_int32)]
 
 
 class NditStepParams(C.Structure):
@@ -48,12 +48,12 @@ SIGNATURES = {
     "ndit_profile_read": (C.c_int, [_vp, C.POINTER(_f32), C.POINTER(_i64), _i32]),
     "ndit_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ndit_op_gemm_bench": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp]),
-    "ndit_op_ln_rope": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
+    "ndit_op_ln_rope": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
     "ndit_op_attention": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
     "ndit_op_attention_hd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _vp]),
     "ndit_op_attention_bench": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32,
                                           C.POINTER(_f32), _vp]),
-    "ndit_op_resid_rms_mod": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+    "ndit_op_resid_rms_mod": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
 }
 
 _lib = None
@@ -74,7 +74,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ndit_abi_version() != 2:
+    if lib.ndit_abi_version() != 3:
         raise RuntimeError("libndit_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -38,38 +38,40 @@ namespace ndit {
 
 constexpr int AT_BQ = 128;            // rows per query tile
 constexpr int AT_BKV = 128;           // kv rows per block
-constexpr int AT_STAGES = 3;
+constexpr int AT_MAX_STAGES = 3;
 constexpr int AT_THREADS = 384;       // warps 0-3 control (TMA, MMA tile A, MMA tile B, idle), 4-7 softmax A, 8-11 softmax B
 
-// shared-memory layout, sized for head_dim 72 (head_dim 48 uses a prefix of each region)
 constexpr int AT_Q64_BYTES = AT_BQ * 128;        // 16 KB  [rows x 64] bf16, 128B swizzle
-constexpr int AT_Q16_BYTES = AT_BQ * 32;         //  4 KB  [rows x 16] bf16, 32B swizzle (head_dim 72 only)
-constexpr int AT_QTILE_BYTES = AT_Q64_BYTES + AT_Q16_BYTES;   // 20 KB
-constexpr int AT_KTILE_BYTES = AT_QTILE_BYTES;
-constexpr int AT_VHALF_BYTES = 80 * 128;         // 10 KB  (up to 80 V^T rows x 64 kv)
-constexpr int AT_VTILE_BYTES = 2 * AT_VHALF_BYTES;
+constexpr int AT_Q16_BYTES = AT_BQ * 32;         //  4 KB  [rows x 16] bf16, 32B swizzle (head_dim 72: one, head_dim 96: two)
 constexpr int AT_PHALF_BYTES = AT_BQ * 128;      // 16 KB
 constexpr int AT_PTILE_BYTES = 2 * AT_PHALF_BYTES;
-
-constexpr int AT_OFF_Q = 0;
-constexpr int AT_OFF_K = AT_OFF_Q + 2 * AT_QTILE_BYTES;
-constexpr int AT_OFF_V = AT_OFF_K + AT_STAGES * AT_KTILE_BYTES;
-constexpr int AT_OFF_P = AT_OFF_V + AT_STAGES * AT_VTILE_BYTES;
-constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_PTILE_BYTES;
-constexpr int AT_SMEM_BYTES = AT_OFF_BAR + 256 + 1024;
-static_assert(AT_SMEM_BYTES <= 227 * 1024, "attention smem budget");
 
 constexpr uint32_t AT_TM_S = 0, AT_TM_O = 256;   // + X*128
 constexpr float AT_RESCALE_LOG2 = 8.0f;          // lazy rescale: keep a stale reference max while exp2 args stay <= 8
 
 template <int HD>
 struct AttnDims {
-    static_assert(HD == 72 || HD == 48, "head_dim 72 (Lumina-Next-T2I 2B / Next-DiT 2B) or 48 (Next-DiT 600M)");
+    static_assert(HD == 72 || HD == 48 || HD == 96,
+                  "head_dim 72 (Lumina-Next-T2I 2B / Next-DiT 2B), 48 (Next-DiT 600M) or 96 (Flag-DiT 5B)");
     static constexpr int NK64 = HD >= 64 ? 4 : HD / 16;     // Q K^T k-steps from the 64-wide chunk
-    static constexpr bool HAS16 = HD == 72;                 // + one k-step from the 16-wide chunk (elements 64..79)
+    static constexpr int N16 = HD > 64 ? (HD - 64 + 15) / 16 : 0;   // + k-steps from 16-wide chunks (elements 64.., zero padded)
     static constexpr int HDP = attn_vrows(HD);              // P V width = V^T rows: head_dim + ones row, padded to 16
-    static constexpr int QK_TX = AT_Q64_BYTES + (HAS16 ? AT_Q16_BYTES : 0);
-    static constexpr int V_TX = 2 * HDP * 128;
+    static constexpr int STAGES = HD > 80 ? 2 : 3;          // K / V^T ring depth (shared-memory budget)
+    // shared-memory layout
+    static constexpr int QTILE_BYTES = AT_Q64_BYTES + N16 * AT_Q16_BYTES;
+    static constexpr int KTILE_BYTES = QTILE_BYTES;
+    static constexpr int VHALF_BYTES = HDP * 128;           // HDP V^T rows x 64 kv
+    static constexpr int VTILE_BYTES = 2 * VHALF_BYTES;
+    static constexpr int OFF_Q = 0;
+    static constexpr int OFF_K = OFF_Q + 2 * QTILE_BYTES;
+    static constexpr int OFF_V = OFF_K + STAGES * KTILE_BYTES;
+    static constexpr int OFF_P = OFF_V + STAGES * VTILE_BYTES;
+    static constexpr int OFF_BAR = OFF_P + 2 * AT_PTILE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+    static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && VHALF_BYTES % 1024 == 0, "swizzle atoms need 1 KB alignment");
+    static_assert(SMEM_BYTES <= 227 * 1024, "attention smem budget");
+    static constexpr int QK_TX = QTILE_BYTES;
+    static constexpr int V_TX = VTILE_BYTES;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -104,12 +106,12 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     constexpr int HDP = Dm::HDP;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar0 = sbase + AT_OFF_BAR;
+    const uint32_t bar0 = sbase + Dm::OFF_BAR;
     auto q_full = [&](int x) { return bar0 + 8u * (0 + x); };
     auto k_full = [&](int s) { return bar0 + 8u * (2 + s); };
-    auto v_full = [&](int s) { return bar0 + 8u * (2 + AT_STAGES + s); };
-    auto kv_empty = [&](int s) { return bar0 + 8u * (2 + 2 * AT_STAGES + s); };
-    constexpr int BB = 2 + 3 * AT_STAGES;
+    auto v_full = [&](int s) { return bar0 + 8u * (2 + Dm::STAGES + s); };
+    auto kv_empty = [&](int s) { return bar0 + 8u * (2 + 2 * Dm::STAGES + s); };
+    constexpr int BB = 2 + 3 * Dm::STAGES;
     auto s_full = [&](int x) { return bar0 + 8u * (BB + 0 + x); };   // S_x = Q K^T landed in TMEM
     auto s_free = [&](int x) { return bar0 + 8u * (BB + 2 + x); };   // softmax x holds S_x in registers
     auto p_full = [&](int x) { return bar0 + 8u * (BB + 4 + x); };   // P_x in smem (and O_x rescaled if needed)
@@ -127,8 +129,8 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ64); tma_prefetch_desc(&tmK64); tma_prefetch_desc(&tmVt);
-        if (Dm::HAS16) { tma_prefetch_desc(&tmQ16); tma_prefetch_desc(&tmK16); }
-        if (n_cross > 0) { tma_prefetch_desc(&tmKy64); tma_prefetch_desc(&tmVyt); if (Dm::HAS16) tma_prefetch_desc(&tmKy16); }
+        if (Dm::N16 > 0) { tma_prefetch_desc(&tmQ16); tma_prefetch_desc(&tmK16); }
+        if (n_cross > 0) { tma_prefetch_desc(&tmKy64); tma_prefetch_desc(&tmVyt); if (Dm::N16 > 0) tma_prefetch_desc(&tmKy16); }
         for (int x = 0; x < 2; ++x) {
             mbar_init(q_full(x), 1);
             mbar_init(s_full(x), 1);
@@ -136,7 +138,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             mbar_init(p_full(x), 4);
             mbar_init(o_full(x), 1);
         }
-        for (int s = 0; s < AT_STAGES; ++s) {
+        for (int s = 0; s < Dm::STAGES; ++s) {
             mbar_init(k_full(s), 1);
             mbar_init(v_full(s), 1);
             mbar_init(kv_empty(s), 2);
@@ -160,10 +162,12 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             // ================================================================= TMA producer
             if (lane == 0) {
                 for (int x = 0; x < 2; ++x) {
-                    const uint32_t dst = sbase + AT_OFF_Q + x * AT_QTILE_BYTES;
+                    const uint32_t dst = sbase + Dm::OFF_Q + x * Dm::QTILE_BYTES;
                     mbar_expect_tx(q_full(x), Dm::QK_TX);
                     tma_load_3d(dst, &tmQ64, q_full(x), 0, h, b * N + q0 + x * AT_BQ);
-                    if (Dm::HAS16) tma_load_3d(dst + AT_Q64_BYTES, &tmQ16, q_full(x), 64, h, b * N + q0 + x * AT_BQ);
+#pragma unroll
+                    for (int c = 0; c < Dm::N16; ++c)
+                        tma_load_3d(dst + AT_Q64_BYTES + c * AT_Q16_BYTES, &tmQ16, q_full(x), 64 + 16 * c, h, b * N + q0 + x * AT_BQ);
                 }
             }
             __syncwarp();
@@ -172,26 +176,30 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             for (int jj = 0; jj < n_total; ++jj) {
                 mbar_wait(kv_empty(s), ph ^ 1);
                 if (lane == 0) {
-                    const uint32_t kd = sbase + AT_OFF_K + s * AT_KTILE_BYTES;
-                    const uint32_t vd = sbase + AT_OFF_V + s * AT_VTILE_BYTES;
+                    const uint32_t kd = sbase + Dm::OFF_K + s * Dm::KTILE_BYTES;
+                    const uint32_t vd = sbase + Dm::OFF_V + s * Dm::VTILE_BYTES;
                     mbar_expect_tx(k_full(s), Dm::QK_TX);
                     mbar_expect_tx(v_full(s), Dm::V_TX);
                     if (jj < n_self) {
                         const int kv0 = jj * AT_BKV;
                         tma_load_3d(kd, &tmK64, k_full(s), 0, g, b * N + kv0);
-                        if (Dm::HAS16) tma_load_3d(kd + AT_Q64_BYTES, &tmK16, k_full(s), 64, g, b * N + kv0);
+#pragma unroll
+                        for (int c = 0; c < Dm::N16; ++c)
+                            tma_load_3d(kd + AT_Q64_BYTES + c * AT_Q16_BYTES, &tmK16, k_full(s), 64 + 16 * c, g, b * N + kv0);
                         tma_load_3d(vd, &tmVt, v_full(s), kv0, 0, b * Hkv + g);
-                        tma_load_3d(vd + AT_VHALF_BYTES, &tmVt, v_full(s), kv0 + 64, 0, b * Hkv + g);
+                        tma_load_3d(vd + Dm::VHALF_BYTES, &tmVt, v_full(s), kv0 + 64, 0, b * Hkv + g);
                     } else {
                         const int kv0 = (jj - n_self) * AT_BKV;
                         tma_load_3d(kd, &tmKy64, k_full(s), 0, g, b * T + kv0);
-                        if (Dm::HAS16) tma_load_3d(kd + AT_Q64_BYTES, &tmKy16, k_full(s), 64, g, b * T + kv0);
+#pragma unroll
+                        for (int c = 0; c < Dm::N16; ++c)
+                            tma_load_3d(kd + AT_Q64_BYTES + c * AT_Q16_BYTES, &tmKy16, k_full(s), 64 + 16 * c, g, b * T + kv0);
                         tma_load_3d(vd, &tmVyt, v_full(s), kv0, 0, b * Hkv + g);
-                        tma_load_3d(vd + AT_VHALF_BYTES, &tmVyt, v_full(s), kv0 + 64, 0, b * Hkv + g);
+                        tma_load_3d(vd + Dm::VHALF_BYTES, &tmVyt, v_full(s), kv0 + 64, 0, b * Hkv + g);
                     }
                 }
                 __syncwarp();
-                if (++s == AT_STAGES) { s = 0; ph ^= 1; }
+                if (++s == Dm::STAGES) { s = 0; ph ^= 1; }
             }
         } else if (warp == 1 || warp == 2) {
             // ================================================================= MMA issuers: warp 1 -> tile A, warp 2 -> tile B
@@ -199,21 +207,22 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, AT_BKV);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, HDP);
             auto issue_qk = [&](int jj) {
-                const int s = jj % AT_STAGES;
-                mbar_wait(k_full(s), (jj / AT_STAGES) & 1);
+                const int s = jj % Dm::STAGES;
+                mbar_wait(k_full(s), (jj / Dm::STAGES) & 1);
                 mbar_wait(s_free(x), (jj & 1) ^ 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t qa = sbase + AT_OFF_Q + x * AT_QTILE_BYTES;
-                    const uint32_t ka = sbase + AT_OFF_K + s * AT_KTILE_BYTES;
+                    const uint32_t qa = sbase + Dm::OFF_Q + x * Dm::QTILE_BYTES;
+                    const uint32_t ka = sbase + Dm::OFF_K + s * Dm::KTILE_BYTES;
                     const uint64_t dq = make_smem_desc_kmajor(qa, 1024, UMMA_SW128);
                     const uint64_t dk = make_smem_desc_kmajor(ka, 1024, UMMA_SW128);
                     const uint32_t d = tmem_base + AT_TM_S + x * 128;
 #pragma unroll
                     for (int k = 0; k < Dm::NK64; ++k) umma_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-                    if (Dm::HAS16) {
-                        const uint64_t dq16 = make_smem_desc_kmajor(qa + AT_Q64_BYTES, 256, UMMA_SW32);
-                        const uint64_t dk16 = make_smem_desc_kmajor(ka + AT_Q64_BYTES, 256, UMMA_SW32);
+#pragma unroll
+                    for (int c = 0; c < Dm::N16; ++c) {
+                        const uint64_t dq16 = make_smem_desc_kmajor(qa + AT_Q64_BYTES + c * AT_Q16_BYTES, 256, UMMA_SW32);
+                        const uint64_t dk16 = make_smem_desc_kmajor(ka + AT_Q64_BYTES + c * AT_Q16_BYTES, 256, UMMA_SW32);
                         umma_ss(d, dq16, dk16, idesc_qk, 1);
                     }
                     umma_commit(s_full(x));
@@ -221,19 +230,19 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 __syncwarp();
             };
             auto issue_pv = [&](int jj) {
-                const int s = jj % AT_STAGES;
+                const int s = jj % Dm::STAGES;
                 const uint32_t acc0 = (jj != 0 && jj != n_self) ? 1u : 0u;   // new softmax segment -> fresh accumulator
-                mbar_wait(v_full(s), (jj / AT_STAGES) & 1);
+                mbar_wait(v_full(s), (jj / Dm::STAGES) & 1);
                 mbar_wait(p_full(x), jj & 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t pa = sbase + AT_OFF_P + x * AT_PTILE_BYTES;
-                    const uint32_t va = sbase + AT_OFF_V + s * AT_VTILE_BYTES;
+                    const uint32_t pa = sbase + Dm::OFF_P + x * AT_PTILE_BYTES;
+                    const uint32_t va = sbase + Dm::OFF_V + s * Dm::VTILE_BYTES;
                     const uint32_t d = tmem_base + AT_TM_O + x * 128;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const uint64_t dp = make_smem_desc_kmajor(pa + (k >> 2) * AT_PHALF_BYTES, 1024, UMMA_SW128) + 2 * (k & 3);
-                        const uint64_t dv = make_smem_desc_kmajor(va + (k >> 2) * AT_VHALF_BYTES, 1024, UMMA_SW128) + 2 * (k & 3);
+                        const uint64_t dv = make_smem_desc_kmajor(va + (k >> 2) * Dm::VHALF_BYTES, 1024, UMMA_SW128) + 2 * (k & 3);
                         umma_ss(d, dp, dv, idesc_pv, acc0 | (k != 0));
                     }
                     umma_commit(o_full(x));
@@ -259,7 +268,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
         const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
         const uint32_t ts = tmem_base + lane_sel + AT_TM_S + x * 128;
         const uint32_t to = tmem_base + lane_sel + AT_TM_O + x * 128;
-        const uint32_t pbase = sbase + AT_OFF_P + x * AT_PTILE_BYTES + r * 128;
+        const uint32_t pbase = sbase + Dm::OFF_P + x * AT_PTILE_BYTES + r * 128;
         const uint32_t rsw = static_cast<uint32_t>(r & 7);
 
         uint32_t o_self[HD / 2];
@@ -446,13 +455,13 @@ static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
     auto kern = attention_fused_kernel<HD>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDims<HD>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const float log2e = 1.4426950408889634f;
     const dim3 grid((p.N + 2 * AT_BQ - 1) / (2 * AT_BQ), p.H, p.B);
-    kern<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask,
+    kern<<<grid, AT_THREADS, AttnDims<HD>::SMEM_BYTES, stream>>>(p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask,
                                                       p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv, p.scale_self * log2e,
                                                       p.scale_cross * log2e);
     return cudaGetLastError();
@@ -462,6 +471,7 @@ cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
     if (p.T < 0 || p.N <= 0) return cudaErrorInvalidValue;
     if (p.hd == 72) return launch_attention<72>(p, stream);
     if (p.hd == 48) return launch_attention<48>(p, stream);
+    if (p.hd == 96) return launch_attention<96>(p, stream);
     return cudaErrorInvalidValue;
 }
 

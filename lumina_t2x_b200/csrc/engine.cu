@@ -67,6 +67,8 @@ struct ndit_engine {
     int D, L, H, Hkv, hd, F, C, cd, O, Wq;   // Wq = fused qkv width
     int vrows = 80;                          // V^T rows per (batch, kv head): head_dim + ones row, padded to 16
     bool cls = false;                        // class-conditional variant (DiT_Llama): labels instead of captions
+    bool flag = false;                       // Flag-DiT (Lumina-T2I DiT_Llama): shift/scale/gate adaLN, 1-D RoPE, eol tokens
+    int NCH = 4;                             // adaLN chunks per layer: 4 (scale, gate) x2 or 6 (shift, scale, gate) x2
     int FD = 1;                              // final-layer adaLN chunks: 1 (scale) or 2 (shift, scale)
     bf16* Yemb = nullptr;                    // [num_classes + 1, cd] label embedding table
     int device = 0, num_sms = 148;
@@ -83,7 +85,7 @@ struct ndit_engine {
     std::vector<void*> allocs;
 
     // weights
-    bf16 *Wx, *bx, *Wt0, *bt0, *Wt2, *bt2, *capln_w, *capln_b, *Wcap, *bcap, *Wada, *bada, *Wout, *bout, *pad_token;
+    bf16 *Wx, *bx, *Wt0, *bt0, *Wt2, *bt2, *capln_w, *capln_b, *Wcap, *bcap, *Wada, *bada, *Wout, *bout, *pad_token, *eol_token;
     bf16 *Wqkv, *Wo, *W13, *W2, *Wkvy;                       // [L][...]
     bf16 *qn_w, *qn_b, *kn_w, *kn_b, *kyn_w, *kyn_b;         // [L][...]
     bf16 *an1, *an2, *fn1, *fn2, *yn;                        // [L][...]
@@ -188,9 +190,12 @@ static int create_impl(ndit_engine* h) {
     if (c.dim <= 0 || c.n_heads <= 0 || c.dim % c.n_heads != 0) return h->fail(NDIT_ERR_INVALID, "bad dim/n_heads");
     h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
     h->cls = c.num_classes > 0;
-    h->FD = h->cls ? 2 : 1;
+    h->flag = c.flag_dit != 0;
+    if (h->cls && h->flag) return h->fail(NDIT_ERR_INVALID, "num_classes > 0 and flag_dit are mutually exclusive");
+    h->FD = (h->cls || h->flag) ? 2 : 1;
+    h->NCH = h->flag ? 6 : 4;
     h->hd = c.dim / c.n_heads; h->C = h->cls ? 0 : c.cap_feat_dim; h->cd = c.dim < 1024 ? c.dim : 1024;
-    if (h->hd != 72 && h->hd != 48) return h->fail(NDIT_ERR_INVALID, "head_dim must be 72 or 48 (got %d)", h->hd);
+    if (h->hd != 72 && h->hd != 48 && h->hd != 96) return h->fail(NDIT_ERR_INVALID, "head_dim must be 72, 48 or 96 (got %d)", h->hd);
     h->vrows = attn_vrows(h->hd);
     if (c.patch_size != 2 || c.in_channels != 4) return h->fail(NDIT_ERR_INVALID, "patch_size 2 / in_channels 4 only");
     if (h->H % h->Hkv != 0) return h->fail(NDIT_ERR_INVALID, "n_heads %% n_kv_heads != 0");
@@ -211,9 +216,10 @@ static int create_impl(ndit_engine* h) {
     const size_t D = h->D, L = h->L, F = h->F, C = h->C, cd = h->cd, KV = (size_t)h->Hkv * h->hd;
     ALLOC(Wx, D * 16); ALLOC(bx, D); ALLOC(Wt0, cd * 256); ALLOC(bt0, cd); ALLOC(Wt2, cd * cd); ALLOC(bt2, cd);
     ALLOC(capln_w, C); ALLOC(capln_b, C); ALLOC(Wcap, cd * C); ALLOC(bcap, cd);
-    ALLOC(Wada, (L * 4 * D + h->FD * D) * cd); ALLOC(bada, L * 4 * D + h->FD * D);
+    const size_t NCH = h->NCH;
+    ALLOC(Wada, (L * NCH * D + h->FD * D) * cd); ALLOC(bada, L * NCH * D + h->FD * D);
     if (h->cls) ALLOC(Yemb, ((size_t)c.num_classes + 1) * cd);
-    ALLOC(Wout, (size_t)h->O * D); ALLOC(bout, h->O); ALLOC(pad_token, D);
+    ALLOC(Wout, (size_t)h->O * D); ALLOC(bout, h->O); ALLOC(pad_token, D); ALLOC(eol_token, D);
     ALLOC(Wqkv, L * h->Wq * D); ALLOC(Wo, L * D * D); ALLOC(W13, L * 2 * F * D); ALLOC(W2, L * D * F);
     ALLOC(Wkvy, L * 2 * KV * C);
     ALLOC(qn_w, L * D); ALLOC(qn_b, L * D); ALLOC(kn_w, L * KV); ALLOC(kn_b, L * KV); ALLOC(kyn_w, L * KV); ALLOC(kyn_b, L * KV);
@@ -224,10 +230,10 @@ static int create_impl(ndit_engine* h) {
     h->Mmax = c.max_batch * c.max_tokens;
     const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
     ALLOC(X, M * D); ALLOC(u, M * D); ALLOC(qkv, M * h->Wq); ALLOC(attn, M * D); ALLOC(o, M * D); ALLOC(hbuf, M * F);
-    ALLOC(vt, B * h->Hkv * h->vrows * c.max_tokens);
+    ALLOC(vt, B * h->Hkv * h->vrows * ((size_t)c.max_tokens + 8));
     ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
     ALLOC(ymask, B * T); ALLOC(pool, B * C); ALLOC(capemb, B * cd); ALLOC(tf, B * 256); ALLOC(h1, B * cd); ALLOC(sc, B * cd);
-    ALLOC(mod, B * (L * 4 * D + h->FD * D)); ALLOC(tok, M * h->O);
+    ALLOC(mod, B * (L * NCH * D + h->FD * D)); ALLOC(tok, M * h->O);
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
     ALLOC(vel, lat); ALLOC(ystate, lat); ALLOC(ymid, lat); ALLOC(stage_z, lat); ALLOC(stage_cap, B * T * C); ALLOC(stage_mask, B * T);
     for (int i = 0; i < 2; ++i) {
@@ -325,6 +331,7 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
         return place(h, dst, cc, src, dtype, rr, cc, 0, 0, 0, s, fresh_); \
     }
     if (!h->cls) { VEC("pad_token", h->pad_token, D) }
+    if (h->flag) { VEC("eol_token", h->eol_token, D) }
     MAT("x_embedder.weight", h->Wx, D, 16) VEC("x_embedder.bias", h->bx, D)
     MAT("t_embedder.mlp.0.weight", h->Wt0, cd, 256) VEC("t_embedder.mlp.0.bias", h->bt0, cd)
     MAT("t_embedder.mlp.2.weight", h->Wt2, cd, cd) VEC("t_embedder.mlp.2.bias", h->bt2, cd)
@@ -335,10 +342,10 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
         MAT("y_embedder.embedding_table.weight", h->Yemb, (size_t)h->cfg.num_classes + 1, cd)
     }
     MAT("final_layer.linear.weight", h->Wout, (size_t)h->O, D) VEC("final_layer.linear.bias", h->bout, (size_t)h->O)
-    const size_t Lz = h->L;
-    // T2I: [scale]; class-conditional: [shift | scale] (models.py:829-833)
-    MAT("final_layer.adaLN_modulation.1.weight", h->Wada + Lz * 4 * D * cd, (size_t)h->FD * D, cd)
-    VEC("final_layer.adaLN_modulation.1.bias", h->bada + Lz * 4 * D, (size_t)h->FD * D)
+    const size_t Lz = h->L, NCH = h->NCH;
+    // Next-DiT T2I: [scale]; class-conditional and Flag-DiT: [shift | scale] (models.py:829-833, lumina_t2i model.py:655-656)
+    MAT("final_layer.adaLN_modulation.1.weight", h->Wada + Lz * NCH * D * cd, (size_t)h->FD * D, cd)
+    VEC("final_layer.adaLN_modulation.1.bias", h->bada + Lz * NCH * D, (size_t)h->FD * D)
 #undef VEC
 #undef MAT
     int li = -1, pos = 0;
@@ -357,7 +364,7 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
             {"feed_forward.w1.weight", h->W13 + l * 2 * F * D, D, F, D, 128, 256, 0},
             {"feed_forward.w3.weight", h->W13 + l * 2 * F * D, D, F, D, 128, 256, 128},
             {"feed_forward.w2.weight", h->W2 + l * D * F, F, D, F, 0, 0, 0},
-            {"adaLN_modulation.1.weight", h->Wada + l * 4 * D * cd, cd, 4 * D, cd, 0, 0, 0},
+            {"adaLN_modulation.1.weight", h->Wada + l * NCH * D * cd, cd, NCH * D, cd, 0, 0, 0},
         };
         for (const Ent& e : ents) {
             if (h->cls && (!strcmp(e.name, "attention.wk_y.weight") || !strcmp(e.name, "attention.wv_y.weight"))) continue;
@@ -386,6 +393,26 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
             {"attention_norm.weight", h->an2 + l * D, D}, {"ffn_norm.weight", h->fn2 + l * D, D},
             {"adaLN_modulation.1.bias", h->bada + l * 4 * D, 4 * D},
         };
+        // Flag-DiT block (lumina_t2i model.py:505-622): one weighted RMSNorm in front of each sub-block, no post-norms
+        const VEnt flag_vents[] = {
+            {"attention.gate", h->gate_raw + l * h->H, (size_t)h->H},
+            {"attention.q_norm.weight", h->qn_w + l * D, D}, {"attention.q_norm.bias", h->qn_b + l * D, D},
+            {"attention.k_norm.weight", h->kn_w + l * KV, KV}, {"attention.k_norm.bias", h->kn_b + l * KV, KV},
+            {"attention.ky_norm.weight", h->kyn_w + l * KV, KV}, {"attention.ky_norm.bias", h->kyn_b + l * KV, KV},
+            {"attention_norm.weight", h->an1 + l * D, D}, {"ffn_norm.weight", h->fn1 + l * D, D},
+            {"attention_y_norm.weight", h->yn + l * C, C},
+            {"adaLN_modulation.1.bias", h->bada + l * 6 * D, 6 * D},
+        };
+        if (h->flag) {
+            for (const VEnt& e : flag_vents) {
+                if (!strcmp(sub, e.name)) {
+                    if (int er = want(e.n, 0)) return er;
+                    const bool fresh = h->seen.insert(key).second;
+                    return place(h, e.dst, 1, src, dtype, e.n, 1, 0, 0, 0, s, fresh);
+                }
+            }
+            return h->fail(NDIT_ERR_INVALID, "unexpected state-dict key: %s", key);
+        }
         if (h->cls) {
             for (const VEnt& e : cls_vents) {
                 if (!strcmp(sub, e.name)) {
@@ -415,6 +442,7 @@ static void expected_keys(const ndit_engine* h, std::vector<std::string>* out) {
     const char* t2i_top[] = {"pad_token", "cap_embedder.0.weight", "cap_embedder.0.bias", "cap_embedder.1.weight", "cap_embedder.1.bias"};
     if (h->cls) out->push_back("y_embedder.embedding_table.weight");
     else for (const char* k : t2i_top) out->push_back(k);
+    if (h->flag) out->push_back("eol_token");
     const char* per[] = {"attention.wq.weight", "attention.wk.weight", "attention.wv.weight", "attention.wo.weight",
                          "attention.q_norm.weight", "attention.q_norm.bias", "attention.k_norm.weight", "attention.k_norm.bias",
                          "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight",
@@ -423,10 +451,13 @@ static void expected_keys(const ndit_engine* h, std::vector<std::string>* out) {
                              "attention.ky_norm.bias", "attention_norm1.weight", "attention_norm2.weight", "ffn_norm1.weight",
                              "ffn_norm2.weight", "attention_y_norm.weight"};
     const char* per_cls[] = {"attention_norm.weight", "ffn_norm.weight"};
+    const char* per_flag[] = {"attention.gate", "attention.wk_y.weight", "attention.wv_y.weight", "attention.ky_norm.weight",
+                              "attention.ky_norm.bias", "attention_norm.weight", "ffn_norm.weight", "attention_y_norm.weight"};
     for (int l = 0; l < h->L; ++l) {
         const std::string pre = "layers." + std::to_string(l) + ".";
         for (const char* k : per) out->push_back(pre + k);
         if (h->cls) for (const char* k : per_cls) out->push_back(pre + k);
+        else if (h->flag) for (const char* k : per_flag) out->push_back(pre + k);
         else for (const char* k : per_t2i) out->push_back(pre + k);
     }
 }
@@ -470,7 +501,7 @@ extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* m
     CKL(cudaGetLastError());
     const bf16* capb = static_cast<const bf16*>(cap);
     CKL(cond_prepare(0.f, capb, h->ymask, h->capln_w, h->capln_b, h->tf, h->pool, batch, T, (int)C, 1, s));
-    CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, nullptr, batch, h->cd, (int)C, 0, POST_NONE, 0, 0, s));
+    CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, nullptr, batch, h->cd, (int)C, 0, POST_NONE, 0, 0, 0, s));
     CKL(rms_rows_layers(capb, h->yn, h->yhat, M, (int)C, (int)L, h->cfg.norm_eps, s));
     const size_t ys = (size_t)M * C, ks = (size_t)M * 2 * KV;
     for (size_t l = 0; l < L; ++l) {
@@ -511,12 +542,12 @@ extern "C" int ndit_set_labels(ndit_handle h, const int64_t* labels, int32_t bat
 // 16-wide box elements [64,80) of head_dim 72.  V^T buffers are [group][vrows][tokens].
 static int build_attn_maps(AttnPlan* a, const bf16* qkv, int Wq, const bf16* vt, const bf16* kvy, const bf16* vyt, int B, int N,
                            int T, int H, int Hkv, int hd) {
-    const int vrows = attn_vrows(hd), KV = Hkv * hd, Tpad = (T + 7) / 8 * 8;
+    const int vrows = attn_vrows(hd), KV = Hkv * hd, Tpad = (T + 7) / 8 * 8, Npad = (N + 7) / 8 * 8;
     const uint64_t rs = (uint64_t)Wq * 2, M = (uint64_t)B * N;
     int e = 0;
     e |= make_tmap_3d(&a->tmQ64, qkv, hd, H, M, hd * 2, rs, 64, 1, 128, 128);
     e |= make_tmap_3d(&a->tmK64, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, 128, 128);
-    e |= make_tmap_3d(&a->tmVt, vt, N, vrows, (uint64_t)B * Hkv, (uint64_t)N * 2, (uint64_t)N * vrows * 2, 64, vrows, 1, 128);
+    e |= make_tmap_3d(&a->tmVt, vt, N, vrows, (uint64_t)B * Hkv, (uint64_t)Npad * 2, (uint64_t)Npad * vrows * 2, 64, vrows, 1, 128);
     if (hd > 64) {
         e |= make_tmap_3d(&a->tmQ16, qkv, hd, H, M, hd * 2, rs, 16, 1, 128, 32);
         e |= make_tmap_3d(&a->tmK16, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, 128, 32);
@@ -576,7 +607,7 @@ static int get_rope(ndit_engine* h, int Hp, int Wp, float theta, float lin, cuda
     }
     RopeSlot& r = h->rope[h->rope_next];
     h->rope_next ^= 1;
-    CKL(rope_table(r.tab, Hp, Wp, h->hd, theta, lin, s));
+    CKL(rope_table(r.tab, Hp, Wp, h->hd, theta, lin, h->flag ? 1 : 0, s));
     r.Hp = Hp; r.Wp = Wp; r.theta = theta; r.lin = lin;
     *out = r.tab;
     return 0;
@@ -588,20 +619,22 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
     if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
     if ((Hh & 1) || (Ww & 1) || Hh <= 0 || Ww <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");
-    const int Hp = Hh / 2, Wp = Ww / 2, N = Hp * Wp, M = batch * N;
+    const int Hp = Hh / 2, Wp = Ww / 2, eol = h->flag ? 1 : 0;
+    const int N = Hp * (Wp + eol), M = batch * N, Npad = (N + 7) / 8 * 8;     // Flag-DiT: one [eol] token per row of patches
     if (N > h->cfg.max_tokens) return h->fail(NDIT_ERR_INVALID, "%d tokens > max_tokens %d", N, h->cfg.max_tokens);
-    if (N % 8 != 0) return h->fail(NDIT_ERR_INVALID, "token count %d must be a multiple of 8", N);
-    if (Hp > 384 || Wp > 384) return h->fail(NDIT_ERR_INVALID, "rope table covers 384x384 patches (model.py:733)");
+    if (!h->flag && (Hp > 384 || Wp > 384)) return h->fail(NDIT_ERR_INVALID, "rope table covers 384x384 patches (model.py:733)");
+    if (h->flag && N > 40000) return h->fail(NDIT_ERR_INVALID, "rope table covers 40000 tokens (lumina_t2i model.py:722-727)");
     if (int e = ensure_plans(h, batch, N)) return e;
     const int D = h->D, L = h->L, hd = h->hd;
     if (!h->vt_ones_valid) {
-        CK(cudaMemsetAsync(h->vt, 0, (size_t)batch * h->Hkv * h->vrows * N * sizeof(bf16), s));
-        CKL(fill_ones_row(h->vt, N, 0, batch * h->Hkv, N, hd, h->vrows, 1, s));
+        CK(cudaMemsetAsync(h->vt, 0, (size_t)batch * h->Hkv * h->vrows * Npad * sizeof(bf16), s));
+        CKL(fill_ones_row(h->vt, Npad, 0, batch * h->Hkv, N, hd, h->vrows, 1, s));
         h->vt_ones_valid = true;
     }
-    const int mod_stride = L * 4 * D + h->FD * D;
+    const int NCH = h->NCH;
+    const int mod_stride = L * NCH * D + h->FD * D;
     float lin, ntk;
-    if (h->cls) {   // DiT_Llama.precompute_freqs_cis(rope_scaling_factor, ntk_factor) (models.py:977-1012)
+    if (h->cls || h->flag) {   // DiT_Llama.precompute_freqs_cis(rope_scaling_factor, ntk_factor) (models.py:977-1012; lumina_t2i model.py:925-960)
         lin = sp->scale_factor > 0.f ? sp->scale_factor : 1.0f;
         ntk = sp->ntk_factor > 0.f ? sp->ntk_factor : 1.0f;
     } else if (t < sp->scale_watershed) {   // time-aware RoPE scaling (model.py:944-952)
@@ -611,7 +644,7 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     }
     const float theta = 10000.0f * ntk;
     const float2* rope = nullptr;
-    if (int e = get_rope(h, Hp, Wp, theta, lin, s, &rope)) return e;
+    if (int e = get_rope(h, h->flag ? N : Hp, h->flag ? 1 : Wp, theta, lin, s, &rope)) return e;
     float scale_self;
     if (sp->proportional_attn) {
         if (sp->base_seqlen <= 1) return h->fail(NDIT_ERR_INVALID, "proportional_attn needs base_seqlen > 1");
@@ -621,15 +654,22 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     }
     const float scale_cross = (float)(1.0 / sqrt((double)hd));
 
-    PROF(KC_ROWWISE, patch_embed(x, h->Wx, h->bx, h->X, batch, batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
+    PROF(KC_ROWWISE, patch_embed(x, h->Wx, h->bx, h->flag ? h->eol_token : nullptr, h->X, batch, batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
     PROF(KC_COND, cond_prepare(t, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
-    PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, nullptr, batch, h->cd, 256, 0, POST_SILU, 0, 0, s));
+    PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, nullptr, batch, h->cd, 256, 0, POST_SILU, 0, 0, 0, s));
     // sc = bf16(silu(c)), c = bf16(temb + cap_emb)
-    PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, nullptr, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, s));
-    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, h->cls ? -L : L, s));
-    PROF(KC_ROWWISE, resid_rms_mod(h->X, nullptr, nullptr, nullptr, h->an1, h->mod, h->u, M, N, D, mod_stride, h->cfg.norm_eps, s));
+    PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, nullptr, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, 0, s));
+    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L,
+                            h->flag ? ADALN_FLAG : (h->cls ? ADALN_CLASS : ADALN_NEXT), s));
+    // per-layer modulation chunks (offsets in units of D): Next-DiT [1+scale_msa, tanh gate_msa, 1+scale_mlp, tanh gate_mlp];
+    // Flag-DiT [shift_msa, 1+scale_msa, gate_msa, shift_mlp, 1+scale_mlp, gate_mlp]
+    const int o_sc1 = h->flag ? 1 : 0, o_g1 = h->flag ? 2 : 1, o_sc2 = h->flag ? 4 : 2, o_g2 = h->flag ? 5 : 3;
+    const bf16* mod0 = h->mod;
+    PROF(KC_ROWWISE, resid_rms_mod(h->X, nullptr, nullptr, nullptr, h->an1, mod0 + (size_t)o_sc1 * D, h->flag ? mod0 : nullptr, h->u, M, N, D,
+                                   mod_stride, h->cfg.norm_eps, s));
     for (int l = 0; l < L; ++l) {
-        const bf16* ml = h->mod + (size_t)l * 4 * D;
+        const bf16* ml = h->mod + (size_t)l * NCH * D;
+        const bf16* mn = ml + (size_t)NCH * D;      // next layer's chunks
         PROF(KC_GEMM_QKV, gemm_bf16_tn(h->p_qkv[l], s));
         PROF(KC_ROWWISE, ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
                        h->kn_b + (size_t)l * h->Hkv * hd, rope, M, N, h->H, h->Hkv, hd, s));
@@ -638,28 +678,31 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                               h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
                               scale_cross, s));
         } else {
-            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, N, 0, batch, N, h->Hkv, hd, h->vrows, 1, s));
+            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, Npad, 0, batch, N, h->Hkv, hd, h->vrows, 1, s));
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
             PROF(KC_ATTN, attention_fused(a, s));
         }
         PROF(KC_GEMM_WO, gemm_bf16_tn(h->p_wo[l], s));
-        PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->an2 + (size_t)l * D, ml + D, h->fn1 + (size_t)l * D, ml + 2 * D, h->u, M, N, D,
-                          mod_stride, h->cfg.norm_eps, s));
+        PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->flag ? nullptr : h->an2 + (size_t)l * D, ml + (size_t)o_g1 * D, h->fn1 + (size_t)l * D,
+                                       ml + (size_t)o_sc2 * D, h->flag ? ml + 3 * (size_t)D : nullptr, h->u, M, N, D, mod_stride,
+                                       h->cfg.norm_eps, s));
         PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[l], s));
         PROF(KC_GEMM_W2, gemm_bf16_tn(h->p_w2[l], s));
         if (l + 1 < L) {
-            PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->an1 + (size_t)(l + 1) * D, ml + 4 * D, h->u, M, N,
-                              D, mod_stride, h->cfg.norm_eps, s));
+            PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->flag ? nullptr : h->fn2 + (size_t)l * D, ml + (size_t)o_g2 * D,
+                                           h->an1 + (size_t)(l + 1) * D, mn + (size_t)o_sc1 * D, h->flag ? mn : nullptr, h->u, M, N, D,
+                                           mod_stride, h->cfg.norm_eps, s));
         } else {
-            // final adaLN: T2I [scale]; class-conditional [shift | scale]
-            const bf16* fin = h->mod + (size_t)L * 4 * D;
-            PROF(KC_ROWWISE, final_layer(h->X, h->o, h->fn2 + (size_t)l * D, ml + 3 * D, h->cls ? fin + D : fin, h->cls ? fin : nullptr,
-                                         h->Wout, h->bout, h->tok, M, N, D, h->O, mod_stride, h->cfg.norm_eps, s));
+            // final adaLN: Next-DiT T2I [scale]; class-conditional and Flag-DiT [shift | scale]
+            const bf16* fin = h->mod + (size_t)L * NCH * D;
+            const bool fsh = h->cls || h->flag;
+            PROF(KC_ROWWISE, final_layer(h->X, h->o, h->flag ? nullptr : h->fn2 + (size_t)l * D, ml + (size_t)o_g2 * D, fsh ? fin + D : fin,
+                                         fsh ? fin : nullptr, h->Wout, h->bout, h->tok, M, N, D, h->O, mod_stride, h->cfg.norm_eps, s));
         }
     }
-    PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, s));
+    PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, eol, s));
     return NDIT_OK;
 }
 
@@ -793,12 +836,12 @@ extern "C" int ndit_op_gemm_bench(const void* A, const void* W, void* C, int32_t
 
 extern "C" int ndit_op_ln_rope(void* qkv, const void* qw, const void* qb, const void* kw, const void* kb, int32_t batch,
                                int32_t Hp, int32_t Wp, int32_t H, int32_t Hkv, int32_t hd, float theta, float linear_factor,
-                               void* stream) {
+                               int32_t one_d, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float2* tab = nullptr;
     cudaError_t e = cudaMalloc(&tab, (size_t)Hp * Wp * (hd / 2) * sizeof(float2));
     if (e != cudaSuccess) return op_fail(NDIT_ERR_NOMEM, "ndit_op_ln_rope", e);
-    e = rope_table(tab, Hp, Wp, hd, theta, linear_factor, s);
+    e = rope_table(tab, Hp, Wp, hd, theta, linear_factor, one_d, s);
     if (e == cudaSuccess)
         e = ln_rope_qk(static_cast<bf16*>(qkv), (H + 2 * Hkv) * hd, static_cast<const bf16*>(qw), static_cast<const bf16*>(qb),
                        static_cast<const bf16*>(kw), static_cast<const bf16*>(kb), tab, batch * Hp * Wp, Hp * Wp, H, Hkv, hd, s);
@@ -812,7 +855,7 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
                              int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self, float scale_cross,
                              int32_t use_ref, void* stream, int bench_iters, float* bench_ms, int hd) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (hd != 72 && hd != 48) return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: head_dim must be 72 or 48", cudaErrorInvalidValue);
+    if (hd != 72 && hd != 48 && hd != 96) return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: head_dim must be 72, 48 or 96", cudaErrorInvalidValue);
     const int vrows = attn_vrows(hd);
     const bf16* qkv = static_cast<const bf16*>(qkv_);
     const bf16* kvy = static_cast<const bf16*>(kvy_);
@@ -822,18 +865,17 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
                                       scale_self, scale_cross, s);
         return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_attention(ref)", e);
     }
-    if (N % 8 != 0) return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: N % 8 != 0", cudaErrorInvalidValue);
-    const int Tpad = (T + 7) / 8 * 8;
+    const int Tpad = (T + 7) / 8 * 8, Npad = (N + 7) / 8 * 8;
     bf16 *vt = nullptr, *vyt = nullptr;
-    const size_t vt_elems = (size_t)B * Hkv * vrows * N, vyt_elems = (size_t)B * Hkv * vrows * Tpad;
+    const size_t vt_elems = (size_t)B * Hkv * vrows * Npad, vyt_elems = (size_t)B * Hkv * vrows * Tpad;
     cudaError_t e = cudaMalloc(&vt, vt_elems * 2);
     if (e == cudaSuccess) e = cudaMalloc(&vyt, vyt_elems * 2 + 256);
     if (e != cudaSuccess) return op_fail(NDIT_ERR_NOMEM, "ndit_op_attention", e);
     cudaMemsetAsync(vt, 0, vt_elems * 2, s);
     cudaMemsetAsync(vyt, 0, vyt_elems * 2, s);
-    e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, N, 0, B, N, Hkv, hd, vrows, 1, s);
+    e = transpose_v(qkv, Wq, (H + Hkv) * hd, 0, vt, Npad, 0, B, N, Hkv, hd, vrows, 1, s);
     if (e == cudaSuccess && T > 0) e = transpose_v(kvy, 2 * KV, KV, 0, vyt, Tpad, 0, B, T, Hkv, hd, vrows, 1, s);
-    if (e == cudaSuccess) e = fill_ones_row(vt, N, 0, B * Hkv, N, hd, vrows, 1, s);
+    if (e == cudaSuccess) e = fill_ones_row(vt, Npad, 0, B * Hkv, N, hd, vrows, 1, s);
     if (e == cudaSuccess && T > 0) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, vrows, 1, s);
     AttnPlan a;
     memset(&a, 0, sizeof(a));
@@ -888,11 +930,12 @@ extern "C" int ndit_op_attention_bench(const void* qkv_, const void* kvy_, const
 }
 
 extern "C" int ndit_op_resid_rms_mod(void* X, const void* o, const void* w_post, const void* tanh_g, const void* w_pre,
-                                     const void* onepls, void* u, int32_t M, int32_t rows_per_batch, int32_t D, float eps,
-                                     void* stream) {
+                                     const void* onepls, const void* shift, void* u, int32_t M, int32_t rows_per_batch, int32_t D,
+                                     float eps, void* stream) {
     cudaError_t e = resid_rms_mod(static_cast<bf16*>(X), static_cast<const bf16*>(o), static_cast<const bf16*>(w_post),
                                   static_cast<const bf16*>(tanh_g), static_cast<const bf16*>(w_pre),
-                                  static_cast<const bf16*>(onepls), static_cast<bf16*>(u), M, rows_per_batch, D, D, eps,
+                                  static_cast<const bf16*>(onepls), static_cast<const bf16*>(shift), static_cast<bf16*>(u), M,
+                                  rows_per_batch, D, D, eps,
                                   static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_resid_rms_mod", e);
 }

@@ -46,7 +46,7 @@ struct AttnPlan {
     const uint8_t* ymask;        // [B, T] bytes (0/1)
     const float* gate_tanh;      // [H] bf16-rounded tanh(gate)
     bf16* out;                   // [B*N, H*hd]
-    int B, N, T, H, Hkv, hd;     // T = 0: no caption segment (class-conditional model); hd = 72 or 48
+    int B, N, T, H, Hkv, hd;     // T = 0: no caption segment (class-conditional model); hd = 72, 48 or 96
     float scale_self, scale_cross;
 };
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream);
@@ -57,20 +57,23 @@ cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_k
 
 // ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
 // X[token, :] = bf16(patch(x[b % n]) . Wx^T + bx)
-cudaError_t patch_embed(const bf16* x, const bf16* Wx, const bf16* bx, bf16* X, int B, int n_unique, int C, int Hh,
-                        int Ww, int D, cudaStream_t s);
+// eol != nullptr (Flag-DiT): every row of patches is closed by the learned [eol] token -> Hp * (Wp + 1) tokens
+cudaError_t patch_embed(const bf16* x, const bf16* Wx, const bf16* bx, const bf16* eol, bf16* X, int B, int n_unique, int C,
+                        int Hh, int Ww, int D, cudaStream_t s);
 // tf[b, 0:256] = bf16(sinusoid(t)); pool[b, :] = bf16(LN(masked mean of cap[b]))  (fp32 storage)
 cudaError_t cond_prepare(float t, const bf16* cap, const uint8_t* mask, const bf16* ln_w, const bf16* ln_b, float* tf,
                          float* pool, int B, int T, int C, int do_caption, cudaStream_t s);
 enum { POST_NONE = 0, POST_SILU = 1, POST_ADALN = 2 };
+enum { ADALN_NEXT = 0, ADALN_CLASS = 1, ADALN_FLAG = 2 };   // chunk layout of the packed adaLN output (see gemv_rows_kernel)
 // out[b,o] = post(bf16(sum_k in'[b,k] W[o,k] + bias[o]) (+ addend[b,o]));  in' = silu(in) if in_silu
 // result goes to out_b (bf16) when non-null, else to out (fp32 storage of bf16 values)
 cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const float* addend, float* out, bf16* out_b,
-                      int B, int O, int K, int in_silu, int post, int adaln_D, int adaln_blocks, cudaStream_t s);
-// optional residual update  X += tanh_g * RMS(o; w_post)   then   u = RMS(X; w_pre) * onepls
+                      int B, int O, int K, int in_silu, int post, int adaln_D, int adaln_blocks, int adaln_kind, cudaStream_t s);
+// optional residual update  X += tanh_g * RMS(o; w_post)  (w_post == nullptr: X += tanh_g * o)
+// then   u = RMS(X; w_pre) * onepls (+ shift)
 cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* w_pre,
-                          const bf16* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
-                          cudaStream_t s);
+                          const bf16* onepls, const bf16* shift, bf16* u, int M, int rows_per_batch, int D, int mod_stride,
+                          float eps, cudaStream_t s);
 // residual update then LN(no affine, eps 1e-6) * onepls -> bf16 -> Linear(D->O)+bias -> out [M,O] (fp32 of bf16 values)
 // (shift: optional additive term of the final modulate, class-conditional model)
 cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
@@ -78,7 +81,7 @@ cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const 
                         int mod_stride, float eps, cudaStream_t s);
 cudaError_t gather_label_rows(const bf16* table, const long long* labels, float* out, int B, int n_rows, int width, cudaStream_t s);
 // rope table [N][hd/2] (cos,sin)
-cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, cudaStream_t s);
+cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, int one_d, cudaStream_t s);
 // in place on qkv [M, ld]: q = bf16(rope(LN(q))), k = bf16(rope(LN(k)))
 cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const bf16* kw, const bf16* kb,
                        const float2* rope, int M, int N_tokens, int H, int Hkv, int hd, cudaStream_t s);
@@ -97,7 +100,7 @@ cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int gr
 __host__ __device__ constexpr int attn_vrows(int hd) { return (hd + 1 + 15) / 16 * 16; }
 // unpatchify + learn_sigma slice + 3-channel CFG combine (+ optional fused Euler update)
 //   tok [2n*N, O] (fp32 of bf16 values) -> v [2n,4,Hh,Ww] bf16;  if y_inout: y = bf16(y + bf16(dt*v))
-cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale,
+cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
                            cudaStream_t s);
 cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s);
 

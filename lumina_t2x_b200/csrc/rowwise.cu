@@ -58,8 +58,8 @@ template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 2)
 resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
                      const bf16* __restrict__ tanh_g, const bf16* __restrict__ w_pre,
-                     const bf16* __restrict__ onepls, bf16* __restrict__ u, int M, int rows_per_batch, int D,
-                     int mod_stride, float eps) {
+                     const bf16* __restrict__ onepls, const bf16* __restrict__ shift, bf16* __restrict__ u, int M,
+                     int rows_per_batch, int D, int mod_stride, float eps) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -94,13 +94,14 @@ resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf1
                 }
             }
         }
-        const float rinv = rsqrtf(warp_sum(ss) / D + eps);
+        // w_post == nullptr: no post-norm, the branch output is gated as it is (Flag-DiT, lumina_t2i model.py:596-609)
+        const float rinv = w_post != nullptr ? rsqrtf(warp_sum(ss) / D + eps) : 0.f;
         const bf16* tg = tanh_g + static_cast<size_t>(b) * mod_stride;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int v = lane + i * 32;
             if (v < nvec) {
-                const uint4 wq = *reinterpret_cast<const uint4*>(w_post + v * 8);
+                const uint4 wq = w_post != nullptr ? *reinterpret_cast<const uint4*>(w_post + v * 8) : make_uint4(0, 0, 0, 0);
                 const uint4 gq = *reinterpret_cast<const uint4*>(tg + v * 8);
                 const uint32_t o4[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
                 const uint32_t w4[4] = {wq.x, wq.y, wq.z, wq.w};
@@ -108,9 +109,12 @@ resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf1
                 uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 of = unpack_bf16(o4[j]);
-                    const bf162 n2 = __floats2bfloat162_rn(of.x * rinv, of.y * rinv);
-                    const bf162 r2 = __hmul2_rn(n2, as_bf162(w4[j]));
+                    bf162 r2 = as_bf162(o4[j]);
+                    if (w_post != nullptr) {
+                        const float2 of = unpack_bf16(o4[j]);
+                        const bf162 n2 = __floats2bfloat162_rn(of.x * rinv, of.y * rinv);
+                        r2 = __hmul2_rn(n2, as_bf162(w4[j]));
+                    }
                     const bf162 p2 = __hmul2_rn(as_bf162(g4[j]), r2);
                     const bf162 x2 = __hadd2_rn(as_bf162(x4[j]), p2);
                     x4[j] = as_u32(x2);
@@ -146,15 +150,20 @@ resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf1
         if (v < nvec) {
             const uint4 wq = *reinterpret_cast<const uint4*>(w_pre + v * 8);
             const uint4 sq = *reinterpret_cast<const uint4*>(op + v * 8);
+            const uint4 hq = shift != nullptr ? *reinterpret_cast<const uint4*>(shift + static_cast<size_t>(b) * mod_stride + v * 8)
+                                              : make_uint4(0, 0, 0, 0);
             const uint32_t w4[4] = {wq.x, wq.y, wq.z, wq.w};
             const uint32_t s4[4] = {sq.x, sq.y, sq.z, sq.w};
+            const uint32_t h4[4] = {hq.x, hq.y, hq.z, hq.w};
             const uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
             uint32_t r4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 xf = unpack_bf16(x4[j]);
                 const bf162 n2 = __floats2bfloat162_rn(xf.x * rinv, xf.y * rinv);
-                r4[j] = as_u32(__hmul2_rn(__hmul2_rn(n2, as_bf162(w4[j])), as_bf162(s4[j])));
+                bf162 m2 = __hmul2_rn(__hmul2_rn(n2, as_bf162(w4[j])), as_bf162(s4[j]));
+                if (shift != nullptr) m2 = __hadd2_rn(m2, as_bf162(h4[j]));      // modulate with shift (lumina_t2i model.py:28-29)
+                r4[j] = as_u32(m2);
             }
             *reinterpret_cast<uint4*>(u + off + v * 8) = make_uint4(r4[0], r4[1], r4[2], r4[3]);
         }
@@ -162,16 +171,17 @@ resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf1
 }
 
 cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* w_pre,
-                          const bf16* onepls, bf16* u, int M, int rows_per_batch, int D, int mod_stride, float eps,
-                          cudaStream_t s) {
+                          const bf16* onepls, const bf16* shift, bf16* u, int M, int rows_per_batch, int D, int mod_stride,
+                          float eps, cudaStream_t s) {
     if (D % 8 != 0 || D > MAX_VEC * 256 || mod_stride % 8 != 0) return cudaErrorInvalidValue;
     const int nv = (D / 8 + 31) / 32;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
 #define LAUNCH(NVV)                                                                                             \
-    resid_rms_mod_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, w_pre, onepls, u, M, rows_per_batch, \
-                                                     D, mod_stride, eps)
+    resid_rms_mod_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, w_pre, onepls, shift, u, M,         \
+                                                     rows_per_batch, D, mod_stride, eps)
     if (nv <= 3) LAUNCH(3);
     else if (nv <= 9) LAUNCH(9);
+    else if (nv <= 12) LAUNCH(12);
     else LAUNCH(MAX_VEC);
 #undef LAUNCH
     return cudaGetLastError();
@@ -220,12 +230,12 @@ final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const
         for (int i = 0; i < NV; ++i) {
             const int v = lane + i * 32;
             if (v < nvec) {
-                float w[8], g[8];
-                load8(w_post + v * 8, w);
+                float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g[8];
+                if (w_post != nullptr) load8(w_post + v * 8, w);
                 load8(tg + v * 8, g);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float n = bf16_round(bf16_round(ov[i][e] * rinv) * w[e]);
+                    const float n = w_post != nullptr ? bf16_round(bf16_round(ov[i][e] * rinv) * w[e]) : ov[i][e];
                     x[i][e] = bf16_round(x[i][e] + bf16_round(g[e] * n));
                 }
             }
@@ -291,6 +301,7 @@ cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const 
                                                    rows_per_batch, D, O, mod_stride, eps)
     if (nv <= 3) LAUNCH(3);
     else if (nv <= 9) LAUNCH(9);
+    else if (nv <= 12) LAUNCH(12);
     else LAUNCH(MAX_VEC);
 #undef LAUNCH
     return cudaGetLastError();
@@ -314,13 +325,18 @@ cudaError_t gather_label_rows(const bf16* table, const long long* labels, float*
 // ---------------------------------------------------------------------------------------------
 // Patchify + x_embedder.  One block per token, thread d-strided over D.
 __global__ void patch_embed_kernel(const bf16* __restrict__ x, const bf16* __restrict__ Wx, const bf16* __restrict__ bx,
-                                   bf16* __restrict__ X, int n_unique, int C, int Hh, int Ww, int D) {
+                                   const bf16* __restrict__ eol, bf16* __restrict__ X, int n_unique, int C, int Hh, int Ww, int D) {
     const int Wp = Ww >> 1, Hp = Hh >> 1;
-    const int tok = blockIdx.x;               // over B * Hp * Wp
-    const int N = Hp * Wp;
+    const int Wt = Wp + (eol != nullptr ? 1 : 0);   // Flag-DiT: a learned [eol] token closes every row of patches
+    const int tok = blockIdx.x;               // over B * Hp * Wt
+    const int N = Hp * Wt;
     const int b = tok / N, t = tok % N;
     const int bi = b % n_unique;              // second half of the batch re-uses the first (model.py:901-902)
-    const int i = t / Wp, j = t % Wp;
+    const int i = t / Wt, j = t % Wt;
+    if (j == Wp) {                            // lumina_t2i model.py:779-785
+        for (int d = threadIdx.x; d < D; d += blockDim.x) X[static_cast<size_t>(tok) * D + d] = eol[d];
+        return;
+    }
     __shared__ float patch[64];
     const int K = C * 4;
     if (threadIdx.x < K) {
@@ -340,10 +356,10 @@ __global__ void patch_embed_kernel(const bf16* __restrict__ x, const bf16* __res
     }
 }
 
-cudaError_t patch_embed(const bf16* x, const bf16* Wx, const bf16* bx, bf16* X, int B, int n_unique, int C, int Hh,
-                        int Ww, int D, cudaStream_t s) {
+cudaError_t patch_embed(const bf16* x, const bf16* Wx, const bf16* bx, const bf16* eol, bf16* X, int B, int n_unique, int C,
+                        int Hh, int Ww, int D, cudaStream_t s) {
     if (C * 4 > 64 || (C * 4) % 8 != 0 || (Hh & 1) || (Ww & 1)) return cudaErrorInvalidValue;
-    patch_embed_kernel<<<B * (Hh / 2) * (Ww / 2), 256, 0, s>>>(x, Wx, bx, X, n_unique, C, Hh, Ww, D);
+    patch_embed_kernel<<<B * (Hh / 2) * (Ww / 2 + (eol != nullptr ? 1 : 0)), 256, 0, s>>>(x, Wx, bx, eol, X, n_unique, C, Hh, Ww, D);
     return cudaGetLastError();
 }
 
@@ -416,7 +432,7 @@ template <int NB>
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const float* __restrict__ in, const bf16* __restrict__ W, const bf16* __restrict__ bias,
                  const float* __restrict__ addend, float* __restrict__ out, bf16* __restrict__ out_b, int O, int K,
-                 int in_silu, int post, int adaln_D, int adaln_blocks) {
+                 int in_silu, int post, int adaln_D, int adaln_blocks, int adaln_kind) {
     extern __shared__ float xin[];            // [NB][K]
     for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
         float v = in[i];
@@ -472,14 +488,22 @@ gemv_rows_kernel(const float* __restrict__ in, const bf16* __restrict__ W, const
                 if (addend) y = bf16_round(y + addend[static_cast<size_t>(b) * O + o]);
                 if (post == POST_SILU) y = bf16_round(silu_f(y));
                 else if (post == POST_ADALN) {
-                    // per layer chunks [scale_msa | gate_msa | scale_mlp | gate_mlp] (model.py:595), then the
-                    // final layer's scale: scale -> bf16(1+scale); gate -> bf16(tanh(gate))
-                    // adaln_blocks < 0: the final layer has [shift | scale] (class-conditional model), shift stays raw
-                    const int nb = adaln_blocks < 0 ? -adaln_blocks : adaln_blocks;
+                    // ADALN_NEXT  per layer [scale_msa | gate_msa | scale_mlp | gate_mlp] (model.py:595), final [scale]
+                    // ADALN_CLASS same layers, final [shift | scale] (Next-DiT-ImageNet models.py:829-833)
+                    // ADALN_FLAG  per layer [shift | scale | gate] x2, plain gates (lumina_t2i model.py:596-609), final [shift | scale]
+                    // stored: scale -> bf16(1+scale); Next-DiT gate -> bf16(tanh(gate)); shift and Flag-DiT gate as they are
                     const int chunk = o / adaln_D;
-                    const bool is_gate = (chunk < nb * 4) && (chunk & 1);
-                    const bool is_shift = adaln_blocks < 0 && chunk == nb * 4;
-                    if (!is_shift) y = is_gate ? bf16_round(tanhf(y)) : bf16_round(1.0f + y);
+                    int kind;                 // 0 shift / plain gate (raw), 1 scale, 2 tanh gate
+                    if (adaln_kind == ADALN_FLAG) {
+                        const int per = chunk < adaln_blocks * 6 ? chunk % 3 : (chunk - adaln_blocks * 6);   // final: 0 shift, 1 scale
+                        kind = per == 1 ? 1 : 0;
+                    } else if (chunk < adaln_blocks * 4) {
+                        kind = (chunk & 1) ? 2 : 1;
+                    } else {
+                        kind = (adaln_kind == ADALN_CLASS && chunk == adaln_blocks * 4) ? 0 : 1;
+                    }
+                    if (kind == 1) y = bf16_round(1.0f + y);
+                    else if (kind == 2) y = bf16_round(tanhf(y));
                 }
                 if (out_b) out_b[static_cast<size_t>(b) * O + o] = __float2bfloat16_rn(y);   // y is bf16-representable
                 else out[static_cast<size_t>(b) * O + o] = y;
@@ -489,12 +513,21 @@ gemv_rows_kernel(const float* __restrict__ in, const bf16* __restrict__ W, const
 }
 
 cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const float* addend, float* out, bf16* out_b,
-                      int B, int O, int K, int in_silu, int post, int adaln_D, int adaln_blocks, cudaStream_t s) {
-    if (B < 1 || B > GEMV_MAXB || K % 8 != 0 || static_cast<size_t>(B) * K * sizeof(float) > 48 * 1024) return cudaErrorInvalidValue;
+                      int B, int O, int K, int in_silu, int post, int adaln_D, int adaln_blocks, int adaln_kind, cudaStream_t s) {
+    if (B < 1 || B > GEMV_MAXB || K % 8 != 0 || static_cast<size_t>(B) * K * sizeof(float) > 64 * 1024) return cudaErrorInvalidValue;
     const int grid = (O + 8 * GEMV_RPW - 1) / (8 * GEMV_RPW);
     const size_t sh = static_cast<size_t>(B) * K * sizeof(float);
+    if (sh > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(gemv_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+    }
 #define LAUNCH(NBB) \
-    gemv_rows_kernel<NBB><<<grid, 256, sh, s>>>(in, W, bias, addend, out, out_b, O, K, in_silu, post, adaln_D, adaln_blocks)
+    gemv_rows_kernel<NBB><<<grid, 256, sh, s>>>(in, W, bias, addend, out, out_b, O, K, in_silu, post, adaln_D, adaln_blocks, adaln_kind)
     switch (B) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
@@ -508,11 +541,21 @@ cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const fl
 // ---------------------------------------------------------------------------------------------
 // RoPE table: tab[token][m] = (cos, sin)(pos * w_{m/2}), m even -> row index, m odd -> column index
 // (model.py:951-961).  w_i = (theta)^(-4i/hd) / linear_factor computed like the reference in fp32.
-__global__ void rope_table_kernel(float2* __restrict__ tab, int Hp, int Wp, int hd, float theta, float linear_factor) {
+__global__ void rope_table_kernel(float2* __restrict__ tab, int Hp, int Wp, int hd, float theta, float linear_factor, int one_d) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = hd >> 1;
     if (idx >= Hp * Wp * half) return;
     const int m = idx % half, tok = idx / half;
+    if (one_d) {
+        // Flag-DiT (lumina_t2i model.py:925-960): 1-D table over the token index (eol tokens included),
+        // freqs 1/theta^(2m/hd), positions divided by the rope scaling factor BEFORE the outer product
+        const float freq = 1.0f / powf(theta, static_cast<float>(2 * m) / static_cast<float>(hd));
+        const float a = (static_cast<float>(tok) / linear_factor) * freq;
+        float sn, cs;
+        sincosf(a, &sn, &cs);
+        tab[idx] = make_float2(cs, sn);
+        return;
+    }
     const int i = tok / Wp, j = tok % Wp;
     const int fi = m >> 1;
     const float freq = 1.0f / powf(theta, static_cast<float>(4 * fi) / static_cast<float>(hd)) / linear_factor;
@@ -523,9 +566,9 @@ __global__ void rope_table_kernel(float2* __restrict__ tab, int Hp, int Wp, int 
     tab[idx] = make_float2(cs, sn);
 }
 
-cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, cudaStream_t s) {
+cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, int one_d, cudaStream_t s) {
     const int n = Hp * Wp * (hd / 2);
-    rope_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(tab, Hp, Wp, hd, theta, linear_factor);
+    rope_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(tab, Hp, Wp, hd, theta, linear_factor, one_d);
     return cudaGetLastError();
 }
 
@@ -617,9 +660,11 @@ ln_rope_qk_kernel(bf16* __restrict__ qkv, int ld, const bf16* __restrict__ qw, c
 
 cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const bf16* kw, const bf16* kb,
                        const float2* rope, int M, int N_tokens, int H, int Hkv, int hd, cudaStream_t s) {
-    if (hd % 8 != 0 || H * hd > 9 * 256 || Hkv * hd > 9 * 256 || ld % 8 != 0) return cudaErrorInvalidValue;
+    if (hd % 8 != 0 || H * hd > 12 * 256 || Hkv * hd > 12 * 256 || ld % 8 != 0) return cudaErrorInvalidValue;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
-    if (Hkv * hd <= 3 * 256)
+    if (H * hd > 9 * 256)
+        ln_rope_qk_kernel<12, 12><<<grid, block, 0, s>>>(qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
+    else if (Hkv * hd <= 3 * 256)
         ln_rope_qk_kernel<9, 3><<<grid, block, 0, s>>>(qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
     else
         ln_rope_qk_kernel<9, 9><<<grid, block, 0, s>>>(qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
@@ -633,15 +678,15 @@ ln_rows_kernel(bf16* __restrict__ x, int ld, size_t lsx, const bf16* __restrict_
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int l = blockIdx.y;
-    uint4 raw[9];
+    uint4 raw[12];
     bf16* xp = x + l * lsx + static_cast<size_t>(row) * ld;
-    ln_segment_load<9>(xp, width, threadIdx.x & 31, raw);
-    ln_rope_segment<9>(xp, width, w + l * lsw, b + l * lsw, nullptr, 8, threadIdx.x & 31, raw);
+    ln_segment_load<12>(xp, width, threadIdx.x & 31, raw);
+    ln_rope_segment<12>(xp, width, w + l * lsw, b + l * lsw, nullptr, 8, threadIdx.x & 31, raw);
 }
 
 cudaError_t ln_rows(bf16* x, int ld, size_t layer_stride_x, const bf16* w, const bf16* b, size_t layer_stride_w, int M,
                     int width, int layers, cudaStream_t s) {
-    if (width % 8 != 0 || width > 9 * 256) return cudaErrorInvalidValue;
+    if (width % 8 != 0 || width > 12 * 256) return cudaErrorInvalidValue;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS, layers), block(ROW_WARPS * 32);
     ln_rows_kernel<<<grid, block, 0, s>>>(x, ld, layer_stride_x, w, b, layer_stride_w, M, width);
     return cudaGetLastError();
@@ -752,13 +797,13 @@ cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int gr
 // unpatchify (token feature order (ph,pw,c_out), model.py:753-754) + keep first C of 2C channels (:859-861)
 // + CFG on channels 0..2 only (:904-913).
 __global__ void unpatchify_cfg_kernel(const float* __restrict__ tok, bf16* __restrict__ v_out, int n, int C, int Hh,
-                                      int Ww, int O, float cfg_scale) {
+                                      int Ww, int O, float cfg_scale, int eol) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over n * C * Hh * Ww
     const int total = n * C * Hh * Ww;
     if (idx >= total) return;
     const int x = idx % Ww, y = (idx / Ww) % Hh, c = (idx / (Ww * Hh)) % C, s = idx / (Ww * Hh * C);
-    const int Wp = Ww >> 1, N = (Hh >> 1) * Wp;
-    const int t = (y >> 1) * Wp + (x >> 1);
+    const int Wt = (Ww >> 1) + eol, N = (Hh >> 1) * Wt;      // eol = 1: the [eol] column is dropped (lumina_t2i model.py:745-755)
+    const int t = (y >> 1) * Wt + (x >> 1);
     const int Cout = O / 4;
     const int f = ((y & 1) * 2 + (x & 1)) * Cout + c;
     const float cond = tok[(static_cast<size_t>(s) * N + t) * O + f];
@@ -775,10 +820,10 @@ __global__ void unpatchify_cfg_kernel(const float* __restrict__ tok, bf16* __res
     }
 }
 
-cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale,
+cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
                            cudaStream_t s) {
     const int total = n * C * Hh * Ww;
-    unpatchify_cfg_kernel<<<(total + 255) / 256, 256, 0, s>>>(tok, v_out, n, C, Hh, Ww, O, cfg_scale);
+    unpatchify_cfg_kernel<<<(total + 255) / 256, 256, 0, s>>>(tok, v_out, n, C, Hh, Ww, O, cfg_scale, eol);
     return cudaGetLastError();
 }
 

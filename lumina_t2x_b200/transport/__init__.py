@@ -15,6 +15,7 @@ from typing import Callable, Optional
 import torch as th
 
 from ..models.dit_llama import DiT_Llama
+from ..models.lumina_t2i import DiT_Llama as FlagDiT
 from ..models.nextdit import NextDiT
 
 __all__ = ["create_transport", "Sampler", "Transport", "ModelType", "PathType", "WeightType", "ODE"]
@@ -91,14 +92,16 @@ _ENGINE_KW = {
     NextDiT: (("cap_feats", "cap_mask", "cfg_scale", "scale_factor", "scale_watershed", "base_seqlen", "proportional_attn"),
               ("cap_feats", "cap_mask", "cfg_scale")),
     DiT_Llama: (("y", "cfg_scale", "rope_scaling_factor", "ntk_factor"), ("y", "cfg_scale")),
+    FlagDiT: (("cap_feats", "cap_mask", "cfg_scale", "rope_scaling_factor", "ntk_factor", "base_seqlen", "proportional_attn"),
+              ("cap_feats", "cap_mask", "cfg_scale")),
 }
 
 
 def _engine_of(model_fn):
     owner = getattr(model_fn, "__self__", None)
-    for cls in _ENGINE_KW:
-        if isinstance(owner, cls) and getattr(model_fn, "__func__", None) is cls.forward_with_cfg:
-            return owner
+    cls = type(owner)
+    if cls in _ENGINE_KW and getattr(model_fn, "__func__", None) is cls.forward_with_cfg:
+        return owner
     return None
 
 

@@ -117,6 +117,23 @@ def import_reference_imagenet():
     return mod
 
 
+def import_reference_flag_dit():
+    """Returns the unmodified lumina_t2i ``models.model`` module (Flag-DiT ``DiT_Llama`` / ``DiT_Llama_5B_patch2``)."""
+    import importlib.util
+    install_shims()
+    _install_fairscale_stub()
+    pkg_dir = REF_ROOT + "/lumina_t2i/models"
+    # the file does ``from .components import RMSNorm``: load it as a submodule of a synthetic package
+    pkg = types.ModuleType("ref_lumina_t2i_models")
+    pkg.__path__ = [pkg_dir]
+    sys.modules["ref_lumina_t2i_models"] = pkg
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("ref_lumina_t2i_models.model")
+    return mod
+
+
 def import_reference_mini():
     """Returns (models_module, transport_module) of lumina_next_t2i_mini, unmodified."""
     install_shims()

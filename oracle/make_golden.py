@@ -131,5 +131,41 @@ def make_imagenet() -> None:
         del m, W
 
 
+def make_flag_dit() -> None:
+    """Flag-DiT (Lumina-T2I, BASELINE config 4 / SURVEY 8a15): unmodified lumina_t2i/models/model.py (fp32, CPU, fairscale
+    at world size 1).  Tiny models with the flagship head_dim 96: default call, proportional attention + NTK factor (the
+    demo's high-resolution kwargs, lumina_t2i/demo.py:169-178), rope scaling on a non-square latent."""
+    from oracle import flag_dit_oracle as FD
+    from oracle.harness.ref_import import import_reference_flag_dit
+    ref = import_reference_flag_dit()
+    torch.set_grad_enabled(False)
+    cases = {
+        "flagdit_tiny_default": dict(hw=(16, 16), T=16, t=0.3, cfg_scale=4.0, kw={}),
+        "flagdit_tiny_prop_ntk": dict(hw=(24, 24), T=24, t=0.7, cfg_scale=2.0,
+                                      kw=dict(proportional_attn=True, base_seqlen=8 * 8 + 8 * 2, ntk_factor=2.25)),
+        "flagdit_tiny_ropescale": dict(hw=(16, 32), T=8, t=0.05, cfg_scale=1.5, kw=dict(rope_scaling_factor=2.0, ntk_factor=1.0)),
+    }
+    cfg = FD.config_tiny96()
+    W = FD.synthetic_weights(cfg, seed=0)
+    for name, c in cases.items():
+        m = ref.DiT_Llama(patch_size=2, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, qk_norm=True,
+                          cap_feat_dim=cfg.cap_feat_dim)
+        m.load_state_dict({k: v.float() for k, v in W.items()}, strict=True)
+        m = m.eval().float()
+        z, cap, mask = FD.synthetic_inputs(cfg, c["hw"], T=c["T"], uncond_len=4, seed=1)
+        t = torch.full((2,), c["t"])
+        out = m.forward_with_cfg(z.float(), t, cap.float(), mask, c["cfg_scale"], **c["kw"])
+        fx = dict(case=name, cfg=dict(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads,
+                                      cap_feat_dim=cfg.cap_feat_dim),
+                  hw=c["hw"], T=c["T"], uncond_len=4, t=c["t"], cfg_scale=c["cfg_scale"], kw=c["kw"], weight_seed=0, input_seed=1,
+                  out_fp32=out.clone())
+        torch.save(fx, os.path.join(OUT, f"{name}.pt"))
+        o = FD.forward_with_cfg(cfg, W, z.float(), t, cap.float(), mask, c["cfg_scale"], precision="fp32", **c["kw"])
+        ob = FD.forward_with_cfg(cfg, W, z, t, cap, mask, c["cfg_scale"], precision="bf16", **c["kw"])
+        print(name, tuple(out.shape), "absmax", out.abs().max().item(), "oracle fp32 rel", ((o - out).abs().max() / out.abs().max()).item(),
+              "bf16-mode rel", ((ob - out).abs().max() / out.abs().max()).item())
+        del m
+
+
 if __name__ == "__main__":
     main()

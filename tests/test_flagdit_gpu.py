@@ -1,0 +1,116 @@
+"""GPU parity of the Flag-DiT path (Lumina-T2I, BASELINE config 4 / SURVEY 8a15) through the drop-in
+``lumina_t2x_b200.models.lumina_t2i`` mirror -> C ABI -> sm_100a kernels, against the oracle and the golden fixtures
+produced by the unmodified lumina_t2i reference.  Tolerances as in test_model_gpu.py."""
+import ctypes as C
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import flag_dit_oracle as FD
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+
+
+def _build(cfg, W, **kw):
+    from lumina_t2x_b200.models import lumina_t2i as models
+    m = models.DiT_Llama(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=True,
+                         cap_feat_dim=cfg.cap_feat_dim, **kw)
+    m.load_state_dict(W, strict=True)
+    return m.eval().to("cuda", dtype=torch.bfloat16)
+
+
+@pytest.mark.parametrize("name", ["flagdit_tiny_default", "flagdit_tiny_prop_ntk", "flagdit_tiny_ropescale"])
+@pytest.mark.parametrize("attn", ["tcgen05", "refkernel"])
+def test_forward_with_cfg_vs_reference_and_oracle(name, attn):
+    fx = torch.load(os.path.join(GOLD, f"{name}.pt"), map_location="cpu", weights_only=False)
+    cfg = FD.FlagDiTConfig(**fx["cfg"])
+    W = FD.synthetic_weights(cfg, seed=fx["weight_seed"])
+    z, cap, mask = FD.synthetic_inputs(cfg, tuple(fx["hw"]), T=fx["T"], uncond_len=fx["uncond_len"], seed=fx["input_seed"])
+    t = torch.full((2,), fx["t"])
+    m = _build(cfg, W, max_tokens=512, max_cap_len=32)
+    m.set_option("attn_ref", 1 if attn == "refkernel" else 0)
+    out = m.forward_with_cfg(z.cuda(), t.cuda(), cap.cuda(), mask.cuda(), fx["cfg_scale"], **fx["kw"]).float().cpu()
+    assert out.shape == z.shape and torch.isfinite(out).all()
+    orc = FD.forward_with_cfg(cfg, W, z, t, cap, mask, fx["cfg_scale"], precision="bf16", **fx["kw"])
+    assert _rel(out, orc) < 2e-2, _rel(out, orc)
+    assert _rel(out, fx["out_fp32"]) < 3e-2, _rel(out, fx["out_fp32"])
+    assert torch.equal(out[:1, :3], out[1:, :3])
+    assert m.parameter_count() == sum(v.numel() for v in W.values())
+
+
+def test_sampler_midpoint_fused_equals_generic_loop():
+    """lumina_t2i/demo.py:169-186: midpoint solve with the demo's high-resolution kwargs, inside the engine vs the
+    PyTorch-driven fixed-grid loop calling forward_with_cfg."""
+    from lumina_t2x_b200 import transport
+    cfg = FD.config_tiny96()
+    W = FD.synthetic_weights(cfg, seed=3)
+    m = _build(cfg, W, max_tokens=512, max_cap_len=32)
+    z, cap, mask = FD.synthetic_inputs(cfg, (16, 24), T=16, uncond_len=4, seed=5)
+    z, cap, mask = z.cuda(), cap.cuda(), mask.cuda()
+    kw = dict(cap_feats=cap, cap_mask=mask, cfg_scale=4.0, proportional_attn=True, base_seqlen=80, ntk_factor=1.5)
+    fn = transport.Sampler(transport.create_transport("Linear", "velocity")).sample_ode(sampling_method="midpoint", num_steps=4,
+                                                                                      time_shifting_factor=4.0)
+    a = fn(z, m.forward_with_cfg, **kw)
+    grid = transport._time_grid(0, 1, 4, 4.0).cuda()
+    b = transport._fixed_grid_torch(lambda t, x: m.forward_with_cfg(x, torch.ones(2, device="cuda") * t, **kw), z, grid, "midpoint")
+    assert a.shape == (4, 2, 4, 16, 24) and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,N,T,H,Hkv", [(2, 256, 40, 4, 4), (1, 520, 0, 2, 2), (2, 4160, 128, 4, 2)])
+@pytest.mark.parametrize("use_ref", [1, 0], ids=["refkernel", "tcgen05"])
+def test_attention_head_dim_96(B, N, T, H, Hkv, use_ref):
+    """fused self + gated caption attention at head_dim 96, ragged token counts (4160 = 64 x 65 tokens of a 1024^2 image)."""
+    from lumina_t2x_b200 import _lib
+    lib = _lib.load()
+    hd = 96
+    g = torch.Generator(device="cuda").manual_seed(N + T)
+    qkv = torch.randn(B * N, (H + 2 * Hkv) * hd, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.full((B * N, H * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    kvy = torch.randn(B * max(T, 1), 2 * Hkv * hd, device="cuda", generator=g).to(torch.bfloat16)
+    ymask = torch.ones(B, max(T, 1), dtype=torch.uint8, device="cuda")
+    if T:
+        ymask[-1, T // 3:] = 0
+    gate = torch.tanh(torch.randn(H, device="cuda", generator=g)).to(torch.bfloat16).float()
+    ss, sc = math.sqrt(math.log(N, 64) / hd), 1 / math.sqrt(hd)
+    rc = lib.ndit_op_attention_hd(C.c_void_p(qkv.data_ptr()), C.c_void_p(kvy.data_ptr()) if T else None,
+                                  C.c_void_p(ymask.data_ptr()) if T else None, C.c_void_p(gate.data_ptr()) if T else None,
+                                  C.c_void_p(out.data_ptr()), B, N, T, H, Hkv, hd, ss, sc, use_ref, None)
+    torch.cuda.synchronize()
+    assert rc == 0, lib.ndit_last_error(None)
+    rep = H // Hkv
+    q = qkv[:, : H * hd].float().view(B, N, H, hd).permute(0, 2, 1, 3)
+    k = qkv[:, H * hd: (H + Hkv) * hd].float().view(B, N, Hkv, hd).repeat_interleave(rep, 2).permute(0, 2, 1, 3)
+    v = qkv[:, (H + Hkv) * hd:].float().view(B, N, Hkv, hd).repeat_interleave(rep, 2).permute(0, 2, 1, 3)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * ss, -1) @ v).to(torch.bfloat16).float()
+    if T:
+        ky = kvy[:, : Hkv * hd].float().view(B, T, Hkv, hd).repeat_interleave(rep, 2).permute(0, 2, 1, 3)
+        vy = kvy[:, Hkv * hd:].float().view(B, T, Hkv, hd).repeat_interleave(rep, 2).permute(0, 2, 1, 3)
+        s = (q @ ky.transpose(-1, -2) * sc).masked_fill(ymask[:, None, None, :] == 0, float("-inf"))
+        oy = (torch.softmax(s, -1) @ vy).to(torch.bfloat16).float()
+        ref = ref + (oy * gate.view(1, -1, 1, 1)).to(torch.bfloat16).float()
+    ref = ref.permute(0, 2, 1, 3).reshape(B * N, H * hd)
+    assert torch.isfinite(out.float()).all()
+    assert ((out.float() - ref).abs() <= 2e-2 * ref.abs().max()).all()
+
+
+def test_flagship_5b_dims_two_layers_1024px():
+    """BASELINE config 4 dims (DiT_Llama_5B_patch2: D=3072, H=32 MHA, head_dim 96, F=8192, LLaMA-7B captions C=4096),
+    1024x1024 image = latent 128x128 = 64 x 65 = 4160 tokens, demo kwargs; 2 of the 32 layers so the CPU oracle finishes
+    in seconds on the GPU box's host cores."""
+    cfg = FD.FlagDiTConfig(n_layers=2)
+    W = FD.synthetic_weights(cfg, seed=0)
+    z, cap, mask = FD.synthetic_inputs(cfg, (128, 128), T=64, uncond_len=8, seed=1)
+    t = torch.full((2,), 0.4)
+    kw = dict(proportional_attn=True, base_seqlen=64 * 64 + 64 * 2, ntk_factor=1.0)
+    m = _build(cfg, W, max_tokens=4160, max_cap_len=64)
+    out = m.forward_with_cfg(z.cuda(), t.cuda(), cap.cuda(), mask.cuda(), 4.0, **kw).float().cpu()
+    orc = FD.forward_with_cfg(cfg, W, z, t, cap, mask, 4.0, precision="bf16", **kw)
+    assert torch.isfinite(out).all()
+    assert _rel(out, orc) < 2e-2, _rel(out, orc)

@@ -25,7 +25,7 @@ def test_cabi_loads_and_exports_header_symbols():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ndit_abi_version() == 2
+    assert lib.ndit_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
@@ -65,6 +65,19 @@ def test_class_conditional_state_dict_keys_match_reference_inventory():
     assert hasattr(models, "DiT_Llama_600M_patch2") and hasattr(models, "DiT_Llama_2B_patch2")
     with pytest.raises(RuntimeError):        # no GPU / no CUDA library -> loud failure, never a CPU fallback
         m.forward_with_cfg(torch.zeros(2, 4, 16, 16), torch.zeros(2), torch.tensor([1, cfg.num_classes]), 2.0)
+
+
+def test_flag_dit_state_dict_keys_match_reference_inventory():
+    from lumina_t2x_b200.models import lumina_t2i as models
+    from oracle import flag_dit_oracle as FD
+    cfg = FD.config_tiny96()
+    m = models.DiT_Llama(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, qk_norm=True, cap_feat_dim=cfg.cap_feat_dim)
+    want = FD.state_dict_shapes(cfg)         # pinned against the reference by make_golden.make_flag_dit (strict load)
+    have = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert have == want
+    assert hasattr(models, "DiT_Llama_5B_patch2")
+    with pytest.raises(RuntimeError):
+        m.forward_with_cfg(torch.zeros(2, 4, 16, 16), torch.zeros(2), torch.zeros(2, 8, cfg.cap_feat_dim), torch.ones(2, 8), 2.0)
 
 
 def test_create_transport_and_grid_semantics():

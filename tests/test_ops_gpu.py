@@ -130,7 +130,7 @@ def test_ln_rope(lib, B, Hp, Wp, H, Hkv, theta, lin):
     kb = (0.1 * torch.randn(Hkv * hd, device="cuda", generator=g)).to(torch.bfloat16)
     ref = _ln_rope_ref(qkv, qw, qb, kw, kb, B, Hp, Wp, H, Hkv, hd, theta, lin)
     got = qkv.clone()
-    rc = lib.ndit_op_ln_rope(ptr(got), ptr(qw), ptr(qb), ptr(kw), ptr(kb), B, Hp, Wp, H, Hkv, hd, theta, lin, None)
+    rc = lib.ndit_op_ln_rope(ptr(got), ptr(qw), ptr(qb), ptr(kw), ptr(kb), B, Hp, Wp, H, Hkv, hd, theta, lin, 0, None)
     torch.cuda.synchronize()
     assert rc == 0, lib.ndit_last_error(None)
     assert torch.equal(got[:, (H + Hkv) * hd:], qkv[:, (H + Hkv) * hd:]), "v must be untouched"
@@ -210,7 +210,7 @@ def test_resid_rms_mod(lib, M, rows, D, with_o):
     Xg = X.clone()
     u = torch.full((M, D), float("nan"), device="cuda", dtype=torch.bfloat16)
     rc = lib.ndit_op_resid_rms_mod(ptr(Xg), ptr(o) if with_o else None, ptr(w_post), ptr(tanh_g_b), ptr(w_pre), ptr(onepls_b),
-                                   ptr(u), M, rows, D, 1e-5, None)
+                                   None, ptr(u), M, rows, D, 1e-5, None)
     torch.cuda.synchronize()
     assert rc == 0, lib.ndit_last_error(None)
     # identical rounding points; reduction order may flip a bf16 rounding: <= 1 ulp on a few elements
