@@ -1,4 +1,4 @@
-// Fused image self-attention (+ optional gated caption cross-attention) for one Next-DiT block; head_dim 72 or 48.
+// Fused image self-attention (+ optional gated caption cross-attention) for one DiT block; head_dim 72, 48 or 96.
 //
 // Replaces, in lumina_next_t2i/models/model.py: _upad_input/flash_attn_varlen_func/pad_input (:387-404),
 // the GQA repeat + masked SDPA over the caption tokens (:421-432), the tanh(gate) scale and add (:433-434);
@@ -10,7 +10,7 @@
 //   warp  0     TMA producer: Q tiles once, then a 3-stage ring of K / V^T tiles (self blocks, then caption blocks)
 //   warps 1,2   MMA issuers (one per 128-row query tile):  S = Q K^T (tcgen05.mma 128x128x16; for head_dim 72: 4 k-steps
 //               from a 128B-swizzled [rows x 64] tile + 1 from a 32B-swizzled [rows x 16] tile, the zero padding 72 -> 80
-//               comes from TMA out-of-bounds fill; for head_dim 48: 3 k-steps), then O += P V (128 x HDP x 16, 8 k-steps,
+//               comes from TMA out-of-bounds fill; head_dim 48: 3 k-steps; head_dim 96: 4 + 2), then O += P V (128 x HDP x 16, 8 k-steps,
 //               P from shared memory).  One issuer per tile with plain blocking waits, so the two tiles are free to run
 //               half a softmax period apart (tile B is started late on purpose).
 //   warps 4-7   softmax warpgroup for query tile A (rows 0..127): one thread per row (TMEM lane)
