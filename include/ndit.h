@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NDIT_ABI_VERSION 3
+#define NDIT_ABI_VERSION 4
 
 typedef struct ndit_engine* ndit_handle;
 
@@ -63,6 +63,12 @@ typedef struct ndit_config {
                              * a 1-D RoPE over the token index :925-960, a learned [eol] token closing each row of patches
                              * :779-785 (max_tokens counts them: H/2 * (W/2 + 1)) and shift + scale in the final layer
                              * :655-656.  head_dim = dim / n_heads must be 72, 48 or 96 in all variants. */
+    int32_t moe_time_experts;   /* class-conditional model only (Next-DiT-MoE/models/): mixture-of-experts FFN, top-2.   */
+    int32_t moe_space_experts;  /* (8, 0): models.py, gate = Linear(timestep embedding) :451-477 -> one pair of experts per
+                                 * sample and layer; (0, 8): models1.py, gate = Linear(token) :451-477; (4, 4): models2.py,
+                                 * time MoE then space MoE, 6-chunk adaLN :451-506,760-808.  (0, 0): dense FFN.  Expert
+                                 * outputs are accumulated in expert-index order in bf16, like the reference's
+                                 * ``results[idx] += w * expert(x[idx])``; top-k ties go to the lower expert index. */
 } ndit_config;
 
 /* Per-call arguments of NextDiT.forward_with_cfg (model.py:866-913) that are not tensors. */

@@ -17,7 +17,8 @@ class NditConfig(C.Structure):
                 ("cap_feat_dim", C.c_int32), ("in_channels", C.c_int32), ("patch_size", C.c_int32),
                 ("multiple_of", C.c_int32), ("learn_sigma", C.c_int32), ("norm_eps", C.c_float),
                 ("max_tokens", C.c_int32), ("max_cap_len", C.c_int32), ("max_batch", C.c_int32),
-                ("num_classes", C.c_int32), ("flag_dit", C.c_int32)]
+                ("num_classes", C.c_int32), ("flag_dit", C.c_int32),
+                ("moe_time_experts", C.c_int32), ("moe_space_experts", C.c_int32)]
 
 
 class NditStepParams(C.Structure):
@@ -74,7 +75,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ndit_abi_version() != 3:
+    if lib.ndit_abi_version() != 4:
         raise RuntimeError("libndit_b200.so ABI version mismatch")
     _lib = lib
     return lib

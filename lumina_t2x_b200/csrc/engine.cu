@@ -68,7 +68,17 @@ struct ndit_engine {
     int vrows = 80;                          // V^T rows per (batch, kv head): head_dim + ones row, padded to 16
     bool cls = false;                        // class-conditional variant (DiT_Llama): labels instead of captions
     bool flag = false;                       // Flag-DiT (Lumina-T2I DiT_Llama): shift/scale/gate adaLN, 1-D RoPE, eol tokens
-    int NCH = 4;                             // adaLN chunks per layer: 4 (scale, gate) x2 or 6 (shift, scale, gate) x2
+    int NCH = 4;                             // adaLN chunks per layer: 4 (scale, gate) x2, 6 (shift, scale, gate) x2, 6 = MoE "both"
+    // FFN sub-blocks of one layer (Next-DiT-MoE): kind 0 dense, 1 time-gated MoE, 2 token-gated MoE
+    int NF = 1;
+    int ffn_kind[2] = {0, 0}, ffn_E[2] = {0, 0}, ffn_slot0[2] = {0, 0};
+    const char* ffn_name[2] = {"feed_forward", nullptr};
+    const char* ffn_norm_name[2] = {"ffn_norm", nullptr};
+    int S = 1;                               // FFN weight slots per layer (sum over sub-blocks of max(E, 1))
+    bf16 *Wg_time = nullptr, *Wg_space = nullptr;   // [L][E][cd] / [L][E][D]
+    bf16 *oE = nullptr, *wtok = nullptr;     // expert outputs [E][M][D], token weights [M][E]
+    float *temb = nullptr, *tlogits = nullptr;      // [B][cd], [B][L*E]
+    float* tlogits_host = nullptr;           // pinned, [L*E]
     int FD = 1;                              // final-layer adaLN chunks: 1 (scale) or 2 (shift, scale)
     bf16* Yemb = nullptr;                    // [num_classes + 1, cd] label embedding table
     int device = 0, num_sms = 148;
@@ -194,6 +204,22 @@ static int create_impl(ndit_engine* h) {
     if (h->cls && h->flag) return h->fail(NDIT_ERR_INVALID, "num_classes > 0 and flag_dit are mutually exclusive");
     h->FD = (h->cls || h->flag) ? 2 : 1;
     h->NCH = h->flag ? 6 : 4;
+    if (c.moe_time_experts < 0 || c.moe_space_experts < 0 || c.moe_time_experts > 8 || c.moe_space_experts > 8 ||
+        c.moe_time_experts == 1 || c.moe_space_experts == 1)
+        return h->fail(NDIT_ERR_INVALID, "MoE expert counts must be 0 or 2..8");
+    if ((c.moe_time_experts || c.moe_space_experts) && !h->cls)
+        return h->fail(NDIT_ERR_INVALID, "the MoE FFN belongs to the class-conditional model (num_classes > 0)");
+    if (c.moe_time_experts && c.moe_space_experts) {          // models2.py: time MoE then space MoE, 6-chunk adaLN
+        h->NF = 2; h->NCH = 6;
+        h->ffn_kind[0] = 1; h->ffn_E[0] = c.moe_time_experts; h->ffn_name[0] = "feed_forward_time"; h->ffn_norm_name[0] = "ffn_norm_time";
+        h->ffn_kind[1] = 2; h->ffn_E[1] = c.moe_space_experts; h->ffn_name[1] = "feed_forward_space"; h->ffn_norm_name[1] = "ffn_norm_space";
+    } else if (c.moe_time_experts) {                          // models.py
+        h->ffn_kind[0] = 1; h->ffn_E[0] = c.moe_time_experts;
+    } else if (c.moe_space_experts) {                         // models1.py
+        h->ffn_kind[0] = 2; h->ffn_E[0] = c.moe_space_experts;
+    }
+    h->S = 0;
+    for (int f = 0; f < h->NF; ++f) { h->ffn_slot0[f] = h->S; h->S += h->ffn_E[f] > 0 ? h->ffn_E[f] : 1; }
     h->hd = c.dim / c.n_heads; h->C = h->cls ? 0 : c.cap_feat_dim; h->cd = c.dim < 1024 ? c.dim : 1024;
     if (h->hd != 72 && h->hd != 48 && h->hd != 96) return h->fail(NDIT_ERR_INVALID, "head_dim must be 72, 48 or 96 (got %d)", h->hd);
     h->vrows = attn_vrows(h->hd);
@@ -220,10 +246,13 @@ static int create_impl(ndit_engine* h) {
     ALLOC(Wada, (L * NCH * D + h->FD * D) * cd); ALLOC(bada, L * NCH * D + h->FD * D);
     if (h->cls) ALLOC(Yemb, ((size_t)c.num_classes + 1) * cd);
     ALLOC(Wout, (size_t)h->O * D); ALLOC(bout, h->O); ALLOC(pad_token, D); ALLOC(eol_token, D);
-    ALLOC(Wqkv, L * h->Wq * D); ALLOC(Wo, L * D * D); ALLOC(W13, L * 2 * F * D); ALLOC(W2, L * D * F);
+    const size_t S = h->S, NF = h->NF;
+    ALLOC(Wqkv, L * h->Wq * D); ALLOC(Wo, L * D * D); ALLOC(W13, L * S * 2 * F * D); ALLOC(W2, L * S * D * F);
+    if (c.moe_time_experts) ALLOC(Wg_time, L * c.moe_time_experts * cd);
+    if (c.moe_space_experts) ALLOC(Wg_space, L * c.moe_space_experts * D);
     ALLOC(Wkvy, L * 2 * KV * C);
     ALLOC(qn_w, L * D); ALLOC(qn_b, L * D); ALLOC(kn_w, L * KV); ALLOC(kn_b, L * KV); ALLOC(kyn_w, L * KV); ALLOC(kyn_b, L * KV);
-    ALLOC(an1, L * D); ALLOC(an2, L * D); ALLOC(fn1, L * D); ALLOC(fn2, L * D); ALLOC(yn, L * C);
+    ALLOC(an1, L * D); ALLOC(an2, L * D); ALLOC(fn1, L * D); ALLOC(fn2, NF * L * D); ALLOC(yn, L * C);
     ALLOC(gate_raw, L * h->H); ALLOC(gate_tanh, L * h->H);
 
     h->Bmax = c.max_batch; h->Tmax = h->cls ? 0 : c.max_cap_len; h->Tpad_max = (h->Tmax + 7) / 8 * 8;
@@ -234,6 +263,11 @@ static int create_impl(ndit_engine* h) {
     ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
     ALLOC(ymask, B * T); ALLOC(pool, B * C); ALLOC(capemb, B * cd); ALLOC(tf, B * 256); ALLOC(h1, B * cd); ALLOC(sc, B * cd);
     ALLOC(mod, B * (L * NCH * D + h->FD * D)); ALLOC(tok, M * h->O);
+    if (S > 1) {
+        int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
+        ALLOC(oE, (size_t)emax * M * D); ALLOC(wtok, M * 8); ALLOC(temb, B * cd); ALLOC(tlogits, B * L * 8);
+        CK(cudaMallocHost(&h->tlogits_host, L * 8 * sizeof(float)));
+    }
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
     ALLOC(vel, lat); ALLOC(ystate, lat); ALLOC(ymid, lat); ALLOC(stage_z, lat); ALLOC(stage_cap, B * T * C); ALLOC(stage_mask, B * T);
     for (int i = 0; i < 2; ++i) {
@@ -273,6 +307,7 @@ extern "C" int ndit_destroy(ndit_handle h) {
     if (!h) return NDIT_OK;
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    if (h->tlogits_host) cudaFreeHost(h->tlogits_host);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return NDIT_OK;
@@ -352,6 +387,46 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
     if (sscanf(key, "layers.%d.%n", &li, &pos) >= 1 && pos > 0 && li >= 0 && li < h->L) {
         const char* sub = key + pos;
         const size_t l = li;
+        // FFN sub-blocks: "<name>.w{1,2,3}.weight" (dense) or "<name>.experts.<j>.w{1,2,3}.weight" + "<name>.gate.weight" (MoE)
+        for (int f = 0; f < h->NF; ++f) {
+            const size_t nl = strlen(h->ffn_name[f]);
+            if (strncmp(sub, h->ffn_name[f], nl) != 0 || sub[nl] != '.') continue;
+            const char* rest = sub + nl + 1;
+            const int E = h->ffn_E[f];
+            size_t slot = h->ffn_slot0[f];
+            if (E > 0) {
+                if (!strcmp(rest, "gate.weight")) {
+                    const bool time = h->ffn_kind[f] == 1;
+                    const size_t gc = time ? cd : D;
+                    if (int er = want((size_t)E, gc)) return er;
+                    const bool fresh = h->seen.insert(key).second;
+                    return place(h, (time ? h->Wg_time : h->Wg_space) + l * E * gc, gc, src, dtype, (size_t)E, gc, 0, 0, 0, s, fresh);
+                }
+                int ej = -1, p2 = 0;
+                if (sscanf(rest, "experts.%d.%n", &ej, &p2) < 1 || p2 == 0 || ej < 0 || ej >= E)
+                    return h->fail(NDIT_ERR_INVALID, "unexpected state-dict key: %s", key);
+                rest += p2;
+                slot += ej;
+            }
+            const size_t S_ = h->S;
+            bf16* w13 = h->W13 + (l * S_ + slot) * 2 * F * D;
+            bf16* w2 = h->W2 + (l * S_ + slot) * D * F;
+            const bool fresh = h->seen.count(key) == 0;
+            if (!strcmp(rest, "w1.weight")) { if (int er = want(F, D)) return er; h->seen.insert(key); return place(h, w13, D, src, dtype, F, D, 128, 256, 0, s, fresh); }
+            if (!strcmp(rest, "w3.weight")) { if (int er = want(F, D)) return er; h->seen.insert(key); return place(h, w13, D, src, dtype, F, D, 128, 256, 128, s, fresh); }
+            if (!strcmp(rest, "w2.weight")) { if (int er = want(D, F)) return er; h->seen.insert(key); return place(h, w2, F, src, dtype, D, F, 0, 0, 0, s, fresh); }
+            return h->fail(NDIT_ERR_INVALID, "unexpected state-dict key: %s", key);
+        }
+        if (h->cls) {
+            for (int f = 0; f < h->NF; ++f) {
+                const std::string nk = std::string(h->ffn_norm_name[f]) + ".weight";
+                if (nk == sub) {
+                    if (int er = want(D, 0)) return er;
+                    const bool fresh = h->seen.insert(key).second;
+                    return place(h, h->fn2 + ((size_t)f * h->L + l) * D, 1, src, dtype, D, 1, 0, 0, 0, s, fresh);
+                }
+            }
+        }
         struct Ent { const char* name; bf16* dst; size_t dst_ld, rows, cols, blk, blk_stride, row0; };
         const Ent ents[] = {
             {"attention.wq.weight", h->Wqkv + l * Wq * D, D, D, D, 0, 0, 0},
@@ -360,10 +435,7 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
             {"attention.wo.weight", h->Wo + l * D * D, D, D, D, 0, 0, 0},
             {"attention.wk_y.weight", h->Wkvy + l * 2 * KV * C, C, KV, C, 0, 0, 0},
             {"attention.wv_y.weight", h->Wkvy + l * 2 * KV * C, C, KV, C, 0, 0, KV},
-            // w1|w3 interleaved per 256-row block for the SwiGLU epilogue
-            {"feed_forward.w1.weight", h->W13 + l * 2 * F * D, D, F, D, 128, 256, 0},
-            {"feed_forward.w3.weight", h->W13 + l * 2 * F * D, D, F, D, 128, 256, 128},
-            {"feed_forward.w2.weight", h->W2 + l * D * F, F, D, F, 0, 0, 0},
+            // (feed_forward.w1|w3|w2 are handled above: w1|w3 interleaved per 256-row block for the SwiGLU epilogue)
             {"adaLN_modulation.1.weight", h->Wada + l * NCH * D * cd, cd, NCH * D, cd, 0, 0, 0},
         };
         for (const Ent& e : ents) {
@@ -390,8 +462,8 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
         const VEnt cls_vents[] = {
             {"attention.q_norm.weight", h->qn_w + l * D, D}, {"attention.q_norm.bias", h->qn_b + l * D, D},
             {"attention.k_norm.weight", h->kn_w + l * KV, KV}, {"attention.k_norm.bias", h->kn_b + l * KV, KV},
-            {"attention_norm.weight", h->an2 + l * D, D}, {"ffn_norm.weight", h->fn2 + l * D, D},
-            {"adaLN_modulation.1.bias", h->bada + l * 4 * D, 4 * D},
+            {"attention_norm.weight", h->an2 + l * D, D},
+            {"adaLN_modulation.1.bias", h->bada + l * NCH * D, NCH * D},
         };
         // Flag-DiT block (lumina_t2i model.py:505-622): one weighted RMSNorm in front of each sub-block, no post-norms
         const VEnt flag_vents[] = {
@@ -445,17 +517,26 @@ static void expected_keys(const ndit_engine* h, std::vector<std::string>* out) {
     if (h->flag) out->push_back("eol_token");
     const char* per[] = {"attention.wq.weight", "attention.wk.weight", "attention.wv.weight", "attention.wo.weight",
                          "attention.q_norm.weight", "attention.q_norm.bias", "attention.k_norm.weight", "attention.k_norm.bias",
-                         "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight",
                          "adaLN_modulation.1.weight", "adaLN_modulation.1.bias"};
     const char* per_t2i[] = {"attention.gate", "attention.wk_y.weight", "attention.wv_y.weight", "attention.ky_norm.weight",
                              "attention.ky_norm.bias", "attention_norm1.weight", "attention_norm2.weight", "ffn_norm1.weight",
                              "ffn_norm2.weight", "attention_y_norm.weight"};
-    const char* per_cls[] = {"attention_norm.weight", "ffn_norm.weight"};
+    const char* per_cls[] = {"attention_norm.weight"};
     const char* per_flag[] = {"attention.gate", "attention.wk_y.weight", "attention.wv_y.weight", "attention.ky_norm.weight",
                               "attention.ky_norm.bias", "attention_norm.weight", "ffn_norm.weight", "attention_y_norm.weight"};
     for (int l = 0; l < h->L; ++l) {
         const std::string pre = "layers." + std::to_string(l) + ".";
         for (const char* k : per) out->push_back(pre + k);
+        for (int f = 0; f < h->NF; ++f) {
+            const std::string fp = pre + h->ffn_name[f] + ".";
+            const int E = h->ffn_E[f];
+            for (int j = 0; j < (E > 0 ? E : 1); ++j) {
+                const std::string ep = E > 0 ? fp + "experts." + std::to_string(j) + "." : fp;
+                out->push_back(ep + "w1.weight"); out->push_back(ep + "w2.weight"); out->push_back(ep + "w3.weight");
+            }
+            if (E > 0) out->push_back(fp + "gate.weight");
+            if (h->cls) out->push_back(pre + h->ffn_norm_name[f] + ".weight");
+        }
         if (h->cls) for (const char* k : per_cls) out->push_back(pre + k);
         else if (h->flag) for (const char* k : per_flag) out->push_back(pre + k);
         else for (const char* k : per_t2i) out->push_back(pre + k);
@@ -565,13 +646,17 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
     const int M = batch * N;
     const size_t D = h->D, F = h->F, L = h->L, Wq = h->Wq, KV = (size_t)h->Hkv * h->hd, C = h->C;
     if (M != h->plan_M) {
-        h->p_qkv.resize(L); h->p_wo.resize(L); h->p_w13.resize(L); h->p_w2.resize(L);
+        const size_t S = h->S;      // FFN weight slots per layer (experts); slot plans write to h->o unless the launch overrides C
+        h->p_qkv.resize(L); h->p_wo.resize(L); h->p_w13.resize(L * S); h->p_w2.resize(L * S);
         for (size_t l = 0; l < L; ++l) {
             int e = 0;
             e |= make_gemm_plan(&h->p_qkv[l], h->u, (int)D, h->Wqkv + l * Wq * D, h->qkv, (int)Wq, M, (int)Wq, (int)D, EPI_STORE, h->num_sms);
             e |= make_gemm_plan(&h->p_wo[l], h->attn, (int)D, h->Wo + l * D * D, h->o, (int)D, M, (int)D, (int)D, EPI_STORE, h->num_sms);
-            e |= make_gemm_plan(&h->p_w13[l], h->u, (int)D, h->W13 + l * 2 * F * D, h->hbuf, (int)F, M, (int)(2 * F), (int)D, EPI_SWIGLU, h->num_sms);
-            e |= make_gemm_plan(&h->p_w2[l], h->hbuf, (int)F, h->W2 + l * D * F, h->o, (int)D, M, (int)D, (int)F, EPI_STORE, h->num_sms);
+            for (size_t sl = 0; sl < S; ++sl) {
+                const size_t i = l * S + sl;
+                e |= make_gemm_plan(&h->p_w13[i], h->u, (int)D, h->W13 + i * 2 * F * D, h->hbuf, (int)F, M, (int)(2 * F), (int)D, EPI_SWIGLU, h->num_sms);
+                e |= make_gemm_plan(&h->p_w2[i], h->hbuf, (int)F, h->W2 + i * D * F, h->o, (int)D, M, (int)D, (int)F, EPI_STORE, h->num_sms);
+            }
             if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
         }
         h->plan_M = M;
@@ -659,8 +744,31 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, nullptr, batch, h->cd, 256, 0, POST_SILU, 0, 0, 0, s));
     // sc = bf16(silu(c)), c = bf16(temb + cap_emb)
     PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, nullptr, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, 0, s));
-    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L,
+    PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L * NCH,
                             h->flag ? ADALN_FLAG : (h->cls ? ADALN_CLASS : ADALN_NEXT), s));
+    // time-gated MoE (Next-DiT-MoE models.py:459-477): the gate sees only the timestep embedding, so one pair of experts
+    // serves the whole batch in every layer.  Logits for all layers in one GEMV, one small D2H read, selection on the host.
+    int t_sel[64][2];
+    float t_w[64][2];
+    const int Et = h->cfg.moe_time_experts;
+    if (Et > 0) {
+        if (L > 64) return h->fail(NDIT_ERR_INVALID, "time-gated MoE supports at most 64 layers");
+        PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, nullptr, h->temb, nullptr, batch, h->cd, h->cd, 0, POST_NONE, 0, 0, 0, s));
+        PROF(KC_COND, gemv_rows(h->temb, h->Wg_time, nullptr, nullptr, h->tlogits, nullptr, batch, L * Et, h->cd, 0, POST_NONE, 0, 0, 0, s));
+        CK(cudaMemcpyAsync(h->tlogits_host, h->tlogits, (size_t)L * Et * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int l = 0; l < L; ++l) {
+            const float* lg = h->tlogits_host + (size_t)l * Et;
+            int i0 = 0, i1 = -1;                              // top-2, ties: lower expert index first
+            for (int e = 1; e < Et; ++e) if (lg[e] > lg[i0]) i0 = e;
+            for (int e = 0; e < Et; ++e) if (e != i0 && (i1 < 0 || lg[e] > lg[i1])) i1 = e;
+            const float e1 = expf(lg[i1] - lg[i0]);
+            const float w0 = host_bf16_round(1.0f / (1.0f + e1)), w1 = host_bf16_round(e1 / (1.0f + e1));
+            // accumulation runs in expert-index order
+            if (i0 < i1) { t_sel[l][0] = i0; t_sel[l][1] = i1; t_w[l][0] = w0; t_w[l][1] = w1; }
+            else { t_sel[l][0] = i1; t_sel[l][1] = i0; t_w[l][0] = w1; t_w[l][1] = w0; }
+        }
+    }
     // per-layer modulation chunks (offsets in units of D): Next-DiT [1+scale_msa, tanh gate_msa, 1+scale_mlp, tanh gate_mlp];
     // Flag-DiT [shift_msa, 1+scale_msa, gate_msa, shift_mlp, 1+scale_mlp, gate_mlp]
     const int o_sc1 = h->flag ? 1 : 0, o_g1 = h->flag ? 2 : 1, o_sc2 = h->flag ? 4 : 2, o_g2 = h->flag ? 5 : 3;
@@ -688,18 +796,48 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
         PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->flag ? nullptr : h->an2 + (size_t)l * D, ml + (size_t)o_g1 * D, h->fn1 + (size_t)l * D,
                                        ml + (size_t)o_sc2 * D, h->flag ? ml + 3 * (size_t)D : nullptr, h->u, M, N, D, mod_stride,
                                        h->cfg.norm_eps, s));
-        PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[l], s));
-        PROF(KC_GEMM_W2, gemm_bf16_tn(h->p_w2[l], s));
-        if (l + 1 < L) {
-            PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->flag ? nullptr : h->fn2 + (size_t)l * D, ml + (size_t)o_g2 * D,
-                                           h->an1 + (size_t)(l + 1) * D, mn + (size_t)o_sc1 * D, h->flag ? mn : nullptr, h->u, M, N, D,
-                                           mod_stride, h->cfg.norm_eps, s));
-        } else {
-            // final adaLN: Next-DiT T2I [scale]; class-conditional and Flag-DiT [shift | scale]
-            const bf16* fin = h->mod + (size_t)L * NCH * D;
-            const bool fsh = h->cls || h->flag;
-            PROF(KC_ROWWISE, final_layer(h->X, h->o, h->flag ? nullptr : h->fn2 + (size_t)l * D, ml + (size_t)o_g2 * D, fsh ? fin + D : fin,
-                                         fsh ? fin : nullptr, h->Wout, h->bout, h->tok, M, N, D, h->O, mod_stride, h->cfg.norm_eps, s));
+        for (int f = 0; f < h->NF; ++f) {
+            // ---- FFN sub-block f -> h->o
+            const size_t base = (size_t)l * h->S + h->ffn_slot0[f];
+            const size_t MD = (size_t)M * D;
+            if (h->ffn_kind[f] == 0) {
+                PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[base], s));
+                PROF(KC_GEMM_W2, gemm_bf16_tn(h->p_w2[base], s));
+            } else if (h->ffn_kind[f] == 1) {           // time-gated: the two selected experts, ascending index
+                for (int k = 0; k < 2; ++k) {
+                    PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[base + t_sel[l][k]], s));
+                    GemmPlan p2 = h->p_w2[base + t_sel[l][k]];
+                    p2.C = h->oE + k * MD;
+                    PROF(KC_GEMM_W2, gemm_bf16_tn(p2, s));
+                }
+                PROF(KC_ROWWISE, moe_combine(h->oE, MD, 2, nullptr, t_w[l], h->o, M, D, s));
+            } else {                                    // token-gated: every expert runs densely, the gate weights select
+                const int E = h->ffn_E[f];
+                PROF(KC_ROWWISE, moe_space_gate(h->u, h->Wg_space + (size_t)l * E * D, h->wtok, M, D, E, s));
+                for (int e = 0; e < E; ++e) {
+                    PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[base + e], s));
+                    GemmPlan p2 = h->p_w2[base + e];
+                    p2.C = h->oE + e * MD;
+                    PROF(KC_GEMM_W2, gemm_bf16_tn(p2, s));
+                }
+                PROF(KC_ROWWISE, moe_combine(h->oE, MD, E, h->wtok, nullptr, h->o, M, D, s));
+            }
+            // ---- gated (post-normed) residual, then the pre-norm + modulation of whatever runs next
+            const bf16* post = h->flag ? nullptr : h->fn2 + ((size_t)f * L + l) * D;
+            const bf16* gch = h->flag ? ml + (size_t)o_g2 * D : ml + (size_t)(3 + 2 * f) * D;
+            if (f + 1 < h->NF) {
+                PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, post, gch, h->fn1 + (size_t)l * D, ml + (size_t)(4 + 2 * f) * D, nullptr, h->u, M, N, D,
+                                               mod_stride, h->cfg.norm_eps, s));
+            } else if (l + 1 < L) {
+                PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, post, gch, h->an1 + (size_t)(l + 1) * D, mn + (size_t)o_sc1 * D, h->flag ? mn : nullptr,
+                                               h->u, M, N, D, mod_stride, h->cfg.norm_eps, s));
+            } else {
+                // final adaLN: Next-DiT T2I [scale]; class-conditional and Flag-DiT [shift | scale]
+                const bf16* fin = h->mod + (size_t)L * NCH * D;
+                const bool fsh = h->cls || h->flag;
+                PROF(KC_ROWWISE, final_layer(h->X, h->o, post, gch, fsh ? fin + D : fin, fsh ? fin : nullptr, h->Wout, h->bout, h->tok, M, N,
+                                             D, h->O, mod_stride, h->cfg.norm_eps, s));
+            }
         }
     }
     PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, eol, s));

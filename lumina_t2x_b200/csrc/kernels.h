@@ -102,6 +102,10 @@ __host__ __device__ constexpr int attn_vrows(int hd) { return (hd + 1 + 15) / 16
 //   tok [2n*N, O] (fp32 of bf16 values) -> v [2n,4,Hh,Ww] bf16;  if y_inout: y = bf16(y + bf16(dt*v))
 cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
                            cudaStream_t s);
+// mixture-of-experts (class-conditional Next-DiT-MoE): token gate + expert-order bf16 accumulation (see rowwise.cu)
+cudaError_t moe_space_gate(const bf16* u, const bf16* Wg, bf16* wtok, int M, int D, int E, cudaStream_t s);
+cudaError_t moe_combine(const bf16* oe, size_t estride, int E, const bf16* wtok, const float* uniform_w, bf16* out, int M, int D,
+                        cudaStream_t s);
 cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s);
 
 }  // namespace ndit

@@ -494,13 +494,14 @@ gemv_rows_kernel(const float* __restrict__ in, const bf16* __restrict__ W, const
                     // stored: scale -> bf16(1+scale); Next-DiT gate -> bf16(tanh(gate)); shift and Flag-DiT gate as they are
                     const int chunk = o / adaln_D;
                     int kind;                 // 0 shift / plain gate (raw), 1 scale, 2 tanh gate
+                    // adaln_blocks = number of per-layer chunks in front of the final layer's
                     if (adaln_kind == ADALN_FLAG) {
-                        const int per = chunk < adaln_blocks * 6 ? chunk % 3 : (chunk - adaln_blocks * 6);   // final: 0 shift, 1 scale
+                        const int per = chunk < adaln_blocks ? chunk % 3 : (chunk - adaln_blocks);   // final: 0 shift, 1 scale
                         kind = per == 1 ? 1 : 0;
-                    } else if (chunk < adaln_blocks * 4) {
-                        kind = (chunk & 1) ? 2 : 1;
+                    } else if (chunk < adaln_blocks) {
+                        kind = (chunk & 1) ? 2 : 1;               // (scale, gate) pairs: attention, FFN, (second FFN of the MoE "both" block)
                     } else {
-                        kind = (adaln_kind == ADALN_CLASS && chunk == adaln_blocks * 4) ? 0 : 1;
+                        kind = (adaln_kind == ADALN_CLASS && chunk == adaln_blocks) ? 0 : 1;
                     }
                     if (kind == 1) y = bf16_round(1.0f + y);
                     else if (kind == 2) y = bf16_round(tanhf(y));
@@ -824,6 +825,79 @@ cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, 
                            cudaStream_t s) {
     const int total = n * C * Hh * Ww;
     unpatchify_cfg_kernel<<<(total + 255) / 256, 256, 0, s>>>(tok, v_out, n, C, Hh, Ww, O, cfg_scale, eol);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mixture-of-experts helpers (Next-DiT-MoE models.py:459-477, models2.py:459-506).
+// Token gate: logits = bf16(u . Wg^T) (E <= 8), top-2 (ties: lower expert index first), weights = bf16(softmax over the two
+// selected logits, fp32); wtok[row][e] = weight of expert e for this token, 0 if not selected.
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+moe_space_gate_kernel(const bf16* __restrict__ u, const bf16* __restrict__ Wg, bf16* __restrict__ wtok, int M, int D, int E) {
+    const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 8; k < D; k += 256) {
+        float x[8];
+        load8(u + static_cast<size_t>(row) * D + k, x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (e < E) {
+                float w[8];
+                load8(Wg + static_cast<size_t>(e) * D + k, w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[e] = fmaf(x[j], w[j], acc[e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bf16_round(warp_sum(acc[e]));
+    if (lane == 0) {
+        int i0 = 0, i1 = -1;
+        for (int e = 1; e < E; ++e) if (acc[e] > acc[i0]) i0 = e;
+        for (int e = 0; e < E; ++e) if (e != i0 && (i1 < 0 || acc[e] > acc[i1])) i1 = e;
+        const float e1 = expf(acc[i1] - acc[i0]);           // softmax over (l0, l1), l0 >= l1
+        const float w0 = bf16_round(1.0f / (1.0f + e1)), w1 = bf16_round(e1 / (1.0f + e1));
+        for (int e = 0; e < E; ++e)
+            wtok[static_cast<size_t>(row) * E + e] = __float2bfloat16_rn(e == i0 ? w0 : (e == i1 ? w1 : 0.f));
+    }
+}
+
+cudaError_t moe_space_gate(const bf16* u, const bf16* Wg, bf16* wtok, int M, int D, int E, cudaStream_t s) {
+    if (E < 2 || E > 8 || D % 8 != 0) return cudaErrorInvalidValue;
+    moe_space_gate_kernel<<<(M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(u, Wg, wtok, M, D, E);
+    return cudaGetLastError();
+}
+
+// out = sum over experts in index order, accumulated in bf16 like ``results[idx] += w * expert(x[idx])`` on a zero tensor:
+// r = bf16(r + bf16(w_e * o_e)) for every selected expert.  wtok != nullptr: per-token weights [M, E] (0 = not selected);
+// else the E buffers are the selected experts of a time-gated layer with the uniform weights uw[0..E).
+struct MoeUniform { float w[8]; };
+__global__ void moe_combine_kernel(const bf16* __restrict__ oe, size_t estride, int E, const bf16* __restrict__ wtok, MoeUniform uw,
+                                   bf16* __restrict__ out, size_t count8, int D) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // one 8-element vector
+    if (i >= count8) return;
+    const size_t row = (i * 8) / D;
+    float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < E; ++e) {
+        const float w = wtok != nullptr ? __bfloat162float(wtok[row * E + e]) : uw.w[e];
+        if (wtok != nullptr && w == 0.f) continue;
+        float o[8];
+        load8(oe + e * estride + i * 8, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = bf16_round(r[j] + bf16_round(w * o[j]));
+    }
+    store8(out + i * 8, r);
+}
+
+cudaError_t moe_combine(const bf16* oe, size_t estride, int E, const bf16* wtok, const float* uniform_w, bf16* out, int M, int D,
+                        cudaStream_t s) {
+    if (E < 1 || E > 8 || D % 8 != 0) return cudaErrorInvalidValue;
+    MoeUniform uw;
+    for (int e = 0; e < 8; ++e) uw.w[e] = (uniform_w != nullptr && e < E) ? uniform_w[e] : 0.f;
+    const size_t count8 = static_cast<size_t>(M) * D / 8;
+    moe_combine_kernel<<<static_cast<unsigned>((count8 + 255) / 256), 256, 0, s>>>(oe, estride, E, wtok, uw, out, count8, D);
     return cudaGetLastError();
 }
 

@@ -1,8 +1,11 @@
 """Drop-in mirror of the reference's class-conditional Next-DiT (``Next-DiT-ImageNet/models/models.py:836-1056``,
 ``DiT_Llama`` with ``TransformerBlockSandwichNorm2`` blocks) on the same B200 engine: same constructor
 arguments, factory names, state-dict keys and ``forward_with_cfg(x, t, y, cfg_scale, rope_scaling_factor,
-ntk_factor)`` signature as used by ``Next-DiT-ImageNet/sample.py:168-186``.  head_dim must be 72 or 48
-(the 600M and 2B factories); the 3B / 7B factories (head_dim 96 / 128) are not supported by the attention kernel yet."""
+ntk_factor)`` signature as used by ``Next-DiT-ImageNet/sample.py:168-186``.  head_dim must be 48, 72 or 96
+(the 600M, 2B and 3B factories); the 7B factory (head_dim 128) is not supported by the attention kernel.
+
+``moe`` selects the mixture-of-experts FFN of ``Next-DiT-MoE/models/`` (see ``lumina_t2x_b200.models.moe`` for the
+factory names of that package): "time" (models.py), "space" (models1.py), "both" (models2.py)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -26,15 +29,37 @@ class _Attention(nn.Module):
             self.q_norm = self.k_norm = nn.Identity()
 
 
+class _MoeLayer(nn.Module):
+    """MoeLayer / TimeMoeLayer / SpaceMoeLayer (Next-DiT-MoE models.py:451-477, models2.py:451-506): parameter holder."""
+
+    def __init__(self, dim, hidden, gate_in, num_experts):
+        super().__init__()
+        self.experts = nn.ModuleList([_FeedForward(dim, hidden) for _ in range(num_experts)])
+        self.gate = nn.Linear(gate_in, num_experts, bias=False)
+
+
+# moe kind -> ((module name, post-norm name, gate input "time"|"space", experts), ...)
+_MOE_BLOCKS = {
+    "": (("feed_forward", "ffn_norm", "", 0),),
+    "time": (("feed_forward", "ffn_norm", "time", 8),),
+    "space": (("feed_forward", "ffn_norm", "space", 8),),
+    "both": (("feed_forward_time", "ffn_norm_time", "time", 4), ("feed_forward_space", "ffn_norm_space", "space", 4)),
+}
+
+
 class _Block(nn.Module):
     """TransformerBlockSandwichNorm2 (models.py:692-796): the pre-norms (PFRMSNorm) carry no parameters."""
 
-    def __init__(self, dim, n_heads, n_kv_heads, hidden, qk_norm):
+    def __init__(self, dim, n_heads, n_kv_heads, hidden, qk_norm, moe=""):
         super().__init__()
         self.attention = _Attention(dim, n_heads, n_kv_heads, qk_norm)
-        self.feed_forward = _FeedForward(dim, hidden)
-        self.attention_norm, self.ffn_norm = _Weight(dim), _Weight(dim)
-        self.adaLN_modulation = nn.Sequential(nn.SiLU(), _linear(min(dim, 1024), 4 * dim, True, "zeros"))
+        for name, norm, gate, E in _MOE_BLOCKS[moe]:
+            ffn = _FeedForward(dim, hidden) if E == 0 else _MoeLayer(dim, hidden, min(dim, 1024) if gate == "time" else dim, E)
+            setattr(self, name, ffn)
+        self.attention_norm = _Weight(dim)
+        for name, norm, gate, E in _MOE_BLOCKS[moe]:
+            setattr(self, norm, _Weight(dim))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), _linear(min(dim, 1024), (2 + 2 * len(_MOE_BLOCKS[moe])) * dim, True, "zeros"))
 
 
 class _LabelEmbedder(nn.Module):
@@ -57,8 +82,9 @@ class DiT_Llama(EngineModule):
                  n_heads: int = 32, n_kv_heads: Optional[int] = None, multiple_of: int = 256,
                  ffn_dim_multiplier: Optional[float] = None, norm_eps: float = 1e-5, class_dropout_prob: float = 0.1,
                  num_classes: int = 1000, learn_sigma: bool = True, qk_norm: bool = False,
-                 max_tokens: Optional[int] = None, max_batch: int = 2) -> None:
+                 max_tokens: Optional[int] = None, max_batch: int = 2, moe: str = "") -> None:
         super().__init__()
+        self.moe = moe
         self.learn_sigma, self.in_channels, self.input_size, self.patch_size = learn_sigma, in_channels, input_size, patch_size
         self.out_channels = in_channels * 2 if learn_sigma else in_channels
         self.dim, self.n_heads, self.n_layers = dim, n_heads, n_layers
@@ -72,7 +98,7 @@ class DiT_Llama(EngineModule):
         self.x_embedder = _linear(patch_size * patch_size * in_channels, dim, True)
         self.t_embedder = _TimestepEmbedder(min(dim, 1024))
         self.y_embedder = _LabelEmbedder(num_classes, min(dim, 1024), class_dropout_prob)
-        self.layers = nn.ModuleList([_Block(dim, n_heads, n_kv_heads, hidden, qk_norm) for _ in range(n_layers)])
+        self.layers = nn.ModuleList([_Block(dim, n_heads, n_kv_heads, hidden, qk_norm, moe) for _ in range(n_layers)])
         self.final_layer = _FinalLayer(dim, patch_size, self.out_channels)
         assert (dim // n_heads) % 4 == 0, "2d rope needs head dim to be divisible by 4"
         self._init_engine_state(max_tokens or max(256, (input_size // patch_size) ** 2), 0, max_batch)
@@ -85,13 +111,13 @@ class DiT_Llama(EngineModule):
             raise NotImplementedError("ffn_dim_multiplier is not supported by the B200 engine")
         if self._class_dropout_prob <= 0:
             raise NotImplementedError("the B200 engine expects the CFG null-class row (class_dropout_prob > 0)")
-        if self.dim // self.n_heads not in (48, 72):
-            raise NotImplementedError("the B200 attention kernel supports head_dim 48 and 72 (600M / 2B factories)")
+        if self.dim // self.n_heads not in (48, 72, 96):
+            raise NotImplementedError("the B200 attention kernel supports head_dim 48, 72 and 96 (600M / 2B / 3B factories)")
 
     def _ndit_config(self):
         return _lib.NditConfig(self.dim, self.n_layers, self.n_heads, self.n_kv_heads, 0, self.in_channels, self.patch_size,
                                self.multiple_of, int(self.learn_sigma), float(self.norm_eps), self._limits[0], 0, self._limits[2],
-                               self.num_classes)
+                               self.num_classes, 0, *{"": (0, 0), "time": (8, 0), "space": (0, 8), "both": (4, 4)}[self.moe])
 
     def _set_labels(self, lib, h, y: torch.Tensor, stream):
         key = (y.data_ptr(), y._version, tuple(y.shape), y.dtype)
@@ -145,3 +171,8 @@ def DiT_Llama_600M_patch2(**kwargs):
 def DiT_Llama_2B_patch2(**kwargs):
     """models.py:1046-1047."""
     return DiT_Llama(patch_size=2, dim=2304, n_layers=24, n_heads=32, **kwargs)
+
+
+def DiT_Llama_3B_patch2(**kwargs):
+    """models.py:1050-1051 (head_dim 96)."""
+    return DiT_Llama(patch_size=2, dim=3072, n_layers=32, n_heads=32, **kwargs)

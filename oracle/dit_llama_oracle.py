@@ -17,6 +17,16 @@ Reference citations (relative to /root/reference/Next-DiT-ImageNet/):
 ``precision="bf16"`` uses the same rounding points as the T2I oracle (autocast-like: LayerNorm outputs stay fp32),
 which is how the CUDA engine computes; the reference's sample.py runs this model without autocast (fp32/tf32 by
 default), so the fp32 mode is the one compared with the reference, the bf16 mode is the engine's contract.
+
+Mixture-of-experts variants (BASELINE config 5 / SURVEY.md 8a16; /root/reference/Next-DiT-MoE/models/), ``cfg.moe``:
+  "time"   models.py   MoeLayer :451-477 gated by the timestep embedding (8 experts, top-2): every token of a sample
+                       uses the same two experts; block :663-771, forward passes time_input = t_embedder(t) :895-903
+  "space"  models1.py  MoeLayer :451-477 gated per token by its own (modulated) input (8 experts, top-2)
+  "both"   models2.py  TimeMoeLayer :451-477 then SpaceMoeLayer :480-506 (4 experts each), 6-chunk adaLN
+                       (scale, gate) x {attention, time FFN, space FFN} :760-808
+Expert outputs are accumulated in expert-index order into a zero tensor of the activation dtype
+(``results[idx] += w * expert(x[idx])``), weights = softmax over the top-k logits in fp32, cast to the activation dtype.
+Pinned by ``make_golden.make_moe`` -> ``tests/golden/moe_*.pt``.
 """
 from __future__ import annotations
 
@@ -44,6 +54,15 @@ class DiTLlamaConfig:
     multiple_of: int = 256
     norm_eps: float = 1e-5
     learn_sigma: bool = True
+    moe: str = ""               # "", "time", "space", "both"
+
+    @property
+    def ffn_blocks(self):
+        """(state-dict prefix, post-norm key, gate kind, experts) of the FFN sub-blocks of one layer, in execution order."""
+        return {"": (("feed_forward", "ffn_norm", "", 0),),
+                "time": (("feed_forward", "ffn_norm", "time", 8),),
+                "space": (("feed_forward", "ffn_norm", "space", 8),),
+                "both": (("feed_forward_time", "ffn_norm_time", "time", 4), ("feed_forward_space", "ffn_norm_space", "space", 4))}[self.moe]
 
     @property
     def kv_heads(self) -> int:
@@ -80,6 +99,15 @@ def config_tiny72(n_layers: int = 2) -> DiTLlamaConfig:
     return DiTLlamaConfig(dim=576, n_layers=n_layers, n_heads=8, num_classes=10)
 
 
+def config_600m_moe(moe: str = "both") -> DiTLlamaConfig:
+    """DiT_Llama_600M_patch2 / _Spatial / _Both of Next-DiT-MoE (models.py:1015, models1.py:1015, models2.py:1063)."""
+    return DiTLlamaConfig(moe=moe)
+
+
+def config_tiny_moe(moe: str, n_layers: int = 2) -> DiTLlamaConfig:
+    return DiTLlamaConfig(dim=384, n_layers=n_layers, n_heads=8, num_classes=10, moe=moe)
+
+
 def state_dict_shapes(cfg: DiTLlamaConfig) -> Dict[str, tuple]:
     D, KV, Fh, cd = cfg.dim, cfg.kv_heads * cfg.head_dim, cfg.ffn_dim, cfg.cond_dim
     po = cfg.patch_size ** 2
@@ -100,14 +128,20 @@ def state_dict_shapes(cfg: DiTLlamaConfig) -> Dict[str, tuple]:
         for n, w in (("q_norm", D), ("k_norm", KV)):
             s[a + n + ".weight"] = (w,)
             s[a + n + ".bias"] = (w,)
-        f = f"layers.{i}.feed_forward."
-        s[f + "w1.weight"] = (Fh, D)
-        s[f + "w2.weight"] = (D, Fh)
-        s[f + "w3.weight"] = (Fh, D)
+        for name, norm, gate, E in cfg.ffn_blocks:
+            f = f"layers.{i}.{name}."
+            for pre in ([f] if E == 0 else [f"{f}experts.{j}." for j in range(E)]):
+                s[pre + "w1.weight"] = (Fh, D)
+                s[pre + "w2.weight"] = (D, Fh)
+                s[pre + "w3.weight"] = (Fh, D)
+            if E:
+                s[f + "gate.weight"] = (E, cd if gate == "time" else D)
+        nch = 2 + 2 * len(cfg.ffn_blocks)
         s[f"layers.{i}.attention_norm.weight"] = (D,)
-        s[f"layers.{i}.ffn_norm.weight"] = (D,)
-        s[f"layers.{i}.adaLN_modulation.1.weight"] = (4 * D, cd)
-        s[f"layers.{i}.adaLN_modulation.1.bias"] = (4 * D,)
+        for name, norm, gate, E in cfg.ffn_blocks:
+            s[f"layers.{i}.{norm}.weight"] = (D,)
+        s[f"layers.{i}.adaLN_modulation.1.weight"] = (nch * D, cd)
+        s[f"layers.{i}.adaLN_modulation.1.bias"] = (nch * D,)
     return s
 
 
@@ -142,6 +176,27 @@ def rope_angles(head_dim: int, hp: int, wp: int, rope_scaling_factor: float, ntk
     return T.rope_angles(head_dim, hp, wp, rope_scaling_factor, 2.0, 0.0, theta=theta * ntk_factor)
 
 
+def moe_layer(p, W: Dict[str, Tensor], pre: str, x: Tensor, cond: Optional[Tensor], E: int, top_k: int = 2) -> Tensor:
+    """MoeLayer / TimeMoeLayer / SpaceMoeLayer.forward (Next-DiT-MoE models.py:459-477, models2.py:459-506).
+    cond [B, cd] -> time gate (same logits for every token of a sample); cond None -> gate on the token itself."""
+    B, N, D = x.shape
+    xs = x.reshape(B * N, D)
+    if cond is not None:
+        logits = p.linear(cond, W[pre + "gate.weight"]).repeat(1, N).view(B * N, -1)
+    else:
+        logits = p.linear(xs, W[pre + "gate.weight"])
+    wts, sel = torch.topk(logits, top_k)
+    wts = p.r(torch.softmax(wts.float(), dim=1))
+    res = torch.zeros_like(xs)
+    for e in range(E):
+        rows, nth = torch.where(sel == e)
+        if rows.numel() == 0:
+            continue
+        oe = T.feed_forward(p, W, f"{pre}experts.{e}.", xs[rows])
+        res[rows] = p.r(res[rows] + p.r(wts[rows, nth, None] * oe))
+    return res.view(B, N, D)
+
+
 def forward_with_cfg(cfg: DiTLlamaConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, y: Tensor, cfg_scale: float,
                      rope_scaling_factor: Optional[float] = None, ntk_factor: Optional[float] = None,
                      precision: str = "fp32", taps: Optional[dict] = None) -> Tensor:
@@ -163,7 +218,8 @@ def forward_with_cfg(cfg: DiTLlamaConfig, W: Dict[str, Tensor], x: Tensor, t: Te
     for i in range(cfg.n_layers):
         pre = f"layers.{i}."
         mod = p.linear(p.r(F.silu(c)), W[pre + "adaLN_modulation.1.weight"], W[pre + "adaLN_modulation.1.bias"])
-        s_a, g_a, s_m, g_m = mod.chunk(4, dim=1)
+        chunks = mod.chunk(2 + 2 * len(cfg.ffn_blocks), dim=1)
+        s_a, g_a = chunks[0], chunks[1]
         ones = torch.ones(cfg.dim)
         u = T.modulate(p, T.rms_norm(p, X, ones, cfg.norm_eps), s_a)                       # PFRMSNorm = unit weight
         a = pre + "attention."
@@ -178,9 +234,14 @@ def forward_with_cfg(cfg: DiTLlamaConfig, W: Dict[str, Tensor], x: Tensor, t: Te
         o = T._sdpa(p, xq, xk, v, scale_attn, None).permute(0, 2, 1, 3).reshape(B, N, H * hd)
         o = p.linear(o, W[a + "wo.weight"])
         X = p.r(X + p.r(p.r(torch.tanh(g_a)).unsqueeze(1) * T.rms_norm(p, o, W[pre + "attention_norm.weight"], cfg.norm_eps)))
-        m = T.modulate(p, T.rms_norm(p, X, ones, cfg.norm_eps), s_m)
-        f = T.feed_forward(p, W, pre + "feed_forward.", m)
-        X = p.r(X + p.r(p.r(torch.tanh(g_m)).unsqueeze(1) * T.rms_norm(p, f, W[pre + "ffn_norm.weight"], cfg.norm_eps)))
+        for bi, (name, norm, gate, E) in enumerate(cfg.ffn_blocks):
+            s_m, g_m = chunks[2 + 2 * bi], chunks[3 + 2 * bi]
+            m = T.modulate(p, T.rms_norm(p, X, ones, cfg.norm_eps), s_m)
+            if E == 0:
+                f = T.feed_forward(p, W, f"{pre}{name}.", m)
+            else:
+                f = moe_layer(p, W, f"{pre}{name}.", m, temb if gate == "time" else None, E)
+            X = p.r(X + p.r(p.r(torch.tanh(g_m)).unsqueeze(1) * T.rms_norm(p, f, W[f"{pre}{norm}.weight"], cfg.norm_eps)))
         if taps is not None:
             taps[f"block{i}"] = X.clone()
     fin = p.linear(p.r(F.silu(c)), W["final_layer.adaLN_modulation.1.weight"], W["final_layer.adaLN_modulation.1.bias"])

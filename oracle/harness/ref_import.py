@@ -117,6 +117,22 @@ def import_reference_imagenet():
     return mod
 
 
+def import_reference_moe(which: str):
+    """Unmodified Next-DiT-MoE model module: which = "models" (time MoE), "models1" (space MoE), "models2" (both)."""
+    import importlib.util
+    import os
+    os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+    install_shims()
+    _install_fairscale_stub()
+    spec = importlib.util.spec_from_file_location("ref_moe_" + which, f"{REF_ROOT}/Next-DiT-MoE/models/{which}.py")
+    mod = importlib.util.module_from_spec(spec)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    return mod
+
+
 def import_reference_flag_dit():
     """Returns the unmodified lumina_t2i ``models.model`` module (Flag-DiT ``DiT_Llama`` / ``DiT_Llama_5B_patch2``)."""
     import importlib.util

@@ -131,6 +131,37 @@ def make_imagenet() -> None:
         del m, W
 
 
+def make_moe() -> None:
+    """Next-DiT-MoE (BASELINE config 5 / SURVEY 8a16): the unmodified time / space / both MoE models (fp32, CPU)."""
+    from oracle.harness.ref_import import import_reference_moe
+    torch.set_grad_enabled(False)
+    cases = {
+        "moe_tiny_time": dict(moe="time", file="models", hw=(16, 16), labels=(3,), t=0.35, cfg_scale=3.0),
+        "moe_tiny_space": dict(moe="space", file="models1", hw=(16, 16), labels=(7,), t=0.6, cfg_scale=2.0),
+        "moe_tiny_both": dict(moe="both", file="models2", hw=(16, 24), labels=(1,), t=0.8, cfg_scale=1.5),
+    }
+    for name, c in cases.items():
+        ref = import_reference_moe(c["file"])
+        cfg = DL.config_tiny_moe(c["moe"])
+        W = DL.synthetic_weights(cfg, seed=0)
+        m = ref.DiT_Llama(input_size=c["hw"][0], patch_size=2, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                          num_classes=cfg.num_classes, qk_norm=True)
+        m.load_state_dict({k: v.float() for k, v in W.items()}, strict=True)
+        m = m.eval().float()
+        z, y = DL.synthetic_inputs(cfg, c["hw"], c["labels"], seed=1)
+        t = torch.full((len(z),), c["t"])
+        out = m.forward_with_cfg(z.float(), t, y, c["cfg_scale"])
+        fx = dict(case=name, cfg=dict(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, num_classes=cfg.num_classes, moe=cfg.moe),
+                  hw=c["hw"], labels=c["labels"], t=c["t"], cfg_scale=c["cfg_scale"], rope=None, weight_seed=0, input_seed=1,
+                  out_fp32=out.clone())
+        torch.save(fx, os.path.join(OUT, f"{name}.pt"))
+        o = DL.forward_with_cfg(cfg, W, z.float(), t, y, c["cfg_scale"], precision="fp32")
+        ob = DL.forward_with_cfg(cfg, W, z, t, y, c["cfg_scale"], precision="bf16")
+        print(name, tuple(out.shape), "absmax", out.abs().max().item(), "oracle fp32 rel", ((o - out).abs().max() / out.abs().max()).item(),
+              "bf16-mode rel", ((ob - out).abs().max() / out.abs().max()).item())
+        del m, W
+
+
 def make_flag_dit() -> None:
     """Flag-DiT (Lumina-T2I, BASELINE config 4 / SURVEY 8a15): unmodified lumina_t2i/models/model.py (fp32, CPU, fairscale
     at world size 1).  Tiny models with the flagship head_dim 96: default call, proportional attention + NTK factor (the

@@ -25,7 +25,7 @@ def test_cabi_loads_and_exports_header_symbols():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ndit_abi_version() == 3
+    assert lib.ndit_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
@@ -65,6 +65,19 @@ def test_class_conditional_state_dict_keys_match_reference_inventory():
     assert hasattr(models, "DiT_Llama_600M_patch2") and hasattr(models, "DiT_Llama_2B_patch2")
     with pytest.raises(RuntimeError):        # no GPU / no CUDA library -> loud failure, never a CPU fallback
         m.forward_with_cfg(torch.zeros(2, 4, 16, 16), torch.zeros(2), torch.tensor([1, cfg.num_classes]), 2.0)
+
+
+@pytest.mark.parametrize("moe", ["time", "space", "both"])
+def test_moe_state_dict_keys_match_reference_inventory(moe):
+    from lumina_t2x_b200 import models
+    from lumina_t2x_b200.models import moe as moe_models
+    from oracle import dit_llama_oracle as DL
+    cfg = DL.config_tiny_moe(moe)
+    m = models.DiT_Llama(input_size=16, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, num_classes=cfg.num_classes,
+                         qk_norm=True, moe=moe)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == DL.state_dict_shapes(cfg)   # pinned by make_golden.make_moe
+    for f in ("DiT_Llama_600M_patch2", "DiT_Llama_600M_patch2_Spatial", "DiT_Llama_600M_patch2_Both"):
+        assert hasattr(moe_models, f)
 
 
 def test_flag_dit_state_dict_keys_match_reference_inventory():

@@ -21,6 +21,7 @@ for g in "$@"; do
     attn48) run attn48ref 120 tests/test_imagenet_gpu.py -k "head_dim_48 and refkernel"; run attn48 120 tests/test_imagenet_gpu.py -k "head_dim_48 and tcgen05";;
     imagenet) run imagenet_ref 300 tests/test_imagenet_gpu.py -k "forward_with_cfg and refkernel"; run imagenet 300 tests/test_imagenet_gpu.py -k "forward_with_cfg and tcgen05"; run imagenet_traj 120 tests/test_imagenet_gpu.py -k "sampler";;
     flag)   run attn96ref 120 tests/test_flagdit_gpu.py -k "head_dim_96 and refkernel"; run attn96 120 tests/test_flagdit_gpu.py -k "head_dim_96 and tcgen05"; run flag_ref 200 tests/test_flagdit_gpu.py -k "forward_with_cfg and refkernel"; run flag 200 tests/test_flagdit_gpu.py -k "forward_with_cfg and tcgen05"; run flag_traj 120 tests/test_flagdit_gpu.py -k "sampler"; run flag5b 400 tests/test_flagdit_gpu.py -k "flagship";;
+    moe)    run moe 300 tests/test_imagenet_gpu.py -k "moe";;
     model)  run model 600 tests/test_model_gpu.py;;
     all)    run all 1200 tests;;
   esac
