@@ -258,7 +258,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
-    const int m_tiles = M / 256;
+    const int m_tiles = (M + 255) / 256;      // ragged last tile: TMA zero-fills the rows >= M, stores are masked
     const int n_tiles = (N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
@@ -373,7 +373,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             o.y = pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
                             o.z = pack_bf16(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
                             o.w = pack_bf16(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-                            *reinterpret_cast<uint4*>(crow + c * 32 + j * 8) = o;
+                            if (row < M) *reinterpret_cast<uint4*>(crow + c * 32 + j * 8) = o;
                         }
                     }
                 }
@@ -398,7 +398,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         uint4 o;
                         o.x = pack_bf16(h[0], h[1]); o.y = pack_bf16(h[2], h[3]);
                         o.z = pack_bf16(h[4], h[5]); o.w = pack_bf16(h[6], h[7]);
-                        *reinterpret_cast<uint4*>(crow + c * 16 + j * 8) = o;
+                        if (row < M) *reinterpret_cast<uint4*>(crow + c * 16 + j * 8) = o;
                     }
                 }
             }
@@ -426,7 +426,7 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int tiles = (M / 256) * ((N + BN - 1) / BN);
+    const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
     kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, C, M, N, K, ldc);
@@ -456,7 +456,7 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     if (p.N % 8 != 0 || p.K % 8 != 0) return cudaErrorInvalidValue;
     if (p.pair) {
-        if (p.M % 256 != 0 || p.N % p.bn != 0) return cudaErrorInvalidValue;
+        if (p.N % p.bn != 0) return cudaErrorInvalidValue;      // ragged M is fine (zero-filled loads, masked stores)
         if (p.epi == EPI_SWIGLU) {
             if (p.bn != 256) return cudaErrorInvalidValue;
             return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);

@@ -88,10 +88,10 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
     static const int pair_env = getenv("NDIT_GEMM_PAIR") ? atoi(getenv("NDIT_GEMM_PAIR")) : 1;
     // (N must be a multiple of the tile width: 256, or 192 for the fused q|k|v projection, N = 3456 = 18 x 192)
     p->pair = 0;
-    if (allow_pair && pair_env && M % 256 == 0) {
+    if (allow_pair && pair_env && M >= 256) {
         // BN = 192 (N = 3456) measured slower than the single-CTA kernel (108 vs 103 us): only behind NDIT_GEMM_PAIR=2
         const int pbn = (N % 256 == 0) ? 256 : ((pair_env >= 2 && N % 192 == 0 && epi != EPI_SWIGLU) ? 192 : 0);
-        if (pbn && (M / 256) * (N / pbn) >= num_sms / 2) { p->pair = 1; p->bn = pbn; }
+        if (pbn && ((M + 255) / 256) * (N / pbn) >= num_sms / 2) { p->pair = 1; p->bn = pbn; }
     }
     if (make_tmap_2d(&p->tmA, A, M, K, lda, 128, 64, 128)) return -1;
     if (make_tmap_2d(&p->tmB, W, N, K, K, p->pair ? p->bn / 2 : bn, 64, 128)) return -1;

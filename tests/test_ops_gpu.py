@@ -47,6 +47,8 @@ GEMM_SHAPES = [
     (2048, 3456, 2304), (1024, 2304, 6144), (64, 1152, 256),
     # large enough for the CTA-pair (cta_group::2) kernel: M % 256 == 0, N % 256 == 0, >= 74 tiles of 256x256
     (4096, 2304, 2304), (8192, 2304, 6144), (2560, 2048, 192),
+    # CTA-pair kernel with a ragged last M tile (Flag-DiT: 2 x 4160 tokens; the second CTA of the last pair is all padding)
+    (8320, 3072, 3072), (4900, 2304, 256), (2700, 2048, 192),
 ]
 
 
@@ -80,7 +82,7 @@ def test_gemm_identity_layout(lib):
 
 
 @pytest.mark.parametrize("M,F,K", [(128, 128, 64), (256, 512, 576), (1024, 6144, 2304), (200, 1536, 576),
-                                   (8192, 6144, 2304)])
+                                   (8192, 6144, 2304), (8320, 8192, 3072), (2700, 2048, 384)])
 def test_gemm_swiglu(lib, M, F, K):
     g = torch.Generator(device="cuda").manual_seed(M + F + K)
     A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
