@@ -87,6 +87,7 @@ struct ndit_engine {
     int64_t n_params = 0;
     bool finalized = false;
     int attn_ref = 0;
+    int attn_tp = 0;                         // 1: P-in-tensor-memory attention kernel (experimental, slower so far: see its header)
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_class;       // class of event pair i (events 2i, 2i+1)
@@ -199,6 +200,7 @@ static int create_impl(ndit_engine* h) {
     const ndit_config& c = h->cfg;
     if (c.dim <= 0 || c.n_heads <= 0 || c.dim % c.n_heads != 0) return h->fail(NDIT_ERR_INVALID, "bad dim/n_heads");
     h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
+    if (getenv("NDIT_ATTN_TP")) h->attn_tp = atoi(getenv("NDIT_ATTN_TP"));
     h->cls = c.num_classes > 0;
     h->flag = c.flag_dit != 0;
     if (h->cls && h->flag) return h->fail(NDIT_ERR_INVALID, "num_classes > 0 and flag_dit are mutually exclusive");
@@ -319,6 +321,7 @@ extern "C" int64_t ndit_launch_count(ndit_handle h) { return h ? h->launches : 0
 extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!h || !name) return NDIT_ERR_INVALID;
     if (!strcmp(name, "attn_ref")) { h->attn_ref = value; return NDIT_OK; }
+    if (!strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
     if (!strcmp(name, "profile")) {
         h->profile = value;
         h->ev_used = 0;
@@ -622,23 +625,23 @@ extern "C" int ndit_set_labels(ndit_handle h, const int64_t* labels, int32_t bat
 // (head_dim, head, token); the 64-wide box covers elements [0,64) (head_dim 48: 48..63 are out-of-bounds zeros), the
 // 16-wide box elements [64,80) of head_dim 72.  V^T buffers are [group][vrows][tokens].
 static int build_attn_maps(AttnPlan* a, const bf16* qkv, int Wq, const bf16* vt, const bf16* kvy, const bf16* vyt, int B, int N,
-                           int T, int H, int Hkv, int hd) {
+                           int T, int H, int Hkv, int hd, int bkv = 128) {
     const int vrows = attn_vrows(hd), KV = Hkv * hd, Tpad = (T + 7) / 8 * 8, Npad = (N + 7) / 8 * 8;
     const uint64_t rs = (uint64_t)Wq * 2, M = (uint64_t)B * N;
     int e = 0;
     e |= make_tmap_3d(&a->tmQ64, qkv, hd, H, M, hd * 2, rs, 64, 1, 128, 128);
-    e |= make_tmap_3d(&a->tmK64, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, 128, 128);
+    e |= make_tmap_3d(&a->tmK64, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 64, 1, bkv, 128);
     e |= make_tmap_3d(&a->tmVt, vt, N, vrows, (uint64_t)B * Hkv, (uint64_t)Npad * 2, (uint64_t)Npad * vrows * 2, 64, vrows, 1, 128);
     if (hd > 64) {
         e |= make_tmap_3d(&a->tmQ16, qkv, hd, H, M, hd * 2, rs, 16, 1, 128, 32);
-        e |= make_tmap_3d(&a->tmK16, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, 128, 32);
+        e |= make_tmap_3d(&a->tmK16, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, bkv, 32);
     }
     if (T > 0) {
-        e |= make_tmap_3d(&a->tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, 128, 128);
-        if (hd > 64) e |= make_tmap_3d(&a->tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, 128, 32);
+        e |= make_tmap_3d(&a->tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, bkv, 128);
+        if (hd > 64) e |= make_tmap_3d(&a->tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, bkv, 32);
         e |= make_tmap_3d(&a->tmVyt, vyt, Tpad, vrows, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * vrows * 2, 64, vrows, 1, 128);
     }
-    a->B = B; a->N = N; a->T = T; a->H = H; a->Hkv = Hkv; a->hd = hd;
+    a->B = B; a->N = N; a->T = T; a->H = H; a->Hkv = Hkv; a->hd = hd; a->bkv = bkv;
     return e;
 }
 
@@ -670,7 +673,8 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
             memset(&a, 0, sizeof(a));
             const bf16* kvy = h->kvy + l * (size_t)batch * T * 2 * KV;
             const bf16* vyt = h->vyt + l * (size_t)batch * h->Hkv * h->vrows * Tpad;
-            if (build_attn_maps(&a, h->qkv, (int)Wq, h->vt, kvy, vyt, batch, N, T, h->H, h->Hkv, h->hd))
+            const int tp = h->attn_tp ? attention_tp_bkv(h->hd) : 0;
+            if (build_attn_maps(&a, h->qkv, (int)Wq, h->vt, kvy, vyt, batch, N, T, h->H, h->Hkv, h->hd, tp ? tp : 128))
                 return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
             a.ymask = h->ymask;
             a.gate_tanh = h->gate_tanh + l * h->H;
@@ -790,7 +794,7 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
-            PROF(KC_ATTN, attention_fused(a, s));
+            PROF(KC_ATTN, a.bkv == 128 ? attention_fused(a, s) : attention_fused_tp(a, s));
         }
         PROF(KC_GEMM_WO, gemm_bf16_tn(h->p_wo[l], s));
         PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->flag ? nullptr : h->an2 + (size_t)l * D, ml + (size_t)o_g1 * D, h->fn1 + (size_t)l * D,
@@ -998,7 +1002,7 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
     const bf16* qkv = static_cast<const bf16*>(qkv_);
     const bf16* kvy = static_cast<const bf16*>(kvy_);
     const int Wq = (H + 2 * Hkv) * hd, KV = Hkv * hd;
-    if (use_ref) {
+    if (use_ref == 1) {
         cudaError_t e = attention_ref(qkv, Wq, kvy, 2 * KV, ymask, gate_tanh, static_cast<bf16*>(out), B, N, T, H, Hkv, hd,
                                       scale_self, scale_cross, s);
         return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_attention(ref)", e);
@@ -1017,20 +1021,26 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
     if (e == cudaSuccess && T > 0) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, vrows, 1, s);
     AttnPlan a;
     memset(&a, 0, sizeof(a));
-    const int te = build_attn_maps(&a, qkv, Wq, vt, kvy, vyt, B, N, T, H, Hkv, hd);
+    static const int tp_env = getenv("NDIT_ATTN_TP") ? atoi(getenv("NDIT_ATTN_TP")) : 0;
+    if (use_ref == 2 && !attention_tp_bkv(hd))
+        return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: the tensor-memory-P kernel covers head_dim 72 only", cudaErrorInvalidValue);
+    const int tpb = (use_ref == 2 || tp_env) ? attention_tp_bkv(hd) : 0;       // use_ref: 0 default kernel, 1 CUDA-core reference, 2 first-generation kernel
+    // use_ref: 0 production kernel, 1 CUDA-core reference, 2 experimental kernel with P in tensor memory
+    const int te = build_attn_maps(&a, qkv, Wq, vt, kvy, vyt, B, N, T, H, Hkv, hd, tpb ? tpb : 128);
+    auto run = [&](const AttnPlan& pl) { return pl.bkv == 128 ? attention_fused(pl, s) : attention_fused_tp(pl, s); };
     int rc = NDIT_OK;
     if (te) rc = op_fail(NDIT_ERR_CUDA, "ndit_op_attention tensor map", cudaSuccess);
     if (!te && e == cudaSuccess) {
         a.ymask = ymask; a.gate_tanh = gate_tanh; a.out = static_cast<bf16*>(out);
         a.scale_self = scale_self; a.scale_cross = scale_cross;
-        e = attention_fused(a, s);
+        e = run(a);
         if (bench_iters > 0 && bench_ms && e == cudaSuccess) {      // micro-benchmark: average of `bench_iters` launches
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
-            for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = attention_fused(a, s);
+            for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = run(a);
             cudaEventRecord(e0, s);
-            for (int i = 0; i < bench_iters && e == cudaSuccess; ++i) e = attention_fused(a, s);
+            for (int i = 0; i < bench_iters && e == cudaSuccess; ++i) e = run(a);
             cudaEventRecord(e1, s);
             cudaEventSynchronize(e1);
             float ms = 0.f;
