@@ -26,7 +26,9 @@
 // bias cancels in O / rowsum.
 // Measured alternatives that were slower and are not kept (profiles/r01_attention_microbench_phase_timing.txt):
 // polynomial exp2 on the FMA pipe for 1/8..3/8 of the columns, hand-pipelined MUFU/pack ordering with volatile asm,
-// two softmax threads per row (640-thread CTA), an explicit XU token between the two tiles.
+// two softmax threads per row (640-thread CTA), an explicit XU token between the two tiles, a speculative (stale) reference
+// maximum with the row maximum accumulated inside the exp loop (480 vs 421 us: the up-front max pass is what keeps the two
+// tiles half a period apart), P kept in tensor memory (attention_tp_tcgen05.cu, 445-466 us).
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,256+HDP) O_B [384,384+HDP).
 #include <math.h>
 #include <stdlib.h>
