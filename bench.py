@@ -15,6 +15,8 @@ CFG=2, bf16, random-init weights, synthetic data.  One JSON line is printed by r
   roofline  for the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of its launches,
             measured with per-launch events inside one extra solve (engine option "profile").
   cpu_baseline  the oracle (CPU port of the reference algorithm, fp32) on a bounded sample.
+  gpu_eager_baseline  the same forward as eager PyTorch bf16 on the same GPU (the reference's stock CUDA path restated;
+                the reference itself cannot travel to the GPU box).
 """
 from __future__ import annotations
 
@@ -166,6 +168,37 @@ def run_reference(args, rank):
             "e2e": {"value": 1.0 / sec, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(m, z_dev, cap_dev, mask_dev, device, engine_out, iters=3):
+    """Same-GPU "stock CUDA path" baseline: the reference forward_with_cfg as eager PyTorch bf16
+    (cuBLAS Linears, fused SDPA attention, one ATen kernel per op) - oracle/nextdit_oracle.py::forward_with_cfg_eager -
+    on the weights of the benchmarked model.  Device time of `iters` model calls, x29 calls per latent."""
+    from oracle import nextdit_oracle as O
+    cfg = O.config_2b_gqa()
+    W = {k: v.detach() for k, v in m.state_dict().items()}
+    t = torch.full((2,), 0.5, device=device)
+    mask = mask_dev.to(torch.int64)
+
+    def call():
+        return O.forward_with_cfg_eager(cfg, W, z_dev, t, cap_dev, mask, CFG_SCALE, 1.0, 1.0, 4096, True)
+
+    with torch.no_grad():
+        out = call()
+        call()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            call()
+        e1.record()
+        torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / iters
+    rel = ((out.float() - engine_out.float()).abs().max() / engine_out.float().abs().max()).item()
+    return {"value": 1e3 / (ms * (NUM_STEPS - 1)), "unit": "latents/s", "ms_per_model_call": ms,
+            "kind": "eager PyTorch bf16 restatement of the reference forward_with_cfg (cuBLAS + SDPA flash) on the same GPU, "
+                    "device time of one model call x29",
+            "rel_linf_vs_engine_one_call": rel}
 
 
 # ------------------------------------------------------------------------------------------ engine arm
@@ -325,6 +358,13 @@ def run_engine(args, rank, local_rank, world):
                      "share_of_step": gemm_ms / prof_total if prof_total else None},
         "kernels": {**prof, "attention_tflops": attn_tflops, "attention_frac_of_peak": attn_tflops / pk["bf16"]},
     }
+    if world == 1 and not args.no_gpu_eager_baseline:
+        try:
+            t05 = torch.full((2,), 0.5, device=device)
+            eng = m.forward_with_cfg(z_dev, t05, cap_dev, mask_dev, CFG_SCALE, 1.0, 1.0, 4096, True)
+            line["gpu_eager_baseline"] = gpu_eager_baseline(m, z_dev, cap_dev, mask_dev, device, eng)
+        except Exception as ex:      # a baseline must never take the benchmark line down
+            line["gpu_eager_baseline"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
     if world == 1 and not args.no_cpu_baseline:
         sec, _, _ = cpu_sample_once()
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -342,6 +382,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -314,6 +314,84 @@ def forward_with_cfg(cfg: NextDiTConfig, W: Dict[str, Tensor], x: Tensor, t: Ten
     return torch.cat([eps, rest], dim=1)
 
 
+# --------------------------------------------------------------------------- eager bf16 (stock-PyTorch stand-in)
+
+
+def forward_with_cfg_eager(cfg: NextDiTConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, cap_feats: Tensor, cap_mask: Tensor,
+                           cfg_scale: float, scale_factor: float = 1.0, scale_watershed: float = 1.0,
+                           base_seqlen: Optional[int] = None, proportional_attn: bool = False) -> Tensor:
+    """The same forward_with_cfg written the way the reference RUNS it on a GPU: native bf16 tensors, cuBLAS Linears,
+    fused SDPA (flash) attention with GQA, fp32 only where ``torch.autocast`` keeps fp32 (norm statistics, LayerNorm,
+    RoPE) - i.e. eager PyTorch, one ATen kernel per op.  Used by ``bench.py`` as the same-GPU "stock CUDA path" baseline
+    (the reference itself cannot travel to the GPU box).  W: bf16 tensors on x's device."""
+    bf = torch.bfloat16
+    dev = x.device
+    ps, D, H, Hkv, hd = cfg.patch_size, cfg.dim, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+    half = x[: len(x) // 2]
+    x = torch.cat([half, half], dim=0).to(bf)
+    B, C, Hh, Wd = x.shape
+    N = (Hh // ps) * (Wd // ps)
+
+    def rms(v, w):
+        vf = v.float()
+        return (vf * torch.rsqrt(vf.pow(2).mean(-1, keepdim=True) + cfg.norm_eps)).to(bf) * w
+
+    X = F.linear(patchify(x, ps), W["x_embedder.weight"], W["x_embedder.bias"])
+    ang = rope_angles(hd, Hh // ps, Wd // ps, scale_factor, scale_watershed, float(t[0])).to(dev)
+    cos, sin = torch.cos(ang)[None, :, None, :], torch.sin(ang)[None, :, None, :]
+
+    def rope(v):                                     # [B,N,h,hd] fp32 in, bf16 out
+        vr = v.reshape(B, N, -1, hd // 2, 2)
+        re = vr[..., 0] * cos - vr[..., 1] * sin
+        im = vr[..., 0] * sin + vr[..., 1] * cos
+        return torch.stack([re, im], dim=-1).flatten(3).to(bf)
+
+    temb = timestep_embedding(t.cpu()).to(dev, bf)
+    temb = F.linear(F.silu(F.linear(temb, W["t_embedder.mlp.0.weight"], W["t_embedder.mlp.0.bias"])),
+                    W["t_embedder.mlp.2.weight"], W["t_embedder.mlp.2.bias"])
+    cap = cap_feats.to(bf)
+    m = cap_mask.float().unsqueeze(-1)
+    pool = ((cap * m).sum(dim=1) / m.sum(dim=1)).to(bf)
+    pool = F.layer_norm(pool.float(), (cfg.cap_feat_dim,), W["cap_embedder.0.weight"].float(), W["cap_embedder.0.bias"].float(), 1e-5)
+    c = temb + F.linear(pool.to(bf), W["cap_embedder.1.weight"], W["cap_embedder.1.bias"])
+    scale_self = math.sqrt(math.log(N, base_seqlen) / hd) if proportional_attn else math.sqrt(1.0 / hd)
+    ymask = cap_mask.bool()[:, None, None, :]
+    sc = F.silu(c)
+    for i in range(cfg.n_layers):
+        pre = f"layers.{i}."
+        a = pre + "attention."
+        s_a, g_a, s_m, g_m = F.linear(sc, W[pre + "adaLN_modulation.1.weight"], W[pre + "adaLN_modulation.1.bias"]).chunk(4, dim=1)
+        u = rms(X, W[pre + "attention_norm1.weight"]) * (1 + s_a.unsqueeze(1))
+        q = F.layer_norm(F.linear(u, W[a + "wq.weight"]).float(), (H * hd,), W[a + "q_norm.weight"].float(), W[a + "q_norm.bias"].float(), 1e-5)
+        k = F.layer_norm(F.linear(u, W[a + "wk.weight"]).float(), (Hkv * hd,), W[a + "k_norm.weight"].float(), W[a + "k_norm.bias"].float(), 1e-5)
+        v = F.linear(u, W[a + "wv.weight"]).view(B, N, Hkv, hd)
+        q = rope(q.view(B, N, H, hd)).permute(0, 2, 1, 3)
+        k = rope(k.view(B, N, Hkv, hd)).permute(0, 2, 1, 3)
+        o = F.scaled_dot_product_attention(q, k, v.permute(0, 2, 1, 3), scale=scale_self, enable_gqa=True)
+        yn = rms(cap, W[pre + "attention_y_norm.weight"])
+        yk = F.layer_norm(F.linear(yn, W[a + "wk_y.weight"]).float(), (Hkv * hd,), W[a + "ky_norm.weight"].float(),
+                          W[a + "ky_norm.bias"].float(), 1e-5).to(bf).view(B, -1, Hkv, hd).permute(0, 2, 1, 3)
+        yv = F.linear(yn, W[a + "wv_y.weight"]).view(B, -1, Hkv, hd).permute(0, 2, 1, 3)
+        oy = F.scaled_dot_product_attention(q, yk, yv, attn_mask=ymask, enable_gqa=True)
+        o = o + oy * torch.tanh(W[a + "gate"]).view(1, -1, 1, 1)
+        o = F.linear(o.permute(0, 2, 1, 3).reshape(B, N, H * hd), W[a + "wo.weight"])
+        X = X + torch.tanh(g_a).unsqueeze(1) * rms(o, W[pre + "attention_norm2.weight"])
+        mm = rms(X, W[pre + "ffn_norm1.weight"]) * (1 + s_m.unsqueeze(1))
+        f = pre + "feed_forward."
+        ff = F.linear(F.silu(F.linear(mm, W[f + "w1.weight"])) * F.linear(mm, W[f + "w3.weight"]), W[f + "w2.weight"])
+        X = X + torch.tanh(g_m).unsqueeze(1) * rms(ff, W[pre + "ffn_norm2.weight"])
+    scale = F.linear(sc, W["final_layer.adaLN_modulation.1.weight"], W["final_layer.adaLN_modulation.1.bias"])
+    Xn = F.layer_norm(X.float(), (D,), None, None, 1e-6) * (1 + scale.unsqueeze(1))
+    O = F.linear(Xn.to(bf), W["final_layer.linear.weight"], W["final_layer.linear.bias"])
+    out = unpatchify(O, Hh, Wd, ps, cfg.out_channels)
+    if cfg.learn_sigma:
+        out = out[:, : cfg.in_channels]
+    eps, rest = out[:, :3], out[:, 3:]
+    cond, unc = torch.split(eps, len(eps) // 2, dim=0)
+    half_eps = unc + cfg_scale * (cond - unc)
+    return torch.cat([torch.cat([half_eps, half_eps], dim=0), rest], dim=1)
+
+
 # --------------------------------------------------------------------------- sampler
 
 
