@@ -34,6 +34,7 @@
 #include <stdlib.h>
 
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace ndit {
@@ -157,6 +158,8 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+    pdl_trigger();
+    pdl_wait();         // q/k/v (and the output buffer) belong to the previous kernels until they have completed
 
     if (warp < 4) {
         setmaxnreg_dec<56>();
@@ -463,10 +466,9 @@ static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
     }
     const float log2e = 1.4426950408889634f;
     const dim3 grid((p.N + 2 * AT_BQ - 1) / (2 * AT_BQ), p.H, p.B);
-    kern<<<grid, AT_THREADS, AttnDims<HD>::SMEM_BYTES, stream>>>(p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask,
+    return launch_k(kern, grid, dim3(AT_THREADS), AttnDims<HD>::SMEM_BYTES, stream, p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask,
                                                       p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv, p.scale_self * log2e,
                                                       p.scale_cross * log2e);
-    return cudaGetLastError();
 }
 
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {

@@ -13,8 +13,14 @@
 
 #include "../../include/ndit.h"
 #include "kernels.h"
+#include "launch.cuh"
 
 using namespace ndit;
+
+namespace ndit {
+// programmatic dependent launch for the hot-loop kernels (launch.cuh); process-wide, set by ndit_set_option("pdl") / NDIT_PDL
+int g_pdl = getenv("NDIT_PDL") ? atoi(getenv("NDIT_PDL")) : 0;   // measured: no gain on the power-capped B200 (934.4 vs 934.5 ms / latent)
+}  // namespace ndit
 
 namespace {
 
@@ -321,6 +327,7 @@ extern "C" int64_t ndit_launch_count(ndit_handle h) { return h ? h->launches : 0
 extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!h || !name) return NDIT_ERR_INVALID;
     if (!strcmp(name, "attn_ref")) { h->attn_ref = value; return NDIT_OK; }
+    if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
     if (!strcmp(name, "profile")) {
         h->profile = value;
@@ -705,6 +712,11 @@ static int get_rope(ndit_engine* h, int Hp, int Wp, float theta, float lin, cuda
 static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int Hh, int Ww, const ndit_step_params* sp,
                         bf16* out, cudaStream_t s) {
     if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    struct PdlGuard {       // per-launch CUDA events (profile mode) and overlapping launches do not mix
+        int saved;
+        explicit PdlGuard(bool off) : saved(g_pdl) { if (off) g_pdl = 0; }
+        ~PdlGuard() { g_pdl = saved; }
+    } pdl_guard(h->profile != 0);
     if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
     if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
     if ((Hh & 1) || (Ww & 1) || Hh <= 0 || Ww <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");

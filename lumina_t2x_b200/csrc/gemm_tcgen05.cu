@@ -12,6 +12,7 @@
 // and the epilogue writes silu(a)*b for the pair (FeedForward._forward_silu_gating, model.py:498-499),
 // rounding to bf16 where the reference materialises bf16 tensors.
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace ndit {
@@ -81,6 +82,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();      // the next kernel may start its prologue on SMs this grid has left
+    pdl_wait();         // A (and the buffer behind C) belong to the previous kernel until it has completed
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
@@ -289,6 +292,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_before();
     cluster_sync_all();              // barriers of both CTAs initialised before any remote arrive / multicast commit
     tc_fence_after();
+    pdl_trigger();
+    pdl_wait();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
@@ -429,8 +434,7 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, C, M, N, K, ldc);
-    return cudaGetLastError();
+    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, M, N, K, ldc);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -449,8 +453,7 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
     int grid = m_tiles * n_tiles;
     if (grid > num_sms) grid = num_sms;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, C, M, N, K, ldc);
-    return cudaGetLastError();
+    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, M, N, K, ldc);
 }
 
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {

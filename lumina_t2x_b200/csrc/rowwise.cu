@@ -11,6 +11,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace ndit {
@@ -60,6 +61,8 @@ resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf1
                      const bf16* __restrict__ tanh_g, const bf16* __restrict__ w_pre,
                      const bf16* __restrict__ onepls, const bf16* __restrict__ shift, bf16* __restrict__ u, int M,
                      int rows_per_batch, int D, int mod_stride, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -177,8 +180,8 @@ cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16
     const int nv = (D / 8 + 31) / 32;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
 #define LAUNCH(NVV)                                                                                             \
-    resid_rms_mod_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, w_pre, onepls, shift, u, M,         \
-                                                     rows_per_batch, D, mod_stride, eps)
+    return launch_k(resid_rms_mod_kernel<NVV>, grid, block, 0, s, X, o, w_post, tanh_g, w_pre, onepls, shift, u, M, \
+                    rows_per_batch, D, mod_stride, eps)
     if (nv <= 3) LAUNCH(3);
     else if (nv <= 9) LAUNCH(9);
     else if (nv <= 12) LAUNCH(12);
@@ -647,6 +650,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_rope_qk_kernel(bf16* __restrict__ qkv, int ld, const bf16* __restrict__ qw, const bf16* __restrict__ qb,
                   const bf16* __restrict__ kw, const bf16* __restrict__ kb, const float2* __restrict__ rope, int M,
                   int N_tokens, int H, int Hkv, int hd) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -664,11 +669,11 @@ cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const 
     if (hd % 8 != 0 || H * hd > 12 * 256 || Hkv * hd > 12 * 256 || ld % 8 != 0) return cudaErrorInvalidValue;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
     if (H * hd > 9 * 256)
-        ln_rope_qk_kernel<12, 12><<<grid, block, 0, s>>>(qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
+        return launch_k(ln_rope_qk_kernel<12, 12>, grid, block, 0, s, qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
     else if (Hkv * hd <= 3 * 256)
-        ln_rope_qk_kernel<9, 3><<<grid, block, 0, s>>>(qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
+        return launch_k(ln_rope_qk_kernel<9, 3>, grid, block, 0, s, qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
     else
-        ln_rope_qk_kernel<9, 9><<<grid, block, 0, s>>>(qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
+        return launch_k(ln_rope_qk_kernel<9, 9>, grid, block, 0, s, qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
     return cudaGetLastError();
 }
 
@@ -745,6 +750,8 @@ transpose_v_kernel(const bf16* __restrict__ src, int ld, int col0, size_t sls, b
     // one block = 64 tokens of one (batch, kv head): 16-byte loads along head_dim, token PAIRS packed into 32-bit words
     // in shared memory (pitch 33 words), 128-byte coalesced stores along the token axis.
     __shared__ uint32_t tile[128 * 33];
+    pdl_trigger();
+    pdl_wait();
     const int l = blockIdx.z;
     const int bg = blockIdx.y;                 // b * G + g
     const int b = bg / G, g = bg % G;
@@ -777,8 +784,8 @@ cudaError_t transpose_v(const bf16* src, int ld, int col0, size_t src_layer_stri
                         size_t dst_layer_stride, int B, int N, int G, int hd, int grows, int layers, cudaStream_t s) {
     if (hd % 8 != 0 || hd > 128 || (ld_dst & 1) || ld_dst < ((N + 1) & ~1) || (ld & 7) || (col0 & 7)) return cudaErrorInvalidValue;
     const dim3 grid((N + 63) / 64, B * G, layers);
-    transpose_v_kernel<<<grid, 256, 0, s>>>(src, ld, col0, src_layer_stride, dst, ld_dst, dst_layer_stride, N, G, hd, grows);
-    return cudaGetLastError();
+    return launch_k(transpose_v_kernel, grid, dim3(256), 0, s, src, ld, col0, src_layer_stride, dst, ld_dst, dst_layer_stride, N, G, hd,
+                    grows);
 }
 
 __global__ void fill_ones_row_kernel(bf16* __restrict__ dst, int ld_dst, size_t dls, int n_cols, int hd, int grows) {
