@@ -29,7 +29,9 @@
 // two softmax threads per row (640-thread CTA), an explicit XU token between the two tiles, a speculative (stale) reference
 // maximum with the row maximum accumulated inside the exp loop (480 vs 421 us: the up-front max pass is what keeps the two
 // tiles half a period apart), P kept in tensor memory (attention_tp_tcgen05.cu, 445-466 us).
-// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,256+HDP) O_B [384,384+HDP).
+// Q is a TENSOR-MEMORY operand (head_dim 72 / 48): copied once per CTA from its TMA tile into free TMEM columns, so Q K^T
+// reads only K from shared memory (416.7 -> 412.9 us on the config-2 shape; -14 % shared-memory traffic).
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,256+HDP) Q_A [256+HDP, ..+40) O_B [384,384+HDP) Q_B [384+HDP, ..+40).
 #include <math.h>
 #include <stdlib.h>
 
@@ -75,6 +77,16 @@ struct AttnDims {
     static_assert(SMEM_BYTES <= 227 * 1024, "attention smem budget");
     static constexpr int QK_TX = QTILE_BYTES;
     static constexpr int V_TX = VTILE_BYTES;
+    // Q as a TENSOR-MEMORY operand: Q never changes during the KV loop, so after its TMA load each softmax thread copies
+    // its row (packed bf16 pairs, one 32-bit column per pair) into the free TMEM columns next to O_x, and S = Q K^T is issued
+    // with the A operand in TMEM.  The tensor core then fetches only K from shared memory for Q K^T: -40 KB of the 288 KB
+    // of shared-memory traffic per pair of blocks.  Needs (64 + 16 N16) / 2 free columns per tile: head_dim 72 and 48.
+#ifdef AT_NO_Q_TMEM
+    static constexpr bool Q_TMEM = false;
+#else
+    static constexpr bool Q_TMEM = HDP + (64 + 16 * N16) / 2 <= 128;
+#endif
+    static constexpr uint32_t TM_Q = 256 + HDP;             // + x * 128 (inside the 128-column slot of O_x)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -120,7 +132,8 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     auto p_full = [&](int x) { return bar0 + 8u * (BB + 4 + x); };   // P_x in smem (and O_x rescaled if needed)
     auto o_full = [&](int x) { return bar0 + 8u * (BB + 6 + x); };   // O_x += P_x V finished (P_x smem reusable)
     const uint32_t stagger_bar = bar0 + 8u * (BB + 8);                // tile B starts ~half a softmax period after tile A
-    const uint32_t tmem_ptr_addr = bar0 + 8u * (BB + 9);
+    auto q_ready = [&](int x) { return bar0 + 8u * (BB + 9 + x); };  // Q_x copied to tensor memory
+    const uint32_t tmem_ptr_addr = bar0 + 8u * (BB + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (2 * AT_BQ);
@@ -147,6 +160,8 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             mbar_init(kv_empty(s), 2);
         }
         mbar_init(stagger_bar, 4);
+        mbar_init(q_ready(0), 4);
+        mbar_init(q_ready(1), 4);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -222,13 +237,18 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                     const uint64_t dq = make_smem_desc_kmajor(qa, 1024, UMMA_SW128);
                     const uint64_t dk = make_smem_desc_kmajor(ka, 1024, UMMA_SW128);
                     const uint32_t d = tmem_base + AT_TM_S + x * 128;
+                    const uint32_t tq = tmem_base + Dm::TM_Q + x * 128;
 #pragma unroll
-                    for (int k = 0; k < Dm::NK64; ++k) umma_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+                    for (int k = 0; k < Dm::NK64; ++k) {
+                        if (Dm::Q_TMEM) umma_ts(d, tq + 8 * k, dk + 2 * k, idesc_qk, k != 0);
+                        else umma_ss(d, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+                    }
 #pragma unroll
                     for (int c = 0; c < Dm::N16; ++c) {
                         const uint64_t dq16 = make_smem_desc_kmajor(qa + AT_Q64_BYTES + c * AT_Q16_BYTES, 256, UMMA_SW32);
                         const uint64_t dk16 = make_smem_desc_kmajor(ka + AT_Q64_BYTES + c * AT_Q16_BYTES, 256, UMMA_SW32);
-                        umma_ss(d, dq16, dk16, idesc_qk, 1);
+                        if (Dm::Q_TMEM) umma_ts(d, tq + 32 + 8 * c, dk16, idesc_qk, 1);
+                        else umma_ss(d, dq16, dk16, idesc_qk, 1);
                     }
                     umma_commit(s_full(x));
                 }
@@ -255,7 +275,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 }
                 __syncwarp();
             };
-            mbar_wait(q_full(x), 0);
+            mbar_wait(Dm::Q_TMEM ? q_ready(x) : q_full(x), 0);
             issue_qk(0);
             for (int jj = 0; jj < n_total; ++jj) {
                 // S_x(jj+1) is issued as soon as softmax x holds S_x(jj) in registers, well ahead of P_x(jj) V
@@ -275,6 +295,39 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
         const uint32_t to = tmem_base + lane_sel + AT_TM_O + x * 128;
         const uint32_t pbase = sbase + Dm::OFF_P + x * AT_PTILE_BYTES + r * 128;
         const uint32_t rsw = static_cast<uint32_t>(r & 7);
+
+        if (Dm::Q_TMEM) {
+            // ---- Q_x row r: shared memory (TMA swizzle layouts) -> tensor memory columns TM_Q .. (lane = row)
+            const uint32_t tq = tmem_base + lane_sel + Dm::TM_Q + x * 128;
+            const uint32_t qs = sbase + Dm::OFF_Q + x * Dm::QTILE_BYTES;
+            mbar_wait(q_full(x), 0);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {                 // 64-wide chunk: 16-byte piece j sits at (j ^ (r & 7)) (128B swizzle)
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t addr = qs + r * 128 + ((static_cast<uint32_t>(j + u) ^ rsw) << 4);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(v[4 * u]), "=r"(v[4 * u + 1]), "=r"(v[4 * u + 2]), "=r"(v[4 * u + 3]) : "r"(addr));
+                }
+                tmem_st_32x32b_x8(tq + 4 * j, v);
+            }
+#pragma unroll
+            for (int c = 0; c < Dm::N16; ++c) {              // 16-wide chunks: piece j at (j ^ ((r >> 2) & 1)) (32B swizzle)
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t addr = qs + AT_Q64_BYTES + c * AT_Q16_BYTES + r * 32 + ((static_cast<uint32_t>(u) ^ ((r >> 2) & 1u)) << 4);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(v[4 * u]), "=r"(v[4 * u + 1]), "=r"(v[4 * u + 2]), "=r"(v[4 * u + 3]) : "r"(addr));
+                }
+                tmem_st_32x32b_x8(tq + 32 + 8 * c, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready(x));
+        }
 
         uint32_t o_self[HD / 2];
 #pragma unroll
