@@ -4,12 +4,16 @@ Mirrors ``lumina_next_t2i/transport/__init__.py:4-66`` (create_transport), ``tra
 (Sampler.sample_ode), ``integrators.py:79-116`` (the ``ode`` helper) and the mini flavour's
 ``lumina_next_t2i_mini/transport.py:57-111`` (``ODE``).  Fixed-grid ``euler`` / ``midpoint`` solves whose model
 function is ``NextDiT.forward_with_cfg`` of the B200 engine run entirely inside libndit_b200.so
-(``ndit_sample``); any other model function is driven by the same fixed-grid loop in PyTorch.  Training
-losses, SDE sampling and likelihoods are out of scope.
+(``ndit_sample``); any other model function is driven by the same fixed-grid loop in PyTorch.
+``Sampler.sample_sde`` (``transport.py:285-344``, ``integrators.py:5-76``, ``path.py`` ICPlan) is mirrored for the
+velocity-prediction / Linear-path configuration as a host loop around the model function: the
+stochastic sampler draws fresh noise on the host every step, so there is nothing to fuse.  Training losses and
+likelihoods are out of scope.
 """
 from __future__ import annotations
 
 import enum
+import math
 from typing import Callable, Optional
 
 import torch as th
@@ -176,8 +180,97 @@ class Sampler:
 
         return _sample
 
-    def sample_sde(self, *a, **k):
-        raise NotImplementedError("SDE sampling is out of scope for the B200 engine (SURVEY.md 8f)")
+    # ------------------------------------------------------------------ SDE sampling (velocity model, Linear path)
+    @staticmethod
+    def _expand(t, x):
+        return t.view(t.size(0), *([1] * (x.dim() - 1)))
+
+    def _diffusion(self, x, t, form, norm):
+        """path.py ICPlan.compute_diffusion / compute_drift (alpha_t = t, sigma_t = 1 - t)."""
+        t = self._expand(t, x)
+        if form == "constant":
+            return norm
+        if form == "SBDM":
+            sigma_t, d_sigma_t = 1 - t, -1
+            return norm * ((1 / t) * (sigma_t ** 2) - sigma_t * d_sigma_t)
+        if form in ("sigma", "linear"):
+            return norm * (1 - t)
+        if form == "decreasing":
+            return 0.25 * (norm * th.cos(math.pi * t) + 1) ** 2
+        if form == "inccreasing-decreasing":          # (sic) the reference's key
+            return norm * th.sin(math.pi * t) ** 2
+        raise NotImplementedError(f"Diffusion form {form} not implemented")
+
+    def _score(self, velocity, x, t):
+        """path.py ICPlan.get_score_from_velocity."""
+        t = self._expand(t, x)
+        alpha_t, d_alpha_t, sigma_t, d_sigma_t = t, 1, 1 - t, -1
+        reverse_alpha_ratio = alpha_t / d_alpha_t
+        var = sigma_t ** 2 - reverse_alpha_ratio * d_sigma_t * sigma_t
+        return (reverse_alpha_ratio * velocity - x) / var
+
+    def sample_sde(self, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean",
+                   last_step_size=0.04, num_steps=250):
+        """transport.py:285-344 + integrators.py:5-76.  Returns ``fn(init, model, **kw) -> list of num_steps tensors``.
+        The reference evaluates the model twice per drift (once for the drift, once for the score) on identical inputs;
+        one evaluation is reused here."""
+        tr = self.transport
+        if tr.model_type != ModelType.VELOCITY or tr.path_type != PathType.LINEAR:
+            raise NotImplementedError("the B200 transport implements SDE sampling for the velocity / Linear-path configuration")
+        if sampling_method not in ("Euler", "Heun"):
+            raise NotImplementedError("Smapler type not implemented.")
+        if last_step not in (None, "Mean", "Tweedie", "Euler"):
+            raise NotImplementedError()
+        if last_step is None:
+            last_step_size = 0.0
+        t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, diffusion_form=diffusion_form, sde=True, eval=True, reverse=False,
+                                   last_step_size=last_step_size)
+        assert t0 < t1, "SDE sampler has to be in forward time"
+        grid = th.linspace(t0, t1, num_steps)
+        dt = grid[1] - grid[0]
+
+        def drift_and_score(x, t, model, kw):
+            v = model(x, t, **kw)
+            assert v.shape == x.shape, "Output shape from ODE solver must match input shape"
+            return v, self._score(v, x, t)
+
+        def sde_drift(x, t, model, kw):
+            v, sc = drift_and_score(x, t, model, kw)
+            return v + self._diffusion(x, t, diffusion_form, diffusion_norm) * sc
+
+        def _sample(init, model, **kw):
+            x, xs = init, []
+            with th.no_grad():
+                for ti in grid[:-1]:
+                    w_cur = th.randn(x.size()).to(x)
+                    dw = w_cur * th.sqrt(dt)
+                    t = th.ones(x.size(0)).to(x) * ti
+                    if sampling_method == "Euler":      # Euler-Maruyama
+                        drift = sde_drift(x, t, model, kw)
+                        diffusion = self._diffusion(x, t, diffusion_form, diffusion_norm)
+                        x = x + drift * dt + th.sqrt(2 * diffusion) * dw
+                    else:                               # Heun
+                        diffusion = self._diffusion(x, t, diffusion_form, diffusion_norm)
+                        xhat = x + th.sqrt(2 * diffusion) * dw
+                        k1 = sde_drift(xhat, t, model, kw)
+                        xp = xhat + dt * k1
+                        k2 = sde_drift(xp, t + dt, model, kw)
+                        x = xhat + 0.5 * dt * (k1 + k2)
+                    xs.append(x)
+                ts = th.ones(init.size(0), device=init.device) * t1
+                x = xs[-1]
+                if last_step == "Mean":
+                    x = x + sde_drift(x, ts, model, kw) * last_step_size
+                elif last_step == "Euler":
+                    x = x + model(x, ts, **kw) * last_step_size
+                elif last_step == "Tweedie":
+                    _, sc = drift_and_score(x, ts, model, kw)
+                    x = x / ts[0] + ((1 - ts[0]) ** 2) / ts[0] * sc
+                xs.append(x)
+            assert len(xs) == num_steps, "Samples does not match the number of steps"
+            return xs
+
+        return _sample
 
 
 class ODE:

@@ -150,6 +150,21 @@ def import_reference_flag_dit():
     return mod
 
 
+def import_reference_full_transport():
+    """Unmodified ``lumina_next_t2i/transport`` package (create_transport, Sampler with sample_ode AND sample_sde)."""
+    import importlib.util
+    install_shims()
+    d = REF_ROOT + "/lumina_next_t2i/transport"
+    spec = importlib.util.spec_from_file_location("ref_full_transport", d + "/__init__.py", submodule_search_locations=[d])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_full_transport"] = mod
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    return mod
+
+
 def import_reference_mini():
     """Returns (models_module, transport_module) of lumina_next_t2i_mini, unmodified."""
     install_shims()

@@ -162,6 +162,31 @@ def make_moe() -> None:
         del m, W
 
 
+def make_sde() -> None:
+    """Stochastic sampler of the full transport package (transport.py:285-344) with a toy velocity function: pins the step
+    formulas, the noise consumption order of the global torch RNG and the last-step variants."""
+    from oracle.harness.ref_import import import_reference_full_transport
+    T = import_reference_full_transport()
+
+    def toy(x, t, **kw):
+        return torch.sin(3.0 * x) * (1.0 + t.view(-1, 1, 1, 1)) - 0.5 * x
+
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(11))
+    cases = [dict(sampling_method="Euler", diffusion_form="sigma", diffusion_norm=1.0, last_step="Mean", last_step_size=0.04, num_steps=8),
+             dict(sampling_method="Heun", diffusion_form="linear", diffusion_norm=0.5, last_step="Euler", last_step_size=0.02, num_steps=6),
+             dict(sampling_method="Euler", diffusion_form="decreasing", diffusion_norm=1.0, last_step="Tweedie", last_step_size=0.05, num_steps=5),
+             dict(sampling_method="Euler", diffusion_form="inccreasing-decreasing", diffusion_norm=0.3, last_step=None, last_step_size=0.04,
+                  num_steps=5)]      # ("constant" makes the reference itself fail: th.sqrt of a Python float)
+    out = []
+    for i, c in enumerate(cases):
+        fn = T.Sampler(T.create_transport("Linear", "velocity")).sample_sde(**c)
+        torch.manual_seed(100 + i)
+        xs = fn(z.clone(), toy)
+        out.append(dict(kw=c, seed=100 + i, xs=torch.stack(xs)))
+        print("sde", c["sampling_method"], c["diffusion_form"], c["last_step"], tuple(out[-1]["xs"].shape), out[-1]["xs"][-1].abs().max().item())
+    torch.save(dict(z=z, cases=out), os.path.join(OUT, "toy_sde.pt"))
+
+
 def make_flag_dit() -> None:
     """Flag-DiT (Lumina-T2I, BASELINE config 4 / SURVEY 8a15): unmodified lumina_t2i/models/model.py (fp32, CPU, fairscale
     at world size 1).  Tiny models with the flagship head_dim 96: default call, proportional attention + NTK factor (the

@@ -135,6 +135,26 @@ def test_generic_fixed_grid_loop(method):
         T.Sampler(tr).sample_ode(sampling_method="dopri5", num_steps=5)(x0, model)
 
 
+def test_sde_sampler_matches_reference_fixture():
+    """Sampler.sample_sde (Euler-Maruyama / Heun, four diffusion forms, all last-step variants) against trajectories of the
+    unmodified reference transport package on a toy velocity (tests/golden/toy_sde.pt, oracle/make_golden.py::make_sde):
+    same formulas AND same consumption order of the global torch RNG -> bit-identical."""
+    from lumina_t2x_b200 import transport as T
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "toy_sde.pt"), map_location="cpu", weights_only=False)
+
+    def toy(x, t, **kw):
+        return torch.sin(3.0 * x) * (1.0 + t.view(-1, 1, 1, 1)) - 0.5 * x
+
+    for c in fx["cases"]:
+        fn = T.Sampler(T.create_transport("Linear", "velocity")).sample_sde(**c["kw"])
+        torch.manual_seed(c["seed"])
+        xs = fn(fx["z"].clone(), toy)
+        assert len(xs) == c["kw"]["num_steps"] and torch.isfinite(c["xs"]).all()
+        assert torch.equal(torch.stack(xs), c["xs"]), c["kw"]
+    with pytest.raises(NotImplementedError):
+        T.Sampler(T.create_transport("Linear", "noise")).sample_sde()
+
+
 def test_shard_ranges():
     from lumina_t2x_b200.parallel import shard_range, shard_sizes
     for total in (0, 1, 7, 8, 9, 64):
