@@ -130,8 +130,10 @@ int ndit_sample_host(ndit_handle h, const void* z_host, const void* cap_feats_ho
 
 /* --- instrumentation */
 int64_t ndit_launch_count(ndit_handle h);          /* kernels launched by this handle so far */
-int ndit_set_option(ndit_handle h, const char* name, int32_t value);   /* "attn_ref" = 1: debug attention;
-                                                                          "profile" = 1: CUDA events around every launch */
+int ndit_set_option(ndit_handle h, const char* name, int32_t value);
+/* options: "attn_ref" = 1: CUDA-core debug attention kernel; "attn_tp" = 1: experimental attention kernel with P in tensor
+ * memory (head_dim 72); "pdl" = 1: programmatic dependent launch for the hot-loop kernels (process-wide); "profile" = 1:
+ * record a CUDA-event pair around every kernel launch, read back with ndit_profile_read. */
 /* Sums the per-launch CUDA-event durations recorded since "profile" was switched on (or since the last read),
  * per kernel class: 0 gemm_qkv, 1 gemm_wo, 2 gemm_w13(swiglu), 3 gemm_w2, 4 attention, 5 row-wise, 6 conditioning. */
 #define NDIT_PROFILE_CLASSES 7
