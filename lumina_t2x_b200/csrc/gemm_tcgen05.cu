@@ -26,8 +26,8 @@ struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+    static constexpr int TMEM_COLS = BN > 128 ? 512 : 256;  // two accumulator stages of BN columns, power-of-two allocation
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -472,6 +472,7 @@ cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
         return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
     }
     if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
     return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
 }
 

@@ -83,6 +83,16 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
     const int m_tiles = (M + 127) / 128;
     int bn = 256;
     if (epi != EPI_SWIGLU && m_tiles * ((N + 255) / 256) < num_sms) bn = 128;
+    // wave quantisation: the fused q|k|v projection (N = 3456 = 13.5 x 256 = 18 x 192) needs 7 rounds of 256-wide tiles on 148
+    // SMs (6.05 waves) but 8 rounds of 192-wide ones: 8 x 0.75 = 6.0 tile-times instead of 6.5
+    // MEASURED (B200, 8192 x 3456 x 2304): 108.7 us with 192-wide tiles vs 104.1 us with 256-wide ones - the extra shared-memory
+    // operand traffic per flop costs more than the saved half round.  Off unless NDIT_GEMM_BN192=1.
+    static const int bn192_env = getenv("NDIT_GEMM_BN192") ? atoi(getenv("NDIT_GEMM_BN192")) : 0;
+    if (bn192_env && bn == 256 && epi != EPI_SWIGLU && N % 192 == 0 && N % 256 != 0) {
+        const long t256 = (long)m_tiles * ((N + 255) / 256), t192 = (long)m_tiles * (N / 192);
+        const long r256 = (t256 + num_sms - 1) / num_sms, r192 = (t192 + num_sms - 1) / num_sms;
+        if (r192 * 3 < r256 * 4) bn = 192;
+    }
     p->bn = bn;
     // CTA-pair kernel for the large GEMMs: 256x256 tiles, each CTA loads 128 rows of A and 128 rows of W
     static const int pair_env = getenv("NDIT_GEMM_PAIR") ? atoi(getenv("NDIT_GEMM_PAIR")) : 1;
