@@ -45,7 +45,6 @@ namespace ndit {
 
 constexpr int AT_BQ = 128;            // rows per query tile
 constexpr int AT_BKV = 128;           // kv rows per block
-constexpr int AT_MAX_STAGES = 3;
 constexpr int AT_THREADS = 384;       // warps 0-3 control (TMA, MMA tile A, MMA tile B, idle), 4-7 softmax A, 8-11 softmax B
 
 constexpr int AT_Q64_BYTES = AT_BQ * 128;        // 16 KB  [rows x 64] bf16, 128B swizzle

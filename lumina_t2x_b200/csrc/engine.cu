@@ -938,10 +938,9 @@ extern "C" int ndit_profile_read(ndit_handle h, float* ms_out, int64_t* count_ou
 
 // ------------------------------------------------------------------------------------ single ops
 
-static thread_local char g_op_err[512] = "";
+// errors of the handle-less entry points are reported through ndit_last_error(NULL), like ndit_create's
 static int op_fail(int code, const char* what, cudaError_t e) {
     snprintf(g_create_err, sizeof(g_create_err), "%s: %s", what, e == cudaSuccess ? tmap_last_error() : cudaGetErrorString(e));
-    (void)g_op_err;
     return code;
 }
 static int op_num_sms() {
