@@ -30,7 +30,8 @@
 // maximum with the row maximum accumulated inside the exp loop (480 vs 421 us: the up-front max pass is what keeps the two
 // tiles half a period apart), P kept in tensor memory (attention_tp_tcgen05.cu, 445-466 us), a second buffer for the first half
 // of P in the dead Q tile so that the softmax never waits for P V before it starts writing (449 vs 409 us: same story - every
-// change that lets a softmax warpgroup run ahead destroys the half-period offset between the two tiles).
+// change that lets a softmax warpgroup run ahead destroys the half-period offset between the two tiles), and enforcing that
+// offset with "half of my exponentials are issued" barriers between the two warpgroups (440 us, 443 us with the extra buffer).
 // Q is a TENSOR-MEMORY operand (head_dim 72 / 48): copied once per CTA from its TMA tile into free TMEM columns, so Q K^T
 // reads only K from shared memory (416.7 -> 412.9 us on the config-2 shape; -14 % shared-memory traffic).
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,256+HDP) Q_A [256+HDP, ..+40) O_B [384,384+HDP) Q_B [384+HDP, ..+40).
