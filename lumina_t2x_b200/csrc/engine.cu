@@ -303,6 +303,7 @@ extern "C" int ndit_create(const ndit_config* cfg, ndit_handle* out) {
     if (r) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
         for (void* p : h->allocs) cudaFree(p);
+        if (h->tlogits_host) cudaFreeHost(h->tlogits_host);
         delete h;
         *out = nullptr;
         return r;
