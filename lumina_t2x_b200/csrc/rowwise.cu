@@ -10,6 +10,8 @@
 //   timestep embed    model.py:64-87; caption pool :847-851
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -176,11 +178,152 @@ resid_rms_mod_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf1
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same op with ONE ROW PER 4 WARPS (128-thread block, <= 3 vectors per thread): ~50 registers instead of 108, so 8 blocks
+// = 32 warps per SM instead of 16 - the register-resident kernel above is latency-bound at 23 % occupancy
+// (profiles/r01_ncu_resid_rms_mod_full_final.txt).  Two block-level reductions (warp shuffle + 4 partials in shared memory).
+template <int NV>
+__global__ void __launch_bounds__(128, 8)
+resid_rms_mod4_kernel(bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
+                      const bf16* __restrict__ tanh_g, const bf16* __restrict__ w_pre, const bf16* __restrict__ onepls,
+                      const bf16* __restrict__ shift, bf16* __restrict__ u, int M, int rows_per_batch, int D, int mod_stride,
+                      float eps) {
+    __shared__ float red1[4], red2[4];
+    pdl_trigger();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nvec = D >> 3;
+    const int b = row / rows_per_batch;
+    const size_t off = static_cast<size_t>(row) * D;
+    uint4 xv[NV];
+    float ss2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * 128;
+        if (v < nvec) xv[i] = *reinterpret_cast<const uint4*>(X + off + v * 8);
+    }
+    if (o != nullptr) {
+        uint4 ov[NV];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = tid + i * 128;
+            if (v < nvec) ov[i] = *reinterpret_cast<const uint4*>(o + off + v * 8);
+        }
+        float rinv = 0.f;
+        if (w_post != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int v = tid + i * 128;
+                if (v < nvec) {
+                    const uint32_t w4[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16(w4[j]);
+                        ss = fmaf(f.x, f.x, ss);
+                        ss = fmaf(f.y, f.y, ss);
+                    }
+                }
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) red1[warp] = ss;
+            __syncthreads();
+            rinv = rsqrtf((red1[0] + red1[1] + red1[2] + red1[3]) / D + eps);
+        }
+        const bf16* tg = tanh_g + static_cast<size_t>(b) * mod_stride;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = tid + i * 128;
+            if (v < nvec) {
+                const uint4 wq = w_post != nullptr ? *reinterpret_cast<const uint4*>(w_post + v * 8) : make_uint4(0, 0, 0, 0);
+                const uint4 gq = *reinterpret_cast<const uint4*>(tg + v * 8);
+                const uint32_t o4[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
+                const uint32_t w4[4] = {wq.x, wq.y, wq.z, wq.w};
+                const uint32_t g4[4] = {gq.x, gq.y, gq.z, gq.w};
+                uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    bf162 r2 = as_bf162(o4[j]);
+                    if (w_post != nullptr) {
+                        const float2 of = unpack_bf16(o4[j]);
+                        const bf162 n2 = __floats2bfloat162_rn(of.x * rinv, of.y * rinv);
+                        r2 = __hmul2_rn(n2, as_bf162(w4[j]));
+                    }
+                    const bf162 p2 = __hmul2_rn(as_bf162(g4[j]), r2);
+                    const bf162 x2 = __hadd2_rn(as_bf162(x4[j]), p2);
+                    x4[j] = as_u32(x2);
+                    const float2 xf = __bfloat1622float2(x2);
+                    ss2 = fmaf(xf.x, xf.x, ss2);
+                    ss2 = fmaf(xf.y, xf.y, ss2);
+                }
+                xv[i] = make_uint4(x4[0], x4[1], x4[2], x4[3]);
+                *reinterpret_cast<uint4*>(X + off + v * 8) = xv[i];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = tid + i * 128;
+            if (v < nvec) {
+                const uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16(x4[j]);
+                    ss2 = fmaf(f.x, f.x, ss2);
+                    ss2 = fmaf(f.y, f.y, ss2);
+                }
+            }
+        }
+    }
+    if (u == nullptr) return;
+    ss2 = warp_sum(ss2);
+    if (lane == 0) red2[warp] = ss2;
+    __syncthreads();
+    const float rinv2 = rsqrtf((red2[0] + red2[1] + red2[2] + red2[3]) / D + eps);
+    const bf16* op = onepls + static_cast<size_t>(b) * mod_stride;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * 128;
+        if (v < nvec) {
+            const uint4 wq = *reinterpret_cast<const uint4*>(w_pre + v * 8);
+            const uint4 sq = *reinterpret_cast<const uint4*>(op + v * 8);
+            const uint4 hq = shift != nullptr ? *reinterpret_cast<const uint4*>(shift + static_cast<size_t>(b) * mod_stride + v * 8)
+                                              : make_uint4(0, 0, 0, 0);
+            const uint32_t w4[4] = {wq.x, wq.y, wq.z, wq.w};
+            const uint32_t s4[4] = {sq.x, sq.y, sq.z, sq.w};
+            const uint32_t h4[4] = {hq.x, hq.y, hq.z, hq.w};
+            const uint32_t x4[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+            uint32_t r4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 xf = unpack_bf16(x4[j]);
+                const bf162 n2 = __floats2bfloat162_rn(xf.x * rinv2, xf.y * rinv2);
+                bf162 m2 = __hmul2_rn(__hmul2_rn(n2, as_bf162(w4[j])), as_bf162(s4[j]));
+                if (shift != nullptr) m2 = __hadd2_rn(m2, as_bf162(h4[j]));
+                r4[j] = as_u32(m2);
+            }
+            *reinterpret_cast<uint4*>(u + off + v * 8) = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+        }
+    }
+}
+
 cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* w_pre,
                           const bf16* onepls, const bf16* shift, bf16* u, int M, int rows_per_batch, int D, int mod_stride,
                           float eps, cudaStream_t s) {
     if (D % 8 != 0 || D > MAX_VEC * 256 || mod_stride % 8 != 0) return cudaErrorInvalidValue;
     const int nv = (D / 8 + 31) / 32;
+    // NDIT_RESID4=1: one row per 128-thread block (32 warps per SM).  Measured at the very end of round 1 with
+    // tools/resid_bench.py: 33.1 us per launch on the 8192 x 2304 shape (one-row-per-warp kernel: 38.4 us under ncu; its
+    // number from the same harness was not captured before the GPU budget ran out) - opt-in until round 2 has re-measured
+    // it inside the step.  Outputs differ from the default kernel in 1 ulp on ~1e-5 of the elements (reduction order).
+    static const int resid4_env = getenv("NDIT_RESID4") ? atoi(getenv("NDIT_RESID4")) : 0;
+    if (resid4_env && M >= 1024 && D / 8 <= 3 * 128) {
+        if (D / 8 <= 2 * 128) return launch_k(resid_rms_mod4_kernel<2>, dim3(M), dim3(128), 0, s, X, o, w_post, tanh_g, w_pre, onepls, shift, u, M,
+                                              rows_per_batch, D, mod_stride, eps);
+        return launch_k(resid_rms_mod4_kernel<3>, dim3(M), dim3(128), 0, s, X, o, w_post, tanh_g, w_pre, onepls, shift, u, M, rows_per_batch,
+                        D, mod_stride, eps);
+    }
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
 #define LAUNCH(NVV)                                                                                             \
     return launch_k(resid_rms_mod_kernel<NVV>, grid, block, 0, s, X, o, w_post, tanh_g, w_pre, onepls, shift, u, M, \
