@@ -73,10 +73,14 @@ def create_transport(path_type="Linear", prediction="velocity", loss_weight=None
     model_type = {"noise": ModelType.NOISE, "score": ModelType.SCORE}.get(prediction, ModelType.VELOCITY)
     loss_type = {"velocity": WeightType.VELOCITY, "likelihood": WeightType.LIKELIHOOD}.get(loss_weight, WeightType.NONE)
     ptype = {"Linear": PathType.LINEAR, "GVP": PathType.GVP, "VP": PathType.VP}[path_type]
+    # the statements are sequential on purpose: like the reference, the sample_eps line tests train_eps AFTER it has been
+    # given its default, so a sample_eps left at None stays None (and check_interval(eval=True) then fails like the reference's)
     if ptype == PathType.VP:
-        train_eps, sample_eps = (1e-5 if train_eps is None else train_eps), (1e-3 if train_eps is None else sample_eps)
+        train_eps = 1e-5 if train_eps is None else train_eps
+        sample_eps = 1e-3 if train_eps is None else sample_eps
     elif model_type != ModelType.VELOCITY:
-        train_eps, sample_eps = (1e-3 if train_eps is None else train_eps), (1e-3 if train_eps is None else sample_eps)
+        train_eps = 1e-3 if train_eps is None else train_eps
+        sample_eps = 1e-3 if train_eps is None else sample_eps
     else:
         train_eps = sample_eps = 0
     return Transport(model_type=model_type, path_type=ptype, loss_type=loss_type, train_eps=train_eps,

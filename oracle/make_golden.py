@@ -187,6 +187,29 @@ def make_sde() -> None:
     torch.save(dict(z=z, cases=out), os.path.join(OUT, "toy_sde.pt"))
 
 
+def make_transport_table() -> None:
+    """Host logic of the full transport package: create_transport's eps selection and Transport.check_interval for every
+    combination the mirror accepts (transport/__init__.py:4-66, transport.py:67-93)."""
+    import itertools
+    from oracle.harness.ref_import import import_reference_full_transport
+    T = import_reference_full_transport()
+    rows = []
+    for path, pred, lw, te, se in itertools.product(("Linear", "GVP", "VP"), ("velocity", "noise", "score"), (None, "velocity", "likelihood"),
+                                                    (None, 1e-4), (None, 2e-3)):
+        tr = T.create_transport(path, pred, lw, te, se)
+        for form, sde, rev, ev, lss in itertools.product(("SBDM", "sigma"), (False, True), (False, True), (False, True), (0.0, 0.04)):
+            row = dict(args=(path, pred, lw, te, se), kw=dict(diffusion_form=form, sde=sde, reverse=rev, eval=ev, last_step_size=lss),
+                       train_eps=tr.train_eps, sample_eps=tr.sample_eps)
+            try:        # some combinations make the reference itself fail (eps left at None): the error type is part of the contract
+                t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, **row["kw"])
+                row.update(t0=None if t0 is None else float(t0), t1=None if t1 is None else float(t1), error=None)
+            except Exception as ex:
+                row.update(t0=None, t1=None, error=type(ex).__name__)
+            rows.append(row)
+    torch.save(rows, os.path.join(OUT, "transport_table.pt"))
+    print("transport table", len(rows), "rows")
+
+
 def make_flag_dit() -> None:
     """Flag-DiT (Lumina-T2I, BASELINE config 4 / SURVEY 8a15): unmodified lumina_t2i/models/model.py (fp32, CPU, fairscale
     at world size 1).  Tiny models with the flagship head_dim 96: default call, proportional attention + NTK factor (the

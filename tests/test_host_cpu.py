@@ -100,7 +100,7 @@ def test_create_transport_and_grid_semantics():
     assert tr.train_eps == 0 and tr.sample_eps == 0 and tr.model_type == T.ModelType.VELOCITY
     assert tr.check_interval(0, 0, sde=False, eval=True, reverse=False, last_step_size=0.0) == (0, 1)
     tr2 = T.create_transport("Linear", "noise")
-    assert tr2.train_eps == 1e-3 and tr2.sample_eps == 1e-3
+    assert tr2.train_eps == 1e-3 and tr2.sample_eps is None          # the reference's quirk, pinned by transport_table.pt
     for n, s in ((30, 1.0), (50, 4.0), (5, None)):
         assert torch.equal(T._time_grid(0, 1, n, s), O.time_grid(n, s))
     g = T._time_grid(0, 1, 30, 4.0)
@@ -133,6 +133,24 @@ def test_generic_fixed_grid_loop(method):
     assert torch.allclose(ode.sample(x0, model, scale=1.0), out)
     with pytest.raises(NotImplementedError):
         T.Sampler(tr).sample_ode(sampling_method="dopri5", num_steps=5)(x0, model)
+
+
+def test_create_transport_and_check_interval_table_matches_reference():
+    """3456 combinations of create_transport(path, prediction, loss_weight, train_eps, sample_eps) x check_interval(...) recorded
+    from the unmodified reference package (tests/golden/transport_table.pt): same eps defaults (including the reference's
+    sample_eps-stays-None quirk), same intervals, same error type where the reference itself fails."""
+    from lumina_t2x_b200 import transport as T
+    rows = torch.load(os.path.join(os.path.dirname(__file__), "golden", "transport_table.pt"), map_location="cpu", weights_only=False)
+    assert len(rows) == 3456
+    for r in rows:
+        tr = T.create_transport(*r["args"])
+        assert (tr.train_eps, tr.sample_eps) == (r["train_eps"], r["sample_eps"]), r
+        try:
+            t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, **r["kw"])
+            got = (None if t0 is None else float(t0), None if t1 is None else float(t1), None)
+        except Exception as ex:
+            got = (None, None, type(ex).__name__)
+        assert got == (r["t0"], r["t1"], r["error"]), (r, got)
 
 
 def test_sde_sampler_matches_reference_fixture():
