@@ -105,8 +105,8 @@ def test_create_transport_and_grid_semantics():
         assert torch.equal(T._time_grid(0, 1, n, s), O.time_grid(n, s))
     g = T._time_grid(0, 1, 30, 4.0)
     assert len(g) == 30 and g[0] == 0 and abs(g[-1] - 1) < 1e-6      # 30 points = 29 integration steps
-    with pytest.raises(NotImplementedError):
-        T.Sampler(tr2).sample_ode(sampling_method="euler")
+    with pytest.raises(NotImplementedError):       # noise / score parameterisations are outside the mirrored ODE path
+        T.Sampler(T.create_transport("Linear", "noise", None, 1e-3, 1e-3)).sample_ode(sampling_method="euler")
 
 
 @pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
