@@ -170,15 +170,17 @@ class Sampler:
                    time_shifting_factor=None):
         tr = self.transport
         t0, t1 = tr.check_interval(tr.train_eps, tr.sample_eps, sde=False, eval=True, reverse=reverse, last_step_size=0.0)
-        velocity_linear = tr.model_type == ModelType.VELOCITY and not reverse
-        if not velocity_linear:
-            raise NotImplementedError("the B200 transport implements velocity-prediction forward-time ODE sampling "
-                                      "(the Lumina-Next configuration); score/noise parameterisations and reverse solves are out of scope")
+        if tr.model_type != ModelType.VELOCITY:
+            raise NotImplementedError("the B200 transport implements velocity-prediction ODE sampling (the Lumina configuration); "
+                                      "score / noise parameterisations are out of scope")
+        # reverse=True: the reference evaluates the drift at 1 - t but also flips the interval to (1, 0), which its own ode class
+        # rejects - same assertion here
         assert t0 < t1, "ODE sampler has to be in forward time"
         grid = _time_grid(t0, t1, num_steps, time_shifting_factor)
+        wrap = (lambda xx, tv, fn, **kw: fn(xx, th.ones_like(tv) * (1 - tv), **kw)) if reverse else None
 
         def _sample(x, model, **model_kwargs):
-            out = _solve(x, model, grid, sampling_method, model_kwargs)
+            out = _solve(x, model, grid, sampling_method, model_kwargs, wrap_drift=wrap)
             assert out.shape[1:] == x.shape, "Output shape from ODE solver must match input shape"
             return out
 
