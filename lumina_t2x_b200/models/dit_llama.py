@@ -176,3 +176,9 @@ def DiT_Llama_2B_patch2(**kwargs):
 def DiT_Llama_3B_patch2(**kwargs):
     """models.py:1050-1051 (head_dim 96)."""
     return DiT_Llama(patch_size=2, dim=3072, n_layers=32, n_heads=32, **kwargs)
+
+
+def DiT_Llama_7B_patch2(**kwargs):
+    """models.py:1054-1055.  head_dim 128: constructs (same state dict as the reference) but the engine refuses to run it -
+    the attention kernel covers head_dim 48 / 72 / 96."""
+    return DiT_Llama(patch_size=2, dim=4096, n_layers=32, n_heads=32, **kwargs)

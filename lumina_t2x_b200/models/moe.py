@@ -22,3 +22,13 @@ def DiT_Llama_600M_patch2_Spatial(**kwargs):
 def DiT_Llama_600M_patch2_Both(**kwargs):
     """Next-DiT-MoE/models/models2.py:1063-1066 (time-gated then token-gated MoE)."""
     return DiT_Llama(patch_size=2, dim=1536, n_layers=16, n_heads=32, moe="both", **kwargs)
+
+
+def DiT_Llama_3B_patch2(**kwargs):
+    """Next-DiT-MoE/models/models.py:1033-1036 (time-gated MoE, head_dim 96)."""
+    return DiT_Llama(patch_size=2, dim=3072, n_layers=32, n_heads=32, moe="time", **kwargs)
+
+
+def DiT_Llama_7B_patch2(**kwargs):
+    """Next-DiT-MoE/models/models.py:1039-1042 (head_dim 128: constructs, but is outside the attention kernel's head dims)."""
+    return DiT_Llama(patch_size=2, dim=4096, n_layers=32, n_heads=32, moe="time", **kwargs)
