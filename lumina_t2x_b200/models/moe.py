@@ -32,3 +32,9 @@ def DiT_Llama_3B_patch2(**kwargs):
 def DiT_Llama_7B_patch2(**kwargs):
     """Next-DiT-MoE/models/models.py:1039-1042 (head_dim 128: constructs, but is outside the attention kernel's head dims)."""
     return DiT_Llama(patch_size=2, dim=4096, n_layers=32, n_heads=32, moe="time", **kwargs)
+
+
+def DiT_Llama_600M_GQA_patch2(**kwargs):
+    """Next-DiT-MoE/models/models.py:1021-1024 (time-gated MoE, 8 kv heads; defined in all three reference files, not
+    re-exported by the reference package)."""
+    return DiT_Llama(patch_size=2, dim=1536, n_layers=16, n_heads=32, n_kv_heads=8, moe="time", **kwargs)

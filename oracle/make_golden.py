@@ -210,6 +210,32 @@ def make_transport_table() -> None:
     print("transport table", len(rows), "rows")
 
 
+def make_signatures() -> None:
+    """Constructor / forward_with_cfg signatures and factory names of the four reference model packages (drop-in surface)."""
+    import inspect
+    import json
+    from oracle.harness.ref_import import import_reference_flag_dit, import_reference_moe
+    mods = {"next_t2i_mini": import_reference_mini()[0].nextdit, "imagenet": import_reference_imagenet(), "lumina_t2i": import_reference_flag_dit(),
+            "moe_time": import_reference_moe("models"), "moe_space": import_reference_moe("models1"), "moe_both": import_reference_moe("models2")}
+
+    def sig(fn):
+        out = []
+        for p in inspect.signature(fn).parameters.values():
+            if p.kind in (p.VAR_KEYWORD, p.VAR_POSITIONAL):
+                continue
+            out.append([p.name, None if p.default is p.empty else repr(p.default)])
+        return out
+
+    table = {}
+    for name, m in mods.items():
+        cls = m.NextDiT if hasattr(m, "NextDiT") else m.DiT_Llama
+        table[name] = {"class": cls.__name__, "init": sig(cls.__init__), "forward_with_cfg": sig(cls.forward_with_cfg),
+                       "factories": sorted(n for n in dir(m) if n.startswith(cls.__name__ + "_") and callable(getattr(m, n)))}
+    with open(os.path.join(OUT, "signatures.json"), "w") as f:
+        json.dump(table, f, indent=1, sort_keys=True)
+    print("signatures", {k: len(v["init"]) for k, v in table.items()})
+
+
 def make_flag_dit() -> None:
     """Flag-DiT (Lumina-T2I, BASELINE config 4 / SURVEY 8a15): unmodified lumina_t2i/models/model.py (fp32, CPU, fairscale
     at world size 1).  Tiny models with the flagship head_dim 96: default call, proportional attention + NTK factor (the

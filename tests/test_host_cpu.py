@@ -135,6 +135,29 @@ def test_generic_fixed_grid_loop(method):
         T.Sampler(tr).sample_ode(sampling_method="dopri5", num_steps=5)(x0, model)
 
 
+def test_model_mirrors_keep_the_reference_signatures():
+    """tests/golden/signatures.json (recorded from the reference by oracle/make_golden.py::make_signatures): every constructor
+    and forward_with_cfg parameter of the reference classes exists in the mirror at the same position with the same default
+    (the mirrors only append engine limits such as max_tokens), and every factory name resolves."""
+    import inspect
+    import json
+    from lumina_t2x_b200 import models
+    from lumina_t2x_b200.models import dit_llama, lumina_t2i, moe
+    table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "signatures.json")))
+    mirrors = {"next_t2i_mini": (models.NextDiT, models), "imagenet": (dit_llama.DiT_Llama, models), "lumina_t2i": (lumina_t2i.DiT_Llama, lumina_t2i),
+               "moe_time": (dit_llama.DiT_Llama, moe), "moe_space": (dit_llama.DiT_Llama, moe), "moe_both": (dit_llama.DiT_Llama, moe)}
+    for name, ref in table.items():
+        cls, pkg = mirrors[name]
+        for meth in ("init", "forward_with_cfg"):
+            mine = [p for p in inspect.signature(getattr(cls, "__init__" if meth == "init" else meth)).parameters.values()]
+            for i, (pname, pdef) in enumerate(ref[meth]):
+                assert mine[i].name == pname, (name, meth, i, pname, mine[i].name)
+                if pdef is not None:
+                    assert repr(mine[i].default) == pdef, (name, meth, pname, pdef, mine[i].default)
+        for f in ref["factories"]:
+            assert hasattr(pkg, f), (name, f)
+
+
 def test_create_transport_and_check_interval_table_matches_reference():
     """3456 combinations of create_transport(path, prediction, loss_weight, train_eps, sample_eps) x check_interval(...) recorded
     from the unmodified reference package (tests/golden/transport_table.pt): same eps defaults (including the reference's
