@@ -286,28 +286,21 @@ def run_engine(args, rank, local_rank, world):
     gathered = torch.empty((world,) + tuple(final_dev.shape), dtype=final_dev.dtype, device=device) if dist_on else None
 
     # ---- device-resident timing
-    def measure():
-        clocks = ClockSampler(physical_gpu_index(local_rank))
-        barrier()
-        clocks.start()
-        l0 = lib.ndit_launch_count(h)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            step_dev()
-        if dist_on:      # the one collective of the path: gather the final latents of all ranks
-            dist.all_gather_into_tensor(gathered, final_dev)
-        e1.record(stream)
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1)), int(lib.ndit_launch_count(h) - l0), clocks.stop()
-
-    ms, launches, clk = measure()
-    # a run that saw a hardware / thermal slowdown is not a measurement: repeat it once (sw_power_cap is normal here and kept)
-    throttled = bool(clk and set(clk["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
-    if max_over_ranks(1.0 if throttled else 0.0) > 0:
-        ms, launches, clk = measure()
-        if clk is not None:
-            clk["remeasured_after_throttle"] = True
+    clocks = ClockSampler(physical_gpu_index(local_rank))
+    barrier()
+    clocks.start()
+    l0 = lib.ndit_launch_count(h)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    if dist_on:      # the one collective of the path: gather the final latents of all ranks
+        dist.all_gather_into_tensor(gathered, final_dev)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(lib.ndit_launch_count(h) - l0)
+    clk = clocks.stop()
     assert torch.isfinite(final_dev.float()).all(), "non-finite latents"
 
     # ---- end to end through the host-buffer C ABI
