@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference modules from /root/reference (authoring container only).
+"""Import the UNMODIFIED reference modules: from /root/reference in the authoring container, from the
+byte-identical copies under ``oracle/_ref/`` (made by ``oracle/make_ref.py``, git-ignored, shipped with the
+gpurun snapshot) on the GPU box.
 
-TEST INFRASTRUCTURE.  Used by ``oracle/make_golden.py`` to pin the oracle against the
-reference's own outputs.  /root/reference does not exist on the GPU box, so nothing
-that runs there imports this file.
+TEST INFRASTRUCTURE.  Used by ``oracle/make_golden.py`` to pin the oracle against the reference's own outputs,
+by ``tests/test_reference_gpu.py`` to run the real reference next to the engine on the B200, and by ``bench.py``
+for the ``stock_cuda_baseline`` / ``--impl reference`` legs.  Never imported by ``lumina_t2x_b200/``.
 
 Shims that live here (not in the reference):
   * ``torchdiffeq.odeint`` stub: torchdiffeq is an unpinned third-party dependency
@@ -22,7 +24,14 @@ import types
 
 import torch
 
-REF_ROOT = "/root/reference"
+import os
+
+_VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_ref")
+REF_ROOT = "/root/reference" if os.path.isdir("/root/reference") else _VENDORED
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "lumina_next_t2i_mini", "models", "nextdit.py"))
 
 
 def _odeint(func, y0, t, *, method="euler", atol=None, rtol=None, **kw):
@@ -147,6 +156,21 @@ def import_reference_flag_dit():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         mod = importlib.import_module("ref_lumina_t2i_models.model")
+    return mod
+
+
+def import_reference_full_model():
+    """Unmodified canonical ``lumina_next_t2i/models/model.py`` (the fairscale flavour sample.py / demo.py import),
+    with fairscale replaced by the world-size-1 stub above."""
+    install_shims()
+    _install_fairscale_stub()
+    pkg = types.ModuleType("ref_lumina_next_t2i_models")
+    pkg.__path__ = [REF_ROOT + "/lumina_next_t2i/models"]
+    sys.modules["ref_lumina_next_t2i_models"] = pkg
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("ref_lumina_next_t2i_models.model")
     return mod
 
 

@@ -162,6 +162,35 @@ def make_moe() -> None:
         del m, W
 
 
+def make_canonical() -> None:
+    """The canonical fairscale flavour ``lumina_next_t2i/models/model.py`` (what sample.py / demo.py import), fp32 on CPU.
+    Its fp32 SDPA branch does not repeat the kv heads (model.py:407-417), so it only runs MHA models in fp32: a tiny MHA
+    model, proportional attention + time-aware RoPE.  Also asserts that the mini flavour gives the same bits."""
+    import dataclasses
+    from oracle.harness.ref_import import import_reference_full_model
+    full = import_reference_full_model()
+    mini, _ = import_reference_mini()
+    torch.set_grad_enabled(False)
+    cfg = dataclasses.replace(O.config_tiny(n_layers=2), n_kv_heads=O.config_tiny().n_heads)
+    W = O.synthetic_weights(cfg, seed=0, dtype=torch.bfloat16)
+    outs = []
+    for cls in (full.NextDiT, mini.nextdit.NextDiT):
+        m = cls(patch_size=2, in_channels=4, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads,
+                qk_norm=True, cap_feat_dim=cfg.cap_feat_dim)
+        m.load_state_dict({k: v.clone() for k, v in W.items()}, strict=True)
+        m = m.eval().float()
+        z, cap, mask = O.synthetic_inputs(cfg, (16, 24), 24, 8, seed=1)
+        t = torch.full((2,), 0.45)
+        kw = dict(cfg_scale=3.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=32, proportional_attn=True)
+        outs.append(m.forward_with_cfg(z.float(), t, cap.float(), mask, **kw))
+    assert torch.equal(outs[0], outs[1]), "canonical and mini flavours differ"
+    fx = dict(case="canon_tiny_mha", cfg=dict(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads,
+                                              cap_feat_dim=cfg.cap_feat_dim),
+              hw=(16, 24), T=24, ul=8, t=0.45, kw=kw, weight_seed=0, input_seed=1, out_fp32=outs[0].clone())
+    torch.save(fx, os.path.join(OUT, "canon_tiny_mha.pt"))
+    print("canon_tiny_mha", tuple(outs[0].shape), "absmax", outs[0].abs().max().item(), "mini == canonical: True")
+
+
 def make_sde() -> None:
     """Stochastic sampler of the full transport package (transport.py:285-344) with a toy velocity function: pins the step
     formulas, the noise consumption order of the global torch RNG and the last-step variants."""
