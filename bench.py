@@ -14,9 +14,15 @@ CFG=2, bf16, random-init weights, synthetic data.  One JSON line is printed by r
             H2D and the final latent D2H inside the timed region (wall clock around synchronous calls).
   roofline  for the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of its launches,
             measured with per-launch events inside one extra solve (engine option "profile").
-  cpu_baseline  the oracle (CPU port of the reference algorithm, fp32) on a bounded sample.
-  gpu_eager_baseline  the same forward as eager PyTorch bf16 on the same GPU (the reference's stock CUDA path restated;
-                the reference itself cannot travel to the GPU box).
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, fp32, all host cores) on a bounded sample; the oracle port when
+                oracle/_ref is missing.
+  stock_cuda_baseline  the UNMODIFIED reference (oracle/_ref) under autocast(bf16) with flash_attn_varlen_func on the same
+                GPU and the same weights: 3 warm-up + 10 timed forward_with_cfg calls and one full 30-point solve through the
+                reference's own ODE class (CUDA events) - SURVEY.md 8d (i).
+  gpu_eager_baseline  the same forward as eager PyTorch bf16 restated in the oracle (cuBLAS + SDPA), kept for comparison.
+
+  --config 3 runs BASELINE config 3 instead (2048x2048 -> latent [2,4,256,256] = 16384 tokens, time-aware scaled RoPE,
+  one latent per GPU: the north-star's 8-GPU configuration); the default is config 2, the one the metric is quoted on.
 """
 from __future__ import annotations
 
@@ -36,12 +42,23 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-LATENT = 128          # 1024 / 8
 T_CAP = 128
 NUM_STEPS = 30        # grid points -> 29 model calls (transport/integrators.py:97)
 CFG_SCALE = 2.0
-WORKLOAD = ("Lumina-Next-T2I 2B GQA (NextDiT_2B_GQA_patch2, qk_norm, cap_feat_dim 2048), 1024x1024 -> latent "
-            "[2,4,128,128] (4096 tokens x cond/uncond), T=128 caption tokens, 30-step Euler (29 model calls), CFG=2")
+# BASELINE.json configs[1] (the one the metric is quoted on) and configs[2] (2048^2, NTK / linear time-aware RoPE, 1 latent per GPU)
+CONFIGS = {
+    2: dict(latent=128, tokens=4096, scale_factor=1.0, scale_watershed=1.0, base_seqlen=4096,
+            workload=("Lumina-Next-T2I 2B GQA (NextDiT_2B_GQA_patch2, qk_norm, cap_feat_dim 2048), 1024x1024 -> latent "
+                      "[2,4,128,128] (4096 tokens x cond/uncond), T=128 caption tokens, 30-step Euler (29 model calls), CFG=2")),
+    3: dict(latent=256, tokens=16384, scale_factor=2.0, scale_watershed=0.3, base_seqlen=4096,
+            workload=("Lumina-Next-T2I 2B GQA (NextDiT_2B_GQA_patch2, qk_norm, cap_feat_dim 2048), 2048x2048 -> latent "
+                      "[2,4,256,256] (16384 tokens x cond/uncond), time-aware scaled RoPE (scale_factor 2, watershed 0.3), "
+                      "proportional attention (base_seqlen 4096), T=128 caption tokens, 30-step Euler (29 model calls), CFG=2, "
+                      "one latent per GPU")),
+}
+LATENT = 128          # set by main() from --config
+WORKLOAD = CONFIGS[2]["workload"]
+WL = CONFIGS[2]
 
 
 def flops_per_forward(D=2304, L=24, H=32, Hkv=8, hd=72, F=6144, Cc=2048, B=2, N=4096, T=128):
@@ -127,47 +144,128 @@ def physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
-# ------------------------------------------------------------------------------------------ CPU baseline (oracle)
-def cpu_sample_once(full_layers=24, sample_layers=2):
-    """One bounded sample of the reference algorithm on the host: forward_with_cfg at the full token count
-    with 0 and `sample_layers` transformer blocks; per-block time extrapolated to `full_layers` blocks and
-    29 model calls.  Returns seconds per latent (extrapolated) and the measured pieces."""
+# ------------------------------------------------------------------------------------------ CPU baseline (reference)
+CPU_SAMPLE_LAYERS = 6
+
+
+def host_threads() -> int:
+    """All host cores, regardless of the OMP_NUM_THREADS=1 that torch.distributed.run exports to its workers."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
+def _cpu_models(sample_layers):
+    """The unmodified reference NextDiT (oracle/_ref, fp32 on the host) with 0 and `sample_layers` blocks at the 2B widths;
+    the oracle port (same algorithm restated) when oracle/_ref was not built."""
+    from oracle.harness import ref_import
     from oracle import nextdit_oracle as O
-    out = {}
     torch.set_grad_enabled(False)
+    out = {}
+    real = ref_import.reference_available()
     for nl in (0, sample_layers):
         cfg = O.NextDiTConfig(n_layers=nl)
         W = {k: v.float() for k, v in O.synthetic_weights(cfg, seed=0).items()}
-        z, cap, mask = O.synthetic_inputs(cfg, (LATENT, LATENT), T_CAP, 8, seed=1)
-        t = torch.full((2,), 0.3)
+        if real:
+            mod = ref_import.import_reference_mini()[0].nextdit
+            m = mod.NextDiT(patch_size=2, in_channels=4, dim=cfg.dim, n_layers=nl, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads,
+                            qk_norm=True, cap_feat_dim=cfg.cap_feat_dim, use_flash_attn=False)
+            m.load_state_dict(W, strict=True)
+            m = m.eval().float()
+            out[nl] = (lambda z, t, cap, mask, m=m: m.forward_with_cfg(z, t, cap, mask, CFG_SCALE, WL["scale_factor"], WL["scale_watershed"],
+                                                                    WL["base_seqlen"], True))
+        else:
+            out[nl] = (lambda z, t, cap, mask, cfg=cfg, W=W: O.forward_with_cfg(cfg, W, z, t, cap, mask, CFG_SCALE, WL["scale_factor"],
+                                                                           WL["scale_watershed"], WL["base_seqlen"], True, precision="fp32"))
+    return out, ("reference" if real else "port")
+
+
+_CPU_CACHE = {}
+
+
+def cpu_sample_once(full_layers=24, sample_layers=CPU_SAMPLE_LAYERS):
+    """One bounded sample of the reference on the host cores: forward_with_cfg at the full token count with 0 and
+    `sample_layers` of the 24 transformer blocks (both MEASURED); the per-block time is extrapolated to 24 blocks and
+    29 model calls.  Returns (seconds per latent, kind, seconds of the 0-block call, seconds per block)."""
+    from oracle import nextdit_oracle as O
+    key = (sample_layers, LATENT)
+    if key not in _CPU_CACHE:
+        _CPU_CACHE[key] = _cpu_models(sample_layers)
+    fns, kind = _CPU_CACHE[key]
+    z, cap, mask = O.synthetic_inputs(O.NextDiTConfig(n_layers=0), (LATENT, LATENT), T_CAP, 8, seed=1)
+    z, cap, t = z.float(), cap.float(), torch.full((2,), 0.3)
+    out = {}
+    for nl, fn in fns.items():
         t0 = time.perf_counter()
-        O.forward_with_cfg(cfg, W, z.float(), t, cap.float(), mask, CFG_SCALE, 1.0, 1.0, 4096, True, precision="fp32")
+        fn(z, t, cap, mask)
         out[nl] = time.perf_counter() - t0
     per_block = (out[sample_layers] - out[0]) / sample_layers
     fwd = out[0] + full_layers * per_block
-    return (NUM_STEPS - 1) * fwd, out[0], per_block
+    return (NUM_STEPS - 1) * fwd, kind, out[0], per_block
+
+
+def cpu_sample_text(kind):
+    what = ("UNMODIFIED reference (oracle/_ref: lumina_next_t2i_mini/models/nextdit.py, fp32, SDPA branch, torch CPU)" if kind == "reference"
+            else "oracle port (oracle/nextdit_oracle.py, fp32, torch CPU)")
+    return (f"{what}: forward_with_cfg at the full 2x{WL['tokens']}-token shape, measured with 0 and {CPU_SAMPLE_LAYERS} of the 24 blocks; "
+            "per-block time x24 + embed/final, x29 model calls")
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's own implementation of the path on the host cores (rank 0 only; the other ranks of a
+    torchrun launch exit without work).  The value is the CPU's latents/s whatever --gpus says."""
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_sample_once()
-    vals = []
+    vals, kind = [], "port"
     for _ in range(args.steps):
-        vals.append(cpu_sample_once()[0])
+        sec, kind, _, _ = cpu_sample_once()
+        vals.append(sec)
     sec = statistics.mean(vals)
-    sample = ("oracle port (oracle/nextdit_oracle.py, fp32, torch CPU) of the reference forward_with_cfg at the full 2x4096-token "
-              "shape with 0 and 2 of the 24 blocks; per-block time x24 + embed/final, x29 model calls")
     line = {"metric": "latents/sec", "value": 1.0 / sec, "unit": "latents/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU; extrapolated from a bounded sample"},
-            "cpu_baseline": {"value": 1.0 / sec, "unit": "latents/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "note": "reference on the host CPU; each step is a bounded sample (0 and 6 of 24 blocks measured), "
+                                                     "extrapolated to one full solve; not scaled by --gpus"},
+            "cpu_baseline": {"value": 1.0 / sec, "unit": "latents/s", "cores": cores, "kind": kind, "sample": cpu_sample_text(kind)},
             "e2e": {"value": 1.0 / sec, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def stock_cuda_baseline(m, z_dev, cap_dev, mask_dev, device, engine_out):
+    """Same-GPU stock CUDA path: the UNMODIFIED reference module (oracle/_ref) with the benchmarked weights under
+    torch.autocast(bf16) -> flash_attn_varlen_func, eager: 3 warm-up + 10 timed forward_with_cfg calls and one full 30-point Euler solve
+    through the reference's own ODE class, CUDA events."""
+    from oracle import ref_gpu
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    ref = ref_gpu.build_reference(sd, dim=2304, n_layers=24, n_heads=32, n_kv_heads=8, cap_feat_dim=2048, dtype=torch.bfloat16, device=device)
+    kw = dict(cfg_scale=CFG_SCALE, scale_factor=WL["scale_factor"], scale_watershed=WL["scale_watershed"], base_seqlen=WL["base_seqlen"],
+              proportional_attn=True)
+    t = torch.full((2,), 0.5, device=device)
+    mask = mask_dev.to(torch.int64)
+    out = None
+    for _ in range(3):
+        out = ref_gpu.ref_forward(ref, z_dev, t, cap_dev, mask, **kw)
+    torch.cuda.synchronize(device)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(10):
+        ref_gpu.ref_forward(ref, z_dev, t, cap_dev, mask, **kw)
+    e1.record()
+    ref_gpu.ref_sample(ref, z_dev, cap_dev, mask, NUM_STEPS, "euler", 1.0, **kw)
+    e2.record()
+    torch.cuda.synchronize(device)
+    ms_call, ms_solve = e0.elapsed_time(e1) / 10, e1.elapsed_time(e2)
+    rel = ref_gpu.rel_linf(out, engine_out)
+    del ref
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / ms_solve, "unit": "latents/s", "ms_per_model_call": ms_call, "ms_per_solve": ms_solve,
+            "kind": "UNMODIFIED reference (oracle/_ref, lumina_next_t2i_mini NextDiT + ODE) under autocast(bf16) with flash_attn_varlen_func, "
+                    "eager, same GPU, same weights; value = 1 / (one full 30-point Euler solve)",
+            "rel_linf_vs_engine_one_call": rel}
 
 
 def gpu_eager_baseline(m, z_dev, cap_dev, mask_dev, device, engine_out, iters=3):
@@ -206,7 +304,7 @@ def build_flagship(device):
     from lumina_t2x_b200 import models
     torch.manual_seed(0)
     with torch.device(device):
-        m = models.NextDiT_2B_GQA_patch2(qk_norm=True, cap_feat_dim=2048, max_tokens=4096, max_cap_len=T_CAP, max_batch=2)
+        m = models.NextDiT_2B_GQA_patch2(qk_norm=True, cap_feat_dim=2048, max_tokens=WL["tokens"], max_cap_len=T_CAP, max_batch=2)
     g = torch.Generator(device=device).manual_seed(0)
     with torch.no_grad():
         for k, p in m.named_parameters():
@@ -257,9 +355,11 @@ def run_engine(args, rank, local_rank, world):
     grid = torch.linspace(0.0, 1.0, NUM_STEPS)          # transport/integrators.py:97-99, time_shifting_factor = 1
     grid = grid / (grid + 1.0 - 1.0 * grid)
     garr = (C.c_float * NUM_STEPS)(*[float(v) for v in grid])
-    step = _lib.NditStepParams(CFG_SCALE, 1.0, 1.0, 1, 4096)
+    step = _lib.NditStepParams(CFG_SCALE, WL["scale_factor"], WL["scale_watershed"], 1, WL["base_seqlen"])
 
     def step_dev():
+        # the per-prompt caption work (24 x wk_y|wv_y GEMM, ky_norm, V^T, pooled embedding) belongs to "one solve per latent"
+        _lib.check(lib.ndit_set_caption(h, C.c_void_p(cap_dev.data_ptr()), C.c_void_p(mask_dev.data_ptr()), 2, T_CAP, sp), h)
         _lib.check(lib.ndit_sample(h, C.c_void_p(z_dev.data_ptr()), 2, LATENT, LATENT, garr, NUM_STEPS, _lib.NDIT_EULER, C.byref(step),
                                    None, C.c_void_p(final_dev.data_ptr()), sp), h)
 
@@ -298,10 +398,17 @@ def run_engine(args, rank, local_rank, world):
         dist.all_gather_into_tensor(gathered, final_dev)
     e1.record(stream)
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    my_ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(my_ms)
     launches = int(lib.ndit_launch_count(h) - l0)
     clk = clocks.stop()
     assert torch.isfinite(final_dev.float()).all(), "non-finite latents"
+    per_rank = None
+    if dist_on:      # which rank is the slow one (the max over ranks is what `value` is computed from)
+        mine = {"rank": rank, "ms_per_step": my_ms / args.steps, "sm_mhz": clk["sm_mhz"] if clk else None,
+                "reasons": clk["reasons"] if clk else None}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
     # ---- end to end through the host-buffer C ABI
     step_e2e()
@@ -329,7 +436,7 @@ def run_engine(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     calls = NUM_STEPS - 1
-    gemm_f, attn_f, cross_f = flops_per_forward()
+    gemm_f, attn_f, cross_f = flops_per_forward(N=WL["tokens"])
     pk = peaks()
     total_tf = (gemm_f + attn_f + cross_f) * calls / 1e12
     lat_per_s = world * args.steps / (ms / 1e3)
@@ -342,10 +449,12 @@ def run_engine(args, rank, local_rank, world):
         "metric": "latents/sec", "value": lat_per_s, "unit": "latents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "latents_per_gpu_per_step": 1, "parallelism": f"dp{world} (independent latents per GPU, weights replicated, "
+        "config": {"workload": WORKLOAD, "baseline_config": args.config, "latents_per_gpu_per_step": 1,
+                   "value_includes": "ndit_set_caption (per-prompt caption preprocessing) + the 29-call solve", "parallelism": f"dp{world} (independent latents per GPU, weights replicated, "
                    "one all-gather of the final latents)", "l2": "inputs larger than L2: 3.3 GB of bf16 weights stream per model call (L2 126 MB)",
                    "timestep_dtype": "bf16 (torchdiffeq casts t to the state dtype)"},
         "clocks": clk,
+        "per_rank": per_rank,
         "e2e": {"value": world * args.steps / e2e_s, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "ndit_sample_host (C ABI, pinned host buffers, H2D + D2H inside the timed region)"},
         "gpu_launches": launches,
@@ -358,18 +467,24 @@ def run_engine(args, rank, local_rank, world):
                      "share_of_step": gemm_ms / prof_total if prof_total else None},
         "kernels": {**prof, "attention_tflops": attn_tflops, "attention_frac_of_peak": attn_tflops / pk["bf16"]},
     }
-    if world == 1 and not args.no_gpu_eager_baseline:
-        try:
-            t05 = torch.full((2,), 0.5, device=device)
-            eng = m.forward_with_cfg(z_dev, t05, cap_dev, mask_dev, CFG_SCALE, 1.0, 1.0, 4096, True)
-            line["gpu_eager_baseline"] = gpu_eager_baseline(m, z_dev, cap_dev, mask_dev, device, eng)
-        except Exception as ex:      # a baseline must never take the benchmark line down
-            line["gpu_eager_baseline"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+    if world == 1 and not (args.no_gpu_eager_baseline and args.no_stock_cuda_baseline):
+        t05 = torch.full((2,), 0.5, device=device)
+        eng = m.forward_with_cfg(z_dev, t05, cap_dev, mask_dev, CFG_SCALE, WL["scale_factor"], WL["scale_watershed"], WL["base_seqlen"], True)
+        if not args.no_stock_cuda_baseline:
+            try:
+                line["stock_cuda_baseline"] = stock_cuda_baseline(m, z_dev, cap_dev, mask_dev, device, eng)
+                line["stock_cuda_baseline"]["engine_speedup"] = lat_per_s / line["stock_cuda_baseline"]["value"]
+            except Exception as ex:      # a baseline must never take the benchmark line down
+                line["stock_cuda_baseline"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        if not args.no_gpu_eager_baseline and args.config == 2:
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(m, z_dev, cap_dev, mask_dev, device, eng)
+            except Exception as ex:
+                line["gpu_eager_baseline"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
     if world == 1 and not args.no_cpu_baseline:
-        sec, _, _ = cpu_sample_once()
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "latents/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "oracle (fp32 torch CPU port of the reference algorithm): full-shape forward_with_cfg with 0 and 2 of 24 "
-                                          "blocks, per-block time extrapolated x24, x29 model calls"}
+        cores = host_threads()
+        sec, kind, _, _ = cpu_sample_once()
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "latents/s", "cores": cores, "kind": kind, "sample": cpu_sample_text(kind)}
     print(json.dumps(line), flush=True)
     if dist_on:
         dist.destroy_process_group()
@@ -383,7 +498,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--no-stock-cuda-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config: 2 (default, 1024^2) or 3 (2048^2)")
     args = ap.parse_args()
+    global LATENT, WORKLOAD, WL
+    WL = CONFIGS[args.config]
+    LATENT, WORKLOAD = WL["latent"], WL["workload"]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -88,6 +88,11 @@ int ndit_create(const ndit_config* cfg, ndit_handle* out);
 int ndit_destroy(ndit_handle h);
 const char* ndit_last_error(ndit_handle h);   /* h may be NULL: last error of a failed ndit_create */
 
+/* Grow the workspace of an existing handle (never shrinks; weights stay packed): the reference allocates activations per
+ * call, so an unmodified caller may pass a larger latent (e.g. 2048x2048 = 16384 tokens) or a longer caption than the handle
+ * was created for - the Python mirror calls this instead of failing.  Invalidates the caption / label state (set it again). */
+int ndit_reserve(ndit_handle h, int32_t max_tokens, int32_t max_cap_len, int32_t max_batch);
+
 /* --- weights: nn.Module.load_state_dict(strict=True) (sample.py:135-142).  `key` is the reference
  * state-dict key; the tensor is copied (bf16 or f32 source, row-major) into
  * engine-owned, GEMM-ready storage.  ndit_finalize_weights fails if a key is missing (strict). */

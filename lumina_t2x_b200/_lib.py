@@ -37,6 +37,7 @@ SIGNATURES = {
     "ndit_set_weight": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _i32, _vp]),
     "ndit_finalize_weights": (C.c_int, [_vp, _vp]),
     "ndit_parameter_count": (_i64, [_vp]),
+    "ndit_reserve": (C.c_int, [_vp, _i32, _i32, _i32]),
     "ndit_set_caption": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "ndit_set_labels": (C.c_int, [_vp, _vp, _i32, _vp]),
     "ndit_forward_cfg": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),

@@ -513,7 +513,8 @@ extern "C" int ndit_debug_attn_timing(long long* out) {   // [2][64][8] clock64 
 template <int HD>
 static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
     auto kern = attention_fused_kernel<HD>;
-    static bool configured = false;
+    static PerDeviceFlag flags;
+    bool& configured = flags.here();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnDims<HD>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -609,7 +610,10 @@ cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_k
     if (hd > 128) return cudaErrorInvalidValue;
     const int L = N > T ? N : T;
     const size_t sh = (L + hd + 32) * sizeof(float);
-    static size_t configured = 0;
+    static size_t configured_sz[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    size_t& configured = configured_sz[dev_ & 63];
     if (sh > 48 * 1024 && sh > configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         if (e != cudaSuccess) return e;

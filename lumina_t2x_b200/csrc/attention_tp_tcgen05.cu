@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace ndit {
@@ -484,7 +485,8 @@ attention_tp_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_cons
 template <int HD, int BKV>
 static cudaError_t launch_attention_tp(const AttnPlan& p, cudaStream_t stream) {
     auto kern = attention_tp_kernel<HD, BKV>;
-    static bool configured = false;
+    static PerDeviceFlag flags;
+    bool& configured = flags.here();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TpDims<HD, BKV>::SMEM_BYTES);
         if (e != cudaSuccess) return e;

@@ -18,8 +18,9 @@
 using namespace ndit;
 
 namespace ndit {
-// programmatic dependent launch for the hot-loop kernels (launch.cuh); process-wide, set by ndit_set_option("pdl") / NDIT_PDL
-int g_pdl = getenv("NDIT_PDL") ? atoi(getenv("NDIT_PDL")) : 0;   // measured: no gain on the power-capped B200 (934.4 vs 934.5 ms / latent)
+// programmatic dependent launch for the hot-loop kernels (launch.cuh): per engine (option "pdl", default NDIT_PDL), copied into
+// this thread-local for the duration of an engine call.  Measured: no gain on the power-capped B200 (934.4 vs 934.5 ms / latent).
+thread_local int g_pdl = 0;
 }  // namespace ndit
 
 namespace {
@@ -95,11 +96,13 @@ struct ndit_engine {
     int attn_ref = 0;
     int attn_tp = 0;                         // 1: P-in-tensor-memory attention kernel (experimental, slower so far: see its header)
     int profile = 0;
+    int pdl = getenv("NDIT_PDL") ? atoi(getenv("NDIT_PDL")) : 0;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_class;       // class of event pair i (events 2i, 2i+1)
     size_t ev_used = 0;
     std::set<std::string> seen;
-    std::vector<void*> allocs;
+    std::vector<void*> allocs;               // weights (live as long as the handle)
+    std::vector<void*> ws_allocs;            // workspace (re-created by ndit_reserve)
 
     // weights
     bf16 *Wx, *bx, *Wt0, *bt0, *Wt2, *bt2, *capln_w, *capln_b, *Wcap, *bcap, *Wada, *bada, *Wout, *bout, *pad_token, *eol_token;
@@ -113,7 +116,8 @@ struct ndit_engine {
     bf16 *X, *u, *qkv, *attn, *o, *hbuf, *vt;
     bf16 *yhat, *kvy, *vyt;
     uint8_t* ymask;
-    float *pool, *capemb, *tf, *h1, *sc, *tok;
+    float *pool, *capemb, *tf, *h1, *sc;
+    bf16* tok;                               // [M, O] final-layer output tokens
     bf16* mod;
     bf16 *vel, *ystate, *ymid;
     bf16 *stage_z, *stage_cap;
@@ -125,9 +129,26 @@ struct ndit_engine {
     // plans
     int plan_M = 0, plan_B = 0, plan_N = 0, plan_T = 0;
     std::vector<GemmPlan> p_qkv, p_wo, p_w13, p_w2;
+    GemmPlan p_final;                        // final_layer.linear: [M, D] x [O, D]^T + bias
     std::vector<AttnPlan> p_attn;
     bool attn_plans_valid = false;
     bool vt_ones_valid = false;
+    // CUDA graphs of whole fixed-grid solves (ndit_sample): key = everything the captured launch sequence depends on
+    struct SolveGraph {
+        std::vector<float> grid;
+        int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0;
+        ndit_step_params sp;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        uint64_t last_use = 0;
+        RopeSlot rope_after[2];              // what a replay leaves in the two RoPE table slots
+        int rope_next_after = 0;
+    };
+    std::vector<SolveGraph> graphs;
+    uint64_t graph_clock = 0;
+    int use_graph = 1;                       // option "graph" / NDIT_GRAPH: replay a captured graph for repeated solves
+    bf16* traj_buf = nullptr;                // internal trajectory buffer of graph-captured solves [traj_cap][count]
+    size_t traj_cap_elems = 0;
 
     int fail(int code, const char* fmt, ...) {
         va_list ap;
@@ -182,13 +203,13 @@ static int prof_end(ndit_engine* h, cudaStream_t s) {
     } while (0)
 
 template <typename T>
-static int dev_alloc(ndit_engine* h, T** p, size_t count) {
+static int dev_alloc(ndit_engine* h, T** p, size_t count, bool workspace = false) {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
     if (e != cudaSuccess) return h->fail(NDIT_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
     e = cudaMemset(q, 0, count * sizeof(T) + 256);
     if (e != cudaSuccess) return h->fail(NDIT_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
-    h->allocs.push_back(q);
+    (workspace ? h->ws_allocs : h->allocs).push_back(q);
     *p = static_cast<T*>(q);
     return 0;
 }
@@ -197,16 +218,62 @@ static int dev_alloc(ndit_engine* h, T** p, size_t count) {
         int r_ = dev_alloc(h, &(h->ptr), (size_t)(count)); \
         if (r_) return r_;                               \
     } while (0)
+#define WALLOC(ptr, count)                                     \
+    do {                                                       \
+        int r_ = dev_alloc(h, &(h->ptr), (size_t)(count), true); \
+        if (r_) return r_;                                     \
+    } while (0)
 
 extern "C" int ndit_abi_version(void) { return NDIT_ABI_VERSION; }
 
 extern "C" const char* ndit_last_error(ndit_handle h) { return h ? h->err : g_create_err; }
+
+// Workspace sized by cfg.max_batch / max_tokens / max_cap_len.  Separate from the weights so that ndit_reserve can grow it.
+static int alloc_workspace(ndit_engine* h) {
+    const ndit_config& c = h->cfg;
+    const size_t D = h->D, L = h->L, F = h->F, C = h->C, cd = h->cd, KV = (size_t)h->Hkv * h->hd, NCH = h->NCH, S = h->S;
+    h->Bmax = c.max_batch; h->Tmax = h->cls ? 0 : c.max_cap_len; h->Tpad_max = (h->Tmax + 7) / 8 * 8;
+    h->Mmax = c.max_batch * c.max_tokens;
+    const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
+    WALLOC(X, M * D); WALLOC(u, M * D); WALLOC(qkv, M * h->Wq); WALLOC(attn, M * D); WALLOC(o, M * D); WALLOC(hbuf, M * F);
+    WALLOC(vt, B * h->Hkv * h->vrows * ((size_t)c.max_tokens + 8));
+    WALLOC(yhat, L * B * T * C); WALLOC(kvy, L * B * T * 2 * KV); WALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
+    WALLOC(ymask, B * T); WALLOC(pool, B * C); WALLOC(capemb, B * cd); WALLOC(tf, B * 256); WALLOC(h1, B * cd); WALLOC(sc, B * cd);
+    WALLOC(mod, B * (L * NCH * D + h->FD * D)); WALLOC(tok, M * h->O);
+    if (S > 1) {
+        int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
+        WALLOC(oE, (size_t)emax * M * D); WALLOC(wtok, M * 8); WALLOC(temb, B * cd); WALLOC(tlogits, B * L * 8);
+        CK(cudaMallocHost(&h->tlogits_host, L * 8 * sizeof(float)));
+    }
+    const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
+    WALLOC(vel, lat); WALLOC(ystate, lat); WALLOC(ymid, lat); WALLOC(stage_z, lat); WALLOC(stage_cap, B * T * C); WALLOC(stage_mask, B * T);
+    for (int i = 0; i < 2; ++i) {
+        int r = dev_alloc(h, &h->rope[i].tab, (size_t)c.max_tokens * (h->hd / 2), true);
+        h->rope[i].Hp = 0;
+        if (r) return r;
+    }
+    h->plan_M = h->plan_B = h->plan_N = h->plan_T = 0;
+    h->attn_plans_valid = false;
+    h->vt_ones_valid = false;
+    h->cap_batch = h->cap_T = 0;
+    for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    h->graphs.clear();
+    h->traj_buf = nullptr; h->traj_cap_elems = 0;
+    return 0;
+}
+
+static void free_workspace(ndit_engine* h) {
+    for (void* p : h->ws_allocs) cudaFree(p);
+    h->ws_allocs.clear();
+    if (h->tlogits_host) { cudaFreeHost(h->tlogits_host); h->tlogits_host = nullptr; }
+}
 
 static int create_impl(ndit_engine* h) {
     const ndit_config& c = h->cfg;
     if (c.dim <= 0 || c.n_heads <= 0 || c.dim % c.n_heads != 0) return h->fail(NDIT_ERR_INVALID, "bad dim/n_heads");
     h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
     if (getenv("NDIT_ATTN_TP")) h->attn_tp = atoi(getenv("NDIT_ATTN_TP"));
+    if (getenv("NDIT_GRAPH")) h->use_graph = atoi(getenv("NDIT_GRAPH"));
     h->cls = c.num_classes > 0;
     h->flag = c.flag_dit != 0;
     if (h->cls && h->flag) return h->fail(NDIT_ERR_INVALID, "num_classes > 0 and flag_dit are mutually exclusive");
@@ -263,25 +330,7 @@ static int create_impl(ndit_engine* h) {
     ALLOC(an1, L * D); ALLOC(an2, L * D); ALLOC(fn1, L * D); ALLOC(fn2, NF * L * D); ALLOC(yn, L * C);
     ALLOC(gate_raw, L * h->H); ALLOC(gate_tanh, L * h->H);
 
-    h->Bmax = c.max_batch; h->Tmax = h->cls ? 0 : c.max_cap_len; h->Tpad_max = (h->Tmax + 7) / 8 * 8;
-    h->Mmax = c.max_batch * c.max_tokens;
-    const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
-    ALLOC(X, M * D); ALLOC(u, M * D); ALLOC(qkv, M * h->Wq); ALLOC(attn, M * D); ALLOC(o, M * D); ALLOC(hbuf, M * F);
-    ALLOC(vt, B * h->Hkv * h->vrows * ((size_t)c.max_tokens + 8));
-    ALLOC(yhat, L * B * T * C); ALLOC(kvy, L * B * T * 2 * KV); ALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
-    ALLOC(ymask, B * T); ALLOC(pool, B * C); ALLOC(capemb, B * cd); ALLOC(tf, B * 256); ALLOC(h1, B * cd); ALLOC(sc, B * cd);
-    ALLOC(mod, B * (L * NCH * D + h->FD * D)); ALLOC(tok, M * h->O);
-    if (S > 1) {
-        int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
-        ALLOC(oE, (size_t)emax * M * D); ALLOC(wtok, M * 8); ALLOC(temb, B * cd); ALLOC(tlogits, B * L * 8);
-        CK(cudaMallocHost(&h->tlogits_host, L * 8 * sizeof(float)));
-    }
-    const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
-    ALLOC(vel, lat); ALLOC(ystate, lat); ALLOC(ymid, lat); ALLOC(stage_z, lat); ALLOC(stage_cap, B * T * C); ALLOC(stage_mask, B * T);
-    for (int i = 0; i < 2; ++i) {
-        int r = dev_alloc(h, &h->rope[i].tab, (size_t)c.max_tokens * (h->hd / 2));
-        if (r) return r;
-    }
+    if (int r = alloc_workspace(h)) return r;
     if (h->cls) {
         // weight-free pre-norms (PFRMSNorm, models.py:76-117) = RMSNorm with unit weight
         std::vector<uint16_t> ones(L * D, 0x3F80);
@@ -303,7 +352,7 @@ extern "C" int ndit_create(const ndit_config* cfg, ndit_handle* out) {
     if (r) {
         snprintf(g_create_err, sizeof(g_create_err), "%s", h->err);
         for (void* p : h->allocs) cudaFree(p);
-        if (h->tlogits_host) cudaFreeHost(h->tlogits_host);
+        free_workspace(h);
         delete h;
         *out = nullptr;
         return r;
@@ -315,10 +364,34 @@ extern "C" int ndit_create(const ndit_config* cfg, ndit_handle* out) {
 extern "C" int ndit_destroy(ndit_handle h) {
     if (!h) return NDIT_OK;
     cudaDeviceSynchronize();
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->tlogits_host) cudaFreeHost(h->tlogits_host);
+    free_workspace(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
+    return NDIT_OK;
+}
+
+extern "C" int ndit_reserve(ndit_handle h, int32_t max_tokens, int32_t max_cap_len, int32_t max_batch) {
+    if (!h) return NDIT_ERR_INVALID;
+    ndit_config& c = h->cfg;
+    const int nt = max_tokens > c.max_tokens ? max_tokens : c.max_tokens;
+    const int nc = max_cap_len > c.max_cap_len ? max_cap_len : c.max_cap_len;
+    const int nb = max_batch > c.max_batch ? max_batch : c.max_batch;
+    if (nt == c.max_tokens && nc == c.max_cap_len && nb == c.max_batch) return NDIT_OK;
+    if (nb > 4 || (nb & 1)) return h->fail(NDIT_ERR_INVALID, "max_batch must be 2 or 4");
+    CK(cudaDeviceSynchronize());
+    const ndit_config old = c;
+    free_workspace(h);
+    c.max_tokens = nt; c.max_cap_len = nc; c.max_batch = nb;
+    if (int r = alloc_workspace(h)) {          // out of memory: go back to the old size so the handle stays usable
+        free_workspace(h);
+        c = old;
+        char msg[512];
+        snprintf(msg, sizeof(msg), "%s", h->err);
+        if (alloc_workspace(h)) return h->fail(NDIT_ERR_NOMEM, "ndit_reserve: could not restore the workspace after: %s", msg);
+        return h->fail(r, "ndit_reserve(%d tokens, %d caption tokens, batch %d): %s", nt, nc, nb, msg);
+    }
     return NDIT_OK;
 }
 
@@ -328,7 +401,8 @@ extern "C" int64_t ndit_launch_count(ndit_handle h) { return h ? h->launches : 0
 extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!h || !name) return NDIT_ERR_INVALID;
     if (!strcmp(name, "attn_ref")) { h->attn_ref = value; return NDIT_OK; }
-    if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return NDIT_OK; }
+    if (!strcmp(name, "graph")) { h->use_graph = value ? 1 : 0; return NDIT_OK; }
+    if (!strcmp(name, "pdl")) { h->pdl = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
     if (!strcmp(name, "profile")) {
         h->profile = value;
@@ -670,6 +744,9 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
             }
             if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
         }
+        if (make_gemm_plan(&h->p_final, h->u, (int)D, h->Wout, h->tok, h->O, M, h->O, (int)D, EPI_STORE, h->num_sms, 0))
+            return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
+        h->p_final.bias = h->bout;
         h->plan_M = M;
         h->attn_plans_valid = false;
     }
@@ -715,9 +792,9 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
     struct PdlGuard {       // per-launch CUDA events (profile mode) and overlapping launches do not mix
         int saved;
-        explicit PdlGuard(bool off) : saved(g_pdl) { if (off) g_pdl = 0; }
+        explicit PdlGuard(int v) : saved(g_pdl) { g_pdl = v; }
         ~PdlGuard() { g_pdl = saved; }
-    } pdl_guard(h->profile != 0);
+    } pdl_guard(h->profile != 0 ? 0 : h->pdl);
     if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
     if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
     if ((Hh & 1) || (Ww & 1) || Hh <= 0 || Ww <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");
@@ -852,8 +929,9 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                 // final adaLN: Next-DiT T2I [scale]; class-conditional and Flag-DiT [shift | scale]
                 const bf16* fin = h->mod + (size_t)L * NCH * D;
                 const bool fsh = h->cls || h->flag;
-                PROF(KC_ROWWISE, final_layer(h->X, h->o, post, gch, fsh ? fin + D : fin, fsh ? fin : nullptr, h->Wout, h->bout, h->tok, M, N,
-                                             D, h->O, mod_stride, h->cfg.norm_eps, s));
+                PROF(KC_ROWWISE, final_norm(h->X, h->o, post, gch, fsh ? fin + D : fin, fsh ? fin : nullptr, h->u, M, N, D, mod_stride,
+                                            h->cfg.norm_eps, s));
+                PROF(KC_ROWWISE, gemm_bf16_tn(h->p_final, s));
             }
         }
     }
@@ -868,19 +946,11 @@ extern "C" int ndit_forward_cfg(ndit_handle h, const void* x, float t, int32_t b
                         static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int ndit_sample(ndit_handle h, const void* z, int32_t batch, int32_t height, int32_t width, const float* grid,
-                           int32_t n_grid, int32_t method, const ndit_step_params* sp, void* traj, void* final_out,
-                           void* stream) {
-    if (!h || !z || !grid || !sp || !final_out) return NDIT_ERR_INVALID;
-    if (n_grid < 2) return h->fail(NDIT_ERR_INVALID, "need at least 2 grid points");
-    if (method != NDIT_EULER && method != NDIT_MIDPOINT) return h->fail(NDIT_ERR_INVALID, "method must be euler or midpoint");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+// The fixed-grid solve on the engine's own state buffer (h->ystate); trajectory rows 1.. go to `tr` when non-null.
+static int sample_body(ndit_engine* h, int batch, int height, int width, const float* grid, int n_grid, int method,
+                       const ndit_step_params* sp, bf16* tr, cudaStream_t s) {
     const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
-    if (count > (size_t)h->Bmax * h->cfg.in_channels * h->cfg.max_tokens * 4) return h->fail(NDIT_ERR_INVALID, "latent too large");
     bf16* y = h->ystate;
-    bf16* tr = static_cast<bf16*>(traj);
-    CK(cudaMemcpyAsync(y, z, count * 2, cudaMemcpyDeviceToDevice, s));
-    if (tr) CK(cudaMemcpyAsync(tr, z, count * 2, cudaMemcpyDeviceToDevice, s));
     for (int i = 0; i + 1 < n_grid; ++i) {
         const float t0 = grid[i], t1 = grid[i + 1];
         const float dt = t1 - t0;
@@ -898,6 +968,114 @@ extern "C" int ndit_sample(ndit_handle h, const void* z, int32_t batch, int32_t 
             CKL(axpy_bf16(y, y, h->vel, dt_b, count, s));
         }
         if (tr) CK(cudaMemcpyAsync(tr + (size_t)(i + 1) * count, y, count * 2, cudaMemcpyDeviceToDevice, s));
+    }
+    return NDIT_OK;
+}
+
+// Replays the CUDA graph of this solve (captured the second time the same solve is requested; the first one runs directly and
+// leaves every lazily initialised piece - plans, kernel attributes, RoPE tables - in place): ~20 k kernel launches of a
+// 30-point solve become one graph launch, which is what the launch-bound small configurations need (class-conditional 600M:
+// 151 launches in 2.2 ms per model call).  Returns 1 when the solve ran through a graph, 0 when the caller must run it
+// directly, an NDIT_ERR_* code (< 0) on error.
+static int sample_graph(ndit_engine* h, int batch, int height, int width, const float* grid, int n_grid, int method,
+                        const ndit_step_params* sp, bool with_traj, cudaStream_t s) {
+    if (!h->use_graph || h->profile || h->cfg.moe_time_experts > 0) return 0;     // (time-gated MoE reads its gate on the host)
+    const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
+    if (with_traj) {
+        const size_t need = (size_t)n_grid * count;
+        if (need > h->traj_cap_elems) {
+            if (need * 2 > ((size_t)1 << 30)) return 0;
+            bf16* nb = nullptr;
+            if (cudaMalloc(&nb, need * 2) != cudaSuccess) { cudaGetLastError(); return 0; }
+            for (auto& g : h->graphs) if (g.exec && g.with_traj) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }   // they point at the old buffer
+            if (h->traj_buf) {
+                cudaStreamSynchronize(s);
+                for (size_t i = 0; i < h->ws_allocs.size(); ++i) if (h->ws_allocs[i] == h->traj_buf) { h->ws_allocs.erase(h->ws_allocs.begin() + i); break; }
+                cudaFree(h->traj_buf);
+            }
+            h->traj_buf = nb; h->traj_cap_elems = need; h->ws_allocs.push_back(nb);
+        }
+    }
+    ndit_engine::SolveGraph* hit = nullptr;
+    for (auto& g : h->graphs) {
+        if (g.batch == batch && g.height == height && g.width == width && g.method == method && g.cap_T == h->cap_T &&
+            g.with_traj == (int)with_traj && g.attn_ref == h->attn_ref && g.attn_tp == h->attn_tp && g.pdl == h->pdl &&
+            (int)g.grid.size() == n_grid && !memcmp(g.grid.data(), grid, n_grid * sizeof(float)) && !memcmp(&g.sp, sp, sizeof(*sp))) {
+            hit = &g;
+            break;
+        }
+    }
+    if (!hit) {          // first sight of this solve: remember it, run it directly
+        if (h->graphs.size() < 4) h->graphs.emplace_back();
+        ndit_engine::SolveGraph* slot = &h->graphs[0];
+        for (auto& g : h->graphs) { if (g.last_use < slot->last_use) slot = &g; }
+        if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+        slot->grid.assign(grid, grid + n_grid);
+        slot->batch = batch; slot->height = height; slot->width = width; slot->method = method; slot->cap_T = h->cap_T;
+        slot->with_traj = with_traj; slot->attn_ref = h->attn_ref; slot->attn_tp = h->attn_tp; slot->pdl = h->pdl; slot->sp = *sp;
+        slot->launches = 0;
+        slot->last_use = ++h->graph_clock;
+        return 0;
+    }
+    if (!hit->exec) {
+        const int eol = h->flag ? 1 : 0;
+        if (int e = ensure_plans(h, batch, (height / 2) * (width / 2 + eol))) return e;
+        cudaGraph_t graph = nullptr;
+        // a graph must be self-contained: it (re)builds the V^T ones rows and its RoPE tables itself, because solves of other
+        // shapes may run between two replays
+        h->vt_ones_valid = false;
+        for (auto& r : h->rope) r.Hp = 0;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+        const int64_t l0 = h->launches;
+        const int rc = sample_body(h, batch, height, width, grid, n_grid, method, sp, with_traj ? h->traj_buf : nullptr, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const int64_t captured = h->launches - l0;
+        h->launches = l0;
+        if (rc != NDIT_OK || ce != cudaSuccess || graph == nullptr) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->vt_ones_valid = false;      // nothing recorded during a failed capture has run
+            for (auto& r : h->rope) r.Hp = 0;
+            return rc != NDIT_OK ? rc : 0;
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); h->vt_ones_valid = false; for (auto& r : h->rope) r.Hp = 0; return 0; }
+        hit->exec = exec; hit->launches = captured;
+        hit->rope_after[0] = h->rope[0]; hit->rope_after[1] = h->rope[1]; hit->rope_next_after = h->rope_next;
+    }
+    hit->last_use = ++h->graph_clock;
+    if (cudaGraphLaunch(hit->exec, s) != cudaSuccess) return h->fail(NDIT_ERR_CUDA, "cudaGraphLaunch of the captured solve failed");
+    h->launches += hit->launches;
+    h->rope[0] = hit->rope_after[0]; h->rope[1] = hit->rope_after[1]; h->rope_next = hit->rope_next_after;
+    h->vt_ones_valid = (h->plan_B == batch && h->plan_N == (height / 2) * (width / 2 + (h->flag ? 1 : 0)));
+    return 1;
+}
+
+extern "C" int ndit_sample(ndit_handle h, const void* z, int32_t batch, int32_t height, int32_t width, const float* grid,
+                           int32_t n_grid, int32_t method, const ndit_step_params* sp, void* traj, void* final_out,
+                           void* stream) {
+    if (!h || !z || !grid || !sp || !final_out) return NDIT_ERR_INVALID;
+    if (n_grid < 2) return h->fail(NDIT_ERR_INVALID, "need at least 2 grid points");
+    if (method != NDIT_EULER && method != NDIT_MIDPOINT) return h->fail(NDIT_ERR_INVALID, "method must be euler or midpoint");
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
+    if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
+    if ((height & 1) || (width & 1) || height <= 0 || width <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
+    if (count > (size_t)h->Bmax * h->cfg.in_channels * h->cfg.max_tokens * 4) return h->fail(NDIT_ERR_INVALID, "latent too large");
+    bf16* y = h->ystate;
+    bf16* tr = static_cast<bf16*>(traj);
+    CK(cudaMemcpyAsync(y, z, count * 2, cudaMemcpyDeviceToDevice, s));
+    if (tr) CK(cudaMemcpyAsync(tr, z, count * 2, cudaMemcpyDeviceToDevice, s));
+    const int g = sample_graph(h, batch, height, width, grid, n_grid, method, sp, tr != nullptr, s);
+    if (g < 0) return g;
+    if (g == 1) {
+        if (tr) CK(cudaMemcpyAsync(tr + count, h->traj_buf + count, (size_t)(n_grid - 1) * count * 2, cudaMemcpyDeviceToDevice, s));
+    } else {
+        if (int e = sample_body(h, batch, height, width, grid, n_grid, method, sp, tr, s)) return e;
     }
     if (final_out != y) CK(cudaMemcpyAsync(final_out, y, count * 2, cudaMemcpyDeviceToDevice, s));
     return NDIT_OK;

@@ -34,7 +34,7 @@ struct GemmCfg {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    bf16* __restrict__ C, int M, int N, int K, int ldc) {
+                    bf16* __restrict__ C, const bf16* __restrict__ bias, int M, int N, int K, int ldc) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -166,6 +166,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (col0 + j * 8 < N) {  // N % 8 == 0
+                                if (bias != nullptr) {   // Linear bias: added to the fp32 accumulator, one rounding (final_layer.linear)
+                                    const uint4 bq = *reinterpret_cast<const uint4*>(bias + col0 + j * 8);
+                                    const uint32_t b4[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 bf = unpack_bf16(b4[e]);
+                                        v[j * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * e]) + bf.x);
+                                        v[j * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * e + 1]) + bf.y);
+                                    }
+                                }
                                 uint4 o;
                                 o.x = pack_bf16(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
                                 o.y = pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
@@ -267,10 +277,22 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int n_full = N / BN;
     const int full_tiles = m_tiles * n_full;
+    const int n_rem = N - n_full * BN;        // width of the ragged last-N tile (0: none); a multiple of 32
     auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
         if (tile < full_tiles) { m_blk = tile / n_full; n_blk = tile - m_blk * n_full; }
         else { m_blk = tile - full_tiles; n_blk = n_full; }
     };
+    // Static schedule.  Full tiles go round-robin over the pairs.  The narrow last-N tiles (fused q|k|v: N = 3456 = 13 x 256 + 128,
+    // 32 half-width tiles) are dealt to the pairs that received one full tile fewer, so no pair carries more than
+    // ceil(work / pairs): 6.0 tile-times instead of 6.5 on 74 pairs for the 8192 x 3456 projection.
+    const int rag_tiles = num_tiles - full_tiles;
+    const int rem_pairs = full_tiles % num_pairs;
+    int rag_first = pair, rag_stride = num_pairs;
+    if (rem_pairs != 0) { rag_first = pair >= rem_pairs ? pair - rem_pairs : -1; rag_stride = num_pairs - rem_pairs; }
+    const int my_full = full_tiles > pair ? (full_tiles - pair + num_pairs - 1) / num_pairs : 0;
+    const int my_rag = (rag_first >= 0 && rag_tiles > rag_first) ? (rag_tiles - rag_first + rag_stride - 1) / rag_stride : 0;
+    const int my_tiles = my_full + my_rag;
+    auto my_tile = [&](int it) { return it < my_full ? pair + it * num_pairs : full_tiles + rag_first + (it - my_full) * rag_stride; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -301,16 +323,19 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ------------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        for (int it = 0; it < my_tiles; ++it) {
             int m_blk, n_blk;
-            tile_coords(tile, m_blk, n_blk);
+            tile_coords(my_tile(it), m_blk, n_blk);
+            // this CTA's half of the W tile: rows [w0, w0 + width/2) land at the start of its B buffer (a narrow tile's box
+            // runs past its half - and possibly past N, zero-filled - which the narrower MMA never reads)
+            const int w0 = n_blk * BN + static_cast<int>(rank) * ((n_blk < n_full ? BN : n_rem) / 2);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land on this barrier
                     tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * 256 + rank * 128);
-                    tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN + rank * (BN / 2));
+                    tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, w0);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -321,11 +346,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (leader) {
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            for (int it = 0; it < my_tiles; ++it) {
                 int m_blk, n_blk;
-                tile_coords(tile, m_blk, n_blk);
-                constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+                tile_coords(my_tile(it), m_blk, n_blk);
+                const uint32_t idesc = make_idesc_bf16(256, n_blk < n_full ? BN : n_rem);
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(tempty_bar(as), aph ^ 1);
@@ -351,10 +375,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
         const int q = warp & 3;
-        int it = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        for (int it = 0; it < my_tiles; ++it) {
             int m_blk, n_blk;
-            tile_coords(tile, m_blk, n_blk);
+            tile_coords(my_tile(it), m_blk, n_blk);
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tfull_bar(as), aph);
@@ -425,7 +448,8 @@ template <int BN, int EPI>
 static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, int M, int N, int K, int ldc,
                                 int num_sms, cudaStream_t stream) {
     auto kern = gemm2_bf16_tn_kernel<BN, EPI>;
-    static bool configured = false;
+    static PerDeviceFlag flags;
+    bool& configured = flags.here();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -440,11 +464,12 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
 // ---------------------------------------------------------------------------- host side
 
 template <int BN, int EPI>
-static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, int M, int N, int K, int ldc,
+static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const bf16* bias, int M, int N, int K, int ldc,
                                int num_sms, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tn_kernel<BN, EPI>;
-    static bool configured = false;
+    static PerDeviceFlag flags;
+    bool& configured = flags.here();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
@@ -453,13 +478,15 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
     int grid = m_tiles * n_tiles;
     if (grid > num_sms) grid = num_sms;
-    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, M, N, K, ldc);
+    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, bias, M, N, K, ldc);
 }
 
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     if (p.N % 8 != 0 || p.K % 8 != 0) return cudaErrorInvalidValue;
+    if (p.bias != nullptr && (p.pair || p.epi != EPI_STORE)) return cudaErrorInvalidValue;
     if (p.pair) {
-        if (p.N % p.bn != 0) return cudaErrorInvalidValue;      // ragged M is fine (zero-filled loads, masked stores)
+        // ragged M is fine (zero-filled loads, masked stores); a ragged last-N tile (multiple of 32 wide) only for plain stores
+        if (p.N % p.bn != 0 && (p.epi != EPI_STORE || p.bn != 256 || (p.N % 256) % 32 != 0)) return cudaErrorInvalidValue;
         if (p.epi == EPI_SWIGLU) {
             if (p.bn != 256) return cudaErrorInvalidValue;
             return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
@@ -469,11 +496,11 @@ cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     }
     if (p.epi == EPI_SWIGLU) {
         if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;
-        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
     }
-    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
 }
 
 }  // namespace ndit

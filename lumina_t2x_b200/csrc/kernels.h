@@ -25,6 +25,7 @@ struct GemmPlan {
     CUtensorMap tmA;  // A [M,K], box 128 x 64
     CUtensorMap tmB;  // W [N,K], box bn  x 64
     bf16* C;
+    const bf16* bias;   // optional [N] bias added to the fp32 accumulator (single-CTA kernel, EPI_STORE only); nullptr: none
     int M, N, K, ldc;
     int bn;   // 128 or 256
     int pair; // 1: CTA-pair kernel (cta_group::2, 256x256 tiles; W box is 128 rows)
@@ -79,11 +80,10 @@ cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const fl
 cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* w_pre,
                           const bf16* onepls, const bf16* shift, bf16* u, int M, int rows_per_batch, int D, int mod_stride,
                           float eps, cudaStream_t s);
-// residual update then LN(no affine, eps 1e-6) * onepls -> bf16 -> Linear(D->O)+bias -> out [M,O] (fp32 of bf16 values)
-// (shift: optional additive term of the final modulate, class-conditional model)
-cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
-                        const bf16* shift, const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
-                        int mod_stride, float eps, cudaStream_t s);
+// last gated residual update then xn = bf16(LN(no affine, eps 1e-6)(X) * onepls (+ shift)) -> xn [M, D]; the Linear(D->O)+bias
+// of the final layer runs as a tcgen05 GEMM with a bias epilogue on xn (shift: class-conditional model / Flag-DiT)
+cudaError_t final_norm(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
+                       const bf16* shift, bf16* xn, int M, int rows_per_batch, int D, int mod_stride, float eps, cudaStream_t s);
 cudaError_t gather_label_rows(const bf16* table, const long long* labels, float* out, int B, int n_rows, int width, cudaStream_t s);
 // rope table [N][hd/2] (cos,sin)
 cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, int one_d, cudaStream_t s);
@@ -104,8 +104,8 @@ cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int gr
 // rows per (batch, kv head) group in the V^T buffers: head_dim data rows + the all-ones row, padded to a multiple of 16
 __host__ __device__ constexpr int attn_vrows(int hd) { return (hd + 1 + 15) / 16 * 16; }
 // unpatchify + learn_sigma slice + 3-channel CFG combine (+ optional fused Euler update)
-//   tok [2n*N, O] (fp32 of bf16 values) -> v [2n,4,Hh,Ww] bf16;  if y_inout: y = bf16(y + bf16(dt*v))
-cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
+//   tok [2n*N, O] bf16 -> v [2n,4,Hh,Ww] bf16
+cudaError_t unpatchify_cfg(const bf16* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
                            cudaStream_t s);
 // mixture-of-experts (class-conditional Next-DiT-MoE): token gate + expert-order bf16 accumulation (see rowwise.cu)
 cudaError_t moe_space_gate(const bf16* u, const bf16* Wg, bf16* wtok, int M, int D, int E, cudaStream_t s);

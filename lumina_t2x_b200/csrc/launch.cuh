@@ -12,10 +12,23 @@
 
 namespace ndit {
 
-extern int g_pdl;      // 1: launch with the PDL attribute (engine option "pdl" / NDIT_PDL)
+// 1: launch with the PDL attribute.  Thread-local: an engine call sets it from its own option ("pdl" / NDIT_PDL) for the
+// duration of the call, so two engines in one process do not share the switch.
+extern thread_local int g_pdl;
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// cudaFuncSetAttribute is per (function, device): remember it per device, not per process (two engines on two devices in
+// one process).  `flags` is a function-local static of the launcher, one slot per device ordinal.
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool& here() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return done[dev & 63];
+    }
+};
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

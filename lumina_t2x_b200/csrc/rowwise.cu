@@ -337,14 +337,14 @@ cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16
 }
 
 // ---------------------------------------------------------------------------------------------
-// Final layer: last gated residual + LayerNorm(no affine) * (1+scale) -> bf16 -> Linear(D->O)+bias.
+// Final layer, first half: last gated residual + xn = bf16(LayerNorm(no affine, eps 1e-6)(x) * (1+scale) (+ shift)).
+// (model.py:657-662; the Linear D -> patch*patch*C_out + bias that follows is a tcgen05 GEMM with a bias epilogue: the first
+// version of this kernel did the projection itself and re-read the 147 KB weight for every row - 204 us for one launch.)
 template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
-final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
-                   const bf16* __restrict__ tanh_g, const bf16* __restrict__ onepls, const bf16* __restrict__ shift,
-                   const bf16* __restrict__ Wout,
-                   const bf16* __restrict__ bout, float* __restrict__ out, int M, int rows_per_batch, int D, int O,
-                   int mod_stride, float eps_rms) {
+final_norm_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
+                  const bf16* __restrict__ tanh_g, const bf16* __restrict__ onepls, const bf16* __restrict__ shift,
+                  bf16* __restrict__ xn, int M, int rows_per_batch, int D, int mod_stride, float eps_rms) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -415,39 +415,24 @@ final_layer_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const
     for (int i = 0; i < NV; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
-            float sc[8], sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float sc[8], sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r[8];
             load8(op + v * 8, sc);
             if (shift != nullptr) load8(shift + static_cast<size_t>(b) * mod_stride + v * 8, sh);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[i][e] = bf16_round((x[i][e] - mean) * rstd * sc[e] + sh[e]);
+            for (int e = 0; e < 8; ++e) r[e] = (x[i][e] - mean) * rstd * sc[e] + sh[e];
+            store8(xn + off + v * 8, r);
         }
-    }
-    for (int oc = 0; oc < O; ++oc) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int v = lane + i * 32;
-            if (v < nvec) {
-                float w[8];
-                load8(Wout + static_cast<size_t>(oc) * D + v * 8, w);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc += x[i][e] * w[e];
-            }
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) out[static_cast<size_t>(row) * O + oc] = bf16_round(acc + __bfloat162float(bout[oc]));
     }
 }
 
-cudaError_t final_layer(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
-                        const bf16* shift, const bf16* Wout, const bf16* bout, float* out, int M, int rows_per_batch, int D, int O,
-                        int mod_stride, float eps, cudaStream_t s) {
+cudaError_t final_norm(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
+                       const bf16* shift, bf16* xn, int M, int rows_per_batch, int D, int mod_stride, float eps, cudaStream_t s) {
     if (D % 8 != 0 || D > MAX_VEC * 256) return cudaErrorInvalidValue;
     const int nv = (D / 8 + 31) / 32;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
 #define LAUNCH(NVV)                                                                                              \
-    final_layer_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, onepls, shift, Wout, bout, out, M,      \
-                                                   rows_per_batch, D, O, mod_stride, eps)
+    final_norm_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, onepls, shift, xn, M, rows_per_batch, D, \
+                                                  mod_stride, eps)
     if (nv <= 3) LAUNCH(3);
     else if (nv <= 9) LAUNCH(9);
     else if (nv <= 12) LAUNCH(12);
@@ -668,7 +653,8 @@ cudaError_t gemv_rows(const float* in, const bf16* W, const bf16* bias, const fl
     const int grid = (O + 8 * GEMV_RPW - 1) / (8 * GEMV_RPW);
     const size_t sh = static_cast<size_t>(B) * K * sizeof(float);
     if (sh > 48 * 1024) {
-        static bool configured = false;
+        static PerDeviceFlag flags;
+        bool& configured = flags.here();
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(gemv_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(gemv_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -810,9 +796,108 @@ ln_rope_qk_kernel(bf16* __restrict__ qkv, int ld, const bf16* __restrict__ qw, c
     ln_rope_segment<NVK>(p + H * hd, Hkv * hd, kw, kb, rp, hd, lane, rk);
 }
 
+// Same op with ONE ROW PER 4 WARPS (128-thread block): q and k of one token are one contiguous run of (H + Hkv) * hd elements
+// = nq + nk 16-byte vectors (2B GQA: 288 + 72 = 360 -> 3 vectors per thread, ~50 registers), so 8+ blocks = 32+ warps are
+// resident per SM instead of the 16 of the one-row-per-warp kernel above, which ncu shows latency-bound at 0.38 of the HBM
+// peak (profiles/r01_ncu_ln_rope_qk_full_final.txt).  Both LayerNorms (q over H*hd, k over Hkv*hd) are reduced together:
+// two block-level reductions of a (q, k) pair each (mean, then centred second moment - the same two-pass form as above).
+template <int NV>
+__global__ void __launch_bounds__(128, NV <= 3 ? 8 : 4)
+ln_rope_qk4_kernel(bf16* __restrict__ qkv, int ld, const bf16* __restrict__ qw, const bf16* __restrict__ qb,
+                   const bf16* __restrict__ kw, const bf16* __restrict__ kb, const float2* __restrict__ rope, int N_tokens, int nq,
+                   int nk, int hd) {
+    __shared__ float red[2][4][2];
+    pdl_trigger();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntot = nq + nk;
+    bf16* p = qkv + static_cast<size_t>(row) * ld;
+    const float2* rp = rope + static_cast<size_t>(row % N_tokens) * (hd >> 1);
+    uint4 raw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * 128;
+        if (v < ntot) raw[i] = *reinterpret_cast<const uint4*>(p + v * 8);
+    }
+    float x[NV][8];
+    float s_q = 0.f, s_k = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * 128;
+        if (v < ntot) {
+            unpack8(raw[i], x[i]);
+            float a = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a += x[i][e];
+            if (v < nq) s_q += a; else s_k += a;
+        }
+    }
+    s_q = warp_sum(s_q); s_k = warp_sum(s_k);
+    if (lane == 0) { red[0][warp][0] = s_q; red[0][warp][1] = s_k; }
+    __syncthreads();
+    const float mean_q = (red[0][0][0] + red[0][1][0] + red[0][2][0] + red[0][3][0]) / static_cast<float>(nq * 8);
+    const float mean_k = (red[0][0][1] + red[0][1][1] + red[0][2][1] + red[0][3][1]) / static_cast<float>(nk * 8);
+    float v_q = 0.f, v_k = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * 128;
+        if (v < ntot) {
+            const float mu = v < nq ? mean_q : mean_k;
+            float a = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = x[i][e] - mu;
+                a += d * d;
+            }
+            if (v < nq) v_q += a; else v_k += a;
+        }
+    }
+    v_q = warp_sum(v_q); v_k = warp_sum(v_k);
+    if (lane == 0) { red[1][warp][0] = v_q; red[1][warp][1] = v_k; }
+    __syncthreads();
+    const float rstd_q = rsqrtf((red[1][0][0] + red[1][1][0] + red[1][2][0] + red[1][3][0]) / static_cast<float>(nq * 8) + 1e-5f);
+    const float rstd_k = rsqrtf((red[1][0][1] + red[1][1][1] + red[1][2][1] + red[1][3][1]) / static_cast<float>(nk * 8) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = tid + i * 128;
+        if (v < ntot) {
+            const bool isq = v < nq;
+            const int vv = isq ? v : v - nq;                 // vector index inside its segment
+            const float mu = isq ? mean_q : mean_k, rs = isq ? rstd_q : rstd_k;
+            float g[8], bb[8], r[8];
+            load8((isq ? qw : kw) + vv * 8, g);
+            load8((isq ? qb : kb) + vv * 8, bb);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[i][e] = (x[i][e] - mu) * rs * g[e] + bb[e];
+            const int m0 = ((vv * 8) % hd) >> 1;             // hd % 8 == 0: a vector never straddles heads
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+                const float2 cs = rp[m0 + pr];
+                const float a = x[i][2 * pr], bq = x[i][2 * pr + 1];
+                r[2 * pr] = a * cs.x - bq * cs.y;
+                r[2 * pr + 1] = a * cs.y + bq * cs.x;
+            }
+            store8(p + v * 8, r);
+        }
+    }
+}
+
 cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const bf16* kw, const bf16* kb,
                        const float2* rope, int M, int N_tokens, int H, int Hkv, int hd, cudaStream_t s) {
     if (hd % 8 != 0 || H * hd > 12 * 256 || Hkv * hd > 12 * 256 || ld % 8 != 0) return cudaErrorInvalidValue;
+    // one row per 128-thread block (NDIT_LNROPE4=0 selects the one-row-per-warp kernel below)
+    static const int lnrope4_env = getenv("NDIT_LNROPE4") ? atoi(getenv("NDIT_LNROPE4")) : 1;
+    const int nq = H * hd / 8, nk = Hkv * hd / 8;
+    if (lnrope4_env && M >= 1024 && nq + nk <= 6 * 128) {
+        const int nv = (nq + nk + 127) / 128;
+#define LAUNCH4(NVV) return launch_k(ln_rope_qk4_kernel<NVV>, dim3(M), dim3(128), 0, s, qkv, ld, qw, qb, kw, kb, rope, N_tokens, nq, nk, hd)
+        if (nv <= 2) LAUNCH4(2);
+        if (nv <= 3) LAUNCH4(3);
+        if (nv <= 4) LAUNCH4(4);
+        LAUNCH4(6);
+#undef LAUNCH4
+    }
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
     if (H * hd > 9 * 256)
         return launch_k(ln_rope_qk_kernel<12, 12>, grid, block, 0, s, qkv, ld, qw, qb, kw, kb, rope, M, N_tokens, H, Hkv, hd);
@@ -950,7 +1035,7 @@ cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int gr
 // ---------------------------------------------------------------------------------------------
 // unpatchify (token feature order (ph,pw,c_out), model.py:753-754) + keep first C of 2C channels (:859-861)
 // + CFG on channels 0..2 only (:904-913).
-__global__ void unpatchify_cfg_kernel(const float* __restrict__ tok, bf16* __restrict__ v_out, int n, int C, int Hh,
+__global__ void unpatchify_cfg_kernel(const bf16* __restrict__ tok, bf16* __restrict__ v_out, int n, int C, int Hh,
                                       int Ww, int O, float cfg_scale, int eol) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over n * C * Hh * Ww
     const int total = n * C * Hh * Ww;
@@ -960,8 +1045,8 @@ __global__ void unpatchify_cfg_kernel(const float* __restrict__ tok, bf16* __res
     const int t = (y >> 1) * Wt + (x >> 1);
     const int Cout = O / 4;
     const int f = ((y & 1) * 2 + (x & 1)) * Cout + c;
-    const float cond = tok[(static_cast<size_t>(s) * N + t) * O + f];
-    const float unc = tok[(static_cast<size_t>(s + n) * N + t) * O + f];
+    const float cond = __bfloat162float(tok[(static_cast<size_t>(s) * N + t) * O + f]);
+    const float unc = __bfloat162float(tok[(static_cast<size_t>(s + n) * N + t) * O + f]);
     const size_t plane = static_cast<size_t>(C) * Hh * Ww;
     const size_t o = static_cast<size_t>(c) * Hh * Ww + static_cast<size_t>(y) * Ww + x;
     if (c < 3) {
@@ -974,7 +1059,7 @@ __global__ void unpatchify_cfg_kernel(const float* __restrict__ tok, bf16* __res
     }
 }
 
-cudaError_t unpatchify_cfg(const float* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
+cudaError_t unpatchify_cfg(const bf16* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
                            cudaStream_t s) {
     const int total = n * C * Hh * Ww;
     unpatchify_cfg_kernel<<<(total + 255) / 256, 256, 0, s>>>(tok, v_out, n, C, Hh, Ww, O, cfg_scale, eol);

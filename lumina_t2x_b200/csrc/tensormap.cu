@@ -100,8 +100,11 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
     p->pair = 0;
     if (allow_pair && pair_env && M >= 256) {
         // BN = 192 (N = 3456) measured slower than the single-CTA kernel (108 vs 103 us): only behind NDIT_GEMM_PAIR=2
-        const int pbn = (N % 256 == 0) ? 256 : ((pair_env >= 2 && N % 192 == 0 && epi != EPI_SWIGLU) ? 192 : 0);
-        if (pbn && ((M + 255) / 256) * (N / pbn) >= num_sms / 2) { p->pair = 1; p->bn = pbn; }
+        // N need not be a multiple of 256: a narrower last-N tile (a multiple of 32 columns) runs as a narrower cta_group::2 MMA
+        // (fused q|k|v, N = 3456: 13 full tiles + one 128-wide per 256 rows).  NDIT_GEMM_PAIR=2: 192-wide tiles instead (slower).
+        int pbn = (N % 256 == 0 || (epi != EPI_SWIGLU && (N % 256) % 32 == 0 && N > 256)) ? 256 : 0;
+        if (pair_env >= 2 && N % 192 == 0 && N % 256 != 0 && epi != EPI_SWIGLU) pbn = 192;
+        if (pbn && ((M + 255) / 256) * ((N + pbn - 1) / pbn) >= num_sms / 2) { p->pair = 1; p->bn = pbn; }
     }
     if (make_tmap_2d(&p->tmA, A, M, K, lda, 128, 64, 128)) return -1;
     if (make_tmap_2d(&p->tmB, W, N, K, K, p->pair ? p->bn / 2 : bn, 64, 128)) return -1;

@@ -120,8 +120,8 @@ class DiT_Llama(EngineModule):
                                self.num_classes, 0, *{"": (0, 0), "time": (8, 0), "space": (0, 8), "both": (4, 4)}[self.moe])
 
     def _set_labels(self, lib, h, y: torch.Tensor, stream):
-        key = (y.data_ptr(), y._version, tuple(y.shape), y.dtype)
-        if key == self._label_key:
+        key = self._tensor_key(y)
+        if key is not None and key == self._label_key:
             return
         yl = y.detach().to(torch.int64).contiguous()
         _lib.check(lib.ndit_set_labels(h, C.c_void_p(yl.data_ptr()), yl.numel(), stream), h)
@@ -134,11 +134,14 @@ class DiT_Llama(EngineModule):
             self._label_key = None
         return lib, h
 
-    @staticmethod
-    def _step_params(cfg_scale, rope_scaling_factor, ntk_factor):
+    def _step_params(self, cfg_scale, rope_scaling_factor, ntk_factor):
+        """models.py:952-960: the kwargs overwrite self.freqs_cis, so an override stays in effect for later calls that pass
+        None (the ctor's table is rope_scaling_factor = ntk_factor = 1)."""
         if rope_scaling_factor is not None or ntk_factor is not None:
             assert rope_scaling_factor is not None and ntk_factor is not None       # models.py:952-953
-        return _lib.NditStepParams(float(cfg_scale), float(rope_scaling_factor or 1.0), 1.0, 0, 0, float(ntk_factor or 1.0))
+            self._rope_override = (float(rope_scaling_factor), float(ntk_factor))
+        lin, ntk = getattr(self, "_rope_override", (1.0, 1.0))
+        return _lib.NditStepParams(float(cfg_scale), lin, 1.0, 0, 0, ntk)
 
     def forward(self, x, t, y):
         raise NotImplementedError("the B200 engine accelerates forward_with_cfg (the sampling path); training forward is out of scope")
@@ -146,18 +149,22 @@ class DiT_Llama(EngineModule):
     @torch.no_grad()
     def forward_with_cfg(self, x, t, y, cfg_scale, rope_scaling_factor=None, ntk_factor=None):
         """models.py:946-974.  x [2n,C,H,W] (first half cond, second half ignored on input); y [2n] labels."""
+        self._check_inputs(x, y)
         lib, h = self._engine(x.device)
         with torch.cuda.device(x.device):
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(x.shape[2], x.shape[3]), 0, x.shape[0])
             self._set_labels(lib, h, y, stream)
             return self._run_forward(lib, h, x, t, self._step_params(cfg_scale, rope_scaling_factor, ntk_factor))
 
     @torch.no_grad()
     def sample_fixed_grid(self, z, t_grid, method: str, y, cfg_scale, rope_scaling_factor=None, ntk_factor=None,
                           return_trajectory: bool = True):
+        self._check_inputs(z, y)
         lib, h = self._engine(z.device)
         with torch.cuda.device(z.device):
             stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(z.shape[2], z.shape[3]), 0, z.shape[0])
             self._set_labels(lib, h, y, stream)
             return self._run_sample(lib, h, z, t_grid, method, self._step_params(cfg_scale, rope_scaling_factor, ntk_factor),
                                     return_trajectory)

@@ -77,6 +77,9 @@ class DiT_Llama(NextDiT):
         return _lib.NditConfig(self.dim, self.n_layers, self.n_heads, self.n_kv_heads, self.cap_feat_dim, self.in_channels,
                                self.patch_size, self.multiple_of, int(self.learn_sigma), float(self.norm_eps), *self._limits, 0, 1)
 
+    def _tokens_for(self, Hh: int, Ww: int) -> int:          # one learned [eol] token closes every row of patches
+        return (Hh // self.patch_size) * (Ww // self.patch_size + 1)
+
     def _flag_step_params(self, cfg_scale, rope_scaling_factor, ntk_factor, base_seqlen, proportional_attn):
         """model.py:880-899: kwargs override the ctor's rope scaling / NTK factor, and the override is sticky."""
         if rope_scaling_factor is not None or ntk_factor is not None:
@@ -93,9 +96,11 @@ class DiT_Llama(NextDiT):
         """model.py:868-923.  x [2n,C,H,W]; first half = cond, second half ignored on input."""
         if not isinstance(x, torch.Tensor):
             raise NotImplementedError("list-of-tensors (variable resolution) input is not supported by the B200 engine")
+        self._check_inputs(x, cap_feats, cap_mask)
         lib, h = self._engine(x.device)
         with torch.cuda.device(x.device):
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(x.shape[2], x.shape[3]), cap_feats.shape[1], x.shape[0])
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
             sp = self._flag_step_params(cfg_scale, rope_scaling_factor, ntk_factor, base_seqlen, proportional_attn)
             return self._run_forward(lib, h, x, t, sp)
@@ -103,9 +108,11 @@ class DiT_Llama(NextDiT):
     @torch.no_grad()
     def sample_fixed_grid(self, z, t_grid, method: str, cap_feats, cap_mask, cfg_scale, rope_scaling_factor=None, ntk_factor=None,
                           base_seqlen: Optional[int] = None, proportional_attn: bool = False, return_trajectory: bool = True):
+        self._check_inputs(z, cap_feats, cap_mask)
         lib, h = self._engine(z.device)
         with torch.cuda.device(z.device):
             stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(z.shape[2], z.shape[3]), cap_feats.shape[1], z.shape[0])
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
             sp = self._flag_step_params(cfg_scale, rope_scaling_factor, ntk_factor, base_seqlen, proportional_attn)
             return self._run_sample(lib, h, z, t_grid, method, sp, return_trajectory)

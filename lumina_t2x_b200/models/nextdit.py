@@ -9,6 +9,7 @@ libndit_b200.so through the C ABI in include/ndit.h.  There is no PyTorch fallba
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from typing import Optional
 
 import torch
@@ -163,6 +164,56 @@ class EngineModule(nn.Module):
     def parameter_count(self) -> int:
         return sum(p.numel() for p in self.parameters())
 
+    # ------------------------------------------------------------------ shared argument handling
+    def _ensure_capacity(self, lib, h, tokens: int, cap_len: int, batch: int) -> None:
+        """Grow the engine workspace (weights stay packed) when a call needs more tokens / caption tokens / rows than
+        the handle was created for: an unmodified sample.py at 2048x2048 must not fail on a default-constructed model."""
+        t, c, b = self._limits
+        if tokens > t or cap_len > c or batch > b:
+            self._limits = (max(t, tokens), max(c, cap_len), max(b, batch))
+            _lib.check(lib.ndit_reserve(h, *self._limits), h)
+            self._cap_key = None
+            if hasattr(self, "_label_key"):
+                self._label_key = None
+
+    def _tokens_for(self, Hh: int, Ww: int) -> int:
+        return (Hh // self.patch_size) * (Ww // self.patch_size)
+
+    @staticmethod
+    def _tensor_key(*tensors):
+        """Cache key of conditioning tensors; None (= do not cache) for tensors without a version counter
+        (created under torch.inference_mode())."""
+        try:
+            return tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype, str(t.device)) for t in tensors)
+        except RuntimeError:
+            return None
+
+    def _check_inputs(self, x: torch.Tensor, *cond: torch.Tensor) -> None:
+        """The engine computes in bf16 whatever the module / input dtype is (weights are packed to bf16, activations are bf16,
+        fp32 accumulation): say so once instead of silently downgrading, and refuse tensors on another device."""
+        if not x.is_cuda:
+            raise RuntimeError(f"{type(self).__name__} (B200 engine) needs CUDA inputs; there is no CPU path")
+        for c in cond:
+            if isinstance(c, torch.Tensor) and c.device != x.device:
+                raise RuntimeError(f"conditioning tensor on {c.device}, input on {x.device}: all tensors must be on the engine's device")
+        pd = next(self.parameters()).dtype
+        if (pd != torch.bfloat16 or x.dtype != torch.bfloat16) and not getattr(self, "_warned_dtype", False):
+            self._warned_dtype = True
+            warnings.warn(f"{type(self).__name__}: parameters are {pd}, input is {x.dtype}; the B200 engine computes in bfloat16 "
+                          "(bf16 weights and activations, fp32 accumulation) and returns the input dtype - the same numerics as the "
+                          "reference under torch.autocast('cuda', torch.bfloat16) with bf16 parameters", stacklevel=3)
+
+    @staticmethod
+    def _uniform_t(t) -> float:
+        """forward_with_cfg is called with t = ones(B) * t (transport.py:106): one timestep for all rows.  The engine embeds
+        a single t; per-row timesteps would silently be wrong, so they are rejected (one D2H read, like model.py:888)."""
+        if not isinstance(t, torch.Tensor):
+            return float(t)
+        vals = t.detach().reshape(-1).tolist()
+        if any(v != vals[0] for v in vals):
+            raise ValueError("the B200 engine needs the same timestep for every row of a forward_with_cfg call (got %r)" % (vals,))
+        return float(vals[0])
+
     def launch_count(self) -> int:
         return int(_lib.load().ndit_launch_count(self._handle)) if self._handle is not None else 0
 
@@ -177,8 +228,9 @@ class EngineModule(nn.Module):
     def _run_forward(self, lib, h, x, t, sp):
         xb = x.detach().to(torch.bfloat16).contiguous()
         out = torch.empty_like(xb)
-        tv = float(t[0].item()) if isinstance(t, torch.Tensor) else float(t)    # the reference syncs here too (model.py:888)
+        tv = self._uniform_t(t)                                                 # the reference syncs here too (model.py:888)
         B, _, Hh, Ww = xb.shape
+        self._ensure_capacity(lib, h, self._tokens_for(Hh, Ww), 0, B)
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         _lib.check(lib.ndit_forward_cfg(h, C.c_void_p(xb.data_ptr()), tv, B, Hh, Ww, C.byref(sp), C.c_void_p(out.data_ptr()), stream), h)
         return out.to(x.dtype)
@@ -190,6 +242,7 @@ class EngineModule(nn.Module):
         n = len(grid)
         garr = (C.c_float * n)(*grid)
         B, _, Hh, Ww = zb.shape
+        self._ensure_capacity(lib, h, self._tokens_for(Hh, Ww), 0, B)
         traj = torch.empty((n,) + tuple(zb.shape), dtype=torch.bfloat16, device=z.device) if return_trajectory else None
         final = torch.empty_like(zb)
         m = {"euler": _lib.NDIT_EULER, "midpoint": _lib.NDIT_MIDPOINT}[method]
@@ -242,15 +295,15 @@ class NextDiT(EngineModule):
                                self.patch_size, self.multiple_of, int(self.learn_sigma), float(self.norm_eps), *self._limits, 0)
 
     def _set_caption(self, lib, h, cap_feats: torch.Tensor, cap_mask: torch.Tensor, stream):
-        key = (cap_feats.data_ptr(), cap_feats._version, tuple(cap_feats.shape), cap_feats.dtype,
-               cap_mask.data_ptr(), cap_mask._version, tuple(cap_mask.shape))
-        if key == self._cap_key:
+        key = self._tensor_key(cap_feats, cap_mask)
+        if key is not None and key == self._cap_key:
             return
         cap = cap_feats.detach().to(torch.bfloat16).contiguous()
         mask = (cap_mask.detach() != 0).to(torch.uint8).contiguous()
         B, T, Cd = cap.shape
         if Cd != self.cap_feat_dim or tuple(mask.shape) != (B, T):
             raise ValueError(f"cap_feats {tuple(cap.shape)} / cap_mask {tuple(mask.shape)} do not match cap_feat_dim {self.cap_feat_dim}")
+        self._ensure_capacity(lib, h, 0, T, B)
         _lib.check(lib.ndit_set_caption(h, C.c_void_p(cap.data_ptr()), C.c_void_p(mask.data_ptr()), B, T, stream), h)
         self._cap_key = key
         self._cap_keepalive = (cap_feats, cap_mask, cap, mask)   # keep the ids in the cache key alive
@@ -273,9 +326,11 @@ class NextDiT(EngineModule):
         """model.py:866-913.  x [2n,C,H,W]; first half = cond, second half ignored on input."""
         if not isinstance(x, torch.Tensor):
             raise NotImplementedError("list-of-tensors (variable resolution) input is not supported by the B200 engine")
+        self._check_inputs(x, cap_feats, cap_mask)
         lib, h = self._engine(x.device)
         with torch.cuda.device(x.device):
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(x.shape[2], x.shape[3]), cap_feats.shape[1], x.shape[0])
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
             sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
             return self._run_forward(lib, h, x, t, sp)
@@ -284,9 +339,11 @@ class NextDiT(EngineModule):
     def sample_fixed_grid(self, z, t_grid, method: str, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0,
                           base_seqlen: Optional[int] = None, proportional_attn: bool = False, return_trajectory: bool = True):
         """Whole fixed-grid ODE solve inside the engine (used by transport.Sampler for euler / midpoint)."""
+        self._check_inputs(z, cap_feats, cap_mask)
         lib, h = self._engine(z.device)
         with torch.cuda.device(z.device):
             stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(z.shape[2], z.shape[3]), cap_feats.shape[1], z.shape[0])
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
             sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
             return self._run_sample(lib, h, z, t_grid, method, sp, return_trajectory)

@@ -49,6 +49,8 @@ GEMM_SHAPES = [
     (4096, 2304, 2304), (8192, 2304, 6144), (2560, 2048, 192),
     # CTA-pair kernel with a ragged last M tile (Flag-DiT: 2 x 4160 tokens; the second CTA of the last pair is all padding)
     (8320, 3072, 3072), (4900, 2304, 256), (2700, 2048, 192),
+    # CTA-pair kernel with a narrow last-N tile (fused q|k|v: 3456 = 13 x 256 + 128), down to a 32-wide one, also with a ragged M tile
+    (8192, 3456, 2304), (2560, 2336, 192), (4100, 3488, 320),
 ]
 
 
