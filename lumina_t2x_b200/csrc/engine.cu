@@ -85,7 +85,9 @@ struct ndit_engine {
     bf16 *Wg_time = nullptr, *Wg_space = nullptr;   // [L][E][cd] / [L][E][D]
     bf16 *oE = nullptr, *wtok = nullptr;     // expert outputs [E][M][D], token weights [M][E]
     float *temb = nullptr, *tlogits = nullptr;      // [B][cd], [B][L*E]
-    float* tlogits_host = nullptr;           // pinned, [L*E]
+    int* tsel = nullptr;                     // [L][2] experts chosen by the time gate (device; ascending index)
+    float* tw = nullptr;                     // [L][2] their bf16-rounded softmax weights (device)
+    std::vector<GemmPlan> p_w13t, p_w2t;     // [L][2] time-gated layers: W = stack of the layer's experts, chosen on the device
     int FD = 1;                              // final-layer adaLN chunks: 1 (scale) or 2 (shift, scale)
     bf16* Yemb = nullptr;                    // [num_classes + 1, cd] label embedding table
     int device = 0, num_sms = 148;
@@ -243,7 +245,7 @@ static int alloc_workspace(ndit_engine* h) {
     if (S > 1) {
         int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
         WALLOC(oE, (size_t)emax * M * D); WALLOC(wtok, M * 8); WALLOC(temb, B * cd); WALLOC(tlogits, B * L * 8);
-        CK(cudaMallocHost(&h->tlogits_host, L * 8 * sizeof(float)));
+        WALLOC(tsel, L * 2); WALLOC(tw, L * 2);
     }
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
     WALLOC(vel, lat); WALLOC(ystate, lat); WALLOC(ymid, lat); WALLOC(stage_z, lat); WALLOC(stage_cap, B * T * C); WALLOC(stage_mask, B * T);
@@ -265,7 +267,6 @@ static int alloc_workspace(ndit_engine* h) {
 static void free_workspace(ndit_engine* h) {
     for (void* p : h->ws_allocs) cudaFree(p);
     h->ws_allocs.clear();
-    if (h->tlogits_host) { cudaFreeHost(h->tlogits_host); h->tlogits_host = nullptr; }
 }
 
 static int create_impl(ndit_engine* h) {
@@ -744,6 +745,26 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
             }
             if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
         }
+        h->p_w13t.clear(); h->p_w2t.clear();
+        for (int f = 0; f < h->NF; ++f) {
+            if (h->ffn_kind[f] != 1) continue;
+            const int E = h->ffn_E[f];
+            h->p_w13t.resize(L * 2); h->p_w2t.resize(L * 2);
+            for (size_t l = 0; l < L; ++l) {
+                const size_t base = l * S + h->ffn_slot0[f];
+                for (int k = 0; k < 2; ++k) {
+                    GemmPlan& a = h->p_w13t[l * 2 + k];
+                    GemmPlan& b = h->p_w2t[l * 2 + k];
+                    int e = make_gemm_plan(&a, h->u, (int)D, h->W13 + base * 2 * F * D, h->hbuf, (int)F, M, (int)(2 * F), (int)D, EPI_SWIGLU,
+                                           h->num_sms, 1, (int)(E * 2 * F));
+                    e |= make_gemm_plan(&b, h->hbuf, (int)F, h->W2 + base * D * F, h->oE + (size_t)k * M * D, (int)D, M, (int)D, (int)F,
+                                        EPI_STORE, h->num_sms, 1, (int)(E * D));
+                    if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
+                    a.w_row_off = h->tsel + l * 2 + k; a.w_row_mul = (int)(2 * F);
+                    b.w_row_off = h->tsel + l * 2 + k; b.w_row_mul = (int)D;
+                }
+            }
+        }
         if (make_gemm_plan(&h->p_final, h->u, (int)D, h->Wout, h->tok, h->O, M, h->O, (int)D, EPI_STORE, h->num_sms, 0))
             return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
         h->p_final.bias = h->bout;
@@ -841,27 +862,13 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     PROF(KC_COND, gemv_rows(h->sc, h->Wada, h->bada, nullptr, nullptr, h->mod, batch, mod_stride, h->cd, 0, POST_ADALN, D, L * NCH,
                             h->flag ? ADALN_FLAG : (h->cls ? ADALN_CLASS : ADALN_NEXT), s));
     // time-gated MoE (Next-DiT-MoE models.py:459-477): the gate sees only the timestep embedding, so one pair of experts
-    // serves the whole batch in every layer.  Logits for all layers in one GEMV, one small D2H read, selection on the host.
-    int t_sel[64][2];
-    float t_w[64][2];
+    // serves the whole batch in every layer.  Logits for all layers in one GEMV; the top-2 selection stays on the device
+    // (moe_time_select) and the expert GEMMs read "which expert" from device memory: no host round trip, graph-capturable.
     const int Et = h->cfg.moe_time_experts;
     if (Et > 0) {
-        if (L > 64) return h->fail(NDIT_ERR_INVALID, "time-gated MoE supports at most 64 layers");
         PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, nullptr, h->temb, nullptr, batch, h->cd, h->cd, 0, POST_NONE, 0, 0, 0, s));
         PROF(KC_COND, gemv_rows(h->temb, h->Wg_time, nullptr, nullptr, h->tlogits, nullptr, batch, L * Et, h->cd, 0, POST_NONE, 0, 0, 0, s));
-        CK(cudaMemcpyAsync(h->tlogits_host, h->tlogits, (size_t)L * Et * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        for (int l = 0; l < L; ++l) {
-            const float* lg = h->tlogits_host + (size_t)l * Et;
-            int i0 = 0, i1 = -1;                              // top-2, ties: lower expert index first
-            for (int e = 1; e < Et; ++e) if (lg[e] > lg[i0]) i0 = e;
-            for (int e = 0; e < Et; ++e) if (e != i0 && (i1 < 0 || lg[e] > lg[i1])) i1 = e;
-            const float e1 = expf(lg[i1] - lg[i0]);
-            const float w0 = host_bf16_round(1.0f / (1.0f + e1)), w1 = host_bf16_round(e1 / (1.0f + e1));
-            // accumulation runs in expert-index order
-            if (i0 < i1) { t_sel[l][0] = i0; t_sel[l][1] = i1; t_w[l][0] = w0; t_w[l][1] = w1; }
-            else { t_sel[l][0] = i1; t_sel[l][1] = i0; t_w[l][0] = w1; t_w[l][1] = w0; }
-        }
+        PROF(KC_COND, moe_time_select(h->tlogits, L, Et, h->tsel, h->tw, s));
     }
     // per-layer modulation chunks (offsets in units of D): Next-DiT [1+scale_msa, tanh gate_msa, 1+scale_mlp, tanh gate_mlp];
     // Flag-DiT [shift_msa, 1+scale_msa, gate_msa, shift_mlp, 1+scale_mlp, gate_mlp]
@@ -899,12 +906,10 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                 PROF(KC_GEMM_W2, gemm_bf16_tn(h->p_w2[base], s));
             } else if (h->ffn_kind[f] == 1) {           // time-gated: the two selected experts, ascending index
                 for (int k = 0; k < 2; ++k) {
-                    PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[base + t_sel[l][k]], s));
-                    GemmPlan p2 = h->p_w2[base + t_sel[l][k]];
-                    p2.C = h->oE + k * MD;
-                    PROF(KC_GEMM_W2, gemm_bf16_tn(p2, s));
+                    PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13t[(size_t)l * 2 + k], s));
+                    PROF(KC_GEMM_W2, gemm_bf16_tn(h->p_w2t[(size_t)l * 2 + k], s));
                 }
-                PROF(KC_ROWWISE, moe_combine(h->oE, MD, 2, nullptr, t_w[l], h->o, M, D, s));
+                PROF(KC_ROWWISE, moe_combine(h->oE, MD, 2, nullptr, h->tw + (size_t)l * 2, h->o, M, D, s));
             } else {                                    // token-gated: every expert runs densely, the gate weights select
                 const int E = h->ffn_E[f];
                 PROF(KC_ROWWISE, moe_space_gate(h->u, h->Wg_space + (size_t)l * E * D, h->wtok, M, D, E, s));
@@ -979,7 +984,7 @@ static int sample_body(ndit_engine* h, int batch, int height, int width, const f
 // directly, an NDIT_ERR_* code (< 0) on error.
 static int sample_graph(ndit_engine* h, int batch, int height, int width, const float* grid, int n_grid, int method,
                         const ndit_step_params* sp, bool with_traj, cudaStream_t s) {
-    if (!h->use_graph || h->profile || h->cfg.moe_time_experts > 0) return 0;     // (time-gated MoE reads its gate on the host)
+    if (!h->use_graph || h->profile) return 0;
     const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
     if (with_traj) {
         const size_t need = (size_t)n_grid * count;

@@ -34,7 +34,8 @@ struct GemmCfg {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    bf16* __restrict__ C, const bf16* __restrict__ bias, int M, int N, int K, int ldc) {
+                    bf16* __restrict__ C, const bf16* __restrict__ bias, const int* __restrict__ w_row_off, int w_row_mul, int M, int N,
+                    int K, int ldc) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -91,6 +92,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
+        // W may be a stack of matrices (the experts of a time-gated MoE layer): the one to use is chosen on the device
+        const int w_off = w_row_off != nullptr ? (*w_row_off) * w_row_mul : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
@@ -100,7 +103,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
                     tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * GEMM_BM);
-                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n_blk * BN);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, w_off + n_blk * BN);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -254,7 +257,7 @@ struct Gemm2Cfg {
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     bf16* __restrict__ C, int M, int N, int K, int ldc) {
+                     bf16* __restrict__ C, const int* __restrict__ w_row_off, int w_row_mul, int M, int N, int K, int ldc) {
     using Cfg = Gemm2Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -323,12 +326,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ------------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
+        const int w_off = w_row_off != nullptr ? (*w_row_off) * w_row_mul : 0;     // device-selected matrix of a stacked W (MoE experts)
         for (int it = 0; it < my_tiles; ++it) {
             int m_blk, n_blk;
             tile_coords(my_tile(it), m_blk, n_blk);
             // this CTA's half of the W tile: rows [w0, w0 + width/2) land at the start of its B buffer (a narrow tile's box
             // runs past its half - and possibly past N, zero-filled - which the narrower MMA never reads)
-            const int w0 = n_blk * BN + static_cast<int>(rank) * ((n_blk < n_full ? BN : n_rem) / 2);
+            const int w0 = w_off + n_blk * BN + static_cast<int>(rank) * ((n_blk < n_full ? BN : n_rem) / 2);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 if (lane == 0) {
@@ -445,8 +449,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int BN, int EPI>
-static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, int M, int N, int K, int ldc,
-                                int num_sms, cudaStream_t stream) {
+static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const int* w_row_off, int w_row_mul, int M, int N,
+                                int K, int ldc, int num_sms, cudaStream_t stream) {
     auto kern = gemm2_bf16_tn_kernel<BN, EPI>;
     static PerDeviceFlag flags;
     bool& configured = flags.here();
@@ -458,14 +462,14 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, M, N, K, ldc);
+    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc);
 }
 
 // ---------------------------------------------------------------------------- host side
 
 template <int BN, int EPI>
-static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const bf16* bias, int M, int N, int K, int ldc,
-                               int num_sms, cudaStream_t stream) {
+static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const bf16* bias, const int* w_row_off, int w_row_mul,
+                               int M, int N, int K, int ldc, int num_sms, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tn_kernel<BN, EPI>;
     static PerDeviceFlag flags;
@@ -478,7 +482,7 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
     int grid = m_tiles * n_tiles;
     if (grid > num_sms) grid = num_sms;
-    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, bias, M, N, K, ldc);
+    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, bias, w_row_off, w_row_mul, M, N, K, ldc);
 }
 
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
@@ -489,18 +493,18 @@ cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
         if (p.N % p.bn != 0 && (p.epi != EPI_STORE || p.bn != 256 || (p.N % 256) % 32 != 0)) return cudaErrorInvalidValue;
         if (p.epi == EPI_SWIGLU) {
             if (p.bn != 256) return cudaErrorInvalidValue;
-            return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+            return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
         }
-        if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-        return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
     }
     if (p.epi == EPI_SWIGLU) {
         if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;
-        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
     }
-    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
 }
 
 }  // namespace ndit

@@ -25,6 +25,8 @@ struct GemmPlan {
     CUtensorMap tmA;  // A [M,K], box 128 x 64
     CUtensorMap tmB;  // W [N,K], box bn  x 64
     bf16* C;
+    const int* w_row_off;   // optional device int: W is a stack of [N, K] matrices, use the one at row (*w_row_off) * w_row_mul
+    int w_row_mul;
     const bf16* bias;   // optional [N] bias added to the fp32 accumulator (single-CTA kernel, EPI_STORE only); nullptr: none
     int M, N, K, ldc;
     int bn;   // 128 or 256
@@ -34,8 +36,9 @@ struct GemmPlan {
 };
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream);
 // builds the maps of a plan (A: [M,K] ld=lda; W: [N,K] ld=K)
+// w_total_rows > N: W is a stack of matrices (see GemmPlan::w_row_off); the W map then spans all of them
 int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int M, int N, int K, int epi,
-                   int num_sms, int allow_pair = 1);
+                   int num_sms, int allow_pair = 1, int w_total_rows = 0);
 
 // ---------------------------------------------------------------- attention (attention_tcgen05.cu)
 struct AttnPlan {
@@ -109,8 +112,12 @@ cudaError_t unpatchify_cfg(const bf16* tok, bf16* v_out, int n, int C, int Hh, i
                            cudaStream_t s);
 // mixture-of-experts (class-conditional Next-DiT-MoE): token gate + expert-order bf16 accumulation (see rowwise.cu)
 cudaError_t moe_space_gate(const bf16* u, const bf16* Wg, bf16* wtok, int M, int D, int E, cudaStream_t s);
+// uniform_w: E weights in DEVICE memory (time-gated layer: written by moe_time_select)
 cudaError_t moe_combine(const bf16* oe, size_t estride, int E, const bf16* wtok, const float* uniform_w, bf16* out, int M, int D,
                         cudaStream_t s);
+// time gate (Next-DiT-MoE models.py:459-477): per layer the top-2 experts of the gate logits of batch row 0 (ascending expert
+// index = accumulation order) and their bf16-rounded softmax weights: sel [L][2], w [L][2] in device memory
+cudaError_t moe_time_select(const float* logits, int L, int E, int* sel, float* w, cudaStream_t s);
 cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s);
 
 }  // namespace ndit

@@ -313,11 +313,10 @@ cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16
                           float eps, cudaStream_t s) {
     if (D % 8 != 0 || D > MAX_VEC * 256 || mod_stride % 8 != 0) return cudaErrorInvalidValue;
     const int nv = (D / 8 + 31) / 32;
-    // NDIT_RESID4=1: one row per 128-thread block (32 warps per SM).  Measured at the very end of round 1 with
-    // tools/resid_bench.py: 33.1 us per launch on the 8192 x 2304 shape (one-row-per-warp kernel: 38.4 us under ncu; its
-    // number from the same harness was not captured before the GPU budget ran out) - opt-in until round 2 has re-measured
-    // it inside the step.  Outputs differ from the default kernel in 1 ulp on ~1e-5 of the elements (reduction order).
-    static const int resid4_env = getenv("NDIT_RESID4") ? atoi(getenv("NDIT_RESID4")) : 0;
+    // One row per 128-thread block (32 warps per SM).  Measured inside the step (round 2, config 2): row-wise class 112.7 ->
+    // 100.4 ms per solve, 883.5 -> 876.8 ms total (profiles/r02_bench_resid4_ab.json).  NDIT_RESID4=0 selects the one-row-per-warp
+    // kernel; outputs differ from it in 1 ulp on ~1e-5 of the elements (reduction order).
+    static const int resid4_env = getenv("NDIT_RESID4") ? atoi(getenv("NDIT_RESID4")) : 1;
     if (resid4_env && M >= 1024 && D / 8 <= 3 * 128) {
         if (D / 8 <= 2 * 128) return launch_k(resid_rms_mod4_kernel<2>, dim3(M), dim3(128), 0, s, X, o, w_post, tanh_g, w_pre, onepls, shift, u, M,
                                               rows_per_batch, D, mod_stride, eps);
@@ -1111,15 +1110,14 @@ cudaError_t moe_space_gate(const bf16* u, const bf16* Wg, bf16* wtok, int M, int
 // out = sum over experts in index order, accumulated in bf16 like ``results[idx] += w * expert(x[idx])`` on a zero tensor:
 // r = bf16(r + bf16(w_e * o_e)) for every selected expert.  wtok != nullptr: per-token weights [M, E] (0 = not selected);
 // else the E buffers are the selected experts of a time-gated layer with the uniform weights uw[0..E).
-struct MoeUniform { float w[8]; };
-__global__ void moe_combine_kernel(const bf16* __restrict__ oe, size_t estride, int E, const bf16* __restrict__ wtok, MoeUniform uw,
-                                   bf16* __restrict__ out, size_t count8, int D) {
+__global__ void moe_combine_kernel(const bf16* __restrict__ oe, size_t estride, int E, const bf16* __restrict__ wtok,
+                                   const float* __restrict__ uw, bf16* __restrict__ out, size_t count8, int D) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // one 8-element vector
     if (i >= count8) return;
     const size_t row = (i * 8) / D;
     float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int e = 0; e < E; ++e) {
-        const float w = wtok != nullptr ? __bfloat162float(wtok[row * E + e]) : uw.w[e];
+        const float w = wtok != nullptr ? __bfloat162float(wtok[row * E + e]) : uw[e];
         if (wtok != nullptr && w == 0.f) continue;
         float o[8];
         load8(oe + e * estride + i * 8, o);
@@ -1132,10 +1130,30 @@ __global__ void moe_combine_kernel(const bf16* __restrict__ oe, size_t estride, 
 cudaError_t moe_combine(const bf16* oe, size_t estride, int E, const bf16* wtok, const float* uniform_w, bf16* out, int M, int D,
                         cudaStream_t s) {
     if (E < 1 || E > 8 || D % 8 != 0) return cudaErrorInvalidValue;
-    MoeUniform uw;
-    for (int e = 0; e < 8; ++e) uw.w[e] = (uniform_w != nullptr && e < E) ? uniform_w[e] : 0.f;
+    if (wtok == nullptr && uniform_w == nullptr) return cudaErrorInvalidValue;
     const size_t count8 = static_cast<size_t>(M) * D / 8;
-    moe_combine_kernel<<<static_cast<unsigned>((count8 + 255) / 256), 256, 0, s>>>(oe, estride, E, wtok, uw, out, count8, D);
+    moe_combine_kernel<<<static_cast<unsigned>((count8 + 255) / 256), 256, 0, s>>>(oe, estride, E, wtok, uniform_w, out, count8, D);
+    return cudaGetLastError();
+}
+
+// One thread per layer: top-2 of E gate logits (ties: lower expert index first), softmax over the two, bf16-rounded weights,
+// stored in ascending expert order (the reference accumulates ``results += w * expert(x)`` in expert-index order).
+__global__ void moe_time_select_kernel(const float* __restrict__ logits, int L, int E, int* __restrict__ sel, float* __restrict__ w) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const float* lg = logits + static_cast<size_t>(l) * E;
+    int i0 = 0, i1 = -1;
+    for (int e = 1; e < E; ++e) if (lg[e] > lg[i0]) i0 = e;
+    for (int e = 0; e < E; ++e) if (e != i0 && (i1 < 0 || lg[e] > lg[i1])) i1 = e;
+    const float e1 = expf(lg[i1] - lg[i0]);
+    const float w0 = bf16_round(1.0f / (1.0f + e1)), w1 = bf16_round(e1 / (1.0f + e1));
+    if (i0 < i1) { sel[2 * l] = i0; sel[2 * l + 1] = i1; w[2 * l] = w0; w[2 * l + 1] = w1; }
+    else { sel[2 * l] = i1; sel[2 * l + 1] = i0; w[2 * l] = w1; w[2 * l + 1] = w0; }
+}
+
+cudaError_t moe_time_select(const float* logits, int L, int E, int* sel, float* w, cudaStream_t s) {
+    if (E < 2 || E > 8 || L < 1) return cudaErrorInvalidValue;
+    moe_time_select_kernel<<<(L + 63) / 64, 64, 0, s>>>(logits, L, E, sel, w);
     return cudaGetLastError();
 }
 

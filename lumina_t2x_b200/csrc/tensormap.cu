@@ -74,7 +74,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 }
 
 int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int M, int N, int K, int epi,
-                   int num_sms, int allow_pair) {
+                   int num_sms, int allow_pair, int w_total_rows) {
     memset(p, 0, sizeof(*p));
     p->C = C; p->M = M; p->N = N; p->K = K; p->ldc = ldc; p->epi = epi; p->num_sms = num_sms;
     // BN = 256 keeps the per-flop shared-memory operand traffic under the 128 B/clk/SM port limit
@@ -107,7 +107,7 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
         if (pbn && ((M + 255) / 256) * ((N + pbn - 1) / pbn) >= num_sms / 2) { p->pair = 1; p->bn = pbn; }
     }
     if (make_tmap_2d(&p->tmA, A, M, K, lda, 128, 64, 128)) return -1;
-    if (make_tmap_2d(&p->tmB, W, N, K, K, p->pair ? p->bn / 2 : bn, 64, 128)) return -1;
+    if (make_tmap_2d(&p->tmB, W, w_total_rows > N ? w_total_rows : N, K, K, p->pair ? p->bn / 2 : bn, 64, 128)) return -1;
     return 0;
 }
 

@@ -145,7 +145,10 @@ def _fixed_grid_torch(fn: Callable, x: th.Tensor, t: th.Tensor, method: str) -> 
 
 def _solve(x, model_fn, t_grid, method, model_kwargs, wrap_drift=None):
     eng = _engine_of(model_fn) if wrap_drift is None else None
-    if eng is not None and method in ("euler", "midpoint") and isinstance(x, th.Tensor) and x.is_cuda:
+    # The in-engine solve keeps the state in bf16 and rounds t / dt the way torchdiffeq does for a bf16 state.  A state of
+    # another dtype (fp32 latents with an fp32 checkpoint, the Next-DiT-MoE sample.py default) keeps the reference's
+    # semantics through the generic loop below: fp32 state and time, the model call itself computes in bf16.
+    if (eng is not None and method in ("euler", "midpoint") and isinstance(x, th.Tensor) and x.is_cuda and x.dtype == th.bfloat16):
         allowed, required = _ENGINE_KW[type(eng)]
         if set(model_kwargs) <= set(allowed) and set(required) <= set(model_kwargs):
             return eng.sample_fixed_grid(x, t_grid.tolist(), method, **model_kwargs)

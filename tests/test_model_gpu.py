@@ -111,9 +111,10 @@ def test_strict_loading_and_errors():
     m.load_state_dict(W, strict=True)
     m = m.to("cuda", dtype=torch.bfloat16)
     z, cap, mask = O.synthetic_inputs(cfg, (16, 16), 16, 8)
-    with pytest.raises(RuntimeError):           # more tokens than the workspace was sized for
-        m.forward_with_cfg(torch.zeros(2, 4, 64, 64, device="cuda", dtype=torch.bfloat16), torch.zeros(2, device="cuda"),
-                           cap.cuda(), mask.cuda(), 2.0)
+    # more tokens than the workspace was sized for: the engine grows it (tests/test_boundary_gpu.py checks the result)
+    big = m.forward_with_cfg(torch.zeros(2, 4, 64, 64, device="cuda", dtype=torch.bfloat16), torch.zeros(2, device="cuda"),
+                             cap.cuda(), mask.cuda(), 2.0)
+    assert big.shape == (2, 4, 64, 64) and torch.isfinite(big.float()).all()
     out = m.forward_with_cfg(z.cuda(), torch.full((2,), 0.5, device="cuda"), cap.cuda(), mask.cuda(), 2.0)
     assert torch.isfinite(out.float()).all()
     assert m.launch_count() > 0

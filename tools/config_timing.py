@@ -88,9 +88,22 @@ def main():
         n0 = m.launch_count()
         ms = timed(fn)
         per = (m.launch_count() - n0) // 8
-        print(json.dumps({"config": name, "ms_per_forward": round(ms, 3), "kernel_launches_per_forward": per,
-                          "algorithmic_tflop": round((fl[0] + fl[1]) / 1e12, 3),
-                          "tflops": round((fl[0] + fl[1]) / 1e9 / ms, 1), "params_B": round(m.parameter_count() / 1e9, 3)}), flush=True)
+        rec = {"config": name, "ms_per_forward": round(ms, 3), "kernel_launches_per_forward": per,
+               "algorithmic_tflop": round((fl[0] + fl[1]) / 1e12, 3),
+               "tflops": round((fl[0] + fl[1]) / 1e9 / ms, 1), "params_B": round(m.parameter_count() / 1e9, 3)}
+        if c in (1, 5):
+            # whole 30-point Euler solve through transport.Sampler (29 model calls): direct launches vs the captured CUDA graph
+            from lumina_t2x_b200 import transport
+            sfn = transport.Sampler(transport.create_transport("Linear", "velocity", None, None, None)).sample_ode(
+                sampling_method="euler", num_steps=30, atol=1e-6, rtol=1e-3, reverse=False, time_shifting_factor=1.0)
+            outs = {}
+            for gopt in (0, 1):
+                m.set_option("graph", gopt)
+                solve = lambda: sfn(z, m.forward_with_cfg, y=y, cfg_scale=4.0)[-1]  # noqa: E731
+                outs[gopt] = solve()
+                rec["ms_per_model_call_in_solve_graph%d" % gopt] = round(timed(solve, warm=2, iters=5) / 29, 3)
+            rec["graph_equals_direct"] = bool(torch.equal(outs[0], outs[1]))
+        print(json.dumps(rec), flush=True)
         del m
         torch.cuda.empty_cache()
 
