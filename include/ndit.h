@@ -34,7 +34,7 @@ typedef enum ndit_status {
 } ndit_status;
 
 typedef enum ndit_dtype { NDIT_BF16 = 0, NDIT_F32 = 1 } ndit_dtype;
-typedef enum ndit_method { NDIT_EULER = 0, NDIT_MIDPOINT = 1 } ndit_method;
+typedef enum ndit_method { NDIT_EULER = 0, NDIT_MIDPOINT = 1, NDIT_RK4 = 2 /* torchdiffeq's fixed-grid rk4 (3/8 rule) */ } ndit_method;
 
 /* Architecture of a NextDiT instance: the ctor arguments of
  * lumina_next_t2i/models/model.py:665-741 (NextDiT.__init__) fixed by the factories at :994-999. */
@@ -100,6 +100,12 @@ int ndit_set_weight(ndit_handle h, const char* key, const void* dev_ptr, const i
                     int32_t dtype, void* stream);
 int ndit_finalize_weights(ndit_handle h, void* stream);
 int64_t ndit_parameter_count(ndit_handle h);   /* NextDiT.parameter_count (model.py:965-982) */
+/* Checkpoint tooling for this engine (the reference converts .pth <-> .safetensors, lumina_next_t2i/entry_point.py:115-156):
+ * the finalized weights in the engine's own GEMM-ready layout, written to / read from one flat file.  Loading replaces
+ * ndit_set_weight x N + ndit_finalize_weights on a cold start (no re-packing kernels, disk reads overlapped with the H2D
+ * copies); the file is tied to the architecture (ndit_config without the workspace limits) and to the ABI version. */
+int ndit_save_packed(ndit_handle h, const char* path);
+int ndit_load_packed(ndit_handle h, const char* path);
 
 /* --- caption conditioning: the cap_feats / cap_mask kwargs of forward_with_cfg.  They are constant over
  * an ODE solve, so the caption-side work (pooling + cap_embedder, model.py:847-850; attention_y_norm,
@@ -119,7 +125,7 @@ int ndit_forward_cfg(ndit_handle h, const void* x_dev, float t, int32_t batch, i
                      const ndit_step_params* sp, void* out_dev, void* stream);
 
 /* --- transport.Sampler.sample_ode(...)(z, model.forward_with_cfg, **kw) (transport/transport.py:346-391,
- * transport/integrators.py:79-116) with torchdiffeq's fixed-grid euler / midpoint.  t_grid_host: the
+ * transport/integrators.py:79-116) with torchdiffeq's fixed-grid euler / midpoint / rk4.  t_grid_host: the
  * n_grid time points (fp32, host).  z_dev: bf16 initial state [batch,C,height,width]; traj_dev: bf16
  * [n_grid, batch, C, height, width] receiving every grid state (traj[0] = z), or NULL to keep only
  * the final state, which is always written to final_dev (may alias z_dev). */

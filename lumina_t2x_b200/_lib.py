@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libndit_b200.so")
 
 NDIT_BF16, NDIT_F32 = 0, 1
-NDIT_EULER, NDIT_MIDPOINT = 0, 1
+NDIT_EULER, NDIT_MIDPOINT, NDIT_RK4 = 0, 1, 2
 
 
 class NditConfig(C.Structure):
@@ -38,6 +38,8 @@ SIGNATURES = {
     "ndit_finalize_weights": (C.c_int, [_vp, _vp]),
     "ndit_parameter_count": (_i64, [_vp]),
     "ndit_reserve": (C.c_int, [_vp, _i32, _i32, _i32]),
+    "ndit_save_packed": (C.c_int, [_vp, C.c_char_p]),
+    "ndit_load_packed": (C.c_int, [_vp, C.c_char_p]),
     "ndit_set_caption": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "ndit_set_labels": (C.c_int, [_vp, _vp, _i32, _vp]),
     "ndit_forward_cfg": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),

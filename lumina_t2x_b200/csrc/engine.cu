@@ -104,6 +104,7 @@ struct ndit_engine {
     size_t ev_used = 0;
     std::set<std::string> seen;
     std::vector<void*> allocs;               // weights (live as long as the handle)
+    std::vector<size_t> alloc_bytes;         // payload bytes of each weight buffer (ndit_save_packed / ndit_load_packed)
     std::vector<void*> ws_allocs;            // workspace (re-created by ndit_reserve)
 
     // weights
@@ -122,6 +123,7 @@ struct ndit_engine {
     bf16* tok;                               // [M, O] final-layer output tokens
     bf16* mod;
     bf16 *vel, *ystate, *ymid;
+    bf16* kbuf[3];                           // rk4: k2, k3, k4 (k1 = vel)
     bf16 *stage_z, *stage_cap;
     uint8_t* stage_mask;
     RopeSlot rope[2];
@@ -212,6 +214,7 @@ static int dev_alloc(ndit_engine* h, T** p, size_t count, bool workspace = false
     e = cudaMemset(q, 0, count * sizeof(T) + 256);
     if (e != cudaSuccess) return h->fail(NDIT_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
     (workspace ? h->ws_allocs : h->allocs).push_back(q);
+    if (!workspace) h->alloc_bytes.push_back(count * sizeof(T));
     *p = static_cast<T*>(q);
     return 0;
 }
@@ -248,7 +251,7 @@ static int alloc_workspace(ndit_engine* h) {
         WALLOC(tsel, L * 2); WALLOC(tw, L * 2);
     }
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
-    WALLOC(vel, lat); WALLOC(ystate, lat); WALLOC(ymid, lat); WALLOC(stage_z, lat); WALLOC(stage_cap, B * T * C); WALLOC(stage_mask, B * T);
+    WALLOC(vel, lat); WALLOC(ystate, lat); WALLOC(ymid, lat); WALLOC(kbuf[0], lat); WALLOC(kbuf[1], lat); WALLOC(kbuf[2], lat); WALLOC(stage_z, lat); WALLOC(stage_cap, B * T * C); WALLOC(stage_mask, B * T);
     for (int i = 0; i < 2; ++i) {
         int r = dev_alloc(h, &h->rope[i].tab, (size_t)c.max_tokens * (h->hd / 2), true);
         h->rope[i].Hp = 0;
@@ -653,6 +656,104 @@ extern "C" int ndit_finalize_weights(ndit_handle h, void* stream) {
     return NDIT_OK;
 }
 
+// ------------------------------------------------------------------------------------ packed weight files
+// The engine's own weight layout (fused q|k|v, w1|w3 interleaved per 256 rows, packed adaLN matrices, expert stacks,
+// precomputed tanh(gate)) written to / read from one flat file, so a cold start copies ~3.3 GB straight into place instead of
+// re-packing the state dict with one kernel per tensor (the role of the reference's checkpoint tooling,
+// lumina_next_t2i/entry_point.py:115-156, for this engine).  Layout: header | sizes[n] | buffers back to back.
+struct PackedHeader {
+    char magic[8];            // "NDITPK02"
+    int32_t abi, config_bytes;
+    ndit_config cfg;
+    int64_t n_params;
+    int32_t n_buffers, finalized;
+};
+
+extern "C" int ndit_save_packed(ndit_handle h, const char* path) {
+    if (!h || !path) return NDIT_ERR_INVALID;
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "ndit_save_packed: weights not finalized");
+    CK(cudaDeviceSynchronize());
+    FILE* f = fopen(path, "wb");
+    if (!f) return h->fail(NDIT_ERR_INVALID, "ndit_save_packed: cannot open %s for writing", path);
+    PackedHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "NDITPK02", 8);
+    hd.abi = NDIT_ABI_VERSION; hd.config_bytes = (int32_t)sizeof(ndit_config); hd.cfg = h->cfg;
+    hd.cfg.max_tokens = hd.cfg.max_cap_len = hd.cfg.max_batch = 0;      // workspace limits are not part of the weights
+    hd.n_params = h->n_params; hd.n_buffers = (int32_t)h->allocs.size(); hd.finalized = 1;
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+    std::vector<uint64_t> sizes(h->alloc_bytes.begin(), h->alloc_bytes.end());
+    ok = ok && fwrite(sizes.data(), sizeof(uint64_t), sizes.size(), f) == sizes.size();
+    const size_t CH = (size_t)64 << 20;
+    void* bounce = nullptr;
+    if (cudaMallocHost(&bounce, CH) != cudaSuccess) { fclose(f); cudaGetLastError(); return h->fail(NDIT_ERR_NOMEM, "ndit_save_packed: no pinned staging buffer"); }
+    for (size_t i = 0; ok && i < h->allocs.size(); ++i) {
+        for (size_t off = 0; ok && off < sizes[i]; off += CH) {
+            const size_t n = sizes[i] - off < CH ? sizes[i] - off : CH;
+            ok = cudaMemcpy(bounce, static_cast<char*>(h->allocs[i]) + off, n, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(bounce, 1, n, f) == n;
+        }
+    }
+    cudaFreeHost(bounce);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? NDIT_OK : h->fail(NDIT_ERR_CUDA, "ndit_save_packed: write to %s failed", path);
+}
+
+extern "C" int ndit_load_packed(ndit_handle h, const char* path) {
+    if (!h || !path) return NDIT_ERR_INVALID;
+    FILE* f = fopen(path, "rb");
+    if (!f) return h->fail(NDIT_ERR_INVALID, "ndit_load_packed: cannot open %s", path);
+    PackedHeader hd;
+    std::vector<uint64_t> sizes;
+    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && !memcmp(hd.magic, "NDITPK02", 8) && hd.abi == NDIT_ABI_VERSION &&
+              hd.config_bytes == (int32_t)sizeof(ndit_config) && hd.n_buffers == (int32_t)h->allocs.size();
+    if (ok) {
+        ndit_config a = hd.cfg, b = h->cfg;
+        a.max_tokens = a.max_cap_len = a.max_batch = b.max_tokens = b.max_cap_len = b.max_batch = 0;
+        ok = !memcmp(&a, &b, sizeof(a));
+    }
+    if (ok) {
+        sizes.resize(hd.n_buffers);
+        ok = fread(sizes.data(), sizeof(uint64_t), sizes.size(), f) == sizes.size();
+        for (size_t i = 0; ok && i < sizes.size(); ++i) ok = sizes[i] == h->alloc_bytes[i];
+    }
+    if (!ok) { fclose(f); return h->fail(NDIT_ERR_INVALID, "ndit_load_packed: %s is not a packed weight file of this architecture / ABI", path); }
+    const size_t CH = (size_t)64 << 20;
+    void* bounce[2] = {nullptr, nullptr};
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (cudaMallocHost(&bounce[0], CH) != cudaSuccess || cudaMallocHost(&bounce[1], CH) != cudaSuccess || cudaStreamCreate(&cs) != cudaSuccess ||
+        cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess) {
+        fclose(f);
+        cudaGetLastError();
+        if (bounce[0]) cudaFreeHost(bounce[0]);
+        if (bounce[1]) cudaFreeHost(bounce[1]);
+        return h->fail(NDIT_ERR_NOMEM, "ndit_load_packed: no staging resources");
+    }
+    int cur = 0;        // disk read of chunk i+1 overlaps the H2D copy of chunk i
+    bool used[2] = {false, false};
+    for (size_t i = 0; ok && i < h->allocs.size(); ++i) {
+        for (size_t off = 0; ok && off < sizes[i]; off += CH) {
+            const size_t n = sizes[i] - off < CH ? sizes[i] - off : CH;
+            if (used[cur]) ok = cudaEventSynchronize(ev[cur]) == cudaSuccess;
+            ok = ok && fread(bounce[cur], 1, n, f) == n &&
+                 cudaMemcpyAsync(static_cast<char*>(h->allocs[i]) + off, bounce[cur], n, cudaMemcpyHostToDevice, cs) == cudaSuccess &&
+                 cudaEventRecord(ev[cur], cs) == cudaSuccess;
+            used[cur] = true;
+            cur ^= 1;
+        }
+    }
+    ok = cudaStreamSynchronize(cs) == cudaSuccess && ok;
+    cudaFreeHost(bounce[0]); cudaFreeHost(bounce[1]); cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); cudaStreamDestroy(cs);
+    fclose(f);
+    if (!ok) return h->fail(NDIT_ERR_CUDA, "ndit_load_packed: reading %s failed", path);
+    std::vector<std::string> keys;
+    expected_keys(h, &keys);
+    for (const std::string& k : keys) h->seen.insert(k);
+    h->n_params = hd.n_params;
+    h->finalized = true;
+    return NDIT_OK;
+}
+
 // ------------------------------------------------------------------------------------ caption
 
 extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* mask, int32_t batch, int32_t T, void* stream) {
@@ -965,12 +1066,25 @@ static int sample_body(ndit_engine* h, int batch, int height, int width, const f
         if (method == NDIT_EULER) {
             if (int e = forward_impl(h, y, host_bf16_round(t0), batch, height, width, sp, h->vel, s)) return e;
             CKL(axpy_bf16(y, y, h->vel, dt_b, count, s));
-        } else {
+        } else if (method == NDIT_MIDPOINT) {
             const float half_dt = 0.5f * dt;
             if (int e = forward_impl(h, y, host_bf16_round(t0), batch, height, width, sp, h->vel, s)) return e;
             CKL(axpy_bf16(h->ymid, y, h->vel, host_bf16_round(half_dt), count, s));
             if (int e = forward_impl(h, h->ymid, host_bf16_round(t0 + half_dt), batch, height, width, sp, h->vel, s)) return e;
             CKL(axpy_bf16(y, y, h->vel, dt_b, count, s));
+        } else {
+            // torchdiffeq rk4_alt_step_func (3/8 rule): stage times t0 + dt/3, t0 + 2 dt/3, t1 are fp32 scalars, cast to
+            // the state dtype when the model is called
+            bf16 *k1 = h->vel, *k2 = h->kbuf[0], *k3 = h->kbuf[1], *k4 = h->kbuf[2];
+            const float third = 1.0f / 3.0f, two_thirds = 2.0f / 3.0f;
+            if (int e = forward_impl(h, y, host_bf16_round(t0), batch, height, width, sp, k1, s)) return e;
+            CKL(rk4_stage(1, h->ymid, y, k1, k2, k3, k4, dt_b, count, s));
+            if (int e = forward_impl(h, h->ymid, host_bf16_round(t0 + dt * third), batch, height, width, sp, k2, s)) return e;
+            CKL(rk4_stage(2, h->ymid, y, k1, k2, k3, k4, dt_b, count, s));
+            if (int e = forward_impl(h, h->ymid, host_bf16_round(t0 + dt * two_thirds), batch, height, width, sp, k3, s)) return e;
+            CKL(rk4_stage(3, h->ymid, y, k1, k2, k3, k4, dt_b, count, s));
+            if (int e = forward_impl(h, h->ymid, host_bf16_round(t1), batch, height, width, sp, k4, s)) return e;
+            CKL(rk4_stage(4, y, y, k1, k2, k3, k4, dt_b, count, s));
         }
         if (tr) CK(cudaMemcpyAsync(tr + (size_t)(i + 1) * count, y, count * 2, cudaMemcpyDeviceToDevice, s));
     }
@@ -1063,7 +1177,7 @@ extern "C" int ndit_sample(ndit_handle h, const void* z, int32_t batch, int32_t 
                            void* stream) {
     if (!h || !z || !grid || !sp || !final_out) return NDIT_ERR_INVALID;
     if (n_grid < 2) return h->fail(NDIT_ERR_INVALID, "need at least 2 grid points");
-    if (method != NDIT_EULER && method != NDIT_MIDPOINT) return h->fail(NDIT_ERR_INVALID, "method must be euler or midpoint");
+    if (method != NDIT_EULER && method != NDIT_MIDPOINT && method != NDIT_RK4) return h->fail(NDIT_ERR_INVALID, "method must be euler, midpoint or rk4");
     if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
     if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
     if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);

@@ -118,6 +118,9 @@ cudaError_t moe_combine(const bf16* oe, size_t estride, int E, const bf16* wtok,
 // time gate (Next-DiT-MoE models.py:459-477): per layer the top-2 experts of the gate logits of batch row 0 (ascending expert
 // index = accumulation order) and their bf16-rounded softmax weights: sel [L][2], w [L][2] in device memory
 cudaError_t moe_time_select(const float* logits, int L, int E, int* sel, float* w, cudaStream_t s);
+// one stage of torchdiffeq's fixed-grid rk4 (3/8 rule) on a bf16 state (see rowwise.cu); dt already rounded to bf16
+cudaError_t rk4_stage(int stage, bf16* out, const bf16* y, const bf16* k1, const bf16* k2, const bf16* k3, const bf16* k4, float dt,
+                      size_t count, cudaStream_t s);
 cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s);
 
 }  // namespace ndit

@@ -1166,6 +1166,41 @@ __global__ void axpy_bf16_kernel(bf16* __restrict__ y_out, const bf16* __restric
     y_out[i] = __float2bfloat16_rn(__bfloat162float(y_in[i]) + d);
 }
 
+// torchdiffeq's fixed-grid rk4 (rk4_alt_step_func, the 3/8 rule) on a bf16 state, every tensor op rounded to bf16 like
+// PyTorch does (dt is a 0-dim tensor and is rounded to bf16 by type promotion, Python scalars enter in fp32):
+//   stage 1: out = y + (dt * k1) * (1/3)
+//   stage 2: out = y + dt * (k2 - k1 * (1/3))
+//   stage 3: out = y + dt * (k1 - k2 + k3)
+//   stage 4: out = y + (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+__global__ void rk4_stage_kernel(int stage, bf16* __restrict__ out, const bf16* __restrict__ y, const bf16* __restrict__ k1,
+                                 const bf16* __restrict__ k2, const bf16* __restrict__ k3, const bf16* __restrict__ k4, float dt,
+                                 size_t count) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float third = 1.0f / 3.0f;          // float(1 / 3) as PyTorch passes the Python scalar
+    const float yv = __bfloat162float(y[i]), a = __bfloat162float(k1[i]);
+    float d;
+    if (stage == 1) {
+        d = bf16_round(bf16_round(dt * a) * third);
+    } else if (stage == 2) {
+        d = bf16_round(dt * bf16_round(__bfloat162float(k2[i]) - bf16_round(a * third)));
+    } else if (stage == 3) {
+        d = bf16_round(dt * bf16_round(bf16_round(a - __bfloat162float(k2[i])) + __bfloat162float(k3[i])));
+    } else {
+        const float s23 = bf16_round(__bfloat162float(k2[i]) + __bfloat162float(k3[i]));
+        const float acc = bf16_round(bf16_round(a + bf16_round(3.0f * s23)) + __bfloat162float(k4[i]));
+        d = bf16_round(bf16_round(acc * dt) * 0.125f);
+    }
+    out[i] = __float2bfloat16_rn(yv + d);
+}
+
+cudaError_t rk4_stage(int stage, bf16* out, const bf16* y, const bf16* k1, const bf16* k2, const bf16* k3, const bf16* k4, float dt,
+                      size_t count, cudaStream_t s) {
+    if (stage < 1 || stage > 4) return cudaErrorInvalidValue;
+    rk4_stage_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(stage, out, y, k1, k2, k3, k4, dt, count);
+    return cudaGetLastError();
+}
+
 cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s) {
     axpy_bf16_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(y_out, y_in, v, dt, count);
     return cudaGetLastError();

@@ -107,6 +107,7 @@ class EngineModule(nn.Module):
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._dirty = True
+        self._packed_path = None
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def mark_weights_changed(self) -> None:
@@ -133,6 +134,12 @@ class EngineModule(nn.Module):
     def _engine(self, device: torch.device):
         lib = _lib.load()
         if self._handle is not None and not self._dirty:
+            return lib, self._handle
+        if getattr(self, "_packed_path", None) is not None:
+            # the engine was created from a packed weight file (checkpoint.load_packed): the nn.Parameters of this module were
+            # never populated, so a .to() / .cuda() re-creates the engine from the file, not from them
+            from .. import checkpoint
+            checkpoint.load_packed(self, self._packed_path, device)
             return lib, self._handle
         self._check_supported()
         if device.type != "cuda":
@@ -196,7 +203,7 @@ class EngineModule(nn.Module):
         for c in cond:
             if isinstance(c, torch.Tensor) and c.device != x.device:
                 raise RuntimeError(f"conditioning tensor on {c.device}, input on {x.device}: all tensors must be on the engine's device")
-        pd = next(self.parameters()).dtype
+        pd = torch.bfloat16 if getattr(self, "_packed_path", None) is not None else next(self.parameters()).dtype
         if (pd != torch.bfloat16 or x.dtype != torch.bfloat16) and not getattr(self, "_warned_dtype", False):
             self._warned_dtype = True
             warnings.warn(f"{type(self).__name__}: parameters are {pd}, input is {x.dtype}; the B200 engine computes in bfloat16 "
@@ -245,7 +252,7 @@ class EngineModule(nn.Module):
         self._ensure_capacity(lib, h, self._tokens_for(Hh, Ww), 0, B)
         traj = torch.empty((n,) + tuple(zb.shape), dtype=torch.bfloat16, device=z.device) if return_trajectory else None
         final = torch.empty_like(zb)
-        m = {"euler": _lib.NDIT_EULER, "midpoint": _lib.NDIT_MIDPOINT}[method]
+        m = {"euler": _lib.NDIT_EULER, "midpoint": _lib.NDIT_MIDPOINT, "rk4": _lib.NDIT_RK4}[method]
         stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
         _lib.check(lib.ndit_sample(h, C.c_void_p(zb.data_ptr()), B, Hh, Ww, garr, n, m, C.byref(sp),
                                    C.c_void_p(traj.data_ptr()) if traj is not None else None, C.c_void_p(final.data_ptr()), stream), h)

@@ -128,10 +128,11 @@ def _fixed_grid_torch(fn: Callable, x: th.Tensor, t: th.Tensor, method: str) -> 
         elif method == "midpoint":
             half = 0.5 * dt
             dy = dt * f(ta + half, y + f(ta, y) * half)
-        elif method == "rk4":     # torchdiffeq's 3/8-rule rk4
+        elif method == "rk4":     # torchdiffeq's fixed-grid rk4 = rk4_alt_step_func (3/8 rule), same expression order
+            one_third, two_thirds = 1 / 3, 2 / 3
             k1 = f(ta, y)
-            k2 = f(ta + dt / 3, y + dt * k1 / 3)
-            k3 = f(ta + dt * 2 / 3, y + dt * (k2 - k1 / 3))
+            k2 = f(ta + dt * one_third, y + dt * k1 * one_third)
+            k3 = f(ta + dt * two_thirds, y + dt * (k2 - k1 * one_third))
             k4 = f(tb, y + dt * (k1 - k2 + k3))
             dy = (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
         else:
@@ -148,7 +149,7 @@ def _solve(x, model_fn, t_grid, method, model_kwargs, wrap_drift=None):
     # The in-engine solve keeps the state in bf16 and rounds t / dt the way torchdiffeq does for a bf16 state.  A state of
     # another dtype (fp32 latents with an fp32 checkpoint, the Next-DiT-MoE sample.py default) keeps the reference's
     # semantics through the generic loop below: fp32 state and time, the model call itself computes in bf16.
-    if (eng is not None and method in ("euler", "midpoint") and isinstance(x, th.Tensor) and x.is_cuda and x.dtype == th.bfloat16):
+    if (eng is not None and method in ("euler", "midpoint", "rk4") and isinstance(x, th.Tensor) and x.is_cuda and x.dtype == th.bfloat16):
         allowed, required = _ENGINE_KW[type(eng)]
         if set(model_kwargs) <= set(allowed) and set(required) <= set(model_kwargs):
             return eng.sample_fixed_grid(x, t_grid.tolist(), method, **model_kwargs)

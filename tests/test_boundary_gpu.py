@@ -152,3 +152,50 @@ def test_dtype_contract_and_timestep_checks():
         sampling_method="euler", num_steps=4, atol=1e-6, rtol=1e-3, reverse=False, time_shifting_factor=1.0)
     tr32 = fn(z.float(), m.forward_with_cfg, cap_feats=cap, cap_mask=mask, **kw)
     assert tr32.dtype == torch.float32 and torch.isfinite(tr32).all()
+
+
+def test_rk4_in_engine_equals_generic_loop():
+    """sampling_method="rk4" (torchdiffeq's fixed-grid 3/8 rule): the in-engine solve (ndit_sample, NDIT_RK4) must give the bits
+    of the PyTorch-driven loop over the same engine (transport._fixed_grid_torch: one forward_with_cfg per stage, every
+    tensor op in bf16)."""
+    from lumina_t2x_b200 import transport
+    from oracle import nextdit_oracle as O
+    cfg, W, m = _tiny(max_tokens=1024, max_cap_len=64)
+    z, cap, mask = (v.cuda() for v in O.synthetic_inputs(cfg, (32, 32), 24, 8, seed=4))
+    kw = dict(cfg_scale=2.0, scale_factor=1.0, scale_watershed=1.0, base_seqlen=64, proportional_attn=True)
+    fn = transport.Sampler(transport.create_transport("Linear", "velocity", None, None, None)).sample_ode(
+        sampling_method="rk4", num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, time_shifting_factor=4.0)
+    n0 = m.launch_count()
+    fused = fn(z, m.forward_with_cfg, cap_feats=cap, cap_mask=mask, **kw)
+    assert m.launch_count() - n0 > 4 * 4 * 20          # 4 intervals x 4 model calls inside the engine
+    generic = transport._fixed_grid_torch(
+        lambda t, x: m.forward_with_cfg(x, torch.ones(2, device="cuda") * t, cap, mask, **kw),
+        z, transport._time_grid(0, 1, 5, 4.0).cuda(), "rk4")
+    assert fused.shape == generic.shape == (5, 2, 4, 32, 32)
+    assert torch.equal(fused, generic)
+
+
+def test_packed_weight_file_round_trip(tmp_path):
+    """checkpoint.save_packed / load_packed (ndit_save_packed / ndit_load_packed): a cold start from the packed file gives the
+    bits of the engine that was built from the state dict; a file of another architecture is refused."""
+    from lumina_t2x_b200 import checkpoint, models
+    from oracle import nextdit_oracle as O
+    cfg, W, m = _tiny(max_tokens=256, max_cap_len=32)
+    z, cap, mask = (v.cuda() for v in O.synthetic_inputs(cfg, (16, 16), 16, 8, seed=3))
+    t = torch.full((2,), 0.5, device="cuda")
+    ref = m.forward_with_cfg(z, t, cap, mask, 2.0)
+    path = str(tmp_path / "tiny.nditpk")
+    checkpoint.save_packed(m, path)
+    cold = models.NextDiT(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=True,
+                          cap_feat_dim=cfg.cap_feat_dim, max_tokens=64, max_cap_len=8)        # never sees a state dict
+    checkpoint.load_packed(cold, path)
+    n0 = cold.launch_count()
+    out = cold.forward_with_cfg(z, t, cap, mask, 2.0)
+    assert torch.equal(out, ref)
+    assert n0 == 0                                       # no re-packing launches on the cold start
+    cold.to("cuda")                                      # a move re-creates the engine from the file, not from the (unset) parameters
+    assert torch.equal(cold.forward_with_cfg(z, t, cap, mask, 2.0), ref)
+    other = models.NextDiT(dim=cfg.dim, n_layers=cfg.n_layers + 1, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=True,
+                           cap_feat_dim=cfg.cap_feat_dim)
+    with pytest.raises(RuntimeError):
+        checkpoint.load_packed(other, path)

@@ -246,3 +246,30 @@ def test_data_parallel_gather_world2_gloo(total):
     expect = torch.stack([torch.randn(4, 8, 8, generator=torch.Generator().manual_seed(100 + i)) for i in range(total)])
     for rank, out, _ in res:
         assert torch.equal(out, expect), rank
+
+
+def test_checkpoint_tooling_safetensors_and_convert(tmp_path):
+    """checkpoint.convert mirrors `lumina_next convert` (entry_point.py:115-156); the mmap safetensors reader / writer written
+    here must interoperate with the safetensors library the reference uses."""
+    from safetensors.torch import load_file, save_file
+    from lumina_t2x_b200 import checkpoint
+    g = torch.Generator().manual_seed(0)
+    sd = {"layers.0.attention.wq.weight": torch.randn(48, 32, generator=g).to(torch.bfloat16), "pad_token": torch.randn(32, generator=g),
+          "layers.0.attention.gate": torch.zeros(4, dtype=torch.float16), "step": torch.tensor([7], dtype=torch.int64), "empty": torch.empty(0, 3)}
+    p_lib, p_ours = str(tmp_path / "a.safetensors"), str(tmp_path / "b.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, p_lib)
+    checkpoint.write_safetensors(sd, p_ours)
+    for path, reader in ((p_lib, checkpoint.read_safetensors), (p_ours, lambda p: load_file(p, device="cpu"))):
+        got = reader(path)
+        assert set(got) == set(sd)
+        for k, v in sd.items():
+            assert got[k].dtype == v.dtype and got[k].shape == v.shape and torch.equal(got[k], v), k
+    torch.save(sd, str(tmp_path / "consolidated.00-of-01.pth"))
+    out = checkpoint.convert(str(tmp_path / "consolidated.00-of-01.pth"), str(tmp_path / "conv"))
+    assert out.endswith("consolidated.00-of-01.safetensors")
+    back = checkpoint.convert(out, str(tmp_path / "conv2"))
+    assert back.endswith("consolidated.00-of-01.pth")
+    sd2 = torch.load(back, map_location="cpu", weights_only=True)
+    assert all(torch.equal(sd2[k], sd[k]) for k in sd)
+    with pytest.raises(ValueError):
+        checkpoint.convert(str(tmp_path / "x.bin"), str(tmp_path))
