@@ -168,8 +168,9 @@ int ndit_op_ln_rope(void* qkv_dev, const void* qw, const void* qb, const void* k
                     int32_t one_d, void* stream);
 /* fused self + gated cross attention (model.py:373-434).  qkv [B*N,(H+2Hkv)*72] (q,k already normed+roped),
  * kvy [B*T, 2*Hkv*72] (ky normed | vy), ymask uint8 [B,T], gate_tanh f32 [H]; out bf16 [B*N, H*72].
- * use_ref: 0 = production tcgen05 kernel, 1 = CUDA-core reference kernel, 2 = experimental tcgen05 kernel that keeps P in
- * tensor memory (head_dim 72 only; engine option "attn_tp"). */
+ * use_ref: 0 = default tcgen05 kernel (environment NDIT_ATTN_GEN = 1 / 3 overrides), 1 = CUDA-core reference kernel,
+ * 2 = third-generation kernel (P in tensor memory, two softmax threads per row; engine option "attn_gen" = 3),
+ * 3 = first-generation kernel (one softmax thread per row, P through shared memory; "attn_gen" = 1). */
 int ndit_op_attention(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                       void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
                       float scale_cross, int32_t use_ref, void* stream);

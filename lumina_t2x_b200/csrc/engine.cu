@@ -69,6 +69,10 @@ struct RopeSlot {
 
 }  // namespace
 
+// attention kernel generation used when the option / environment says 0
+constexpr int ATTN_DEFAULT_GEN = 1;
+static inline int attn_gen(int opt) { return opt == 1 || opt == 3 ? opt : ATTN_DEFAULT_GEN; }
+
 struct ndit_engine {
     ndit_config cfg;
     int D, L, H, Hkv, hd, F, C, cd, O, Wq;   // Wq = fused qkv width
@@ -96,7 +100,8 @@ struct ndit_engine {
     int64_t n_params = 0;
     bool finalized = false;
     int attn_ref = 0;
-    int attn_tp = 0;                         // 1: P-in-tensor-memory attention kernel (experimental, slower so far: see its header)
+    int attn_tp = 0;                         // attention kernel generation: 0 default (ATTN_DEFAULT_GEN), 1 one thread per row + P through
+                                             // shared memory (attention_tcgen05.cu), 3 half rows + P in tensor memory (attention_hr_tcgen05.cu)
     int profile = 0;
     int pdl = getenv("NDIT_PDL") ? atoi(getenv("NDIT_PDL")) : 0;
     std::vector<cudaEvent_t> ev_pool;
@@ -276,7 +281,7 @@ static int create_impl(ndit_engine* h) {
     const ndit_config& c = h->cfg;
     if (c.dim <= 0 || c.n_heads <= 0 || c.dim % c.n_heads != 0) return h->fail(NDIT_ERR_INVALID, "bad dim/n_heads");
     h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
-    if (getenv("NDIT_ATTN_TP")) h->attn_tp = atoi(getenv("NDIT_ATTN_TP"));
+    if (getenv("NDIT_ATTN_GEN")) h->attn_tp = atoi(getenv("NDIT_ATTN_GEN"));
     if (getenv("NDIT_GRAPH")) h->use_graph = atoi(getenv("NDIT_GRAPH"));
     h->cls = c.num_classes > 0;
     h->flag = c.flag_dit != 0;
@@ -407,7 +412,7 @@ extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!strcmp(name, "attn_ref")) { h->attn_ref = value; return NDIT_OK; }
     if (!strcmp(name, "graph")) { h->use_graph = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "pdl")) { h->pdl = value ? 1 : 0; return NDIT_OK; }
-    if (!strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
+    if (!strcmp(name, "attn_gen") || !strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
     if (!strcmp(name, "profile")) {
         h->profile = value;
         h->ev_used = 0;
@@ -880,8 +885,8 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
             memset(&a, 0, sizeof(a));
             const bf16* kvy = h->kvy + l * (size_t)batch * T * 2 * KV;
             const bf16* vyt = h->vyt + l * (size_t)batch * h->Hkv * h->vrows * Tpad;
-            const int tp = h->attn_tp ? attention_tp_bkv(h->hd) : 0;
-            if (build_attn_maps(&a, h->qkv, (int)Wq, h->vt, kvy, vyt, batch, N, T, h->H, h->Hkv, h->hd, tp ? tp : 128))
+            if (build_attn_maps(&a, h->qkv, (int)Wq, h->vt, kvy, vyt, batch, N, T, h->H, h->Hkv, h->hd,
+                                attn_gen(h->attn_tp) == 3 ? attention_hr_bkv(h->hd) : 128))
                 return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
             a.ymask = h->ymask;
             a.gate_tanh = h->gate_tanh + l * h->H;
@@ -992,7 +997,7 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
-            PROF(KC_ATTN, a.bkv == 128 ? attention_fused(a, s) : attention_fused_tp(a, s));
+            PROF(KC_ATTN, attn_gen(h->attn_tp) == 3 ? attention_fused_hr(a, s) : attention_fused(a, s));
         }
         PROF(KC_GEMM_WO, gemm_bf16_tn(h->p_wo[l], s));
         PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->flag ? nullptr : h->an2 + (size_t)l * D, ml + (size_t)o_g1 * D, h->fn1 + (size_t)l * D,
@@ -1330,13 +1335,12 @@ static int op_attention_impl(const void* qkv_, const void* kvy_, const uint8_t* 
     if (e == cudaSuccess && T > 0) e = fill_ones_row(vyt, Tpad, 0, B * Hkv, Tpad, hd, vrows, 1, s);
     AttnPlan a;
     memset(&a, 0, sizeof(a));
-    static const int tp_env = getenv("NDIT_ATTN_TP") ? atoi(getenv("NDIT_ATTN_TP")) : 0;
-    if (use_ref == 2 && !attention_tp_bkv(hd))
-        return op_fail(NDIT_ERR_INVALID, "ndit_op_attention: the tensor-memory-P kernel covers head_dim 72 only", cudaErrorInvalidValue);
-    const int tpb = (use_ref == 2 || tp_env) ? attention_tp_bkv(hd) : 0;       // use_ref: 0 default kernel, 1 CUDA-core reference, 2 first-generation kernel
-    // use_ref: 0 production kernel, 1 CUDA-core reference, 2 experimental kernel with P in tensor memory
-    const int te = build_attn_maps(&a, qkv, Wq, vt, kvy, vyt, B, N, T, H, Hkv, hd, tpb ? tpb : 128);
-    auto run = [&](const AttnPlan& pl) { return pl.bkv == 128 ? attention_fused(pl, s) : attention_fused_tp(pl, s); };
+    // use_ref: 0 default kernel (NDIT_ATTN_GEN overrides), 1 CUDA-core reference, 2 half-row / tensor-memory-P kernel
+    // (attention_hr_tcgen05.cu), 3 first-generation kernel (attention_tcgen05.cu)
+    static const int gen_env = getenv("NDIT_ATTN_GEN") ? atoi(getenv("NDIT_ATTN_GEN")) : 0;
+    const int gen = use_ref == 2 ? 3 : (use_ref == 3 ? 1 : attn_gen(gen_env));
+    const int te = build_attn_maps(&a, qkv, Wq, vt, kvy, vyt, B, N, T, H, Hkv, hd, gen == 3 ? attention_hr_bkv(hd) : 128);
+    auto run = [&](const AttnPlan& pl) { return gen == 3 ? attention_fused_hr(pl, s) : attention_fused(pl, s); };
     int rc = NDIT_OK;
     if (te) rc = op_fail(NDIT_ERR_CUDA, "ndit_op_attention tensor map", cudaSuccess);
     if (!te && e == cudaSuccess) {

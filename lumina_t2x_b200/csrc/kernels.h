@@ -52,13 +52,14 @@ struct AttnPlan {
     bf16* out;                   // [B*N, H*hd]
     int B, N, T, H, Hkv, hd;     // T = 0: no caption segment (class-conditional model); hd = 72, 48 or 96
     float scale_self, scale_cross;
-    int bkv;                     // kv rows per K box: 128 (attention_fused) or attention_tp_bkv(hd) (attention_fused_tp)
+    int bkv;                     // kv rows per K box: 128 (attention_fused) or attention_hr_bkv(hd) (attention_fused_hr)
 };
+// first-generation kernel: one softmax thread per row, P through shared memory (attention_tcgen05.cu)
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream);
-// second-generation kernel: P stays in tensor memory (attention_tp_tcgen05.cu).  attention_tp_bkv(hd) = its kv block
-// size for this head_dim, 0 if the head_dim is not covered (the caller then uses attention_fused).
-int attention_tp_bkv(int hd);
-cudaError_t attention_fused_tp(const AttnPlan& p, cudaStream_t stream);
+// third-generation kernel: P in tensor memory (aliased onto S), two softmax threads per row (attention_hr_tcgen05.cu);
+// attention_hr_bkv(hd) = its kv block size for this head_dim (the K boxes of the plan must be built with it)
+int attention_hr_bkv(int hd);
+cudaError_t attention_fused_hr(const AttnPlan& p, cudaStream_t stream);
 // slow CUDA-core reference of the same op (debug / NDIT_ATTN=ref); same inputs in plain layouts
 cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_kvy, const uint8_t* ymask,
                           const float* gate_tanh, bf16* out, int B, int N, int T, int H, int Hkv, int hd,

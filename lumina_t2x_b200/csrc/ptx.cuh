@@ -17,6 +17,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// One lane of a fully converged warp.  Unlike `lane == 0`, ptxas knows the elected predicate is warp-uniform-safe: tcgen05.mma /
+// TMA instructions under it are emitted back to back, while under `if (lane == 0)` every single one is wrapped in an
+// ELECT / BRA.U.ANY loop (~45 issue cycles per instruction: as much as a 128 x 80 x 16 MMA takes to execute).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
 
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -53,6 +61,24 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
+}
+// try_wait with a suspend-time hint: the hardware may keep the thread suspended for up to `ns` before it reports "not yet"
+// (the default limit is short: a waiting warp then re-issues SYNCS.TRYWAIT every ~100 cycles through the same MIO queue that
+// feeds MUFU.EX2 of the other warps of its scheduler).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+    }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {

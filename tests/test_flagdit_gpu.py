@@ -64,7 +64,7 @@ def test_sampler_midpoint_fused_equals_generic_loop():
 
 
 @pytest.mark.parametrize("B,N,T,H,Hkv", [(2, 256, 40, 4, 4), (1, 520, 0, 2, 2), (2, 4160, 128, 4, 2)])
-@pytest.mark.parametrize("use_ref", [1, 0], ids=["refkernel", "tcgen05"])
+@pytest.mark.parametrize("use_ref", [1, 0, 2, 3], ids=["refkernel", "tcgen05", "tcgen05_gen3", "tcgen05_gen1"])
 def test_attention_head_dim_96(B, N, T, H, Hkv, use_ref):
     """fused self + gated caption attention at head_dim 96, ragged token counts (4160 = 64 x 65 tokens of a 1024^2 image)."""
     from lumina_t2x_b200 import _lib

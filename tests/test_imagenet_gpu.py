@@ -69,7 +69,7 @@ def test_sampler_runs_fused_and_matches_generic_loop():
 
 
 @pytest.mark.parametrize("B,N,H,Hkv", [(2, 256, 8, 8), (1, 200, 4, 2), (2, 1024, 32, 32)])
-@pytest.mark.parametrize("use_ref", [1, 0], ids=["refkernel", "tcgen05"])
+@pytest.mark.parametrize("use_ref", [1, 0, 2, 3], ids=["refkernel", "tcgen05", "tcgen05_gen3", "tcgen05_gen1"])
 def test_attention_head_dim_48_no_caption(B, N, H, Hkv, use_ref):
     from lumina_t2x_b200 import _lib
     lib = _lib.load()

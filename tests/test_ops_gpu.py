@@ -169,7 +169,7 @@ ATTN_CASES = [
 
 
 @pytest.mark.parametrize("B,N,T,H,Hkv,valid", ATTN_CASES)
-@pytest.mark.parametrize("use_ref", [1, 0, 2], ids=["refkernel", "tcgen05", "tcgen05_tmemP"])
+@pytest.mark.parametrize("use_ref", [1, 0, 2, 3], ids=["refkernel", "tcgen05", "tcgen05_gen3_halfrow_tmemP", "tcgen05_gen1"])
 def test_attention(lib, B, N, T, H, Hkv, valid, use_ref):
     hd = 72
     g = torch.Generator(device="cuda").manual_seed(N + T)
