@@ -100,6 +100,7 @@ struct ndit_engine {
     int64_t n_params = 0;
     bool finalized = false;
     int attn_ref = 0;
+    int vt_epi = 1;                          // 1: the q|k|v GEMM epilogue writes V^T itself (no transpose_v launch); 0: separate kernel
     int attn_tp = 0;                         // attention kernel generation: 0 default (ATTN_DEFAULT_GEN), 1 one thread per row + P through
                                              // shared memory (attention_tcgen05.cu), 3 half rows + P in tensor memory (attention_hr_tcgen05.cu)
     int profile = 0;
@@ -145,7 +146,7 @@ struct ndit_engine {
     // CUDA graphs of whole fixed-grid solves (ndit_sample): key = everything the captured launch sequence depends on
     struct SolveGraph {
         std::vector<float> grid;
-        int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0;
+        int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0, vt_epi = 0;
         ndit_step_params sp;
         cudaGraphExec_t exec = nullptr;
         int64_t launches = 0;
@@ -282,6 +283,7 @@ static int create_impl(ndit_engine* h) {
     if (c.dim <= 0 || c.n_heads <= 0 || c.dim % c.n_heads != 0) return h->fail(NDIT_ERR_INVALID, "bad dim/n_heads");
     h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
     if (getenv("NDIT_ATTN_GEN")) h->attn_tp = atoi(getenv("NDIT_ATTN_GEN"));
+    if (getenv("NDIT_VT_EPI")) h->vt_epi = atoi(getenv("NDIT_VT_EPI"));
     if (getenv("NDIT_GRAPH")) h->use_graph = atoi(getenv("NDIT_GRAPH"));
     h->cls = c.num_classes > 0;
     h->flag = c.flag_dit != 0;
@@ -412,6 +414,7 @@ extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!strcmp(name, "attn_ref")) { h->attn_ref = value; return NDIT_OK; }
     if (!strcmp(name, "graph")) { h->use_graph = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "pdl")) { h->pdl = value ? 1 : 0; return NDIT_OK; }
+    if (!strcmp(name, "vt_epi")) { h->vt_epi = value; return NDIT_OK; }
     if (!strcmp(name, "attn_gen") || !strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
     if (!strcmp(name, "profile")) {
         h->profile = value;
@@ -985,6 +988,9 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     for (int l = 0; l < L; ++l) {
         const bf16* ml = h->mod + (size_t)l * NCH * D;
         const bf16* mn = ml + (size_t)NCH * D;      // next layer's chunks
+        // value heads go straight to the V^T buffer from the GEMM epilogue (the debug attention reads V from the qkv buffer)
+        const bool vt_fused = h->vt_epi && !h->attn_ref;
+        h->p_qkv[l].vt = vt_fused ? GemmVtOut{h->vt, (h->H + h->Hkv) * hd, hd, h->Hkv, h->vrows, Npad, N} : GemmVtOut{};
         PROF(KC_GEMM_QKV, gemm_bf16_tn(h->p_qkv[l], s));
         PROF(KC_ROWWISE, ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
                        h->kn_b + (size_t)l * h->Hkv * hd, rope, M, N, h->H, h->Hkv, hd, s));
@@ -993,7 +999,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                               h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
                               scale_cross, s));
         } else {
-            PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, Npad, 0, batch, N, h->Hkv, hd, h->vrows, 1, s));
+            if (!vt_fused)
+                PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, Npad, 0, batch, N, h->Hkv, hd, h->vrows, 1, s));
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
@@ -1123,7 +1130,7 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
     ndit_engine::SolveGraph* hit = nullptr;
     for (auto& g : h->graphs) {
         if (g.batch == batch && g.height == height && g.width == width && g.method == method && g.cap_T == h->cap_T &&
-            g.with_traj == (int)with_traj && g.attn_ref == h->attn_ref && g.attn_tp == h->attn_tp && g.pdl == h->pdl &&
+            g.with_traj == (int)with_traj && g.attn_ref == h->attn_ref && g.attn_tp == h->attn_tp && g.pdl == h->pdl && g.vt_epi == h->vt_epi &&
             (int)g.grid.size() == n_grid && !memcmp(g.grid.data(), grid, n_grid * sizeof(float)) && !memcmp(&g.sp, sp, sizeof(*sp))) {
             hit = &g;
             break;
@@ -1136,7 +1143,7 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
         if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
         slot->grid.assign(grid, grid + n_grid);
         slot->batch = batch; slot->height = height; slot->width = width; slot->method = method; slot->cap_T = h->cap_T;
-        slot->with_traj = with_traj; slot->attn_ref = h->attn_ref; slot->attn_tp = h->attn_tp; slot->pdl = h->pdl; slot->sp = *sp;
+        slot->with_traj = with_traj; slot->attn_ref = h->attn_ref; slot->attn_tp = h->attn_tp; slot->pdl = h->pdl; slot->vt_epi = h->vt_epi; slot->sp = *sp;
         slot->launches = 0;
         slot->last_use = ++h->graph_clock;
         return 0;

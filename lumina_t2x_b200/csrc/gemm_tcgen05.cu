@@ -21,6 +21,17 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
 
+// Eight consecutive output columns (one 16-byte group) of this thread's row that belong to the value heads: V^T[b, g, d + e, n].
+// hd % 8 == 0, so a group never straddles two heads; the 32 lanes of a warp hold 32 consecutive tokens -> 64-byte segments.
+__device__ __forceinline__ void store_vt8(const GemmVtOut& vt, int row, int col, const uint32_t* v) {
+    const int cv = col - vt.col0;
+    const int g = cv / vt.hd, d = cv - g * vt.hd;
+    const int b = row / vt.ntok, n = row - b * vt.ntok;
+    bf16* dst = vt.ptr + (static_cast<size_t>(b * vt.hkv + g) * vt.vrows + d) * vt.npad + n;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dst[static_cast<size_t>(e) * vt.npad] = __float2bfloat16_rn(__uint_as_float(v[e]));
+}
+
 template <int BN>
 struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -35,7 +46,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     bf16* __restrict__ C, const bf16* __restrict__ bias, const int* __restrict__ w_row_off, int w_row_mul, int M, int N,
-                    int K, int ldc) {
+                    int K, int ldc, const GemmVtOut vt) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -169,6 +180,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (col0 + j * 8 < N) {  // N % 8 == 0
+                                if (vt.ptr != nullptr && col0 + j * 8 >= vt.col0) {
+                                    store_vt8(vt, row, col0 + j * 8, v + j * 8);
+                                    continue;
+                                }
                                 if (bias != nullptr) {   // Linear bias: added to the fp32 accumulator, one rounding (final_layer.linear)
                                     const uint4 bq = *reinterpret_cast<const uint4*>(bias + col0 + j * 8);
                                     const uint32_t b4[4] = {bq.x, bq.y, bq.z, bq.w};
@@ -257,7 +272,8 @@ struct Gemm2Cfg {
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     bf16* __restrict__ C, const int* __restrict__ w_row_off, int w_row_mul, int M, int N, int K, int ldc) {
+                     bf16* __restrict__ C, const int* __restrict__ w_row_off, int w_row_mul, int M, int N, int K, int ldc,
+                     const GemmVtOut vt) {
     using Cfg = Gemm2Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -400,6 +416,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (col0 + j * 8 < N) {
+                            if (vt.ptr != nullptr && col0 + j * 8 >= vt.col0) {
+                                if (row < M) store_vt8(vt, row, col0 + j * 8, v + j * 8);
+                                continue;
+                            }
                             uint4 o;
                             o.x = pack_bf16(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
                             o.y = pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
@@ -450,7 +470,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <int BN, int EPI>
 static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const int* w_row_off, int w_row_mul, int M, int N,
-                                int K, int ldc, int num_sms, cudaStream_t stream) {
+                                int K, int ldc, int num_sms, const GemmVtOut& vt, cudaStream_t stream) {
     auto kern = gemm2_bf16_tn_kernel<BN, EPI>;
     static PerDeviceFlag flags;
     bool& configured = flags.here();
@@ -462,14 +482,14 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc);
+    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt);
 }
 
 // ---------------------------------------------------------------------------- host side
 
 template <int BN, int EPI>
 static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const bf16* bias, const int* w_row_off, int w_row_mul,
-                               int M, int N, int K, int ldc, int num_sms, cudaStream_t stream) {
+                               int M, int N, int K, int ldc, int num_sms, const GemmVtOut& vt, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tn_kernel<BN, EPI>;
     static PerDeviceFlag flags;
@@ -482,29 +502,30 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
     int grid = m_tiles * n_tiles;
     if (grid > num_sms) grid = num_sms;
-    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, bias, w_row_off, w_row_mul, M, N, K, ldc);
+    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, bias, w_row_off, w_row_mul, M, N, K, ldc, vt);
 }
 
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     if (p.N % 8 != 0 || p.K % 8 != 0) return cudaErrorInvalidValue;
     if (p.bias != nullptr && (p.pair || p.epi != EPI_STORE)) return cudaErrorInvalidValue;
+    if (p.vt.ptr != nullptr && (p.epi != EPI_STORE || p.bias != nullptr || p.vt.col0 % 8 != 0 || p.vt.hd % 8 != 0)) return cudaErrorInvalidValue;
     if (p.pair) {
         // ragged M is fine (zero-filled loads, masked stores); a ragged last-N tile (multiple of 32 wide) only for plain stores
         if (p.N % p.bn != 0 && (p.epi != EPI_STORE || p.bn != 256 || (p.N % 256) % 32 != 0)) return cudaErrorInvalidValue;
         if (p.epi == EPI_SWIGLU) {
             if (p.bn != 256) return cudaErrorInvalidValue;
-            return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+            return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
         }
-        if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-        return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
+        return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
     }
     if (p.epi == EPI_SWIGLU) {
         if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;
-        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
     }
-    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
-    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, stream);
+    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
+    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
+    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
 }
 
 }  // namespace ndit

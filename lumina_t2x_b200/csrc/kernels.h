@@ -21,6 +21,14 @@ const char* tmap_last_error();
 
 // ---------------------------------------------------------------- GEMM (gemm_tcgen05.cu)
 enum { EPI_STORE = 0, EPI_SWIGLU = 1 };
+// Optional second destination of an EPI_STORE GEMM (the fused q|k|v projection): output columns >= col0 are the value heads and go,
+// transposed, straight into the attention kernel's V^T buffer [batch * Hkv][vrows][npad] (replaces transpose_v and the 2 x 9.4 MB
+// round trip through the qkv buffer).  ptr == nullptr: plain store.
+struct GemmVtOut {
+    bf16* ptr;
+    int col0;     // first value column = (H + Hkv) * hd
+    int hd, hkv, vrows, npad, ntok;
+};
 struct GemmPlan {
     CUtensorMap tmA;  // A [M,K], box 128 x 64
     CUtensorMap tmB;  // W [N,K], box bn  x 64
@@ -33,6 +41,7 @@ struct GemmPlan {
     int pair; // 1: CTA-pair kernel (cta_group::2, 256x256 tiles; W box is 128 rows)
     int epi;  // EPI_*
     int num_sms;
+    GemmVtOut vt;   // zero-initialised by make_gemm_plan
 };
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream);
 // builds the maps of a plan (A: [M,K] ld=lda; W: [N,K] ld=K)

@@ -42,15 +42,17 @@ def tiny():
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fwd_*.pt"))), ids=os.path.basename)
-@pytest.mark.parametrize("attn", ["tcgen05", "refkernel"])
+@pytest.mark.parametrize("attn", ["tcgen05", "refkernel", "tcgen05_gen3"])
 def test_forward_with_cfg_vs_golden_and_oracle(tiny, path, attn):
     cfg, W, m = tiny
     fx = torch.load(path, map_location="cpu", weights_only=False)
     z, cap, mask = O.synthetic_inputs(cfg, tuple(fx["hw"]), fx["T"], fx["ul"], seed=fx["input_seed"])
     t = torch.full((2,), fx["t"])
     m.set_option("attn_ref", 1 if attn == "refkernel" else 0)
+    m.set_option("attn_gen", 3 if attn == "tcgen05_gen3" else 0)
     out = m.forward_with_cfg(z.cuda(), t.cuda(), cap.cuda(), mask.cuda(), **fx["kw"]).float().cpu()
     m.set_option("attn_ref", 0)
+    m.set_option("attn_gen", 0)
     assert out.shape == z.shape and torch.isfinite(out).all()
     orc = O.forward_with_cfg(cfg, W, z, t, cap, mask, precision="bf16", **fx["kw"])
     ref32 = fx["out_fp32"]
@@ -59,6 +61,21 @@ def test_forward_with_cfg_vs_golden_and_oracle(tiny, path, attn):
     assert _rel(out, ref32) < 1.5 * floor + 2e-3, (_rel(out, ref32), floor)
     # CFG structure (model.py:904-913): guided channels identical for both rows
     assert torch.equal(out[0, :3], out[1, :3])
+
+
+def test_vt_from_gemm_epilogue_is_bit_identical(tiny):
+    """The q|k|v GEMM epilogue writes the value heads straight into the V^T buffer (engine option vt_epi, default on); the
+    separate transpose_v launch (vt_epi = 0) must give the same bits: both round the fp32 accumulator to bf16 once."""
+    cfg, W, m = tiny
+    fx = torch.load(sorted(glob.glob(os.path.join(GOLD, "fwd_*.pt")))[0], map_location="cpu", weights_only=False)
+    z, cap, mask = O.synthetic_inputs(cfg, tuple(fx["hw"]), fx["T"], fx["ul"], seed=fx["input_seed"])
+    t = torch.full((2,), fx["t"]).cuda()
+    outs = []
+    for v in (1, 0, 1):
+        m.set_option("vt_epi", v)
+        outs.append(m.forward_with_cfg(z.cuda(), t, cap.cuda(), mask.cuda(), **fx["kw"]).clone())
+    m.set_option("vt_epi", 1)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 @pytest.mark.parametrize("method", ["euler", "midpoint"])
@@ -149,6 +166,9 @@ def test_flagship_one_forward_properties():
     b = m.forward_with_cfg(z, t, cap, mask, 2.0, **kw)
     assert torch.isfinite(a.float()).all() and torch.equal(a, b)
     assert torch.equal(a[0, :3], a[1, :3])
+    m.set_option("vt_epi", 0)       # separate transpose_v launch instead of the V^T store in the q|k|v GEMM epilogue: same bits
+    assert torch.equal(a, m.forward_with_cfg(z, t, cap, mask, 2.0, **kw))
+    m.set_option("vt_epi", 1)
     c1 = m.forward_with_cfg(z, t, cap, mask, 1.0, **kw).float()     # = cond (up to bf16 rounding of the combine)
     c0 = m.forward_with_cfg(z, t, cap, mask, 0.0, **kw).float()     # = uncond
     lin = c0[0, :3] + 2.0 * (c1[0, :3] - c0[0, :3])
