@@ -124,6 +124,15 @@ int ndit_set_labels(ndit_handle h, const int64_t* labels_dev, int32_t batch, voi
 int ndit_forward_cfg(ndit_handle h, const void* x_dev, float t, int32_t batch, int32_t height, int32_t width,
                      const ndit_step_params* sp, void* out_dev, void* stream);
 
+/* --- NextDiT.forward (model.py:836-864): no classifier-free guidance.  x_dev/out_dev: bf16 [batch, C, height, width]; every row is
+ * its own sample with its own timestep t_host[b] (HOST array of `batch` floats) and its own caption row (ndit_set_caption with
+ * the same batch, 1 <= batch <= max_batch).  out = the first C of the 2C output channels (learn_sigma chunk, :859-861).
+ * The reference uses whatever RoPE table / attention scaling the module currently holds (self.freqs_cis, set by __init__ or by the
+ * last forward_with_cfg; layer.attention.base_seqlen / proportional_attn): sp->scale_factor = its linear factor, sp->ntk_factor =
+ * its NTK factor (0 = 1.0), sp->proportional_attn / base_seqlen as stored; sp->cfg_scale and sp->scale_watershed are ignored. */
+int ndit_forward(ndit_handle h, const void* x_dev, const float* t_host, int32_t batch, int32_t height, int32_t width,
+                 const ndit_step_params* sp, void* out_dev, void* stream);
+
 /* --- transport.Sampler.sample_ode(...)(z, model.forward_with_cfg, **kw) (transport/transport.py:346-391,
  * transport/integrators.py:79-116) with torchdiffeq's fixed-grid euler / midpoint / rk4.  t_grid_host: the
  * n_grid time points (fp32, host).  z_dev: bf16 initial state [batch,C,height,width]; traj_dev: bf16

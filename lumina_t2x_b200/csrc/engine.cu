@@ -125,7 +125,7 @@ struct ndit_engine {
     bf16 *X, *u, *qkv, *attn, *o, *hbuf, *vt;
     bf16 *yhat, *kvy, *vyt;
     uint8_t* ymask;
-    float *pool, *capemb, *tf, *h1, *sc;
+    float *pool, *capemb, *tf, *h1, *sc, *trow;   // trow: per-row timesteps of a plain forward
     bf16* tok;                               // [M, O] final-layer output tokens
     bf16* mod;
     bf16 *vel, *ystate, *ymid;
@@ -249,7 +249,7 @@ static int alloc_workspace(ndit_engine* h) {
     WALLOC(X, M * D); WALLOC(u, M * D); WALLOC(qkv, M * h->Wq); WALLOC(attn, M * D); WALLOC(o, M * D); WALLOC(hbuf, M * F);
     WALLOC(vt, B * h->Hkv * h->vrows * ((size_t)c.max_tokens + 8));
     WALLOC(yhat, L * B * T * C); WALLOC(kvy, L * B * T * 2 * KV); WALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
-    WALLOC(ymask, B * T); WALLOC(pool, B * C); WALLOC(capemb, B * cd); WALLOC(tf, B * 256); WALLOC(h1, B * cd); WALLOC(sc, B * cd);
+    WALLOC(ymask, B * T); WALLOC(pool, B * C); WALLOC(capemb, B * cd); WALLOC(tf, B * 256); WALLOC(trow, B + 8); WALLOC(h1, B * cd); WALLOC(sc, B * cd);
     WALLOC(mod, B * (L * NCH * D + h->FD * D)); WALLOC(tok, M * h->O);
     if (S > 1) {
         int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
@@ -776,7 +776,7 @@ extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* m
     mask_to_u8_kernel<<<(M + 255) / 256, 256, 0, s>>>(h->ymask, mask, M);
     CKL(cudaGetLastError());
     const bf16* capb = static_cast<const bf16*>(cap);
-    CKL(cond_prepare(0.f, capb, h->ymask, h->capln_w, h->capln_b, h->tf, h->pool, batch, T, (int)C, 1, s));
+    CKL(cond_prepare(0.f, nullptr, capb, h->ymask, h->capln_w, h->capln_b, h->tf, h->pool, batch, T, (int)C, 1, s));
     CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, nullptr, batch, h->cd, (int)C, 0, POST_NONE, 0, 0, 0, s));
     CKL(rms_rows_layers(capb, h->yn, h->yhat, M, (int)C, (int)L, h->cfg.norm_eps, s));
     const size_t ys = (size_t)M * C, ks = (size_t)M * 2 * KV;
@@ -917,8 +917,11 @@ static int get_rope(ndit_engine* h, int Hp, int Wp, float theta, float lin, cuda
     return 0;
 }
 
+// t_rows == nullptr: forward_with_cfg (cond/uncond pair rows, one timestep t, guidance in the unpatchify);
+// t_rows != nullptr (host array of `batch` floats): plain NextDiT.forward - every row its own sample and timestep, no guidance.
 static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int Hh, int Ww, const ndit_step_params* sp,
-                        bf16* out, cudaStream_t s) {
+                        bf16* out, cudaStream_t s, const float* t_rows = nullptr) {
+    const bool plain = t_rows != nullptr;
     if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
     struct PdlGuard {       // per-launch CUDA events (profile mode) and overlapping launches do not mix
         int saved;
@@ -926,7 +929,16 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
         ~PdlGuard() { g_pdl = saved; }
     } pdl_guard(h->profile != 0 ? 0 : h->pdl);
     if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
-    if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
+    if (!plain && (batch < 2 || (batch & 1) || batch > h->Bmax)) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
+    if (plain && (batch < 1 || batch > h->Bmax)) return h->fail(NDIT_ERR_INVALID, "batch must be in 1..%d", h->Bmax);
+    if (plain) {
+        t = t_rows[0];
+        bool uniform = true;
+        for (int b = 1; b < batch; ++b) uniform = uniform && t_rows[b] == t;
+        if (!uniform && h->cfg.moe_time_experts > 0)
+            return h->fail(NDIT_ERR_INVALID, "the time-gated mixture of experts selects one expert pair per call: all rows need the same timestep");
+        CK(cudaMemcpyAsync(h->trow, t_rows, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
+    }
     if ((Hh & 1) || (Ww & 1) || Hh <= 0 || Ww <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");
     const int Hp = Hh / 2, Wp = Ww / 2, eol = h->flag ? 1 : 0;
     const int N = Hp * (Wp + eol), M = batch * N, Npad = (N + 7) / 8 * 8;     // Flag-DiT: one [eol] token per row of patches
@@ -943,7 +955,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     const int NCH = h->NCH;
     const int mod_stride = L * NCH * D + h->FD * D;
     float lin, ntk;
-    if (h->cls || h->flag) {   // DiT_Llama.precompute_freqs_cis(rope_scaling_factor, ntk_factor) (models.py:977-1012; lumina_t2i model.py:925-960)
+    if (h->cls || h->flag || plain) {   // plain forward: whatever table self.freqs_cis holds (model.py:735,839) = these two factors
+        // DiT_Llama.precompute_freqs_cis(rope_scaling_factor, ntk_factor) (models.py:977-1012; lumina_t2i model.py:925-960)
         lin = sp->scale_factor > 0.f ? sp->scale_factor : 1.0f;
         ntk = sp->ntk_factor > 0.f ? sp->ntk_factor : 1.0f;
     } else if (t < sp->scale_watershed) {   // time-aware RoPE scaling (model.py:944-952)
@@ -963,8 +976,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     }
     const float scale_cross = (float)(1.0 / sqrt((double)hd));
 
-    PROF(KC_ROWWISE, patch_embed(x, h->Wx, h->bx, h->flag ? h->eol_token : nullptr, h->X, batch, batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
-    PROF(KC_COND, cond_prepare(t, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
+    PROF(KC_ROWWISE, patch_embed(x, h->Wx, h->bx, h->flag ? h->eol_token : nullptr, h->X, batch, plain ? batch : batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
+    PROF(KC_COND, cond_prepare(t, plain ? h->trow : nullptr, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
     PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, nullptr, batch, h->cd, 256, 0, POST_SILU, 0, 0, 0, s));
     // sc = bf16(silu(c)), c = bf16(temb + cap_emb)
     PROF(KC_COND, gemv_rows(h->h1, h->Wt2, h->bt2, h->capemb, h->sc, nullptr, batch, h->cd, h->cd, 0, POST_SILU, 0, 0, 0, s));
@@ -1053,7 +1066,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             }
         }
     }
-    PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, eol, s));
+    if (plain) PROF(KC_ROWWISE, unpatchify_plain(h->tok, out, batch, h->cfg.in_channels, Hh, Ww, h->O, eol, s));
+    else PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, eol, s));
     return NDIT_OK;
 }
 
@@ -1062,6 +1076,13 @@ extern "C" int ndit_forward_cfg(ndit_handle h, const void* x, float t, int32_t b
     if (!h || !x || !sp || !out) return NDIT_ERR_INVALID;
     return forward_impl(h, static_cast<const bf16*>(x), t, batch, height, width, sp, static_cast<bf16*>(out),
                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ndit_forward(ndit_handle h, const void* x, const float* t_host, int32_t batch, int32_t height, int32_t width,
+                            const ndit_step_params* sp, void* out, void* stream) {
+    if (!h || !x || !t_host || !sp || !out) return NDIT_ERR_INVALID;
+    return forward_impl(h, static_cast<const bf16*>(x), 0.f, batch, height, width, sp, static_cast<bf16*>(out),
+                        static_cast<cudaStream_t>(stream), t_host);
 }
 
 // The fixed-grid solve on the engine's own state buffer (h->ystate); trajectory rows 1.. go to `tr` when non-null.

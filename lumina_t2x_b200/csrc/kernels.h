@@ -80,7 +80,7 @@ cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_k
 cudaError_t patch_embed(const bf16* x, const bf16* Wx, const bf16* bx, const bf16* eol, bf16* X, int B, int n_unique, int C,
                         int Hh, int Ww, int D, cudaStream_t s);
 // tf[b, 0:256] = bf16(sinusoid(t)); pool[b, :] = bf16(LN(masked mean of cap[b]))  (fp32 storage)
-cudaError_t cond_prepare(float t, const bf16* cap, const uint8_t* mask, const bf16* ln_w, const bf16* ln_b, float* tf,
+cudaError_t cond_prepare(float t, const float* t_rows, const bf16* cap, const uint8_t* mask, const bf16* ln_w, const bf16* ln_b, float* tf,
                          float* pool, int B, int T, int C, int do_caption, cudaStream_t s);
 enum { POST_NONE = 0, POST_SILU = 1, POST_ADALN = 2 };
 enum { ADALN_NEXT = 0, ADALN_CLASS = 1, ADALN_FLAG = 2 };   // chunk layout of the packed adaLN output (see gemv_rows_kernel)
@@ -118,6 +118,7 @@ cudaError_t fill_ones_row(bf16* dst, int ld_dst, size_t dst_layer_stride, int gr
 __host__ __device__ constexpr int attn_vrows(int hd) { return (hd + 1 + 15) / 16 * 16; }
 // unpatchify + learn_sigma slice + 3-channel CFG combine (+ optional fused Euler update)
 //   tok [2n*N, O] bf16 -> v [2n,4,Hh,Ww] bf16
+cudaError_t unpatchify_plain(const bf16* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, int eol, cudaStream_t s);
 cudaError_t unpatchify_cfg(const bf16* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,
                            cudaStream_t s);
 // mixture-of-experts (class-conditional Next-DiT-MoE): token gate + expert-order bf16 accumulation (see rowwise.cu)

@@ -498,10 +498,11 @@ cudaError_t patch_embed(const bf16* x, const bf16* Wx, const bf16* bx, const bf1
 
 // ---------------------------------------------------------------------------------------------
 // Conditioning inputs: sinusoidal timestep features and LayerNorm'd masked-mean caption.
-__global__ void cond_prepare_kernel(float t, const bf16* __restrict__ cap, const uint8_t* __restrict__ mask,
-                                    const bf16* __restrict__ ln_w, const bf16* __restrict__ ln_b,
+__global__ void cond_prepare_kernel(float t, const float* __restrict__ t_rows, const bf16* __restrict__ cap,
+                                    const uint8_t* __restrict__ mask, const bf16* __restrict__ ln_w, const bf16* __restrict__ ln_b,
                                     float* __restrict__ tf, float* __restrict__ pool, int T, int C, int do_caption) {
     const int b = blockIdx.x;
+    if (t_rows != nullptr) t = t_rows[b];    // NextDiT.forward: one timestep per row
     // model.py:64-87: freqs = exp(-ln(1e4) * i / 128); [cos | sin]; cast to the weight dtype
     for (int i = threadIdx.x; i < 128; i += blockDim.x) {
         const float f = expf(-logf(10000.0f) * static_cast<float>(i) / 128.0f);
@@ -549,9 +550,9 @@ __global__ void cond_prepare_kernel(float t, const bf16* __restrict__ cap, const
     }
 }
 
-cudaError_t cond_prepare(float t, const bf16* cap, const uint8_t* mask, const bf16* ln_w, const bf16* ln_b, float* tf,
+cudaError_t cond_prepare(float t, const float* t_rows, const bf16* cap, const uint8_t* mask, const bf16* ln_w, const bf16* ln_b, float* tf,
                          float* pool, int B, int T, int C, int do_caption, cudaStream_t s) {
-    cond_prepare_kernel<<<B, 256, do_caption ? C * sizeof(float) : 0, s>>>(t, cap, mask, ln_w, ln_b, tf, pool, T, C,
+    cond_prepare_kernel<<<B, 256, do_caption ? C * sizeof(float) : 0, s>>>(t, t_rows, cap, mask, ln_w, ln_b, tf, pool, T, C,
                                                                          do_caption);
     return cudaGetLastError();
 }
@@ -1056,6 +1057,24 @@ __global__ void unpatchify_cfg_kernel(const bf16* __restrict__ tok, bf16* __rest
         v_out[s * plane + o] = __float2bfloat16_rn(cond);
         v_out[(s + n) * plane + o] = __float2bfloat16_rn(unc);
     }
+}
+
+// unpatchify without guidance (NextDiT.forward, model.py:858-863): every row keeps the first C of its 2C output channels
+__global__ void unpatchify_plain_kernel(const bf16* __restrict__ tok, bf16* __restrict__ v_out, int n, int C, int Hh, int Ww, int O,
+                                        int eol) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over n * C * Hh * Ww
+    if (idx >= n * C * Hh * Ww) return;
+    const int x = idx % Ww, y = (idx / Ww) % Hh, c = (idx / (Ww * Hh)) % C, s = idx / (Ww * Hh * C);
+    const int Wt = (Ww >> 1) + eol, N = (Hh >> 1) * Wt;
+    const int t = (y >> 1) * Wt + (x >> 1);
+    const int f = ((y & 1) * 2 + (x & 1)) * (O / 4) + c;
+    v_out[idx] = tok[(static_cast<size_t>(s) * N + t) * O + f];
+}
+
+cudaError_t unpatchify_plain(const bf16* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, int eol, cudaStream_t s) {
+    const int total = n * C * Hh * Ww;
+    unpatchify_plain_kernel<<<(total + 255) / 256, 256, 0, s>>>(tok, v_out, n, C, Hh, Ww, O, eol);
+    return cudaGetLastError();
 }
 
 cudaError_t unpatchify_cfg(const bf16* tok, bf16* v_out, int n, int C, int Hh, int Ww, int O, float cfg_scale, int eol,

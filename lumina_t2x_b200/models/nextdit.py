@@ -323,9 +323,45 @@ class NextDiT(EngineModule):
                                    int(base_seqlen) if base_seqlen is not None else 0)
 
     # ------------------------------------------------------------------ reference API
+    def _remember_call_state(self, t_last: float, scale_factor, scale_watershed, base_seqlen, proportional_attn) -> None:
+        """What the reference module keeps after forward_with_cfg (model.py:883-899): self.freqs_cis (as its two scaling factors)
+        and layer.attention.{base_seqlen, proportional_attn}; a later plain forward() uses them."""
+        self._freqs_state = (float(scale_factor), 1.0) if t_last < scale_watershed else (1.0, float(scale_factor))
+        self._attn_state = (bool(proportional_attn), int(base_seqlen) if proportional_attn else None)
+
+    @torch.no_grad()
     def forward(self, x, t, cap_feats, cap_mask):
-        raise NotImplementedError("the B200 engine accelerates forward_with_cfg (the sampling path); "
-                                  "plain forward (training) is out of scope")
+        """model.py:836-864 (tensor input, inference): x [N,C,H,W], t [N], cap_feats [N,T,cap_feat_dim], cap_mask [N,T];
+        returns the first C output channels [N,C,H,W].  No guidance, one timestep per row; rows are processed in groups of
+        at most max_batch.  Uses the RoPE table / attention scaling the module currently holds, like the reference."""
+        if not isinstance(x, torch.Tensor):
+            raise NotImplementedError("list-of-tensors (variable resolution) input is not supported by the B200 engine")
+        self._check_inputs(x, cap_feats, cap_mask)
+        lib, h = self._engine(x.device)
+        lin, ntk = getattr(self, "_freqs_state", (1.0, float(self.scale_factor)))
+        prop, base = getattr(self, "_attn_state", (False, None))
+        sp = _lib.NditStepParams(0.0, lin, 1.0, int(prop), int(base) if base is not None else 0, ntk)
+        tv = (t.detach().float().reshape(-1).tolist() if isinstance(t, torch.Tensor) else [float(t)] * x.shape[0])
+        if len(tv) == 1:
+            tv = tv * x.shape[0]
+        if len(tv) != x.shape[0]:
+            raise ValueError(f"t has {len(tv)} entries for a batch of {x.shape[0]}")
+        xb = x.detach().to(torch.bfloat16).contiguous()
+        out = torch.empty_like(xb)
+        Bn, _, Hh, Ww = xb.shape
+        with torch.cuda.device(x.device):
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(Hh, Ww), cap_feats.shape[1], 1)
+            step = self._limits[2]
+            for i in range(0, Bn, step):
+                j = min(Bn, i + step)
+                self._cap_key = None
+                self._set_caption(lib, h, cap_feats[i:j], cap_mask[i:j], stream)
+                ta = (C.c_float * (j - i))(*tv[i:j])
+                _lib.check(lib.ndit_forward(h, C.c_void_p(xb[i:j].data_ptr()), ta, j - i, Hh, Ww, C.byref(sp),
+                                            C.c_void_p(out[i:j].data_ptr()), stream), h)
+            self._cap_key = None
+        return out.to(x.dtype)
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0,
@@ -340,7 +376,9 @@ class NextDiT(EngineModule):
             self._ensure_capacity(lib, h, self._tokens_for(x.shape[2], x.shape[3]), cap_feats.shape[1], x.shape[0])
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
             sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
-            return self._run_forward(lib, h, x, t, sp)
+            out = self._run_forward(lib, h, x, t, sp)
+            self._remember_call_state(self._uniform_t(t), scale_factor, scale_watershed, base_seqlen, proportional_attn)
+            return out
 
     @torch.no_grad()
     def sample_fixed_grid(self, z, t_grid, method: str, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0,
@@ -353,7 +391,11 @@ class NextDiT(EngineModule):
             self._ensure_capacity(lib, h, self._tokens_for(z.shape[2], z.shape[3]), cap_feats.shape[1], z.shape[0])
             self._set_caption(lib, h, cap_feats, cap_mask, stream)
             sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
-            return self._run_sample(lib, h, z, t_grid, method, sp, return_trajectory)
+            out = self._run_sample(lib, h, z, t_grid, method, sp, return_trajectory)
+            grid = [float(v) for v in t_grid]
+            t_last = grid[-1] if method == "rk4" else (grid[-2] if method == "euler" else 0.5 * (grid[-2] + grid[-1]))
+            self._remember_call_state(t_last, scale_factor, scale_watershed, base_seqlen, proportional_attn)
+            return out
 
 
 def NextDiT_2B_patch2(**kwargs):

@@ -301,5 +301,45 @@ def make_flag_dit() -> None:
         del m
 
 
+def make_plain_forward() -> None:
+    """NextDiT.forward without guidance (nextdit.py:808-836 == lumina_next_t2i/models/model.py:836-864): odd batch, one timestep per
+    row, (a) on a freshly constructed module (default rope table) and (b) after a forward_with_cfg call whose scale_factor /
+    proportional attention settings stay on the module (self.freqs_cis, layer.attention.base_seqlen)."""
+    models, _ = import_reference_mini()
+    cfg = O.config_tiny(n_layers=2)
+    W = O.synthetic_weights(cfg, seed=0, dtype=torch.bfloat16)
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(11)
+    B, T, hw = 3, 24, (16, 24)
+    x = torch.randn(B, cfg.in_channels, *hw, generator=g).to(torch.bfloat16)
+    cap = torch.randn(B, T, cfg.cap_feat_dim, generator=g).to(torch.bfloat16)
+    mask = torch.zeros(B, T, dtype=torch.int32)
+    for b, n in enumerate((24, 9, 1)):
+        mask[b, :n] = 1
+    t = torch.tensor([0.15, 0.6, 0.95])
+    sticky = dict(cfg_scale=2.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=64, proportional_attn=True)
+    z2, cap2, mask2 = O.synthetic_inputs(cfg, (16, 16), 16, 4, seed=3)
+    fx = dict(hw=hw, T=T, weight_seed=0, x=x, cap=cap, mask=mask, t=t, sticky_call=dict(kw=sticky, t=0.2, hw=(16, 16), T=16, ul=4, seed=3))
+    for state in ("fresh", "sticky"):
+        ref32 = build_ref(models, cfg, W).float()
+        ref16 = build_ref(models, cfg, W).to(torch.bfloat16)
+        if state == "sticky":
+            for m_, dt in ((ref32, torch.float32), (ref16, torch.bfloat16)):
+                m_.forward_with_cfg(z2.to(dt), torch.full((2,), 0.2), cap2.to(dt), mask2, **sticky)
+        out32 = ref32(x.float(), t, cap.float(), mask)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out16 = ref16(x, t, cap, mask)
+        fx[state] = dict(out_fp32=out32.clone(), out_autocast_cpu_bf16=out16.float().to(torch.bfloat16))
+        kw = dict() if state == "fresh" else dict(scale_factor=2.0, scale_watershed=0.3, rope_timestep=0.2, base_seqlen=64, proportional_attn=True)
+        o = O.forward(cfg, W, x.float(), t, cap.float(), mask, precision="fp32", **kw)
+        print(state, tuple(out32.shape), "absmax", out32.abs().max().item(), "oracle fp32 rel", ((o - out32).abs().max() / out32.abs().max()).item(),
+              "ref bf16 vs fp32", ((out16.float() - out32).abs().max() / out32.abs().max()).item())
+    torch.save(fx, os.path.join(OUT, "plain_forward.pt"))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "plain_forward":
+        make_plain_forward()
+    else:
+        main()
+        make_plain_forward()

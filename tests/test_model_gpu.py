@@ -63,6 +63,28 @@ def test_forward_with_cfg_vs_golden_and_oracle(tiny, path, attn):
     assert torch.equal(out[0, :3], out[1, :3])
 
 
+def test_plain_forward_vs_reference_fixture(tiny):
+    """NextDiT.forward (model.py:836-864) through ndit_forward: odd batch (3 rows in groups of max_batch = 2), one timestep per row,
+    first on the module as constructed, then after a forward_with_cfg call whose rope / attention-scale settings stick."""
+    cfg, W, _ = tiny
+    m = _build(cfg, W, max_tokens=256, max_cap_len=32)
+    fx = torch.load(os.path.join(GOLD, "plain_forward.pt"), map_location="cpu", weights_only=False)
+    x, t, cap, mask = fx["x"].cuda(), fx["t"].cuda(), fx["cap"].cuda(), fx["mask"].cuda()
+    for state in ("fresh", "sticky"):
+        if state == "sticky":
+            sc = fx["sticky_call"]
+            z2, cap2, mask2 = O.synthetic_inputs(cfg, sc["hw"], sc["T"], sc["ul"], seed=sc["seed"])
+            m.forward_with_cfg(z2.cuda(), torch.full((2,), sc["t"]).cuda(), cap2.cuda(), mask2.cuda(), **sc["kw"])
+        out = m(x, t, cap, mask).float().cpu()
+        kw = {} if state == "fresh" else dict(scale_factor=2.0, scale_watershed=0.3, rope_timestep=0.2, base_seqlen=64, proportional_attn=True)
+        orc = O.forward(cfg, W, fx["x"], fx["t"], fx["cap"], fx["mask"], precision="bf16", **kw)
+        ref32 = fx[state]["out_fp32"]
+        floor = _rel(fx[state]["out_autocast_cpu_bf16"], ref32)
+        assert out.shape == ref32.shape and torch.isfinite(out).all()
+        assert _rel(out, orc) < 2e-2, (state, _rel(out, orc), floor)
+        assert _rel(out, ref32) < 1.5 * floor + 2e-3, (state, _rel(out, ref32), floor)
+
+
 def test_vt_from_gemm_epilogue_is_bit_identical(tiny):
     """The q|k|v GEMM epilogue writes the value heads straight into the V^T buffer (engine option vt_epi, default on); the
     separate transpose_v launch (vt_epi = 0) must give the same bits: both round the fp32 accumulator to bf16 once."""
