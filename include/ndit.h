@@ -133,6 +133,14 @@ int ndit_forward_cfg(ndit_handle h, const void* x_dev, float t, int32_t batch, i
 int ndit_forward(ndit_handle h, const void* x_dev, const float* t_host, int32_t batch, int32_t height, int32_t width,
                  const ndit_step_params* sp, void* out_dev, void* stream);
 
+/* --- NextDiT.forward with a LIST of latents of different sizes (model.py:789-834, 836-864): x_dev / out_dev are HOST arrays of
+ * `batch` device pointers, bf16 [C, heights[i], widths[i]].  Rows are padded to the longest one with the learned pad token, every
+ * row gets the rope positions of its own (H/2, W/2) grid, keys beyond a row's own tokens are masked in the self-attention (the
+ * reference's flash-attn varlen path), and proportional attention uses the padded length, as the reference does.  Otherwise
+ * like ndit_forward (caption rows from ndit_set_caption, t_host[batch], sp as there).  Text-conditioned Next-DiT only. */
+int ndit_forward_list(ndit_handle h, const void* const* x_dev, const int32_t* heights, const int32_t* widths, const float* t_host,
+                      int32_t batch, const ndit_step_params* sp, void* const* out_dev, void* stream);
+
 /* --- transport.Sampler.sample_ode(...)(z, model.forward_with_cfg, **kw) (transport/transport.py:346-391,
  * transport/integrators.py:79-116) with torchdiffeq's fixed-grid euler / midpoint / rk4.  t_grid_host: the
  * n_grid time points (fp32, host).  z_dev: bf16 initial state [batch,C,height,width]; traj_dev: bf16

@@ -162,7 +162,7 @@ attention_hr_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_cons
                     const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmKy64,
                     const __grid_constant__ CUtensorMap tmKy16, const __grid_constant__ CUtensorMap tmVyt,
                     const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh, bf16* __restrict__ out,
-                    int N, int T, int H, int Hkv, float sl2_self, float sl2_cross) {
+                    int N, int T, int H, int Hkv, float sl2_self, float sl2_cross, const int* __restrict__ kv_len) {
     using Dm = HrDims<HD>;
     constexpr int HDP = Dm::HDP, BKV = Dm::BKV, HC = Dm::HC, PC = Dm::PC;
     extern __shared__ uint8_t smem_raw[];
@@ -193,7 +193,8 @@ attention_hr_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_cons
     const int q0 = blockIdx.x * (2 * HR_BQ);
     const int h = blockIdx.y, b = blockIdx.z;
     const int g = h / (H / Hkv);
-    const int n_self = (N + BKV - 1) / BKV;
+    const int Nv = kv_len != nullptr ? kv_len[b] : N;    // valid image tokens of this batch row (variable-resolution list input)
+    const int n_self = (Nv + BKV - 1) / BKV;
     const int n_cross = (T + BKV - 1) / BKV;      // 0 for the class-conditional model
     const int n_total = n_self + n_cross;
 
@@ -357,7 +358,7 @@ attention_hr_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_cons
             const float sl2 = cross ? sl2_cross : sl2_self;
             uint32_t vw[2];
             if (!cross) {
-                const int nvalid = N - jj * BKV - HC * hf;
+                const int nvalid = Nv - jj * BKV - HC * hf;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int rem = nvalid - c * 32;
@@ -572,7 +573,7 @@ static cudaError_t launch_attention_hr(const AttnPlan& p, cudaStream_t stream) {
     const float log2e = 1.4426950408889634f;
     const dim3 grid((p.N + 2 * HR_BQ - 1) / (2 * HR_BQ), p.H, p.B);
     return launch_k(kern, grid, dim3(HR_THREADS), HrDims<HD>::SMEM_BYTES, stream, p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64,
-                    p.tmKy16, p.tmVyt, p.ymask, p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv, p.scale_self * log2e, p.scale_cross * log2e);
+                    p.tmKy16, p.tmVyt, p.ymask, p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv, p.scale_self * log2e, p.scale_cross * log2e, p.kv_len);
 }
 
 cudaError_t attention_fused_hr(const AttnPlan& p, cudaStream_t stream) {

@@ -32,6 +32,15 @@
 // of P in the dead Q tile so that the softmax never waits for P V before it starts writing (449 vs 409 us: same story - every
 // change that lets a softmax warpgroup run ahead destroys the half-period offset between the two tiles), and enforcing that
 // offset with "half of my exponentials are issued" barriers between the two warpgroups (440 us, 443 us with the extra buffer).
+// Round 2, also measured on this kernel and not kept (tools/attn_bench.py, config-2 shape, 410-414 us baseline):
+//   * tcgen05.mma / TMA issued under elect.sync instead of `lane == 0` (back-to-back UTCHMMA instead of a ~45-cycle ELECT / BRA.U.ANY
+//     loop per instruction, see ptx.cuh): 464 us - the MMAs of a tile complete earlier, the two softmax warpgroups drift out of
+//     their half-period offset (third-generation kernel attention_hr_tcgen05.cu keeps elect.sync, there it is worth 90 us);
+//   * software-pipelining the exponentials by basic block (packs / stores of chunk c-1 and the FFMAs of chunk c+1 in the block of
+//     chunk c's 32 MUFU.EX2, behind always-true branches ptxas cannot fold - it schedules inside basic blocks only, and left alone
+//     puts every PRMT 17 cycles behind its own MUFU pair): the SASS then issues one MUFU every 8 cycles with everything else in
+//     the gaps, but the kernel takes 479 us - same mechanism, the exp phase of one tile now overlaps the other tile's;
+//   * making the PRMT selector depend on the chunk's last exponential: ptxas simply computes that exponential first.
 // Q is a TENSOR-MEMORY operand (head_dim 72 / 48): copied once per CTA from its TMA tile into free TMEM columns, so Q K^T
 // reads only K from shared memory (416.7 -> 412.9 us on the config-2 shape; -14 % shared-memory traffic).
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,256+HDP) Q_A [256+HDP, ..+40) O_B [384,384+HDP) Q_B [384+HDP, ..+40).
@@ -118,7 +127,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                        const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmKy64,
                        const __grid_constant__ CUtensorMap tmKy16, const __grid_constant__ CUtensorMap tmVyt,
                        const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh, bf16* __restrict__ out,
-                       int N, int T, int H, int Hkv, float sl2_self, float sl2_cross) {
+                       int N, int T, int H, int Hkv, float sl2_self, float sl2_cross, const int* __restrict__ kv_len) {
     using Dm = AttnDims<HD>;
     constexpr int HDP = Dm::HDP;
     extern __shared__ uint8_t smem_raw[];
@@ -141,7 +150,10 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     const int q0 = blockIdx.x * (2 * AT_BQ);
     const int h = blockIdx.y, b = blockIdx.z;
     const int g = h / (H / Hkv);
-    const int n_self = (N + AT_BKV - 1) / AT_BKV;
+    // variable-resolution list input: this batch row has only Nv valid image tokens (keys beyond are masked; the padded query
+    // rows are computed like any other and dropped by the caller).  Read before pdl_wait: written by a host copy, not a kernel.
+    const int Nv = kv_len != nullptr ? kv_len[b] : N;
+    const int n_self = (Nv + AT_BKV - 1) / AT_BKV;
     const int n_cross = (T + AT_BKV - 1) / AT_BKV;      // 0 for the class-conditional model
     const int n_total = n_self + n_cross;
 
@@ -376,7 +388,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
             // validity words for this block's 128 kv columns
             uint32_t vw[4];
             if (!cross) {
-                const int nvalid = N - jj * AT_BKV;
+                const int nvalid = Nv - jj * AT_BKV;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int rem = nvalid - c * 32;
@@ -524,7 +536,7 @@ static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
     const dim3 grid((p.N + 2 * AT_BQ - 1) / (2 * AT_BQ), p.H, p.B);
     return launch_k(kern, grid, dim3(AT_THREADS), AttnDims<HD>::SMEM_BYTES, stream, p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask,
                                                       p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv, p.scale_self * log2e,
-                                                      p.scale_cross * log2e);
+                                                      p.scale_cross * log2e, p.kv_len);
 }
 
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
@@ -541,7 +553,7 @@ cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
 __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, const bf16* __restrict__ kvy, int ld_kvy,
                                      const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh,
                                      bf16* __restrict__ out, int N, int T, int H, int Hkv, int hd, float scale_self,
-                                     float scale_cross) {
+                                     float scale_cross, const int* __restrict__ kv_len) {
     extern __shared__ float sh[];            // scores [max(N,T)] + q [hd] + red[32]
     const int n = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int g = h / (H / Hkv);
@@ -554,7 +566,7 @@ __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, c
     __syncthreads();
     float result[2] = {0.f, 0.f};            // this thread owns output dims threadIdx.x (< hd) for both segments
     for (int seg = 0; seg < 2; ++seg) {
-        const int len = seg == 0 ? N : T;
+        const int len = seg == 0 ? (kv_len != nullptr ? kv_len[b] : N) : T;
         if (len == 0) continue;              // no caption segment (uniform for the whole block)
         const float scale = seg == 0 ? scale_self : scale_cross;
         float mx = -INFINITY;
@@ -606,7 +618,7 @@ __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, c
 
 cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_kvy, const uint8_t* ymask,
                           const float* gate_tanh, bf16* out, int B, int N, int T, int H, int Hkv, int hd,
-                          float scale_self, float scale_cross, cudaStream_t stream) {
+                          float scale_self, float scale_cross, cudaStream_t stream, const int* kv_len) {
     if (hd > 128) return cudaErrorInvalidValue;
     const int L = N > T ? N : T;
     const size_t sh = (L + hd + 32) * sizeof(float);
@@ -620,7 +632,7 @@ cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_k
         configured = sh;
     }
     attention_ref_kernel<<<dim3(N, H, B), 128, sh, stream>>>(qkv, ld_qkv, kvy, ld_kvy, ymask, gate_tanh, out, N, T, H, Hkv,
-                                                           hd, scale_self, scale_cross);
+                                                           hd, scale_self, scale_cross, kv_len);
     return cudaGetLastError();
 }
 

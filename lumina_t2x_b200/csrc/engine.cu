@@ -126,6 +126,9 @@ struct ndit_engine {
     bf16 *yhat, *kvy, *vyt;
     uint8_t* ymask;
     float *pool, *capemb, *tf, *h1, *sc, *trow;   // trow: per-row timesteps of a plain forward
+    int* kvlen = nullptr;          // per-row valid token counts of a variable-resolution (list) forward
+    float2* rope_rows = nullptr;   // per-row rope table of a list forward [batch * Lmax][hd/2] (allocated on first use)
+    size_t rope_rows_cap = 0;
     bf16* tok;                               // [M, O] final-layer output tokens
     bf16* mod;
     bf16 *vel, *ystate, *ymid;
@@ -249,7 +252,7 @@ static int alloc_workspace(ndit_engine* h) {
     WALLOC(X, M * D); WALLOC(u, M * D); WALLOC(qkv, M * h->Wq); WALLOC(attn, M * D); WALLOC(o, M * D); WALLOC(hbuf, M * F);
     WALLOC(vt, B * h->Hkv * h->vrows * ((size_t)c.max_tokens + 8));
     WALLOC(yhat, L * B * T * C); WALLOC(kvy, L * B * T * 2 * KV); WALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
-    WALLOC(ymask, B * T); WALLOC(pool, B * C); WALLOC(capemb, B * cd); WALLOC(tf, B * 256); WALLOC(trow, B + 8); WALLOC(h1, B * cd); WALLOC(sc, B * cd);
+    WALLOC(ymask, B * T); WALLOC(pool, B * C); WALLOC(capemb, B * cd); WALLOC(tf, B * 256); WALLOC(trow, B + 8); WALLOC(kvlen, B + 8); WALLOC(h1, B * cd); WALLOC(sc, B * cd);
     WALLOC(mod, B * (L * NCH * D + h->FD * D)); WALLOC(tok, M * h->O);
     if (S > 1) {
         int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
@@ -377,6 +380,7 @@ extern "C" int ndit_destroy(ndit_handle h) {
     cudaDeviceSynchronize();
     for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->rope_rows) cudaFree(h->rope_rows);
     free_workspace(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
@@ -917,11 +921,23 @@ static int get_rope(ndit_engine* h, int Hp, int Wp, float theta, float lin, cuda
     return 0;
 }
 
+// Variable-resolution list input of NextDiT.forward (model.py:789-834): every row its own latent size; rows are padded with the
+// learned pad token to the longest row, keys beyond a row's own tokens are masked in the self-attention.
+struct ListArgs {
+    const void* const* xs;      // host array of device pointers, bf16 [C, heights[i], widths[i]]
+    const int32_t* heights;
+    const int32_t* widths;
+    void* const* outs;          // host array of device pointers, bf16 [C, heights[i], widths[i]]
+};
+
 // t_rows == nullptr: forward_with_cfg (cond/uncond pair rows, one timestep t, guidance in the unpatchify);
-// t_rows != nullptr (host array of `batch` floats): plain NextDiT.forward - every row its own sample and timestep, no guidance.
+// t_rows != nullptr (host array of `batch` floats): plain NextDiT.forward - every row its own sample and timestep, no guidance;
+// list != nullptr (plain only): variable-resolution rows (x, out, Hh, Ww unused).
 static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int Hh, int Ww, const ndit_step_params* sp,
-                        bf16* out, cudaStream_t s, const float* t_rows = nullptr) {
+                        bf16* out, cudaStream_t s, const float* t_rows = nullptr, const ListArgs* list = nullptr) {
     const bool plain = t_rows != nullptr;
+    if (list != nullptr && (!plain || h->flag || h->cls))
+        return h->fail(NDIT_ERR_INVALID, "list input is the plain forward of the text-conditioned Next-DiT");
     if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
     struct PdlGuard {       // per-launch CUDA events (profile mode) and overlapping launches do not mix
         int saved;
@@ -939,11 +955,25 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             return h->fail(NDIT_ERR_INVALID, "the time-gated mixture of experts selects one expert pair per call: all rows need the same timestep");
         CK(cudaMemcpyAsync(h->trow, t_rows, sizeof(float) * batch, cudaMemcpyHostToDevice, s));
     }
+    int lens[64];
+    if (list != nullptr) {
+        if (batch > 64) return h->fail(NDIT_ERR_INVALID, "list input: at most 64 rows");
+        Hh = 2; Ww = 0;             // N = the longest row (below); Hp / Wp are per row
+        for (int i = 0; i < batch; ++i) {
+            const int hi = list->heights[i], wi = list->widths[i];
+            if ((hi & 1) || (wi & 1) || hi <= 0 || wi <= 0 || !list->xs[i] || !list->outs[i]) return h->fail(NDIT_ERR_INVALID, "list input: latent H/W must be even");
+            if (hi / 2 > 384 || wi / 2 > 384) return h->fail(NDIT_ERR_INVALID, "rope table covers 384x384 patches (model.py:733)");
+            lens[i] = (hi / 2) * (wi / 2);
+            if (lens[i] > Ww) Ww = lens[i];
+        }
+        Ww *= 2;                    // so that N = (Hh / 2) * (Ww / 2) = the longest row
+        CK(cudaMemcpyAsync(h->kvlen, lens, sizeof(int) * batch, cudaMemcpyHostToDevice, s));
+    }
     if ((Hh & 1) || (Ww & 1) || Hh <= 0 || Ww <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");
     const int Hp = Hh / 2, Wp = Ww / 2, eol = h->flag ? 1 : 0;
     const int N = Hp * (Wp + eol), M = batch * N, Npad = (N + 7) / 8 * 8;     // Flag-DiT: one [eol] token per row of patches
     if (N > h->cfg.max_tokens) return h->fail(NDIT_ERR_INVALID, "%d tokens > max_tokens %d", N, h->cfg.max_tokens);
-    if (!h->flag && (Hp > 384 || Wp > 384)) return h->fail(NDIT_ERR_INVALID, "rope table covers 384x384 patches (model.py:733)");
+    if (!h->flag && list == nullptr && (Hp > 384 || Wp > 384)) return h->fail(NDIT_ERR_INVALID, "rope table covers 384x384 patches (model.py:733)");
     if (h->flag && N > 40000) return h->fail(NDIT_ERR_INVALID, "rope table covers 40000 tokens (lumina_t2i model.py:722-727)");
     if (int e = ensure_plans(h, batch, N)) return e;
     const int D = h->D, L = h->L, hd = h->hd;
@@ -966,7 +996,24 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     }
     const float theta = 10000.0f * ntk;
     const float2* rope = nullptr;
-    if (int e = get_rope(h, h->flag ? N : Hp, h->flag ? 1 : Wp, theta, lin, s, &rope)) return e;
+    int rope_rows_per_batch = N;       // ln_rope_qk indexes the table with (row % rope_rows_per_batch)
+    if (list != nullptr) {
+        // per-row tables: freqs_cis[:H/2, :W/2] of each image, padded by repeating its last position (model.py:796,817-824)
+        const size_t need = (size_t)M * (hd / 2);
+        if (need > h->rope_rows_cap) {
+            if (h->rope_rows) cudaFree(h->rope_rows);
+            h->rope_rows = nullptr; h->rope_rows_cap = 0;
+            CK(cudaMalloc(&h->rope_rows, need * sizeof(float2)));
+            h->rope_rows_cap = need;
+        }
+        for (int i = 0; i < batch; ++i) {
+            float2* tab = h->rope_rows + (size_t)i * N * (hd / 2);
+            CKL(rope_table(tab, list->heights[i] / 2, list->widths[i] / 2, hd, theta, lin, 0, s));
+            CKL(broadcast_row(tab + (size_t)lens[i] * (hd / 2), tab + (size_t)(lens[i] - 1) * (hd / 2), N - lens[i], (hd / 2) * (int)sizeof(float2), s));
+        }
+        rope = h->rope_rows;
+        rope_rows_per_batch = M;
+    } else if (int e = get_rope(h, h->flag ? N : Hp, h->flag ? 1 : Wp, theta, lin, s, &rope)) return e;
     float scale_self;
     if (sp->proportional_attn) {
         if (sp->base_seqlen <= 1) return h->fail(NDIT_ERR_INVALID, "proportional_attn needs base_seqlen > 1");
@@ -976,6 +1023,13 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     }
     const float scale_cross = (float)(1.0 / sqrt((double)hd));
 
+    if (list != nullptr) {
+        for (int i = 0; i < batch; ++i) {
+            bf16* Xi = h->X + (size_t)i * N * D;
+            PROF(KC_ROWWISE, patch_embed(static_cast<const bf16*>(list->xs[i]), h->Wx, h->bx, nullptr, Xi, 1, 1, h->cfg.in_channels, list->heights[i], list->widths[i], D, s));
+            PROF(KC_ROWWISE, broadcast_row(Xi + (size_t)lens[i] * D, h->pad_token, N - lens[i], D * (int)sizeof(bf16), s));
+        }
+    } else
     PROF(KC_ROWWISE, patch_embed(x, h->Wx, h->bx, h->flag ? h->eol_token : nullptr, h->X, batch, plain ? batch : batch / 2, h->cfg.in_channels, Hh, Ww, D, s));
     PROF(KC_COND, cond_prepare(t, plain ? h->trow : nullptr, nullptr, nullptr, nullptr, nullptr, h->tf, nullptr, batch, 0, 0, 0, s));
     PROF(KC_COND, gemv_rows(h->tf, h->Wt0, h->bt0, nullptr, h->h1, nullptr, batch, h->cd, 256, 0, POST_SILU, 0, 0, 0, s));
@@ -1006,17 +1060,18 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
         h->p_qkv[l].vt = vt_fused ? GemmVtOut{h->vt, (h->H + h->Hkv) * hd, hd, h->Hkv, h->vrows, Npad, N} : GemmVtOut{};
         PROF(KC_GEMM_QKV, gemm_bf16_tn(h->p_qkv[l], s));
         PROF(KC_ROWWISE, ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
-                       h->kn_b + (size_t)l * h->Hkv * hd, rope, M, N, h->H, h->Hkv, hd, s));
+                       h->kn_b + (size_t)l * h->Hkv * hd, rope, M, rope_rows_per_batch, h->H, h->Hkv, hd, s));
         if (h->attn_ref) {
             PROF(KC_ATTN, attention_ref(h->qkv, h->Wq, h->kvy + (size_t)l * batch * h->cap_T * 2 * h->Hkv * hd, 2 * h->Hkv * hd, h->ymask,
                               h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
-                              scale_cross, s));
+                              scale_cross, s, list != nullptr ? h->kvlen : nullptr));
         } else {
             if (!vt_fused)
                 PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, Npad, 0, batch, N, h->Hkv, hd, h->vrows, 1, s));
             AttnPlan& a = h->p_attn[l];
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
+            a.kv_len = list != nullptr ? h->kvlen : nullptr;
             PROF(KC_ATTN, attn_gen(h->attn_tp) == 3 ? attention_fused_hr(a, s) : attention_fused(a, s));
         }
         PROF(KC_GEMM_WO, gemm_bf16_tn(h->p_wo[l], s));
@@ -1066,7 +1121,11 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             }
         }
     }
-    if (plain) PROF(KC_ROWWISE, unpatchify_plain(h->tok, out, batch, h->cfg.in_channels, Hh, Ww, h->O, eol, s));
+    if (list != nullptr) {
+        for (int i = 0; i < batch; ++i)
+            PROF(KC_ROWWISE, unpatchify_plain(h->tok + (size_t)i * N * h->O, static_cast<bf16*>(list->outs[i]), 1, h->cfg.in_channels, list->heights[i],
+                                              list->widths[i], h->O, 0, s));
+    } else if (plain) PROF(KC_ROWWISE, unpatchify_plain(h->tok, out, batch, h->cfg.in_channels, Hh, Ww, h->O, eol, s));
     else PROF(KC_ROWWISE, unpatchify_cfg(h->tok, out, batch / 2, h->cfg.in_channels, Hh, Ww, h->O, sp->cfg_scale, eol, s));
     return NDIT_OK;
 }
@@ -1083,6 +1142,13 @@ extern "C" int ndit_forward(ndit_handle h, const void* x, const float* t_host, i
     if (!h || !x || !t_host || !sp || !out) return NDIT_ERR_INVALID;
     return forward_impl(h, static_cast<const bf16*>(x), 0.f, batch, height, width, sp, static_cast<bf16*>(out),
                         static_cast<cudaStream_t>(stream), t_host);
+}
+
+extern "C" int ndit_forward_list(ndit_handle h, const void* const* x_dev, const int32_t* heights, const int32_t* widths, const float* t_host,
+                                 int32_t batch, const ndit_step_params* sp, void* const* out_dev, void* stream) {
+    if (!h || !x_dev || !heights || !widths || !t_host || !sp || !out_dev) return NDIT_ERR_INVALID;
+    const ListArgs la{x_dev, heights, widths, out_dev};
+    return forward_impl(h, nullptr, 0.f, batch, 0, 0, sp, nullptr, static_cast<cudaStream_t>(stream), t_host, &la);
 }
 
 // The fixed-grid solve on the engine's own state buffer (h->ystate); trajectory rows 1.. go to `tr` when non-null.

@@ -57,6 +57,8 @@ struct AttnPlan {
     CUtensorMap tmKy64, tmKy16;  // ky : dims (hd, Hkv, B*T)
     CUtensorMap tmVyt;           // vy^T: dims (Tpad, 80, B*Hkv), box (64, 80, 1); row 72 = ones
     const uint8_t* ymask;        // [B, T] bytes (0/1)
+    const int* kv_len;           // optional device [B]: valid image tokens of each batch row (variable-resolution list input: rows are
+                                 // padded to N tokens, keys beyond kv_len[b] are masked, model.py:387-404 / flash-attn varlen); nullptr: N
     const float* gate_tanh;      // [H] bf16-rounded tanh(gate)
     bf16* out;                   // [B*N, H*hd]
     int B, N, T, H, Hkv, hd;     // T = 0: no caption segment (class-conditional model); hd = 72, 48 or 96
@@ -72,7 +74,7 @@ cudaError_t attention_fused_hr(const AttnPlan& p, cudaStream_t stream);
 // slow CUDA-core reference of the same op (debug / NDIT_ATTN=ref); same inputs in plain layouts
 cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_kvy, const uint8_t* ymask,
                           const float* gate_tanh, bf16* out, int B, int N, int T, int H, int Hkv, int hd,
-                          float scale_self, float scale_cross, cudaStream_t stream);
+                          float scale_self, float scale_cross, cudaStream_t stream, const int* kv_len = nullptr);
 
 // ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
 // X[token, :] = bf16(patch(x[b % n]) . Wx^T + bx)
@@ -99,6 +101,8 @@ cudaError_t final_norm(const bf16* X, const bf16* o, const bf16* w_post, const b
                        const bf16* shift, bf16* xn, int M, int rows_per_batch, int D, int mod_stride, float eps, cudaStream_t s);
 cudaError_t gather_label_rows(const bf16* table, const long long* labels, float* out, int B, int n_rows, int width, cudaStream_t s);
 // rope table [N][hd/2] (cos,sin)
+// dst[r][:] = src[:] for r in [0, rows): row_bytes a multiple of 16 (pad tokens / pad rope rows of the list input, model.py:811-826)
+cudaError_t broadcast_row(void* dst, const void* src, int rows, int row_bytes, cudaStream_t s);
 cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, int one_d, cudaStream_t s);
 // in place on qkv [M, ld]: q = bf16(rope(LN(q))), k = bf16(rope(LN(k)))
 cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const bf16* kw, const bf16* kb,

@@ -702,6 +702,19 @@ __global__ void rope_table_kernel(float2* __restrict__ tab, int Hp, int Wp, int 
     tab[idx] = make_float2(cs, sn);
 }
 
+__global__ void broadcast_row_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int rows, int vecs) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < rows * vecs) dst[idx] = src[idx % vecs];
+}
+
+cudaError_t broadcast_row(void* dst, const void* src, int rows, int row_bytes, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    if (row_bytes % 16 != 0) return cudaErrorInvalidValue;
+    const int vecs = row_bytes / 16, n = rows * vecs;
+    broadcast_row_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), rows, vecs);
+    return cudaGetLastError();
+}
+
 cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float linear_factor, int one_d, cudaStream_t s) {
     const int n = Hp * Wp * (hd / 2);
     rope_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(tab, Hp, Wp, hd, theta, linear_factor, one_d);

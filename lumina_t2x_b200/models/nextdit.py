@@ -331,11 +331,13 @@ class NextDiT(EngineModule):
 
     @torch.no_grad()
     def forward(self, x, t, cap_feats, cap_mask):
-        """model.py:836-864 (tensor input, inference): x [N,C,H,W], t [N], cap_feats [N,T,cap_feat_dim], cap_mask [N,T];
-        returns the first C output channels [N,C,H,W].  No guidance, one timestep per row; rows are processed in groups of
-        at most max_batch.  Uses the RoPE table / attention scaling the module currently holds, like the reference."""
+        """model.py:836-864 (inference): x [N,C,H,W] (or a list of N tensors [C,H_i,W_i] of different sizes, model.py:789-834),
+        t [N], cap_feats [N,T,cap_feat_dim], cap_mask [N,T]; returns the first C output channels, [N,C,H,W] or a list.
+        No guidance, one timestep per row.  Tensor input is processed in groups of at most max_batch rows; a list is one call
+        (its padded length is part of the result when proportional attention is on), so len(x) <= max_batch is grown on demand.
+        Uses the RoPE table / attention scaling the module currently holds, like the reference."""
         if not isinstance(x, torch.Tensor):
-            raise NotImplementedError("list-of-tensors (variable resolution) input is not supported by the B200 engine")
+            return self._forward_list(list(x), t, cap_feats, cap_mask)
         self._check_inputs(x, cap_feats, cap_mask)
         lib, h = self._engine(x.device)
         lin, ntk = getattr(self, "_freqs_state", (1.0, float(self.scale_factor)))
@@ -362,6 +364,38 @@ class NextDiT(EngineModule):
                                             C.c_void_p(out[i:j].data_ptr()), stream), h)
             self._cap_key = None
         return out.to(x.dtype)
+
+    @torch.no_grad()
+    def _forward_list(self, xs, t, cap_feats, cap_mask):
+        n = len(xs)
+        if n == 0 or any(not isinstance(v, torch.Tensor) or v.dim() != 3 for v in xs):
+            raise ValueError("list input: a non-empty list of [C, H, W] tensors")
+        self._check_inputs(xs[0], cap_feats, cap_mask, *xs[1:])
+        dev = xs[0].device
+        lib, h = self._engine(dev)
+        lin, ntk = getattr(self, "_freqs_state", (1.0, float(self.scale_factor)))
+        prop, base = getattr(self, "_attn_state", (False, None))
+        sp = _lib.NditStepParams(0.0, lin, 1.0, int(prop), int(base) if base is not None else 0, ntk)
+        tv = (t.detach().float().reshape(-1).tolist() if isinstance(t, torch.Tensor) else [float(t)] * n)
+        if len(tv) == 1:
+            tv = tv * n
+        if len(tv) != n or cap_feats.shape[0] != n:
+            raise ValueError(f"t / cap_feats have {len(tv)} / {cap_feats.shape[0]} rows for a list of {n}")
+        xb = [v.detach().to(torch.bfloat16).contiguous() for v in xs]
+        outs = [torch.empty_like(v) for v in xb]
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            self._ensure_capacity(lib, h, max(self._tokens_for(v.shape[1], v.shape[2]) for v in xb), cap_feats.shape[1], n)
+            self._cap_key = None
+            self._set_caption(lib, h, cap_feats, cap_mask, stream)
+            xp = (C.c_void_p * n)(*[v.data_ptr() for v in xb])
+            op = (C.c_void_p * n)(*[v.data_ptr() for v in outs])
+            hs = (C.c_int32 * n)(*[v.shape[1] for v in xb])
+            ws = (C.c_int32 * n)(*[v.shape[2] for v in xb])
+            ta = (C.c_float * n)(*tv)
+            _lib.check(lib.ndit_forward_list(h, xp, hs, ws, ta, n, C.byref(sp), op, stream), h)
+            self._cap_key = None
+        return [o.to(v.dtype) for o, v in zip(outs, xs)]
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0,

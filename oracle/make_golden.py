@@ -337,9 +337,50 @@ def make_plain_forward() -> None:
     torch.save(fx, os.path.join(OUT, "plain_forward.pt"))
 
 
+def make_list_forward() -> None:
+    """NextDiT.forward with a LIST of latents of different sizes (nextdit.py:761-806): pad token, per-image rope grid, masked keys.
+    Recorded on a fresh module and with proportional attention left on the module by a forward_with_cfg call (the scale then sees
+    the PADDED sequence length)."""
+    models, _ = import_reference_mini()
+    cfg = O.config_tiny(n_layers=2)
+    W = O.synthetic_weights(cfg, seed=0, dtype=torch.bfloat16)
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(13)
+    sizes = [(16, 16), (24, 32), (16, 24)]
+    T = 16
+    xs = [torch.randn(cfg.in_channels, hh, ww, generator=g).to(torch.bfloat16) for hh, ww in sizes]
+    cap = torch.randn(len(sizes), T, cfg.cap_feat_dim, generator=g).to(torch.bfloat16)
+    mask = torch.zeros(len(sizes), T, dtype=torch.int32)
+    for b, n in enumerate((16, 5, 11)):
+        mask[b, :n] = 1
+    t = torch.tensor([0.3, 0.8, 0.55])
+    sticky = dict(cfg_scale=2.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=64, proportional_attn=True)
+    z2, cap2, mask2 = O.synthetic_inputs(cfg, (16, 16), 16, 4, seed=3)
+    fx = dict(sizes=sizes, T=T, weight_seed=0, xs=xs, cap=cap, mask=mask, t=t, sticky_call=dict(kw=sticky, t=0.2, hw=(16, 16), T=16, ul=4, seed=3))
+    for state in ("fresh", "sticky"):
+        ref32 = build_ref(models, cfg, W).float()
+        ref16 = build_ref(models, cfg, W).to(torch.bfloat16)
+        if state == "sticky":
+            for m_, dt in ((ref32, torch.float32), (ref16, torch.bfloat16)):
+                m_.forward_with_cfg(z2.to(dt), torch.full((2,), 0.2), cap2.to(dt), mask2, **sticky)
+        out32 = ref32([v.float() for v in xs], t, cap.float(), mask)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out16 = ref16(xs, t, cap, mask)
+        fx[state] = dict(out_fp32=[o.clone() for o in out32], out_autocast_cpu_bf16=[o.float().to(torch.bfloat16) for o in out16])
+        kw = dict() if state == "fresh" else dict(scale_factor=2.0, scale_watershed=0.3, rope_timestep=0.2, base_seqlen=64, proportional_attn=True)
+        o = O.forward_list(cfg, W, [v.float() for v in xs], t, cap.float(), mask, precision="fp32", **kw)
+        for i, (a, b, c) in enumerate(zip(o, out32, out16)):
+            print(state, i, tuple(b.shape), "absmax", b.abs().max().item(), "oracle fp32 rel", ((a - b).abs().max() / b.abs().max()).item(),
+                  "ref bf16 vs fp32", ((c.float() - b).abs().max() / b.abs().max()).item())
+    torch.save(fx, os.path.join(OUT, "list_forward.pt"))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "plain_forward":
         make_plain_forward()
+    elif len(sys.argv) > 1 and sys.argv[1] == "list_forward":
+        make_list_forward()
     else:
         main()
         make_plain_forward()
+        make_list_forward()

@@ -252,9 +252,10 @@ def unpatchify(x: Tensor, H: int, Wd: int, ps: int, out_ch: int) -> Tensor:
 def forward(cfg: NextDiTConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, cap_feats: Tensor, cap_mask: Tensor,
             *, scale_factor: float = 1.0, scale_watershed: float = 1.0, rope_timestep: float = 1.0,
             base_seqlen: Optional[int] = None, proportional_attn: bool = False,
-            precision: str = "fp32", taps: Optional[dict] = None) -> Tensor:
+            precision: str = "fp32", taps: Optional[dict] = None, seqlen_for_scale: Optional[int] = None) -> Tensor:
     """NextDiT.forward (models/nextdit.py:808-836) with the rope table of the enclosing
-    forward_with_cfg call (:846-852).  ``taps``: optional dict filled with intermediates."""
+    forward_with_cfg call (:846-852).  ``taps``: optional dict filled with intermediates.
+    ``seqlen_for_scale``: sequence length the proportional-attention scale sees (the PADDED length of a list input)."""
     p = _Prec(precision)
     ps = cfg.patch_size
     B, C, H, Wd = x.shape
@@ -274,7 +275,7 @@ def forward(cfg: NextDiTConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, cap_
     c = p.r(temb + cap_emb)
     if proportional_attn:
         assert base_seqlen is not None
-        softmax_scale = math.sqrt(math.log(N, base_seqlen) / cfg.head_dim)
+        softmax_scale = math.sqrt(math.log(seqlen_for_scale or N, base_seqlen) / cfg.head_dim)
     else:
         softmax_scale = math.sqrt(1.0 / cfg.head_dim)
     ymask = cap_mask.bool()
@@ -294,6 +295,16 @@ def forward(cfg: NextDiTConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, cap_
     if cfg.learn_sigma:
         out = out[:, : cfg.in_channels]
     return out
+
+
+def forward_list(cfg: NextDiTConfig, W: Dict[str, Tensor], xs, t: Tensor, cap_feats: Tensor, cap_mask: Tensor, **kw):
+    """NextDiT.forward with a list of latents of different sizes (models/nextdit.py:761-806 patchify_and_embed, :362-377 varlen
+    attention): pad tokens are masked out of every valid token's attention and dropped at the end, so each image is an independent
+    batch-1 forward - except that the proportional-attention scale sees the padded (longest) sequence length."""
+    ps = cfg.patch_size
+    lmax = max((v.shape[1] // ps) * (v.shape[2] // ps) for v in xs)
+    return [forward(cfg, W, v.unsqueeze(0), t[i:i + 1], cap_feats[i:i + 1], cap_mask[i:i + 1], seqlen_for_scale=lmax, **kw)[0]
+            for i, v in enumerate(xs)]
 
 
 def forward_with_cfg(cfg: NextDiTConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, cap_feats: Tensor,

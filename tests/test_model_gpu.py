@@ -85,6 +85,34 @@ def test_plain_forward_vs_reference_fixture(tiny):
         assert _rel(out, ref32) < 1.5 * floor + 2e-3, (state, _rel(out, ref32), floor)
 
 
+@pytest.mark.parametrize("attn", ["tcgen05", "refkernel", "tcgen05_gen3"])
+def test_list_forward_vs_reference_fixture(tiny, attn):
+    """NextDiT.forward with a list of latents of different sizes (model.py:789-834) through ndit_forward_list: rows padded with the
+    pad token, own rope grid per row, keys beyond a row's own tokens masked in all three attention kernels."""
+    cfg, W, _ = tiny
+    m = _build(cfg, W, max_tokens=256, max_cap_len=32, max_batch=4)
+    m.set_option("attn_ref", 1 if attn == "refkernel" else 0)
+    m.set_option("attn_gen", 3 if attn == "tcgen05_gen3" else 0)
+    fx = torch.load(os.path.join(GOLD, "list_forward.pt"), map_location="cpu", weights_only=False)
+    xs = [v.cuda() for v in fx["xs"]]
+    t, cap, mask = fx["t"].cuda(), fx["cap"].cuda(), fx["mask"].cuda()
+    for state in ("fresh", "sticky"):
+        if state == "sticky":
+            sc = fx["sticky_call"]
+            z2, cap2, mask2 = O.synthetic_inputs(cfg, sc["hw"], sc["T"], sc["ul"], seed=sc["seed"])
+            m.forward_with_cfg(z2.cuda(), torch.full((2,), sc["t"]).cuda(), cap2.cuda(), mask2.cuda(), **sc["kw"])
+        outs = m(xs, t, cap, mask)
+        kw = {} if state == "fresh" else dict(scale_factor=2.0, scale_watershed=0.3, rope_timestep=0.2, base_seqlen=64, proportional_attn=True)
+        orcs = O.forward_list(cfg, W, fx["xs"], fx["t"], fx["cap"], fx["mask"], precision="bf16", **kw)
+        assert isinstance(outs, list) and len(outs) == len(xs)
+        for i, (out, orc, ref32, ref16) in enumerate(zip(outs, orcs, fx[state]["out_fp32"], fx[state]["out_autocast_cpu_bf16"])):
+            out = out.float().cpu()
+            floor = _rel(ref16, ref32)
+            assert out.shape == ref32.shape and torch.isfinite(out).all()
+            assert _rel(out, orc) < 2e-2, (state, i, _rel(out, orc), floor)
+            assert _rel(out, ref32) < 1.5 * floor + 2e-3, (state, i, _rel(out, ref32), floor)
+
+
 def test_vt_from_gemm_epilogue_is_bit_identical(tiny):
     """The q|k|v GEMM epilogue writes the value heads straight into the V^T buffer (engine option vt_epi, default on); the
     separate transpose_v launch (vt_epi = 0) must give the same bits: both round the fp32 accumulator to bf16 once."""
