@@ -167,6 +167,10 @@ int ndit_set_option(ndit_handle h, const char* name, int32_t value);
 #define NDIT_PROFILE_CLASSES 7
 int ndit_profile_read(ndit_handle h, float* ms_out, int64_t* count_out, int32_t n_classes);
 
+/* Debug tap for per-block parity tests: with ndit_set_option(h, "tap_layer", l) every forward copies the residual stream x after
+ * TransformerBlock l (model.py:624, [batch * tokens, dim] bf16, token-major) aside; this reads it back (device to device). */
+int ndit_debug_read_residual(ndit_handle h, void* out_dev, int64_t rows, void* stream);
+
 /* --- single-operator entry points (parity tests and micro-benchmarks call the kernels through these) */
 /* C[M,N] = A[M,K] W[N,K]^T, bf16, fp32 accumulate.  swiglu != 0: W is [2F,K] block-interleaved
  * (128 rows w1 | 128 rows w3) and C is [M,F] = silu(a)*b.  (F.linear call sites: model.py:358,438,502) */

@@ -100,6 +100,9 @@ struct ndit_engine {
     int64_t n_params = 0;
     bool finalized = false;
     int attn_ref = 0;
+    int tap_layer = -1;                      // debug: >= 0 copies the residual stream after that block into tap_buf (ndit_debug_read_residual)
+    bf16* tap_buf = nullptr;
+    size_t tap_rows = 0;
     int vt_epi = 1;                          // 1: the q|k|v GEMM epilogue writes V^T itself (no transpose_v launch); 0: separate kernel
     int attn_tp = 0;                         // attention kernel generation: 0 default (ATTN_DEFAULT_GEN), 1 one thread per row + P through
                                              // shared memory (attention_tcgen05.cu), 3 half rows + P in tensor memory (attention_hr_tcgen05.cu)
@@ -381,6 +384,7 @@ extern "C" int ndit_destroy(ndit_handle h) {
     for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : h->allocs) cudaFree(p);
     if (h->rope_rows) cudaFree(h->rope_rows);
+    if (h->tap_buf) cudaFree(h->tap_buf);
     free_workspace(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
@@ -419,6 +423,7 @@ extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!strcmp(name, "graph")) { h->use_graph = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "pdl")) { h->pdl = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "vt_epi")) { h->vt_epi = value; return NDIT_OK; }
+    if (!strcmp(name, "tap_layer")) { h->tap_layer = value; return NDIT_OK; }
     if (!strcmp(name, "attn_gen") || !strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
     if (!strcmp(name, "profile")) {
         h->profile = value;
@@ -1116,9 +1121,19 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                 const bf16* fin = h->mod + (size_t)L * NCH * D;
                 const bool fsh = h->cls || h->flag;
                 PROF(KC_ROWWISE, final_norm(h->X, h->o, post, gch, fsh ? fin + D : fin, fsh ? fin : nullptr, h->u, M, N, D, mod_stride,
-                                            h->cfg.norm_eps, s));
+                                            h->cfg.norm_eps, s, h->tap_layer == l ? h->X : nullptr));
                 PROF(KC_ROWWISE, gemm_bf16_tn(h->p_final, s));
             }
+        }
+        if (l == h->tap_layer) {    // debug tap: the residual stream X after block l (the last block's X is complete as well:
+                                    // final_norm reads it, the post-norm of the second sub-block is already applied)
+            if (h->tap_rows < (size_t)M) {
+                if (h->tap_buf) cudaFree(h->tap_buf);
+                h->tap_buf = nullptr; h->tap_rows = 0;
+                CK(cudaMalloc(&h->tap_buf, (size_t)M * D * sizeof(bf16)));
+                h->tap_rows = M;
+            }
+            CK(cudaMemcpyAsync(h->tap_buf, h->X, (size_t)M * D * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
         }
     }
     if (list != nullptr) {
@@ -1142,6 +1157,13 @@ extern "C" int ndit_forward(ndit_handle h, const void* x, const float* t_host, i
     if (!h || !x || !t_host || !sp || !out) return NDIT_ERR_INVALID;
     return forward_impl(h, static_cast<const bf16*>(x), 0.f, batch, height, width, sp, static_cast<bf16*>(out),
                         static_cast<cudaStream_t>(stream), t_host);
+}
+
+extern "C" int ndit_debug_read_residual(ndit_handle h, void* out_dev, int64_t rows, void* stream) {
+    if (!h || !out_dev) return NDIT_ERR_INVALID;
+    if (!h->tap_buf || rows <= 0 || (size_t)rows > h->tap_rows) return h->fail(NDIT_ERR_STATE, "no tap recorded (option tap_layer, then a forward)");
+    cudaError_t e = cudaMemcpyAsync(out_dev, h->tap_buf, (size_t)rows * h->D * sizeof(bf16), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NDIT_OK : h->fail(NDIT_ERR_CUDA, "ndit_debug_read_residual: %s", cudaGetErrorString(e));
 }
 
 extern "C" int ndit_forward_list(ndit_handle h, const void* const* x_dev, const int32_t* heights, const int32_t* widths, const float* t_host,

@@ -98,7 +98,7 @@ cudaError_t resid_rms_mod(bf16* X, const bf16* o, const bf16* w_post, const bf16
 // last gated residual update then xn = bf16(LN(no affine, eps 1e-6)(X) * onepls (+ shift)) -> xn [M, D]; the Linear(D->O)+bias
 // of the final layer runs as a tcgen05 GEMM with a bias epilogue on xn (shift: class-conditional model / Flag-DiT)
 cudaError_t final_norm(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
-                       const bf16* shift, bf16* xn, int M, int rows_per_batch, int D, int mod_stride, float eps, cudaStream_t s);
+                       const bf16* shift, bf16* xn, int M, int rows_per_batch, int D, int mod_stride, float eps, cudaStream_t s, bf16* x_out = nullptr);
 cudaError_t gather_label_rows(const bf16* table, const long long* labels, float* out, int B, int n_rows, int width, cudaStream_t s);
 // rope table [N][hd/2] (cos,sin)
 // dst[r][:] = src[:] for r in [0, rows): row_bytes a multiple of 16 (pad tokens / pad rope rows of the list input, model.py:811-826)

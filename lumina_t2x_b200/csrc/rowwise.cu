@@ -343,7 +343,7 @@ template <int NV>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 final_norm_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const bf16* __restrict__ w_post,
                   const bf16* __restrict__ tanh_g, const bf16* __restrict__ onepls, const bf16* __restrict__ shift,
-                  bf16* __restrict__ xn, int M, int rows_per_batch, int D, int mod_stride, float eps_rms) {
+                  bf16* __restrict__ xn, int M, int rows_per_batch, int D, int mod_stride, float eps_rms, bf16* x_out) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -386,6 +386,7 @@ final_norm_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const 
                     const float n = w_post != nullptr ? bf16_round(bf16_round(ov[i][e] * rinv) * w[e]) : ov[i][e];
                     x[i][e] = bf16_round(x[i][e] + bf16_round(g[e] * n));
                 }
+                if (x_out != nullptr) store8(x_out + off + v * 8, x[i]);     // debug tap of the last block's residual stream
             }
         }
     }
@@ -425,13 +426,13 @@ final_norm_kernel(const bf16* __restrict__ X, const bf16* __restrict__ o, const 
 }
 
 cudaError_t final_norm(const bf16* X, const bf16* o, const bf16* w_post, const bf16* tanh_g, const bf16* onepls,
-                       const bf16* shift, bf16* xn, int M, int rows_per_batch, int D, int mod_stride, float eps, cudaStream_t s) {
+                       const bf16* shift, bf16* xn, int M, int rows_per_batch, int D, int mod_stride, float eps, cudaStream_t s, bf16* x_out) {
     if (D % 8 != 0 || D > MAX_VEC * 256) return cudaErrorInvalidValue;
     const int nv = (D / 8 + 31) / 32;
     const dim3 grid((M + ROW_WARPS - 1) / ROW_WARPS), block(ROW_WARPS * 32);
 #define LAUNCH(NVV)                                                                                              \
     final_norm_kernel<NVV><<<grid, block, 0, s>>>(X, o, w_post, tanh_g, onepls, shift, xn, M, rows_per_batch, D, \
-                                                  mod_stride, eps)
+                                                  mod_stride, eps, x_out)
     if (nv <= 3) LAUNCH(3);
     else if (nv <= 9) LAUNCH(9);
     else if (nv <= 12) LAUNCH(12);

@@ -228,6 +228,16 @@ class EngineModule(nn.Module):
         lib, h = self._engine(next(self.parameters()).device)
         _lib.check(lib.ndit_set_option(h, name.encode(), int(value)), h)
 
+    def read_residual_tap(self, rows: int) -> torch.Tensor:
+        """Debug: the residual stream [rows, dim] (bf16, token-major) recorded after the block chosen with
+        ``set_option("tap_layer", l)`` during the last forward (ndit_debug_read_residual)."""
+        dev = next(self.parameters()).device
+        lib, h = self._engine(dev)
+        out = torch.empty(rows, self.dim, dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.ndit_debug_read_residual(h, C.c_void_p(out.data_ptr()), rows, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), h)
+        return out
+
     def get_fsdp_wrap_module_list(self):
         return list(self.layers)
 

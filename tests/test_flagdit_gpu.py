@@ -97,7 +97,7 @@ def test_attention_head_dim_96(B, N, T, H, Hkv, use_ref):
         ref = ref + (oy * gate.view(1, -1, 1, 1)).to(torch.bfloat16).float()
     ref = ref.permute(0, 2, 1, 3).reshape(B * N, H * hd)
     assert torch.isfinite(out.float()).all()
-    assert ((out.float() - ref).abs() <= 2e-2 * ref.abs().max()).all()
+    assert ((out.float() - ref).abs() <= 1.2e-2 * ref.abs().max()).all()    # measured <= 9.6e-3 (tools/attn_error.py)
 
 
 def test_flagship_5b_dims_two_layers_1024px():

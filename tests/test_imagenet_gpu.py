@@ -88,7 +88,7 @@ def test_attention_head_dim_48_no_caption(B, N, H, Hkv, use_ref):
     v = qkv[:, (H + Hkv) * hd:].float().view(B, N, Hkv, hd).repeat_interleave(rep, 2).permute(0, 2, 1, 3)
     ref = (torch.softmax(q @ k.transpose(-1, -2) * ss, -1) @ v).permute(0, 2, 1, 3).reshape(B * N, H * hd)
     assert torch.isfinite(out.float()).all()
-    assert ((out.float() - ref).abs() <= 2e-2 * ref.abs().max()).all()
+    assert ((out.float() - ref).abs() <= 1.2e-2 * ref.abs().max()).all()    # measured <= 9.6e-3 (tools/attn_error.py)
 
 
 # ---------------------------------------------------------------- mixture-of-experts FFN (Next-DiT-MoE, BASELINE config 5)

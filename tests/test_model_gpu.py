@@ -63,6 +63,29 @@ def test_forward_with_cfg_vs_golden_and_oracle(tiny, path, attn):
     assert torch.equal(out[0, :3], out[1, :3])
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fwd_*.pt"))), ids=os.path.basename)
+def test_per_block_residual_taps_vs_reference(tiny, path):
+    """Residual stream after every TransformerBlock (engine debug tap) against the per-block outputs the fixture recorded from the
+    unmodified reference (fp32 run, forward hooks on ref.layers): localises an error to a block instead of only seeing it at the end."""
+    cfg, W, m = tiny
+    fx = torch.load(path, map_location="cpu", weights_only=False)
+    z, cap, mask = O.synthetic_inputs(cfg, tuple(fx["hw"]), fx["T"], fx["ul"], seed=fx["input_seed"])
+    t = torch.full((2,), fx["t"]).cuda()
+    taps = {}
+    orc = O.forward(cfg, W, torch.cat([z[:1], z[:1]]), torch.full((2,), fx["t"]), cap, mask, precision="bf16", taps=taps,
+                    **{k: v for k, v in fx["kw"].items() if k != "cfg_scale"}, rope_timestep=fx["t"])
+    for l in range(cfg.n_layers):
+        m.set_option("tap_layer", l)
+        m.forward_with_cfg(z.cuda(), t, cap.cuda(), mask.cuda(), **fx["kw"])
+        ref = fx["taps"][f"block{l}"].float()                       # [2, N, dim]
+        got = m.read_residual_tap(ref.shape[0] * ref.shape[1]).float().cpu().view_as(ref)
+        o16 = taps[f"block{l}"].float()
+        assert torch.isfinite(got).all()
+        assert _rel(got, o16) < 2e-2, (l, _rel(got, o16))
+        assert _rel(got, ref) < 1.5 * _rel(o16, ref) + 2e-3, (l, _rel(got, ref), _rel(o16, ref))
+    m.set_option("tap_layer", -1)
+
+
 def test_plain_forward_vs_reference_fixture(tiny):
     """NextDiT.forward (model.py:836-864) through ndit_forward: odd batch (3 rows in groups of max_batch = 2), one timestep per row,
     first on the module as constructed, then after a forward_with_cfg call whose rope / attention-scale settings stick."""

@@ -188,8 +188,11 @@ def test_attention(lib, B, N, T, H, Hkv, valid, use_ref):
     ref = _attn_ref(qkv, kvy, ymask, gate_tanh, B, N, T, H, Hkv, ss, sc)
     assert torch.isfinite(out.float()).all(), "non-finite / unwritten: " + _diag(torch.nan_to_num(out.float(), nan=1e9), ref)
     err = (out.float() - ref.float()).abs()
-    # P is rounded to bf16 before P.V (as in flash-attention) and the result is rounded twice: 2e-2 of the output scale
-    tol = 2e-2 * ref.float().abs().max()
+    # The op rounds to bf16 three times (self part, gated caption part, sum) and feeds bf16 probabilities to P.V.  Measured
+    # (tools/attn_error.py, B200): max|err| / max|ref| <= 9.6e-3 for both tcgen05 generations (P truncated to bf16), 7.8e-3 for the
+    # CUDA-core kernel (P rounded to nearest) - i.e. two to three bf16 ulps of the largest outputs, dominated by the output
+    # roundings, not by the truncation.  Tolerance: 1.2e-2 of the output scale.
+    tol = 1.2e-2 * ref.float().abs().max()
     assert (err <= tol).all(), _diag(out, ref)
 
 
