@@ -150,6 +150,25 @@ int ndit_sample(ndit_handle h, const void* z_dev, int32_t batch, int32_t height,
                 const float* t_grid_host, int32_t n_grid, int32_t method, const ndit_step_params* sp,
                 void* traj_dev, void* final_dev, void* stream);
 
+/* --- transport.Sampler.sample_sde(...)(init, model_fn, **kw) (transport/transport.py:285-344, integrators.py:5-76), velocity model on
+ * the Linear path: the stochastic loop inside the engine.  The reference draws torch.randn on the host in every step; the caller draws
+ * the same tensors in the same order and passes them as noise_dev [n_steps][batch,C,H,W] bf16.  Every PyTorch op of the reference rounds
+ * to bf16, so the caller also supplies the t-dependent scalars of every evaluation point, computed with the same tensor ops on a
+ * one-element bf16 tensor (floats that hold bf16 values): Euler-Maruyama (method 0): pts[i] = point t_i; Heun (method 1): pts[2i] = t_i,
+ * pts[2i+1] = t_i + dt.  dt, sqrt_dt, half_dt enter the products as fp32 scalars: the reference multiplies CUDA bf16 tensors with 0-dim
+ * CPU tensors, which a CUDA op keeps in fp32 (a CPU op would round them to bf16 first).  traj_dev receives the state after every step
+ * [n_steps][batch,C,H,W] (the reference's list xs, without its fp32 last step, which stays with the caller). */
+typedef struct ndit_sde_point {
+    float t;                /* timestep the model sees */
+    float ratio;            /* alpha_t / d_alpha_t */
+    float var;              /* sigma_t^2 - ratio * d_sigma_t * sigma_t */
+    float diffusion;        /* compute_diffusion(t, form, norm) */
+    float sqrt_2diffusion;  /* sqrt(2 * diffusion) */
+} ndit_sde_point;
+int ndit_sample_sde(ndit_handle h, const void* z_dev, int32_t batch, int32_t height, int32_t width, int32_t n_steps, int32_t method,
+                    const ndit_sde_point* pts, float dt, float sqrt_dt, float half_dt, const void* noise_dev,
+                    const ndit_step_params* sp, void* traj_dev, void* stream);
+
 /* Same solve with HOST buffers (the end-to-end entry point): copies z / caption host->device, runs
  * ndit_set_caption + ndit_sample, copies the final latent device->host and synchronises the stream. */
 int ndit_sample_host(ndit_handle h, const void* z_host, const void* cap_feats_host, const uint8_t* cap_mask_host,

@@ -26,6 +26,10 @@ class NditStepParams(C.Structure):
                 ("proportional_attn", C.c_int32), ("base_seqlen", C.c_int32), ("ntk_factor", C.c_float)]
 
 
+class NditSdePoint(C.Structure):
+    _fields_ = [("t", C.c_float), ("ratio", C.c_float), ("var", C.c_float), ("diffusion", C.c_float), ("sqrt_2diffusion", C.c_float)]
+
+
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); every symbol declared in include/ndit.h
@@ -49,6 +53,8 @@ SIGNATURES = {
                                     C.POINTER(NditStepParams), C.POINTER(_vp), _vp]),
     "ndit_sample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_f32), _i32, _i32, C.POINTER(NditStepParams),
                               _vp, _vp, _vp]),
+    "ndit_sample_sde": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(NditSdePoint), _f32, _f32, _f32, _vp,
+                                  C.POINTER(NditStepParams), _vp, _vp]),
     "ndit_sample_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _i32, _i32,
                                    C.POINTER(NditStepParams), _vp, _vp]),
     "ndit_launch_count": (_i64, [_vp]),

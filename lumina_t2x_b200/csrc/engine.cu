@@ -1321,6 +1321,43 @@ extern "C" int ndit_sample(ndit_handle h, const void* z, int32_t batch, int32_t 
     return NDIT_OK;
 }
 
+extern "C" int ndit_sample_sde(ndit_handle h, const void* z, int32_t batch, int32_t height, int32_t width, int32_t n_steps, int32_t method,
+                               const ndit_sde_point* pts, float dt, float sqrt_dt, float half_dt, const void* noise, const ndit_step_params* sp,
+                               void* traj, void* stream) {
+    if (!h || !z || !pts || !noise || !sp || !traj) return NDIT_ERR_INVALID;
+    if (n_steps < 1 || (method != 0 && method != 1)) return h->fail(NDIT_ERR_INVALID, "ndit_sample_sde: n_steps >= 1, method 0 (Euler-Maruyama) or 1 (Heun)");
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
+    if (batch < 2 || (batch & 1) || batch > h->Bmax) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
+    if ((height & 1) || (width & 1) || height <= 0 || width <= 0) return h->fail(NDIT_ERR_INVALID, "latent H/W must be even");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t count = (size_t)batch * h->cfg.in_channels * height * width;
+    if (count > (size_t)h->Bmax * h->cfg.in_channels * h->cfg.max_tokens * 4) return h->fail(NDIT_ERR_INVALID, "latent too large");
+    bf16* y = h->ystate;
+    bf16* tr = static_cast<bf16*>(traj);
+    const bf16* nz = static_cast<const bf16*>(noise);
+    CK(cudaMemcpyAsync(y, z, count * 2, cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i < n_steps; ++i) {
+        const bf16* w = nz + (size_t)i * count;
+        if (method == 0) {                       // Euler-Maruyama (integrators.py:33-47)
+            const ndit_sde_point& p = pts[i];
+            if (int e = forward_impl(h, y, p.t, batch, height, width, sp, h->vel, s)) return e;
+            CKL(sde_step(0, y, nullptr, y, h->vel, w, nullptr, nullptr, p.ratio, p.var, p.diffusion, p.sqrt_2diffusion, dt, sqrt_dt, half_dt, count, s));
+        } else {                                 // Heun (integrators.py:49-66): points 2i (t) and 2i+1 (t + dt)
+            const ndit_sde_point& p = pts[2 * i];
+            const ndit_sde_point& q = pts[2 * i + 1];
+            bf16 *xhat = h->ymid, *k1 = h->kbuf[0], *xp = h->kbuf[1];
+            CKL(sde_step(1, xhat, nullptr, y, nullptr, w, nullptr, nullptr, p.ratio, p.var, p.diffusion, p.sqrt_2diffusion, dt, sqrt_dt, half_dt, count, s));
+            if (int e = forward_impl(h, xhat, p.t, batch, height, width, sp, h->vel, s)) return e;
+            CKL(sde_step(2, xp, k1, xhat, h->vel, nullptr, nullptr, nullptr, p.ratio, p.var, p.diffusion, p.sqrt_2diffusion, dt, sqrt_dt, half_dt, count, s));
+            if (int e = forward_impl(h, xp, q.t, batch, height, width, sp, h->vel, s)) return e;
+            CKL(sde_step(3, y, nullptr, xp, h->vel, nullptr, xhat, k1, q.ratio, q.var, q.diffusion, q.sqrt_2diffusion, dt, sqrt_dt, half_dt, count, s));
+        }
+        CK(cudaMemcpyAsync(tr + (size_t)i * count, y, count * 2, cudaMemcpyDeviceToDevice, s));
+    }
+    return NDIT_OK;
+}
+
 extern "C" int ndit_sample_host(ndit_handle h, const void* z_host, const void* cap_host, const uint8_t* mask_host,
                                 int32_t batch, int32_t height, int32_t width, int32_t T, const float* grid, int32_t n_grid,
                                 int32_t method, const ndit_step_params* sp, void* final_host, void* stream) {

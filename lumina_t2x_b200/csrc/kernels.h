@@ -136,6 +136,10 @@ cudaError_t moe_time_select(const float* logits, int L, int E, int* sel, float* 
 // one stage of torchdiffeq's fixed-grid rk4 (3/8 rule) on a bf16 state (see rowwise.cu); dt already rounded to bf16
 cudaError_t rk4_stage(int stage, bf16* out, const bf16* y, const bf16* k1, const bf16* k2, const bf16* k3, const bf16* k4, float dt,
                       size_t count, cudaStream_t s);
+// one elementwise stage of the SDE samplers on a bf16 state (see sde_step_kernel)
+cudaError_t sde_step(int mode, bf16* out, bf16* kout, const bf16* x, const bf16* v, const bf16* w, const bf16* a, const bf16* kin,
+                     float ratio, float var, float diffusion, float sqrt2d, float dt, float sqrt_dt, float half_dt, size_t count,
+                     cudaStream_t s);
 cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s);
 
 }  // namespace ndit

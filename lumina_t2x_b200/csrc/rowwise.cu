@@ -1234,6 +1234,53 @@ cudaError_t rk4_stage(int stage, bf16* out, const bf16* y, const bf16* k1, const
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// transport.Sampler.sample_sde on a bf16 state (transport.py:285-344, integrators.py:5-76; velocity model, Linear path).  Every
+// PyTorch tensor op of the reference rounds to bf16; the t-dependent scalars (computed by the caller with the same ops on a
+// one-element bf16 tensor) arrive as floats that hold bf16 values: ratio = alpha_t / d_alpha_t, var, diffusion, sqrt(2 diffusion).
+//   score      = ((ratio * v) - x) / var                         (path.py get_score_from_velocity)
+//   sde_drift  = v + diffusion * score
+// mode 0  Euler-Maruyama:  out = (x + drift * dt) + sqrt2d * (w * sqrt_dt)
+// mode 1  Heun, noise:     out = x + sqrt2d * (w * sqrt_dt)                                  (xhat)
+// mode 2  Heun, stage 1:   k = drift(x = xhat, v);  out = xhat + dt * k                       (k1 -> kout, xp -> out)
+// mode 3  Heun, stage 2:   k2 = drift(x = xp, v);   out = xhat + (0.5 dt) * (k1 + k2)         (xp in `x`, xhat in `a`, k1 in `kin`)
+struct SdeCoef { float ratio, var, diffusion, sqrt2d, dt, sqrt_dt, half_dt; };
+__global__ void sde_step_kernel(int mode, bf16* __restrict__ out, bf16* __restrict__ kout, const bf16* __restrict__ x,
+                                const bf16* __restrict__ v, const bf16* __restrict__ w, const bf16* __restrict__ a,
+                                const bf16* __restrict__ kin, SdeCoef c, size_t count) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float xv = __bfloat162float(x[i]);
+    if (mode == 1) {
+        const float n = bf16_round(c.sqrt2d * bf16_round(__bfloat162float(w[i]) * c.sqrt_dt));
+        out[i] = __float2bfloat16_rn(xv + n);
+        return;
+    }
+    const float vv = __bfloat162float(v[i]);
+    const float sc = bf16_round(bf16_round(bf16_round(c.ratio * vv) - xv) / c.var);
+    const float drift = bf16_round(vv + bf16_round(c.diffusion * sc));
+    if (mode == 0) {
+        const float x1 = bf16_round(xv + bf16_round(drift * c.dt));
+        const float n = bf16_round(c.sqrt2d * bf16_round(__bfloat162float(w[i]) * c.sqrt_dt));
+        out[i] = __float2bfloat16_rn(x1 + n);
+    } else if (mode == 2) {
+        kout[i] = __float2bfloat16_rn(drift);
+        out[i] = __float2bfloat16_rn(xv + bf16_round(c.dt * drift));
+    } else {
+        const float ks = bf16_round(__bfloat162float(kin[i]) + drift);
+        out[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + bf16_round(c.half_dt * ks));
+    }
+}
+
+cudaError_t sde_step(int mode, bf16* out, bf16* kout, const bf16* x, const bf16* v, const bf16* w, const bf16* a, const bf16* kin,
+                     float ratio, float var, float diffusion, float sqrt2d, float dt, float sqrt_dt, float half_dt, size_t count,
+                     cudaStream_t s) {
+    if (mode < 0 || mode > 3) return cudaErrorInvalidValue;
+    const SdeCoef c{ratio, var, diffusion, sqrt2d, dt, sqrt_dt, half_dt};
+    sde_step_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(mode, out, kout, x, v, w, a, kin, c, count);
+    return cudaGetLastError();
+}
+
 cudaError_t axpy_bf16(bf16* y_out, const bf16* y_in, const bf16* v, float dt, size_t count, cudaStream_t s) {
     axpy_bf16_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(y_out, y_in, v, dt, count);
     return cudaGetLastError();

@@ -442,6 +442,33 @@ class NextDiT(EngineModule):
             return out
 
 
+def _sample_sde_loop(self, z, pts, dt, sqrt_dt, half_dt, noise, method: int, cap_feats, cap_mask, cfg_scale, scale_factor=1.0,
+                     scale_watershed=1.0, base_seqlen: Optional[int] = None, proportional_attn: bool = False):
+    """The stochastic loop of transport.Sampler.sample_sde inside the engine (ndit_sample_sde); returns the list of states after
+    each step.  ``pts``: (t, ratio, var, diffusion, sqrt(2 diffusion)) per evaluation point, ``noise`` [n_steps, *z.shape] bf16."""
+    self._check_inputs(z, cap_feats, cap_mask, noise)
+    lib, h = self._engine(z.device)
+    n = noise.shape[0]
+    assert len(pts) == n * (2 if method == 1 else 1) and tuple(noise.shape[1:]) == tuple(z.shape)
+    with torch.cuda.device(z.device):
+        stream = C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)
+        self._ensure_capacity(lib, h, self._tokens_for(z.shape[2], z.shape[3]), cap_feats.shape[1], z.shape[0])
+        self._set_caption(lib, h, cap_feats, cap_mask, stream)
+        sp = self._step_params(cfg_scale, scale_factor, scale_watershed, base_seqlen, proportional_attn)
+        zb = z.detach().to(torch.bfloat16).contiguous()
+        nb = noise.detach().to(torch.bfloat16).contiguous()
+        traj = torch.empty_like(nb)
+        arr = (_lib.NditSdePoint * len(pts))(*[_lib.NditSdePoint(*p) for p in pts])
+        B, _, Hh, Ww = zb.shape
+        _lib.check(lib.ndit_sample_sde(h, C.c_void_p(zb.data_ptr()), B, Hh, Ww, n, int(method), arr, float(dt), float(sqrt_dt), float(half_dt),
+                                       C.c_void_p(nb.data_ptr()), C.byref(sp), C.c_void_p(traj.data_ptr()), stream), h)
+        self._remember_call_state(pts[-1][0], scale_factor, scale_watershed, base_seqlen, proportional_attn)
+    return [traj[i].to(z.dtype) for i in range(n)]
+
+
+NextDiT.sample_sde_loop = _sample_sde_loop
+
+
 def NextDiT_2B_patch2(**kwargs):
     """model.py:994-995."""
     return NextDiT(patch_size=2, dim=2304, n_layers=24, n_heads=32, **kwargs)

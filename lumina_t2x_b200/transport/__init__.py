@@ -211,13 +211,32 @@ class Sampler:
             return norm * th.sin(math.pi * t) ** 2
         raise NotImplementedError(f"Diffusion form {form} not implemented")
 
-    def _score(self, velocity, x, t):
-        """path.py ICPlan.get_score_from_velocity."""
-        t = self._expand(t, x)
+    @staticmethod
+    def _score_terms(t):
+        """The t-dependent factors of path.py ICPlan.get_score_from_velocity (alpha_t = t, sigma_t = 1 - t), same op sequence."""
         alpha_t, d_alpha_t, sigma_t, d_sigma_t = t, 1, 1 - t, -1
         reverse_alpha_ratio = alpha_t / d_alpha_t
         var = sigma_t ** 2 - reverse_alpha_ratio * d_sigma_t * sigma_t
+        return reverse_alpha_ratio, var
+
+    def _score(self, velocity, x, t):
+        """path.py ICPlan.get_score_from_velocity."""
+        reverse_alpha_ratio, var = self._score_terms(self._expand(t, x))
         return (reverse_alpha_ratio * velocity - x) / var
+
+    def _sde_points(self, times, like, form, norm):
+        """ndit_sde_point values for the in-engine SDE loop: the reference's own tensor ops on a one-element tensor of the state
+        dtype, so that every scalar carries exactly the roundings the reference applies to its [B,1,1,1] tensors."""
+        pts = []
+        probe = th.zeros(1, 1, 1, 1, dtype=like.dtype, device=like.device)
+        for tt in times:                                            # tt: one-element tensor of the state dtype (the `t` of the loop)
+            te = self._expand(tt, probe)
+            ratio, var = self._score_terms(te)
+            diff = self._diffusion(probe, tt, form, norm)
+            if not isinstance(diff, th.Tensor):
+                return None                                         # "constant": th.sqrt(2 * float) fails in the reference as well
+            pts.append((float(tt), float(ratio), float(var), float(diff), float(th.sqrt(2 * diff))))
+        return pts
 
     def sample_sde(self, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean",
                    last_step_size=0.04, num_steps=250):
@@ -248,10 +267,39 @@ class Sampler:
             v, sc = drift_and_score(x, t, model, kw)
             return v + self._diffusion(x, t, diffusion_form, diffusion_norm) * sc
 
+        def _fused_loop(init, model, kw):
+            """The stochastic loop inside the engine (ndit_sample_sde) when `model` is the engine's forward_with_cfg and the state
+            is bf16 on the GPU: noise drawn here exactly like the reference does (host RNG, one randn per step, same order), the
+            t-dependent scalars computed with the reference's own ops.  Returns the list of states after each step, or None."""
+            eng = _engine_of(model)
+            if eng is None or not hasattr(eng, "sample_sde_loop") or not (isinstance(init, th.Tensor) and init.is_cuda and init.dtype == th.bfloat16):
+                return None
+            allowed, required = _ENGINE_KW[type(eng)]
+            if not (set(kw) <= set(allowed) and set(required) <= set(kw)):
+                return None
+            # On the state's device, like the host loop: CUDA keeps a 0-dim CPU operand (ti, dt) in fp32 inside the op, the CPU
+            # casts it to the tensor dtype first - `t + dt` differs by an ulp between the two, and the loop below must see what
+            # the reference sees on this device.
+            one = th.ones(1).to(init)
+            times = []
+            for ti in grid[:-1]:
+                t = one * ti
+                times.append(t)
+                if sampling_method == "Heun":
+                    times.append(t + dt)
+            pts = self._sde_points(times, init, diffusion_form, diffusion_norm)
+            if pts is None:
+                return None
+            noise = th.stack([th.randn(init.size()).to(init.dtype) for _ in grid[:-1]]).to(init.device)
+            # dt, sqrt(dt), 0.5 * dt are 0-dim CPU tensors: a CUDA op takes them as fp32 scalars (no rounding to bf16)
+            return eng.sample_sde_loop(init, pts, float(dt), float(th.sqrt(dt)), float(0.5 * dt), noise,
+                                       0 if sampling_method == "Euler" else 1, **kw)
+
         def _sample(init, model, **kw):
             x, xs = init, []
             with th.no_grad():
-                for ti in grid[:-1]:
+                fused = _fused_loop(init, model, kw)
+                for ti in (grid[:-1] if fused is None else []):
                     w_cur = th.randn(x.size()).to(x)
                     dw = w_cur * th.sqrt(dt)
                     t = th.ones(x.size(0)).to(x) * ti
@@ -267,6 +315,8 @@ class Sampler:
                         k2 = sde_drift(xp, t + dt, model, kw)
                         x = xhat + 0.5 * dt * (k1 + k2)
                     xs.append(x)
+                if fused is not None:
+                    xs = list(fused)
                 ts = th.ones(init.size(0), device=init.device) * t1
                 x = xs[-1]
                 if last_step == "Mean":

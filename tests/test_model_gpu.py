@@ -176,6 +176,33 @@ def test_sampler_trajectory(tiny, method):
     assert torch.equal(traj, traj2)
 
 
+@pytest.mark.parametrize("method", ["Euler", "Heun"])
+@pytest.mark.parametrize("form", ["sigma", "decreasing", "inccreasing-decreasing"])   # SBDM is 1/t at t0 = 0: infinite in the reference too
+def test_sde_loop_in_engine_equals_host_loop(tiny, method, form):
+    """transport.Sampler.sample_sde: the stochastic loop inside the engine (ndit_sample_sde: bf16 state, the reference's rounding
+    after every tensor op, noise drawn on the host in the reference's order) against the host loop of the mirror - which is
+    bit-identical to the unmodified reference on the CPU fixture (test_host_cpu.py) - around the same engine forward_with_cfg."""
+    from lumina_t2x_b200 import transport
+    cfg, W, m = tiny
+    fx = torch.load(os.path.join(GOLD, "traj_euler.pt"), map_location="cpu", weights_only=False)
+    z, cap, mask = O.synthetic_inputs(cfg, tuple(fx["hw"]), fx["T"], fx["ul"], seed=fx["input_seed"])
+    tr = transport.create_transport("Linear", "velocity", None, None, None)
+    fn = transport.Sampler(tr).sample_sde(sampling_method=method, diffusion_form=form, diffusion_norm=1.0, last_step="Mean",
+                                          last_step_size=0.04, num_steps=6)
+    kw = dict(cap_feats=cap.cuda(), cap_mask=mask.cuda(), **fx["kw"])
+    zb = z.cuda().to(torch.bfloat16)
+    torch.manual_seed(123)
+    n0 = m.launch_count()
+    fused = fn(zb, m.forward_with_cfg, **kw)
+    torch.manual_seed(123)
+    host = fn(zb, lambda x, t, **k: m.forward_with_cfg(x, t, **k), **kw)      # a plain function: the mirror's own host loop
+    assert len(fused) == len(host) == 6
+    for i, (a, b) in enumerate(zip(fused, host)):
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.isfinite(a.float()).all(), i
+        assert torch.equal(a, b), (method, form, i, (a.float() - b.float()).abs().max().item())
+    assert m.launch_count() > n0
+
+
 def test_mini_ode_class_and_determinism(tiny):
     from lumina_t2x_b200 import transport
     cfg, W, m = tiny
