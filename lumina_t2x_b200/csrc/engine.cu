@@ -88,6 +88,12 @@ struct ndit_engine {
     int S = 1;                               // FFN weight slots per layer (sum over sub-blocks of max(E, 1))
     bf16 *Wg_time = nullptr, *Wg_space = nullptr;   // [L][E][cd] / [L][E][D]
     bf16 *oE = nullptr, *wtok = nullptr;     // expert outputs [E][M][D], token weights [M][E]
+    // token-routed experts as a grouped GEMM (option moe_grouped, default on): gathered rows of u / hidden / expert output, per
+    // expert a 256-row padded segment; rt = [cnt 8 | cntp 8 | off 9 | cursor 8] ints, pos = slot of each token in its two segments
+    bf16 *u_perm = nullptr, *h_perm = nullptr, *o_perm = nullptr;
+    int *rt = nullptr, *rpos = nullptr;
+    int moe_grouped = 1;
+    std::vector<GemmPlan> p_w13g, p_w2g;
     float *temb = nullptr, *tlogits = nullptr;      // [B][cd], [B][L*E]
     int* tsel = nullptr;                     // [L][2] experts chosen by the time gate (device; ascending index)
     float* tw = nullptr;                     // [L][2] their bf16-rounded softmax weights (device)
@@ -152,7 +158,7 @@ struct ndit_engine {
     // CUDA graphs of whole fixed-grid solves (ndit_sample): key = everything the captured launch sequence depends on
     struct SolveGraph {
         std::vector<float> grid;
-        int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0, vt_epi = 0;
+        int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0, vt_epi = 0, moe_grouped = 0;
         ndit_step_params sp;
         cudaGraphExec_t exec = nullptr;
         int64_t launches = 0;
@@ -261,6 +267,10 @@ static int alloc_workspace(ndit_engine* h) {
         int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
         WALLOC(oE, (size_t)emax * M * D); WALLOC(wtok, M * 8); WALLOC(temb, B * cd); WALLOC(tlogits, B * L * 8);
         WALLOC(tsel, L * 2); WALLOC(tw, L * 2);
+        if (c.moe_space_experts > 0) {
+            const size_t R = 2 * M + (size_t)c.moe_space_experts * 256;
+            WALLOC(u_perm, R * D); WALLOC(h_perm, R * F); WALLOC(o_perm, R * D); WALLOC(rt, 64); WALLOC(rpos, 2 * M);
+        }
     }
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
     WALLOC(vel, lat); WALLOC(ystate, lat); WALLOC(ymid, lat); WALLOC(kbuf[0], lat); WALLOC(kbuf[1], lat); WALLOC(kbuf[2], lat); WALLOC(stage_z, lat); WALLOC(stage_cap, B * T * C); WALLOC(stage_mask, B * T);
@@ -290,6 +300,7 @@ static int create_impl(ndit_engine* h) {
     h->D = c.dim; h->L = c.n_layers; h->H = c.n_heads; h->Hkv = c.n_kv_heads > 0 ? c.n_kv_heads : c.n_heads;
     if (getenv("NDIT_ATTN_GEN")) h->attn_tp = atoi(getenv("NDIT_ATTN_GEN"));
     if (getenv("NDIT_VT_EPI")) h->vt_epi = atoi(getenv("NDIT_VT_EPI"));
+    if (getenv("NDIT_MOE_GROUPED")) h->moe_grouped = atoi(getenv("NDIT_MOE_GROUPED"));
     if (getenv("NDIT_GRAPH")) h->use_graph = atoi(getenv("NDIT_GRAPH"));
     h->cls = c.num_classes > 0;
     h->flag = c.flag_dit != 0;
@@ -423,6 +434,7 @@ extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!strcmp(name, "graph")) { h->use_graph = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "pdl")) { h->pdl = value ? 1 : 0; return NDIT_OK; }
     if (!strcmp(name, "vt_epi")) { h->vt_epi = value; return NDIT_OK; }
+    if (!strcmp(name, "moe_grouped")) { h->moe_grouped = value; return NDIT_OK; }
     if (!strcmp(name, "tap_layer")) { h->tap_layer = value; return NDIT_OK; }
     if (!strcmp(name, "attn_gen") || !strcmp(name, "attn_tp")) { h->attn_tp = value; h->attn_plans_valid = false; return NDIT_OK; }
     if (!strcmp(name, "profile")) {
@@ -883,6 +895,28 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
                 }
             }
         }
+        h->p_w13g.clear(); h->p_w2g.clear();
+        for (int f = 0; f < h->NF; ++f) {
+            if (h->ffn_kind[f] != 2 || h->u_perm == nullptr) continue;
+            // grouped GEMM over the gathered rows: the maps span the whole gathered buffer, every expert's launch covers at most
+            // roundup(M, 256) rows of it, and which rows (offset, padded count) is read from device memory by the kernel
+            const int E = h->ffn_E[f];
+            const int R = 2 * M + E * 256, Mg = (M + 255) / 256 * 256;
+            h->p_w13g.resize(L * E); h->p_w2g.resize(L * E);
+            for (size_t l = 0; l < L; ++l) {
+                const size_t base = l * S + h->ffn_slot0[f];
+                for (int x = 0; x < E; ++x) {
+                    GemmPlan& a = h->p_w13g[l * E + x];
+                    GemmPlan& b = h->p_w2g[l * E + x];
+                    int e = make_gemm_plan(&a, h->u_perm, (int)D, h->W13 + (base + x) * 2 * F * D, h->h_perm, (int)F, R, (int)(2 * F), (int)D, EPI_SWIGLU, h->num_sms);
+                    e |= make_gemm_plan(&b, h->h_perm, (int)F, h->W2 + (base + x) * D * F, h->o_perm, (int)D, R, (int)D, (int)F, EPI_STORE, h->num_sms);
+                    if (e) return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
+                    a.M = Mg; b.M = Mg;
+                    a.rows = GemmRowWin{h->rt + 8 + x, h->rt + 16 + x};
+                    b.rows = a.rows;
+                }
+            }
+        }
         if (make_gemm_plan(&h->p_final, h->u, (int)D, h->Wout, h->tok, h->O, M, h->O, (int)D, EPI_STORE, h->num_sms, 0))
             return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
         h->p_final.bias = h->bout;
@@ -1099,6 +1133,16 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             } else {                                    // token-gated: every expert runs densely, the gate weights select
                 const int E = h->ffn_E[f];
                 PROF(KC_ROWWISE, moe_space_gate(h->u, h->Wg_space + (size_t)l * E * D, h->wtok, M, D, E, s));
+                if (h->moe_grouped && !h->p_w13g.empty()) {
+                    // every expert only sees the tokens that selected it (models1.py:471-476): gather, grouped GEMMs, routed combine
+                    int* rt = h->rt;
+                    PROF(KC_ROWWISE, moe_route(h->u, h->wtok, rt, rt + 8, rt + 16, rt + 32, h->rpos, h->u_perm, M, D, E, s));
+                    for (int e = 0; e < E; ++e) {
+                        PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13g[(size_t)l * E + e], s));
+                        PROF(KC_GEMM_W2, gemm_bf16_tn(h->p_w2g[(size_t)l * E + e], s));
+                    }
+                    PROF(KC_ROWWISE, moe_combine_routed(h->o_perm, h->rpos, h->wtok, h->o, M, D, E, s));
+                } else {
                 for (int e = 0; e < E; ++e) {
                     PROF(KC_GEMM_W13, gemm_bf16_tn(h->p_w13[base + e], s));
                     GemmPlan p2 = h->p_w2[base + e];
@@ -1106,6 +1150,7 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
                     PROF(KC_GEMM_W2, gemm_bf16_tn(p2, s));
                 }
                 PROF(KC_ROWWISE, moe_combine(h->oE, MD, E, h->wtok, nullptr, h->o, M, D, s));
+                }
             }
             // ---- gated (post-normed) residual, then the pre-norm + modulation of whatever runs next
             const bf16* post = h->flag ? nullptr : h->fn2 + ((size_t)f * L + l) * D;
@@ -1239,7 +1284,7 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
     ndit_engine::SolveGraph* hit = nullptr;
     for (auto& g : h->graphs) {
         if (g.batch == batch && g.height == height && g.width == width && g.method == method && g.cap_T == h->cap_T &&
-            g.with_traj == (int)with_traj && g.attn_ref == h->attn_ref && g.attn_tp == h->attn_tp && g.pdl == h->pdl && g.vt_epi == h->vt_epi &&
+            g.with_traj == (int)with_traj && g.attn_ref == h->attn_ref && g.attn_tp == h->attn_tp && g.pdl == h->pdl && g.vt_epi == h->vt_epi && g.moe_grouped == h->moe_grouped &&
             (int)g.grid.size() == n_grid && !memcmp(g.grid.data(), grid, n_grid * sizeof(float)) && !memcmp(&g.sp, sp, sizeof(*sp))) {
             hit = &g;
             break;
@@ -1252,7 +1297,7 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
         if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
         slot->grid.assign(grid, grid + n_grid);
         slot->batch = batch; slot->height = height; slot->width = width; slot->method = method; slot->cap_T = h->cap_T;
-        slot->with_traj = with_traj; slot->attn_ref = h->attn_ref; slot->attn_tp = h->attn_tp; slot->pdl = h->pdl; slot->vt_epi = h->vt_epi; slot->sp = *sp;
+        slot->with_traj = with_traj; slot->attn_ref = h->attn_ref; slot->attn_tp = h->attn_tp; slot->pdl = h->pdl; slot->vt_epi = h->vt_epi; slot->moe_grouped = h->moe_grouped; slot->sp = *sp;
         slot->launches = 0;
         slot->last_use = ++h->graph_clock;
         return 0;

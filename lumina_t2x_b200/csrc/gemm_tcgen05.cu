@@ -46,7 +46,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     bf16* __restrict__ C, const bf16* __restrict__ bias, const int* __restrict__ w_row_off, int w_row_mul, int M, int N,
-                    int K, int ldc, const GemmVtOut vt) {
+                    int K, int ldc, const GemmVtOut vt, const GemmRowWin rows) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -98,6 +98,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     pdl_wait();         // A (and the buffer behind C) belong to the previous kernel until it has completed
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+    // device-side row window (written by an earlier kernel: read after pdl_wait).  The static tile schedule covers the plan's M;
+    // every role skips the m-blocks past the window, identically, and counts only the tiles it really processes.
+    const int Meff = rows.count != nullptr ? min(M, *rows.count) : M;
+    const int row0 = rows.count != nullptr ? *rows.offset : 0;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -108,12 +112,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
+            if (m_blk * GEMM_BM >= Meff) continue;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d(sa, &tmA, full_bar(stage), kb * GEMM_BK, row0 + m_blk * GEMM_BM);
                     tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, w_off + n_blk * BN);
                 }
                 __syncwarp();
@@ -125,10 +130,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             // a ragged last-N tile only multiplies the columns that exist (UMMA N is a multiple of 16)
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
+            if (m_blk * GEMM_BM >= Meff) continue;
             const int n_rem = N - n_blk * BN;
             const uint32_t idesc = make_idesc_bf16(GEMM_BM, n_rem >= BN ? BN : ((n_rem + 15) & ~15));
             const int as = it & 1;
@@ -154,19 +160,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+            ++it;
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
+            if (m_blk * GEMM_BM >= Meff) continue;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
-            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            const int lrow = m_blk * GEMM_BM + q * 32 + lane;      // row inside the window
+            const int row = row0 + lrow;                            // row of A / C
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
             if (EPI == EPI_STORE) {
                 bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * BN;
@@ -176,7 +185,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tmem_ld_32x32b_x32(taddr + c * 32, v);
                     tmem_ld_wait();
                     const int col0 = n_blk * BN + c * 32;
-                    if (row < M) {
+                    if (lrow < Meff) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (col0 + j * 8 < N) {  // N % 8 == 0
@@ -215,7 +224,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tmem_ld_32x32b_x16(taddr + HN + c * 16, b);
                     tmem_ld_wait();
                     const int col0 = n_blk * HN + c * 16;
-                    if (row < M) {
+                    if (lrow < Meff) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             if (col0 + j * 8 < N / 2) {
@@ -240,6 +249,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
+            ++it;
         }
     }
 
@@ -273,7 +283,7 @@ template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      bf16* __restrict__ C, const int* __restrict__ w_row_off, int w_row_mul, int M, int N, int K, int ldc,
-                     const GemmVtOut vt) {
+                     const GemmVtOut vt, const GemmRowWin rows) {
     using Cfg = Gemm2Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -337,15 +347,19 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     pdl_wait();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+    // device-side row window, as in the single-CTA kernel: m-blocks past it are skipped by every role of both CTAs
+    const int Meff = rows.count != nullptr ? min(M, *rows.count) : M;
+    const int row0 = rows.count != nullptr ? *rows.offset : 0;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
         const int w_off = w_row_off != nullptr ? (*w_row_off) * w_row_mul : 0;     // device-selected matrix of a stacked W (MoE experts)
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int ti = 0; ti < my_tiles; ++ti) {
             int m_blk, n_blk;
-            tile_coords(my_tile(it), m_blk, n_blk);
+            tile_coords(my_tile(ti), m_blk, n_blk);
+            if (m_blk * 256 >= Meff) continue;
             // this CTA's half of the W tile: rows [w0, w0 + width/2) land at the start of its B buffer (a narrow tile's box
             // runs past its half - and possibly past N, zero-filled - which the narrower MMA never reads)
             const int w0 = w_off + n_blk * BN + static_cast<int>(rank) * ((n_blk < n_full ? BN : n_rem) / 2);
@@ -354,7 +368,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land on this barrier
-                    tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * GEMM_BK, m_blk * 256 + rank * 128);
+                    tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * GEMM_BK, row0 + m_blk * 256 + rank * 128);
                     tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, w0);
                 }
                 __syncwarp();
@@ -366,9 +380,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (leader) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < my_tiles; ++it) {
+            int it = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
                 int m_blk, n_blk;
-                tile_coords(my_tile(it), m_blk, n_blk);
+                tile_coords(my_tile(ti), m_blk, n_blk);
+                if (m_blk * 256 >= Meff) continue;
                 const uint32_t idesc = make_idesc_bf16(256, n_blk < n_full ? BN : n_rem);
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
@@ -390,19 +406,23 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
+                ++it;
             }
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
         const int q = warp & 3;
-        for (int it = 0; it < my_tiles; ++it) {
+        int it = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
             int m_blk, n_blk;
-            tile_coords(my_tile(it), m_blk, n_blk);
+            tile_coords(my_tile(ti), m_blk, n_blk);
+            if (m_blk * 256 >= Meff) continue;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
-            const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+            const int lrow = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;     // row inside the window
+            const int row = row0 + lrow;                                                         // row of A / C
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
             if (EPI == EPI_STORE) {
                 bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * BN;
@@ -417,7 +437,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     for (int j = 0; j < 4; ++j) {
                         if (col0 + j * 8 < N) {
                             if (vt.ptr != nullptr && col0 + j * 8 >= vt.col0) {
-                                if (row < M) store_vt8(vt, row, col0 + j * 8, v + j * 8);
+                                if (lrow < Meff) store_vt8(vt, row, col0 + j * 8, v + j * 8);
                                 continue;
                             }
                             uint4 o;
@@ -425,7 +445,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             o.y = pack_bf16(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
                             o.z = pack_bf16(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
                             o.w = pack_bf16(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-                            if (row < M) *reinterpret_cast<uint4*>(crow + c * 32 + j * 8) = o;
+                            if (lrow < Meff) *reinterpret_cast<uint4*>(crow + c * 32 + j * 8) = o;
                         }
                     }
                 }
@@ -450,13 +470,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         uint4 o;
                         o.x = pack_bf16(h[0], h[1]); o.y = pack_bf16(h[2], h[3]);
                         o.z = pack_bf16(h[4], h[5]); o.w = pack_bf16(h[6], h[7]);
-                        if (row < M) *reinterpret_cast<uint4*>(crow + c * 16 + j * 8) = o;
+                        if (lrow < Meff) *reinterpret_cast<uint4*>(crow + c * 16 + j * 8) = o;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);   // the leader's MMA warp owns the accumulator hand-off
+            ++it;
         }
     }
 
@@ -470,7 +491,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <int BN, int EPI>
 static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const int* w_row_off, int w_row_mul, int M, int N,
-                                int K, int ldc, int num_sms, const GemmVtOut& vt, cudaStream_t stream) {
+                                int K, int ldc, int num_sms, const GemmVtOut& vt, const GemmRowWin& rows, cudaStream_t stream) {
     auto kern = gemm2_bf16_tn_kernel<BN, EPI>;
     static PerDeviceFlag flags;
     bool& configured = flags.here();
@@ -482,14 +503,14 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt);
+    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt, rows);
 }
 
 // ---------------------------------------------------------------------------- host side
 
 template <int BN, int EPI>
 static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const bf16* bias, const int* w_row_off, int w_row_mul,
-                               int M, int N, int K, int ldc, int num_sms, const GemmVtOut& vt, cudaStream_t stream) {
+                               int M, int N, int K, int ldc, int num_sms, const GemmVtOut& vt, const GemmRowWin& rows, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tn_kernel<BN, EPI>;
     static PerDeviceFlag flags;
@@ -502,7 +523,7 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + BN - 1) / BN;
     int grid = m_tiles * n_tiles;
     if (grid > num_sms) grid = num_sms;
-    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, bias, w_row_off, w_row_mul, M, N, K, ldc, vt);
+    return launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, C, bias, w_row_off, w_row_mul, M, N, K, ldc, vt, rows);
 }
 
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
@@ -514,18 +535,18 @@ cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
         if (p.N % p.bn != 0 && (p.epi != EPI_STORE || p.bn != 256 || (p.N % 256) % 32 != 0)) return cudaErrorInvalidValue;
         if (p.epi == EPI_SWIGLU) {
             if (p.bn != 256) return cudaErrorInvalidValue;
-            return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
+            return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
         }
-        if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
-        return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
+        if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
+        return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
     }
     if (p.epi == EPI_SWIGLU) {
         if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;
-        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
+        return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
     }
-    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
-    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
-    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, stream);
+    if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
+    if (p.bn == 192) return launch_gemm<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
+    return launch_gemm<128, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
 }
 
 }  // namespace ndit

@@ -29,6 +29,13 @@ struct GemmVtOut {
     int col0;     // first value column = (H + Hkv) * hd
     int hd, hkv, vrows, npad, ntok;
 };
+// Optional device-side row window (token-routed mixture of experts: how many gathered rows an expert owns is only known on the
+// device): the kernel works on rows [*offset, *offset + *count) of A and C, count <= the plan's M (tiles past it are skipped).
+// count == nullptr: rows [0, M).
+struct GemmRowWin {
+    const int* count;
+    const int* offset;
+};
 struct GemmPlan {
     CUtensorMap tmA;  // A [M,K], box 128 x 64
     CUtensorMap tmB;  // W [N,K], box bn  x 64
@@ -42,6 +49,7 @@ struct GemmPlan {
     int epi;  // EPI_*
     int num_sms;
     GemmVtOut vt;   // zero-initialised by make_gemm_plan
+    GemmRowWin rows;
 };
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream);
 // builds the maps of a plan (A: [M,K] ld=lda; W: [N,K] ld=K)
@@ -128,6 +136,10 @@ cudaError_t unpatchify_cfg(const bf16* tok, bf16* v_out, int n, int C, int Hh, i
 // mixture-of-experts (class-conditional Next-DiT-MoE): token gate + expert-order bf16 accumulation (see rowwise.cu)
 cudaError_t moe_space_gate(const bf16* u, const bf16* Wg, bf16* wtok, int M, int D, int E, cudaStream_t s);
 // uniform_w: E weights in DEVICE memory (time-gated layer: written by moe_time_select)
+// token-routed experts as a grouped GEMM: segment bookkeeping + gather (see moe_route_count_kernel) and the routed combine
+cudaError_t moe_route(const bf16* u, const bf16* wtok, int* cnt, int* cntp, int* off, int* cursor, int* pos, bf16* u_perm, int M, int D, int E,
+                      cudaStream_t s);
+cudaError_t moe_combine_routed(const bf16* o_perm, const int* pos, const bf16* wtok, bf16* out, int M, int D, int E, cudaStream_t s);
 cudaError_t moe_combine(const bf16* oe, size_t estride, int E, const bf16* wtok, const float* uniform_w, bf16* out, int M, int D,
                         cudaStream_t s);
 // time gate (Next-DiT-MoE models.py:459-477): per layer the top-2 experts of the gate logits of batch row 0 (ascending expert

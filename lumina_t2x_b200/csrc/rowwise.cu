@@ -1169,6 +1169,94 @@ cudaError_t moe_combine(const bf16* oe, size_t estride, int E, const bf16* wtok,
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Token-routed experts as a grouped GEMM (MoeLayer.forward, Next-DiT-MoE models1.py:459-477: ``results[idx] += w * expert(x[idx])``
+// over the tokens that selected the expert).  The gate kernel left wtok[M][E] (non-zero = selected, exactly two per token).
+//   route_count : cnt[e] = tokens that selected expert e
+//   route_scan  : segment of expert e in the gathered buffers = rows [off[e], off[e] + cnt[e]), padded to 256 rows (GEMM tile);
+//                 cntp[e] = padded count (the GEMM's device-side row window), cursor[e] = 0
+//   route_gather: every token copies its row of u into the segments of its two experts (slot order inside a segment is whatever
+//                 the atomics give - each gathered row is computed on its own, so the result does not depend on it)
+//   combine     : out[token] = bf16(bf16(0 + bf16(w_a o_a)) + bf16(w_b o_b)), a < b the two selected experts - the same
+//                 arithmetic, in the same (expert index) order, as the dense moe_combine
+__global__ void moe_route_count_kernel(const bf16* __restrict__ wtok, int* __restrict__ cnt, int M, int E) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    for (int e = 0; e < E; ++e)
+        if (__bfloat162float(wtok[static_cast<size_t>(row) * E + e]) != 0.f) atomicAdd(cnt + e, 1);
+}
+__global__ void moe_route_scan_kernel(int* __restrict__ cnt, int* __restrict__ cntp, int* __restrict__ off, int* __restrict__ cursor, int E) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int o = 0;
+    for (int e = 0; e < E; ++e) {
+        const int c = cnt[e], cp = (c + 255) / 256 * 256;
+        off[e] = o; cntp[e] = cp; cursor[e] = 0;
+        o += cp;
+        cnt[e] = 0;                       // ready for the next layer
+    }
+    off[E] = o;
+}
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+moe_route_gather_kernel(const bf16* __restrict__ u, const bf16* __restrict__ wtok, const int* __restrict__ off, int* __restrict__ cursor,
+                        int* __restrict__ pos, bf16* __restrict__ u_perm, int M, int D, int E) {
+    const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    int p[2] = {-1, -1};
+    if (lane == 0) {
+        int k = 0;
+        for (int e = 0; e < E && k < 2; ++e)
+            if (__bfloat162float(wtok[static_cast<size_t>(row) * E + e]) != 0.f) p[k++] = off[e] + atomicAdd(cursor + e, 1);
+        pos[2 * row] = p[0];
+        pos[2 * row + 1] = p[1];
+    }
+    p[0] = __shfl_sync(0xffffffffu, p[0], 0);
+    p[1] = __shfl_sync(0xffffffffu, p[1], 0);
+    const uint4* src = reinterpret_cast<const uint4*>(u + static_cast<size_t>(row) * D);
+    for (int v = lane; v < D / 8; v += 32) {
+        const uint4 x = src[v];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (p[k] >= 0) reinterpret_cast<uint4*>(u_perm + static_cast<size_t>(p[k]) * D)[v] = x;
+    }
+}
+__global__ void moe_combine_routed_kernel(const bf16* __restrict__ o_perm, const int* __restrict__ pos, const bf16* __restrict__ wtok,
+                                          bf16* __restrict__ out, size_t count8, int D, int E) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // one 8-element vector
+    if (i >= count8) return;
+    const size_t row = (i * 8) / D;
+    const int col = static_cast<int>(i * 8 - row * D);
+    float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (int e = 0; e < E && k < 2; ++e) {
+        const float w = __bfloat162float(wtok[row * E + e]);
+        if (w == 0.f) continue;
+        const int p = pos[2 * row + k];
+        ++k;
+        float o[8];
+        load8(o_perm + static_cast<size_t>(p) * D + col, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = bf16_round(r[j] + bf16_round(w * o[j]));
+    }
+    store8(out + i * 8, r);
+}
+
+cudaError_t moe_route(const bf16* u, const bf16* wtok, int* cnt, int* cntp, int* off, int* cursor, int* pos, bf16* u_perm, int M, int D, int E,
+                      cudaStream_t s) {
+    if (E < 2 || E > 8 || D % 8 != 0) return cudaErrorInvalidValue;
+    moe_route_count_kernel<<<(M + 255) / 256, 256, 0, s>>>(wtok, cnt, M, E);
+    moe_route_scan_kernel<<<1, 32, 0, s>>>(cnt, cntp, off, cursor, E);
+    moe_route_gather_kernel<<<(M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(u, wtok, off, cursor, pos, u_perm, M, D, E);
+    return cudaGetLastError();
+}
+
+cudaError_t moe_combine_routed(const bf16* o_perm, const int* pos, const bf16* wtok, bf16* out, int M, int D, int E, cudaStream_t s) {
+    if (E < 2 || E > 8 || D % 8 != 0) return cudaErrorInvalidValue;
+    const size_t count8 = static_cast<size_t>(M) * D / 8;
+    moe_combine_routed_kernel<<<static_cast<unsigned>((count8 + 255) / 256), 256, 0, s>>>(o_perm, pos, wtok, out, count8, D, E);
+    return cudaGetLastError();
+}
+
 // One thread per layer: top-2 of E gate logits (ties: lower expert index first), softmax over the two, bf16-rounded weights,
 // stored in ascending expert order (the reference accumulates ``results += w * expert(x)`` in expert-index order).
 __global__ void moe_time_select_kernel(const float* __restrict__ logits, int L, int E, int* __restrict__ sel, float* __restrict__ w) {

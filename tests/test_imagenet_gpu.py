@@ -126,6 +126,26 @@ def test_moe_forward_with_cfg_vs_reference_and_oracle(name):
         assert err.max() < 2.0 * max(_rel(orc, ref), 5e-2), (err.max(), _rel(orc, ref))
 
 
+@pytest.mark.parametrize("name", ["moe_tiny_space", "moe_tiny_both"])
+def test_moe_grouped_gemm_equals_dense_experts(name):
+    """Token-gated experts: the default path gathers every expert's tokens and runs grouped GEMMs over them (device-side row
+    windows, models1.py:471-476); the option moe_grouped = 0 runs every expert densely on all tokens and masks with the gate
+    weights.  Each gathered row is computed exactly as in the dense product, and the combine uses the same order: same bits."""
+    fx = torch.load(os.path.join(GOLD, f"{name}.pt"), map_location="cpu", weights_only=False)
+    cfg = DL.DiTLlamaConfig(**fx["cfg"])
+    W = DL.synthetic_weights(cfg, seed=fx["weight_seed"])
+    z, y = DL.synthetic_inputs(cfg, tuple(fx["hw"]), tuple(fx["labels"]), seed=fx["input_seed"])
+    t = torch.full((len(z),), fx["t"]).cuda()
+    m = _build_moe(cfg, W, fx["hw"][0], max_tokens=512)
+    outs = []
+    for g in (1, 0, 1):
+        m.set_option("moe_grouped", g)
+        outs.append(m.forward_with_cfg(z.cuda(), t, y.cuda(), fx["cfg_scale"]).clone())
+    m.set_option("moe_grouped", 1)
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_moe_600m_both_config5_runs_in_engine_solver():
     """BASELINE config 5: DiT_Llama_600M_patch2_Both, 512x512 (latent 64x64, 1024 tokens), Euler solve inside the engine;
     3 of the 30 grid points keep the test short.  Checks structure (finite, CFG channels tied) and determinism."""
@@ -150,3 +170,6 @@ def test_moe_600m_both_config5_runs_in_engine_solver():
     assert a.shape == (3, 2, 4, 64, 64) and torch.isfinite(a.float()).all()
     assert torch.equal(a, b)
     assert torch.equal(a[-1][0, :3], a[-1][1, :3])
+    m.set_option("moe_grouped", 0)           # dense experts: same bits at full size (1024 tokens, 4 space experts) as well
+    assert torch.equal(a, fn(z, m.forward_with_cfg, y=y, cfg_scale=4.0))
+    m.set_option("moe_grouped", 1)
