@@ -222,6 +222,10 @@ int ndit_op_attention_hd(const void* qkv_dev, const void* kvy_dev, const uint8_t
 int ndit_op_attention_bench(const void* qkv_dev, const void* kvy_dev, const uint8_t* ymask_dev, const float* gate_tanh_dev,
                             void* out_dev, int32_t B, int32_t N, int32_t T, int32_t H, int32_t Hkv, float scale_self,
                             float scale_cross, int32_t iters, float* ms_out, void* stream);
+/* token gate of the mixture-of-experts FFN (Next-DiT-MoE models1.py:461-470): logits = bf16(u Wg^T) (fp32 accumulate), top-2 per
+ * token (ties: lower expert index), weights = bf16(softmax over the two).  u bf16 [M, D], Wg bf16 [E, D], 2 <= E <= 8;
+ * wtok bf16 [M, E]: the weight of each selected expert, 0 for the others. */
+int ndit_op_moe_gate(const void* u_dev, const void* Wg_dev, void* wtok_dev, int32_t M, int32_t D, int32_t E, void* stream);
 /* X += tanh_g * RMS(o; w_post) (skipped if o NULL; w_post NULL: X += tanh_g * o, Flag-DiT);
  * u = RMS(X; w_pre) * onepls (+ shift if not NULL)   (model.py:597-610; lumina_t2i model.py:596-609);
  * tanh_g / onepls / shift: bf16 [M / rows_per_batch, D] */

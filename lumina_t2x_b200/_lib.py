@@ -49,6 +49,7 @@ SIGNATURES = {
     "ndit_forward_cfg": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),
     "ndit_forward": (C.c_int, [_vp, _vp, C.POINTER(_f32), _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),
     "ndit_debug_read_residual": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "ndit_op_moe_gate": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "ndit_forward_list": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f32), _i32,
                                     C.POINTER(NditStepParams), C.POINTER(_vp), _vp]),
     "ndit_sample": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_f32), _i32, _i32, C.POINTER(NditStepParams),

@@ -40,7 +40,12 @@
 //     chunk c's 32 MUFU.EX2, behind always-true branches ptxas cannot fold - it schedules inside basic blocks only, and left alone
 //     puts every PRMT 17 cycles behind its own MUFU pair): the SASS then issues one MUFU every 8 cycles with everything else in
 //     the gaps, but the kernel takes 479 us - same mechanism, the exp phase of one tile now overlaps the other tile's;
-//   * making the PRMT selector depend on the chunk's last exponential: ptxas simply computes that exponential first.
+//   * making the PRMT selector depend on the chunk's last exponential: ptxas simply computes that exponential first;
+//   * the two tiles taking strict turns on the XU pipe (mbarrier token), alone and combined with the two changes above:
+//     460 us (token only), 444 (+ basic-block pipelining), 446 (+ elect.sync) against 423 us on the same box: with the exponentials
+//     of a tile down to ~1070 cycles per block the other tile is NOT ready when the token arrives - its own chain of barrier
+//     waits, TMEM loads, row maximum and P hand-over takes ~2200 cycles per block, and that chain, not the exp loop, is the bound
+//     (profiles/r02_attention_third_generation_log.txt).
 // Q is a TENSOR-MEMORY operand (head_dim 72 / 48): copied once per CTA from its TMA tile into free TMEM columns, so Q K^T
 // reads only K from shared memory (416.7 -> 412.9 us on the config-2 shape; -14 % shared-memory traffic).
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,256+HDP) Q_A [256+HDP, ..+40) O_B [384,384+HDP) Q_B [384+HDP, ..+40).

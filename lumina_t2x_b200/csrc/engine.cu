@@ -1588,6 +1588,12 @@ extern "C" int ndit_op_attention_bench(const void* qkv_, const void* kvy_, const
     return op_attention_impl(qkv_, kvy_, ymask, gate_tanh, out, B, N, T, H, Hkv, scale_self, scale_cross, 0, stream, iters, ms_out, 72);
 }
 
+extern "C" int ndit_op_moe_gate(const void* u, const void* Wg, void* wtok, int32_t M, int32_t D, int32_t E, void* stream) {
+    cudaError_t e = moe_space_gate(static_cast<const bf16*>(u), static_cast<const bf16*>(Wg), static_cast<bf16*>(wtok), M, D, E,
+                                   static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NDIT_OK : op_fail(NDIT_ERR_CUDA, "ndit_op_moe_gate", e);
+}
+
 extern "C" int ndit_op_resid_rms_mod(void* X, const void* o, const void* w_post, const void* tanh_g, const void* w_pre,
                                      const void* onepls, const void* shift, void* u, int32_t M, int32_t rows_per_batch, int32_t D,
                                      float eps, void* stream) {

@@ -227,3 +227,37 @@ def test_resid_rms_mod(lib, M, rows, D, with_o):
         frac_exact = (err == 0).float().mean().item()
         assert (err <= tol).all(), name + " " + _diag(got, ref)
         assert frac_exact > 0.98, (name, frac_exact)
+
+
+@pytest.mark.parametrize("M,D,E", [(512, 1152, 4), (300, 576, 8), (2048, 1536, 2)])
+def test_moe_token_gate_routing(lib, M, D, E):
+    """Token gate of the MoE FFN (models1.py:461-470) against an fp64 evaluation: every token whose top-2 set is decided by more than
+    the bf16 resolution of the logits must be routed identically and its two weights must be the bf16 softmax of the bf16 logits;
+    near-ties (a bf16 logit tie between the 2nd and 3rd expert, or between the two selected ones) may go either way and are counted."""
+    g = torch.Generator(device="cuda").manual_seed(M + E)
+    u = torch.randn(M, D, device="cuda", generator=g).to(torch.bfloat16)
+    Wg = (torch.randn(E, D, device="cuda", generator=g) / D ** 0.5).to(torch.bfloat16)
+    wtok = torch.full((M, E), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rc = lib.ndit_op_moe_gate(ptr(u), ptr(Wg), ptr(wtok), M, D, E, None)
+    torch.cuda.synchronize()
+    assert rc == 0, lib.ndit_last_error(None)
+    w = wtok.float()
+    assert torch.isfinite(w).all() and ((w != 0).sum(1) == 2).all() and (w >= 0).all()
+    logits = (u.double() @ Wg.double().T)
+    lb = logits.float().to(torch.bfloat16).float()                       # what the gate Linear returns under autocast
+    top = torch.topk(lb, min(3, E), dim=1)
+    clear = torch.ones(M, dtype=torch.bool, device="cuda")
+    if E > 2:
+        clear &= (top.values[:, 1] - top.values[:, 2]) > 2.0 ** -6 * top.values[:, 1].abs().clamp_min(1e-3)
+    sel_ref = torch.zeros(M, E, dtype=torch.bool, device="cuda").scatter_(1, top.indices[:, :2], True)
+    agree = ((w != 0) == sel_ref).all(1)
+    assert agree[clear].all(), f"{(~agree[clear]).sum().item()} clearly decided tokens routed differently"
+    assert clear.float().mean() > 0.9
+    # weights: softmax over the two selected bf16 logits, rounded to bf16
+    l0, l1 = top.values[:, 0], top.values[:, 1]
+    e1 = torch.exp(l1 - l0)
+    w0, w1 = (1 / (1 + e1)).to(torch.bfloat16).float(), (e1 / (1 + e1)).to(torch.bfloat16).float()
+    got0 = w.gather(1, top.indices[:, :1]).squeeze(1)
+    got1 = w.gather(1, top.indices[:, 1:2]).squeeze(1)
+    ok = clear & agree
+    assert ((got0 - w0).abs()[ok] <= 2.0 ** -8).all() and ((got1 - w1).abs()[ok] <= 2.0 ** -8).all()
