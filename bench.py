@@ -83,11 +83,13 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    `ncu --set full` capture of one gemm2_bf16_tn_kernel launch (the wo projection, 8192x2304x2304: 86 MB algorithmic,
-    profiles/r01_ncu_gemm2_pair_full.txt -> profiles/ncu_traffic.json via tools/ncu_summarize.py); None if absent."""
+    `ncu --set full` capture of one gemm2_bf16_tn_kernel launch (round 2: the w2 projection of block 0, 8192x2304x6144: 166.7 MB
+    algorithmic, 177.7 MB measured; profiles/r02_ncu_gemm2_bf16_tn_kernel_full.txt -> profiles/ncu_traffic.json); None if absent.
+    ncu cannot run inside the timed region, so this is a recorded per-launch figure of the same kernel and shape, not a live one."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p))["gemm_first_pair"]
+        d = json.load(open(p))
+        return d.get("gemm_w2_pair", d.get("gemm_first_pair"))
     except Exception:
         return None
 
@@ -467,7 +469,9 @@ def run_engine(args, rank, local_rank, world):
         "frac_of_bf16_peak_whole_path": total_tf * lat_per_s / world / pk["bf16"],
         "roofline": {"kernel": "gemm_bf16_tn_kernel (tcgen05, all four projections of the block)", "bound": "tensor",
                      "achieved": gemm_tflops, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["bf16"],
-                     "traffic": ncu_traffic(), "peak_source": pk["src"], "launches_timed": gemm_launches,
+                     "traffic": ncu_traffic(), "traffic_note": "ncu --set full, one launch of the same kernel (w2 projection, 8192x2304x6144; "
+                     "166.7 MB algorithmic), recorded in profiles/ncu_traffic.json - ncu cannot run inside the timed region",
+                     "peak_source": pk["src"], "launches_timed": gemm_launches,
                      "share_of_step": gemm_ms / prof_total if prof_total else None},
         "kernels": {**prof, "attention_tflops": attn_tflops, "attention_frac_of_peak": attn_tflops / pk["bf16"]},
     }
