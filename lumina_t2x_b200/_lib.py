@@ -71,6 +71,22 @@ SIGNATURES = {
     "ndit_op_resid_rms_mod": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
 }
 
+class NtxtConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("vocab_size", "hidden_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads",
+                                         "head_dim", "intermediate_size")] + [("rms_norm_eps", C.c_float), ("rope_theta", C.c_float),
+                                                                              ("max_tokens", C.c_int32)]
+
+
+# include/ndit_text.h (caption-encoder end)
+TEXT_SIGNATURES = {
+    "ntxt_create": (C.c_int, [C.POINTER(NtxtConfig), C.POINTER(_vp)]),
+    "ntxt_destroy": (C.c_int, [_vp]),
+    "ntxt_last_error": (C.c_char_p, [_vp]),
+    "ntxt_set_weight": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _i32, _vp]),
+    "ntxt_finalize_weights": (C.c_int, [_vp, _vp]),
+    "ntxt_encode": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+}
+
 _lib = None
 
 
@@ -85,7 +101,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: the B200 engine has no fallback path. Build it with "
             "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(TEXT_SIGNATURES.items()):
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libndit_b200.so")
-SOURCES = ["engine.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention_hr_tcgen05.cu", "rowwise.cu", "tensormap.cu"]
+SOURCES = ["engine.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention_hr_tcgen05.cu", "rowwise.cu", "tensormap.cu", "text_encoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -37,6 +37,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", defs: s
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "ndit.h"))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "ndit_text.h"))
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

@@ -233,7 +233,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 for (int e = 0; e < 8; ++e) {
                                     const float x1 = bf16_round(__uint_as_float(a[j * 8 + e]));
                                     const float x3 = bf16_round(__uint_as_float(b[j * 8 + e]));
-                                    h[e] = bf16_round(silu_f(x1)) * x3;
+                                    h[e] = bf16_round(EPI == EPI_GEGLU ? gelu_tanh_f(x1) : silu_f(x1)) * x3;
                                 }
                                 uint4 o;
                                 o.x = pack_bf16(h[0], h[1]);
@@ -465,7 +465,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         for (int e = 0; e < 8; ++e) {
                             const float x1 = bf16_round(__uint_as_float(a[j * 8 + e]));
                             const float x3 = bf16_round(__uint_as_float(b[j * 8 + e]));
-                            h[e] = bf16_round(silu_f(x1)) * x3;
+                            h[e] = bf16_round(EPI == EPI_GEGLU ? gelu_tanh_f(x1) : silu_f(x1)) * x3;
                         }
                         uint4 o;
                         o.x = pack_bf16(h[0], h[1]); o.y = pack_bf16(h[2], h[3]);
@@ -528,20 +528,23 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, b
 
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     if (p.N % 8 != 0 || p.K % 8 != 0) return cudaErrorInvalidValue;
+    if (p.epi != EPI_STORE && !epi_gated(p.epi)) return cudaErrorInvalidValue;
     if (p.bias != nullptr && (p.pair || p.epi != EPI_STORE)) return cudaErrorInvalidValue;
     if (p.vt.ptr != nullptr && (p.epi != EPI_STORE || p.bias != nullptr || p.vt.col0 % 8 != 0 || p.vt.hd % 8 != 0)) return cudaErrorInvalidValue;
     if (p.pair) {
         // ragged M is fine (zero-filled loads, masked stores); a ragged last-N tile (multiple of 32 wide) only for plain stores
         if (p.N % p.bn != 0 && (p.epi != EPI_STORE || p.bn != 256 || (p.N % 256) % 32 != 0)) return cudaErrorInvalidValue;
-        if (p.epi == EPI_SWIGLU) {
+        if (epi_gated(p.epi)) {
             if (p.bn != 256) return cudaErrorInvalidValue;
+            if (p.epi == EPI_GEGLU) return launch_gemm2<256, EPI_GEGLU>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
             return launch_gemm2<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
         }
         if (p.bn == 192) return launch_gemm2<192, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
         return launch_gemm2<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
     }
-    if (p.epi == EPI_SWIGLU) {
+    if (epi_gated(p.epi)) {
         if (p.bn != 256 || p.N % 256 != 0) return cudaErrorInvalidValue;
+        if (p.epi == EPI_GEGLU) return launch_gemm<256, EPI_GEGLU>(p.tmA, p.tmB, p.C, nullptr, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
         return launch_gemm<256, EPI_SWIGLU>(p.tmA, p.tmB, p.C, nullptr, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);
     }
     if (p.bn == 256) return launch_gemm<256, EPI_STORE>(p.tmA, p.tmB, p.C, p.bias, p.w_row_off, p.w_row_mul, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream);

@@ -20,7 +20,8 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 const char* tmap_last_error();
 
 // ---------------------------------------------------------------- GEMM (gemm_tcgen05.cu)
-enum { EPI_STORE = 0, EPI_SWIGLU = 1 };
+enum { EPI_STORE = 0, EPI_SWIGLU = 1, EPI_GEGLU = 2 };   // gated epilogues: silu(a) * b (Next-DiT FFN) / gelu_tanh(a) * b (Gemma MLP)
+inline bool epi_gated(int epi) { return epi == EPI_SWIGLU || epi == EPI_GEGLU; }
 // Optional second destination of an EPI_STORE GEMM (the fused q|k|v projection): output columns >= col0 are the value heads and go,
 // transposed, straight into the attention kernel's V^T buffer [batch * Hkv][vrows][npad] (replaces transpose_v and the 2 x 9.4 MB
 // round trip through the qkv buffer).  ptr == nullptr: plain store.

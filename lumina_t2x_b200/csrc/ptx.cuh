@@ -289,5 +289,10 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
     return __bfloat1622float2(h);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// gelu(approximate="tanh") as PyTorch evaluates it in fp32 (transformers ACT2FN["gelu_pytorch_tanh"])
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    const float k = 0.7978845608028654f;      // sqrt(2 / pi)
+    return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
 
 }  // namespace ndit

@@ -82,13 +82,13 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
     // BN = 128 only when there would be too few 256-wide tiles to occupy the SMs.
     const int m_tiles = (M + 127) / 128;
     int bn = 256;
-    if (epi != EPI_SWIGLU && m_tiles * ((N + 255) / 256) < num_sms) bn = 128;
+    if (!epi_gated(epi) && m_tiles * ((N + 255) / 256) < num_sms) bn = 128;
     // wave quantisation: the fused q|k|v projection (N = 3456 = 13.5 x 256 = 18 x 192) needs 7 rounds of 256-wide tiles on 148
     // SMs (6.05 waves) but 8 rounds of 192-wide ones: 8 x 0.75 = 6.0 tile-times instead of 6.5
     // MEASURED (B200, 8192 x 3456 x 2304): 108.7 us with 192-wide tiles vs 104.1 us with 256-wide ones - the extra shared-memory
     // operand traffic per flop costs more than the saved half round.  Off unless NDIT_GEMM_BN192=1.
     static const int bn192_env = getenv("NDIT_GEMM_BN192") ? atoi(getenv("NDIT_GEMM_BN192")) : 0;
-    if (bn192_env && bn == 256 && epi != EPI_SWIGLU && N % 192 == 0 && N % 256 != 0) {
+    if (bn192_env && bn == 256 && !epi_gated(epi) && N % 192 == 0 && N % 256 != 0) {
         const long t256 = (long)m_tiles * ((N + 255) / 256), t192 = (long)m_tiles * (N / 192);
         const long r256 = (t256 + num_sms - 1) / num_sms, r192 = (t192 + num_sms - 1) / num_sms;
         if (r192 * 3 < r256 * 4) bn = 192;
@@ -102,8 +102,8 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
         // BN = 192 (N = 3456) measured slower than the single-CTA kernel (108 vs 103 us): only behind NDIT_GEMM_PAIR=2
         // N need not be a multiple of 256: a narrower last-N tile (a multiple of 32 columns) runs as a narrower cta_group::2 MMA
         // (fused q|k|v, N = 3456: 13 full tiles + one 128-wide per 256 rows).  NDIT_GEMM_PAIR=2: 192-wide tiles instead (slower).
-        int pbn = (N % 256 == 0 || (epi != EPI_SWIGLU && (N % 256) % 32 == 0 && N > 256)) ? 256 : 0;
-        if (pair_env >= 2 && N % 192 == 0 && N % 256 != 0 && epi != EPI_SWIGLU) pbn = 192;
+        int pbn = (N % 256 == 0 || (!epi_gated(epi) && (N % 256) % 32 == 0 && N > 256)) ? 256 : 0;
+        if (pair_env >= 2 && N % 192 == 0 && N % 256 != 0 && !epi_gated(epi)) pbn = 192;
         if (pbn && ((M + 255) / 256) * ((N + pbn - 1) / pbn) >= num_sms / 2) { p->pair = 1; p->bn = pbn; }
     }
     if (make_tmap_2d(&p->tmA, A, M, K, lda, 128, 64, 128)) return -1;

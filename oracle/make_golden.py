@@ -375,8 +375,42 @@ def make_list_forward() -> None:
     torch.save(fx, os.path.join(OUT, "list_forward.pt"))
 
 
+def make_gemma() -> None:
+    """Caption-encoder end: transformers' own GemmaModel (the reference's third-party text encoder, sample.py:46-50,111) with the
+    oracle's seeded weights, small config with the real head_dim / activation; hidden_states[-2] in fp32 and in bf16 (CPU)."""
+    from transformers import GemmaConfig, GemmaModel
+    import transformers
+    from oracle import gemma_oracle as G
+    cfg = G.config_tiny()
+    W = G.synthetic_weights(cfg, seed=0)
+    hc = GemmaConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
+                     num_attention_heads=cfg.num_attention_heads, num_key_value_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim,
+                     intermediate_size=cfg.intermediate_size, hidden_act="gelu_pytorch_tanh", rms_norm_eps=cfg.rms_norm_eps,
+                     max_position_embeddings=1024)
+    torch.set_grad_enabled(False)
+    m32 = GemmaModel(hc).eval()
+    m32.load_state_dict({k: v.float() for k, v in W.items()}, strict=True)
+    m16 = GemmaModel(hc).eval().to(torch.bfloat16)
+    m16.load_state_dict(W, strict=True)
+    cases = []
+    for B, T, seed in ((2, 24, 1), (3, 40, 2), (1, 8, 3)):
+        ids, mask = G.synthetic_inputs(cfg, B, T, seed)
+        h32 = m32(input_ids=ids, attention_mask=mask, output_hidden_states=True).hidden_states[-2]
+        h16 = m16(input_ids=ids, attention_mask=mask, output_hidden_states=True).hidden_states[-2]
+        o32 = G.hidden_states_m2(cfg, W, ids, mask, "fp32")
+        o16 = G.hidden_states_m2(cfg, W, ids, mask, "bf16")
+        valid = mask.bool()
+        rel = lambda a, b: ((a.float() - b.float())[valid].abs().max() / b.float()[valid].abs().max()).item()
+        print(f"gemma B={B} T={T}: |h| max {h32.abs().max().item():.3f}  oracle fp32 vs HF fp32 {rel(o32, h32):.2e}  HF bf16 vs fp32 {rel(h16, h32):.2e}  "
+              f"oracle bf16 vs HF fp32 {rel(o16, h32):.2e}")
+        cases.append(dict(ids=ids, mask=mask, h_fp32=h32.clone(), h_bf16_cpu=h16.clone()))
+    torch.save(dict(cfg=cfg.__dict__, weight_seed=0, transformers=transformers.__version__, cases=cases), os.path.join(OUT, "gemma_tiny.pt"))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "plain_forward":
+    if len(sys.argv) > 1 and sys.argv[1] == "gemma":
+        make_gemma()
+    elif len(sys.argv) > 1 and sys.argv[1] == "plain_forward":
         make_plain_forward()
     elif len(sys.argv) > 1 and sys.argv[1] == "list_forward":
         make_list_forward()
@@ -384,3 +418,4 @@ if __name__ == "__main__":
         main()
         make_plain_forward()
         make_list_forward()
+        make_gemma()

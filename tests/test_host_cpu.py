@@ -26,6 +26,12 @@ def test_cabi_loads_and_exports_header_symbols():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.ndit_abi_version() == 4
+    # the caption-encoder end has its own header
+    theader = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ndit_text.h")).read(), flags=re.S)
+    tdeclared = set(re.findall(r"\b(ntxt_[a-z_0-9]+)\s*\(", theader))
+    assert tdeclared == set(_lib.TEXT_SIGNATURES), tdeclared ^ set(_lib.TEXT_SIGNATURES)
+    for name in tdeclared:
+        assert hasattr(lib, name), name
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
