@@ -176,6 +176,9 @@ class EngineModule(nn.Module):
         """Grow the engine workspace (weights stay packed) when a call needs more tokens / caption tokens / rows than
         the handle was created for: an unmodified sample.py at 2048x2048 must not fail on a default-constructed model."""
         t, c, b = self._limits
+        batch += batch & 1                       # the workspace is sized for 2 or 4 rows
+        if batch > 4:
+            raise ValueError("the B200 engine runs at most 4 rows per call (a CFG pair of 2 samples, or 4 plain rows)")
         if tokens > t or cap_len > c or batch > b:
             self._limits = (max(t, tokens), max(c, cap_len), max(b, batch))
             _lib.check(lib.ndit_reserve(h, *self._limits), h)
