@@ -1244,6 +1244,8 @@ __global__ void moe_combine_routed_kernel(const bf16* __restrict__ o_perm, const
 cudaError_t moe_route(const bf16* u, const bf16* wtok, int* cnt, int* cntp, int* off, int* cursor, int* pos, bf16* u_perm, int M, int D, int E,
                       cudaStream_t s) {
     if (E < 2 || E > 8 || D % 8 != 0) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int) * E, s);     // also after a forward that failed half way
+    if (e != cudaSuccess) return e;
     moe_route_count_kernel<<<(M + 255) / 256, 256, 0, s>>>(wtok, cnt, M, E);
     moe_route_scan_kernel<<<1, 32, 0, s>>>(cnt, cntp, off, cursor, E);
     moe_route_gather_kernel<<<(M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, s>>>(u, wtok, off, cursor, pos, u_perm, M, D, E);
