@@ -143,8 +143,37 @@ class DiT_Llama(EngineModule):
         lin, ntk = getattr(self, "_rope_override", (1.0, 1.0))
         return _lib.NditStepParams(float(cfg_scale), lin, 1.0, 0, 0, ntk)
 
+    @torch.no_grad()
     def forward(self, x, t, y):
-        raise NotImplementedError("the B200 engine accelerates forward_with_cfg (the sampling path); training forward is out of scope")
+        """models.py:920-944 (inference): x [N,C,H,W], t [N], y [N] labels -> first C output channels [N,C,H,W]; no guidance, one
+        timestep and label per row, rows in groups of at most max_batch (ndit_forward).  Uses the rope factors the module currently
+        holds (ctor: 1, 1; a forward_with_cfg call with explicit factors overwrites them, :952-960)."""
+        self._check_inputs(x, y)
+        lib, h = self._engine(x.device)
+        lin, ntk = getattr(self, "_rope_override", (1.0, 1.0))
+        sp = _lib.NditStepParams(0.0, lin, 1.0, 0, 0, ntk)
+        n = x.shape[0]
+        tv = (t.detach().float().reshape(-1).tolist() if isinstance(t, torch.Tensor) else [float(t)] * n)
+        if len(tv) == 1:
+            tv = tv * n
+        if len(tv) != n or y.numel() != n:
+            raise ValueError(f"t / y have {len(tv)} / {y.numel()} entries for a batch of {n}")
+        xb = x.detach().to(torch.bfloat16).contiguous()
+        out = torch.empty_like(xb)
+        _, _, Hh, Ww = xb.shape
+        with torch.cuda.device(x.device):
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(Hh, Ww), 0, 1)
+            step = self._limits[2]
+            for i in range(0, n, step):
+                j = min(n, i + step)
+                self._label_key = None
+                self._set_labels(lib, h, y[i:j], stream)
+                ta = (C.c_float * (j - i))(*tv[i:j])
+                _lib.check(lib.ndit_forward(h, C.c_void_p(xb[i:j].data_ptr()), ta, j - i, Hh, Ww, C.byref(sp),
+                                            C.c_void_p(out[i:j].data_ptr()), stream), h)
+            self._label_key = None
+        return out.to(x.dtype)
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, y, cfg_scale, rope_scaling_factor=None, ntk_factor=None):

@@ -197,13 +197,15 @@ def moe_layer(p, W: Dict[str, Tensor], pre: str, x: Tensor, cond: Optional[Tenso
     return res.view(B, N, D)
 
 
-def forward_with_cfg(cfg: DiTLlamaConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, y: Tensor, cfg_scale: float,
-                     rope_scaling_factor: Optional[float] = None, ntk_factor: Optional[float] = None,
-                     precision: str = "fp32", taps: Optional[dict] = None) -> Tensor:
+def forward(cfg: DiTLlamaConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, y: Tensor,
+            rope_scaling_factor: Optional[float] = None, ntk_factor: Optional[float] = None,
+            precision: str = "fp32", taps: Optional[dict] = None) -> Tensor:
+    """DiT_Llama.forward (Next-DiT-ImageNet/models/models.py:920-944): every row its own sample, timestep and label; returns the first
+    C of the 2C output channels.  The rope table is the one the module currently holds (ctor: both factors 1; forward_with_cfg
+    overwrites it, :952-960)."""
     p = T._Prec(precision)
     ps, H, hd, Hkv = cfg.patch_size, cfg.n_heads, cfg.head_dim, cfg.kv_heads
-    half = x[: len(x) // 2]
-    x = p.r(torch.cat([half, half], dim=0).float())
+    x = p.r(x.float())
     B, C, Hh, Ww = x.shape
     N = (Hh // ps) * (Ww // ps)
     X = p.linear(T.patchify(x, ps), W["x_embedder.weight"], W["x_embedder.bias"])
@@ -252,6 +254,16 @@ def forward_with_cfg(cfg: DiTLlamaConfig, W: Dict[str, Tensor], x: Tensor, t: Te
     out = T.unpatchify(O, Hh, Ww, ps, cfg.out_channels)
     if cfg.learn_sigma:
         out = out[:, : cfg.in_channels]
+    return out
+
+
+def forward_with_cfg(cfg: DiTLlamaConfig, W: Dict[str, Tensor], x: Tensor, t: Tensor, y: Tensor, cfg_scale: float,
+                     rope_scaling_factor: Optional[float] = None, ntk_factor: Optional[float] = None,
+                     precision: str = "fp32", taps: Optional[dict] = None) -> Tensor:
+    """DiT_Llama.forward_with_cfg (models.py:946-974): cond rows duplicated, guidance on the first three channels."""
+    p = T._Prec(precision)
+    half = x[: len(x) // 2]
+    out = forward(cfg, W, torch.cat([half, half], dim=0), t, y, rope_scaling_factor, ntk_factor, precision, taps)
     eps, rest = out[:, :3], out[:, 3:]
     cond, unc = torch.split(eps, len(eps) // 2, dim=0)
     half_eps = p.r(unc + p.r(cfg_scale * p.r(cond - unc)))

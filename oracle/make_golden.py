@@ -131,6 +131,37 @@ def make_imagenet() -> None:
         del m, W
 
 
+def make_imagenet_plain_forward() -> None:
+    """DiT_Llama.forward of the class-conditional model (models.py:920-944): odd batch, one timestep and label per row, fresh module
+    and after a forward_with_cfg call that left scaled rope factors on the module."""
+    ref = import_reference_imagenet()
+    torch.set_grad_enabled(False)
+    cfg = DL.config_tiny72()
+    W = DL.synthetic_weights(cfg, seed=0)
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(3, cfg.in_channels, 16, 24, generator=g).to(torch.bfloat16)
+    t = torch.tensor([0.1, 0.55, 0.9])
+    y = torch.tensor([2, 9, cfg.num_classes])
+    fx = dict(cfg=dict(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, num_classes=cfg.num_classes), weight_seed=0, x=x, t=t, y=y,
+              sticky_call=dict(rope_scaling_factor=2.0, ntk_factor=1.5, cfg_scale=2.0, hw=(16, 16), labels=(1,), seed=5, t=0.3))
+    for state in ("fresh", "sticky"):
+        m = ref.DiT_Llama(input_size=16, patch_size=2, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, num_classes=cfg.num_classes, qk_norm=True)
+        m.load_state_dict({k: v.float() for k, v in W.items()}, strict=True)
+        m = m.eval().float()
+        kw = {}
+        if state == "sticky":
+            z2, y2 = DL.synthetic_inputs(cfg, (16, 16), (1,), seed=5)
+            m.forward_with_cfg(z2.float(), torch.full((len(z2),), 0.3), y2, 2.0, rope_scaling_factor=2.0, ntk_factor=1.5)
+            kw = dict(rope_scaling_factor=2.0, ntk_factor=1.5)
+        out = m(x.float(), t, y)
+        o = DL.forward(cfg, W, x.float(), t, y, precision="fp32", **kw)
+        ob = DL.forward(cfg, W, x, t, y, precision="bf16", **kw)
+        fx[state] = dict(out_fp32=out.clone())
+        print(state, tuple(out.shape), "absmax", out.abs().max().item(), "oracle fp32 rel", ((o - out).abs().max() / out.abs().max()).item(),
+              "oracle bf16 rel", ((ob - out).abs().max() / out.abs().max()).item())
+    torch.save(fx, os.path.join(OUT, "imagenet_plain_forward.pt"))
+
+
 def make_moe() -> None:
     """Next-DiT-MoE (BASELINE config 5 / SURVEY 8a16): the unmodified time / space / both MoE models (fp32, CPU)."""
     from oracle.harness.ref_import import import_reference_moe
@@ -410,6 +441,8 @@ def make_gemma() -> None:
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gemma":
         make_gemma()
+    elif len(sys.argv) > 1 and sys.argv[1] == "imagenet_plain_forward":
+        make_imagenet_plain_forward()
     elif len(sys.argv) > 1 and sys.argv[1] == "plain_forward":
         make_plain_forward()
     elif len(sys.argv) > 1 and sys.argv[1] == "list_forward":
@@ -419,3 +452,4 @@ if __name__ == "__main__":
         make_plain_forward()
         make_list_forward()
         make_gemma()
+        make_imagenet_plain_forward()

@@ -100,6 +100,34 @@ def _build_moe(cfg, W, input_size, **kw):
     return m.eval().to("cuda", dtype=torch.bfloat16)
 
 
+def test_plain_forward_vs_reference_fixture():
+    """DiT_Llama.forward (models.py:920-944) through ndit_forward: odd batch, one timestep and label per row, on the module as
+    constructed and with the rope factors a forward_with_cfg call leaves behind; fixture from the unmodified reference."""
+    from lumina_t2x_b200 import models
+    fx = torch.load(os.path.join(GOLD, "imagenet_plain_forward.pt"), map_location="cpu", weights_only=False)
+    cfg = DL.DiTLlamaConfig(**fx["cfg"])
+    W = DL.synthetic_weights(cfg, seed=fx["weight_seed"])
+    m = models.DiT_Llama(input_size=16, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, num_classes=cfg.num_classes, qk_norm=True,
+                         max_tokens=256)
+    m.load_state_dict(W, strict=True)
+    m = m.eval().to("cuda", dtype=torch.bfloat16)
+    x, t, y = fx["x"].cuda(), fx["t"].cuda(), fx["y"].cuda()
+    for state in ("fresh", "sticky"):
+        kw = {}
+        if state == "sticky":
+            sc = fx["sticky_call"]
+            z2, y2 = DL.synthetic_inputs(cfg, tuple(sc["hw"]), tuple(sc["labels"]), seed=sc["seed"])
+            m.forward_with_cfg(z2.cuda(), torch.full((len(z2),), sc["t"]).cuda(), y2.cuda(), sc["cfg_scale"],
+                               rope_scaling_factor=sc["rope_scaling_factor"], ntk_factor=sc["ntk_factor"])
+            kw = dict(rope_scaling_factor=sc["rope_scaling_factor"], ntk_factor=sc["ntk_factor"])
+        out = m(x, t, y).float().cpu()
+        orc = DL.forward(cfg, W, fx["x"], fx["t"], fx["y"], precision="bf16", **kw)
+        ref = fx[state]["out_fp32"]
+        assert out.shape == ref.shape and torch.isfinite(out).all()
+        assert _rel(out, orc) < 2e-2, (state, _rel(out, orc))
+        assert _rel(out, ref) < 1.5 * _rel(orc, ref) + 2e-3, (state, _rel(out, ref), _rel(orc, ref))
+
+
 @pytest.mark.parametrize("name", ["moe_tiny_time", "moe_tiny_space", "moe_tiny_both"])
 def test_moe_forward_with_cfg_vs_reference_and_oracle(name):
     """Routing is a discrete decision on bf16 logits: a token whose two best experts are within rounding noise of each other
