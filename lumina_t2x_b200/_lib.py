@@ -87,6 +87,22 @@ TEXT_SIGNATURES = {
     "ntxt_encode": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
 }
 
+
+class NvaeConfig(C.Structure):
+    _fields_ = [("latent_channels", C.c_int32), ("out_channels", C.c_int32), ("block_out_channels", C.c_int32 * 4),
+                ("layers_per_block", C.c_int32), ("norm_num_groups", C.c_int32)]
+
+
+# include/ndit_vae.h (VAE-decode end)
+VAE_SIGNATURES = {
+    "nvae_create": (C.c_int, [C.POINTER(NvaeConfig), C.POINTER(_vp)]),
+    "nvae_destroy": (C.c_int, [_vp]),
+    "nvae_last_error": (C.c_char_p, [_vp]),
+    "nvae_set_weight": (C.c_int, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _i32, _vp]),
+    "nvae_finalize_weights": (C.c_int, [_vp, _vp]),
+    "nvae_decode": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+}
+
 _lib = None
 
 
@@ -101,7 +117,7 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: the B200 engine has no fallback path. Build it with "
             "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in list(SIGNATURES.items()) + list(TEXT_SIGNATURES.items()):
+    for name, (res, args) in list(SIGNATURES.items()) + list(TEXT_SIGNATURES.items()) + list(VAE_SIGNATURES.items()):
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args

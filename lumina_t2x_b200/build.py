@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libndit_b200.so")
-SOURCES = ["engine.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention_hr_tcgen05.cu", "rowwise.cu", "tensormap.cu", "text_encoder.cu"]
+SOURCES = ["engine.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention_hr_tcgen05.cu", "rowwise.cu", "tensormap.cu", "text_encoder.cu", "vae_decoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

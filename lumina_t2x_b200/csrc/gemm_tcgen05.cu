@@ -274,16 +274,16 @@ struct Gemm2Cfg {
     static constexpr int A_BYTES = 128 * GEMM_BK * 2;        // this CTA's A rows
     static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB / 28 KB
-    static constexpr int STAGES = 6;
+    static constexpr int STAGES = BN_ == 128 ? 8 : 6;
     static constexpr int TMEM_COLS = 512;                    // accumulator stages at columns 0 and 256
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool EXT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      bf16* __restrict__ C, const int* __restrict__ w_row_off, int w_row_mul, int M, int N, int K, int ldc,
-                     const GemmVtOut vt, const GemmRowWin rows) {
+                     const GemmVtOut vt, const GemmRowWin rows, const GemmExt ext) {
     using Cfg = Gemm2Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -368,7 +368,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land on this barrier
-                    tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * GEMM_BK, row0 + m_blk * 256 + rank * 128);
+                    int a_col = kb * GEMM_BK, a_row = row0 + m_blk * 256 + static_cast<int>(rank) * 128;
+                    if (EXT && ext.kpt > 0) {       // implicit 3x3 convolution: tap (dy, dx) reads the rows shifted by dy * wp + dx
+                        const int tap = kb / ext.kpt;
+                        a_col = (kb - tap * ext.kpt) * GEMM_BK;
+                        a_row += (tap / 3 - 1) * ext.wp + (tap % 3 - 1);
+                    }
+                    tma_load_2d_pair(sa, &tmA, full_bar(stage), a_col, a_row);
                     tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, w0);
                 }
                 __syncwarp();
@@ -426,6 +432,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
             if (EPI == EPI_STORE) {
                 bf16* crow = C + static_cast<size_t>(row) * ldc + static_cast<size_t>(n_blk) * BN;
+                bool on_border = false;
+                if (EXT && ext.hp > 0) {
+                    const int rr = row % (ext.hp * ext.wp);
+                    const int y = rr / ext.wp, x = rr - y * ext.wp;
+                    on_border = y == 0 || y == ext.hp - 1 || x == 0 || x == ext.wp - 1;
+                }
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     const int col0 = n_blk * BN + c * 32;
@@ -439,6 +451,40 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             if (vt.ptr != nullptr && col0 + j * 8 >= vt.col0) {
                                 if (lrow < Meff) store_vt8(vt, row, col0 + j * 8, v + j * 8);
                                 continue;
+                            }
+                            if (EXT) {
+                                if (ext.out_f32 != nullptr) {
+                                    if (lrow < Meff) {
+                                        float* dst = ext.out_f32 + static_cast<size_t>(row) * ldc + col0 + j * 8;
+                                        *reinterpret_cast<uint4*>(dst) = make_uint4(v[j * 8], v[j * 8 + 1], v[j * 8 + 2], v[j * 8 + 3]);
+                                        *reinterpret_cast<uint4*>(dst + 4) = make_uint4(v[j * 8 + 4], v[j * 8 + 5], v[j * 8 + 6], v[j * 8 + 7]);
+                                    }
+                                    continue;
+                                }
+                                if (ext.bias != nullptr) {
+                                    const uint4 bq = *reinterpret_cast<const uint4*>(ext.bias + col0 + j * 8);
+                                    const uint32_t b4[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 bf = unpack_bf16(b4[e]);
+                                        v[j * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * e]) + bf.x);
+                                        v[j * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * e + 1]) + bf.y);
+                                    }
+                                }
+                                if (ext.resid != nullptr && lrow < Meff) {
+                                    const uint4 rq = *reinterpret_cast<const uint4*>(ext.resid + static_cast<size_t>(row) * ext.ldr + col0 + j * 8);
+                                    const uint32_t r4[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 rf = unpack_bf16(r4[e]);
+                                        v[j * 8 + 2 * e] = __float_as_uint(bf16_round(__uint_as_float(v[j * 8 + 2 * e])) + rf.x);
+                                        v[j * 8 + 2 * e + 1] = __float_as_uint(bf16_round(__uint_as_float(v[j * 8 + 2 * e + 1])) + rf.y);
+                                    }
+                                }
+                                if (on_border) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[j * 8 + e] = 0u;
+                                }
                             }
                             uint4 o;
                             o.x = pack_bf16(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
@@ -489,10 +535,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool EXT = false>
 static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const int* w_row_off, int w_row_mul, int M, int N,
-                                int K, int ldc, int num_sms, const GemmVtOut& vt, const GemmRowWin& rows, cudaStream_t stream) {
-    auto kern = gemm2_bf16_tn_kernel<BN, EPI>;
+                                int K, int ldc, int num_sms, const GemmVtOut& vt, const GemmRowWin& rows, cudaStream_t stream,
+                                const GemmExt& ext = GemmExt{}) {
+    auto kern = gemm2_bf16_tn_kernel<BN, EPI, EXT>;
     static PerDeviceFlag flags;
     bool& configured = flags.here();
     if (!configured) {
@@ -503,7 +550,7 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt, rows);
+    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt, rows, ext);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -531,6 +578,17 @@ cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
     if (p.epi != EPI_STORE && !epi_gated(p.epi)) return cudaErrorInvalidValue;
     if (p.bias != nullptr && (p.pair || p.epi != EPI_STORE)) return cudaErrorInvalidValue;
     if (p.vt.ptr != nullptr && (p.epi != EPI_STORE || p.bias != nullptr || p.vt.col0 % 8 != 0 || p.vt.hd % 8 != 0)) return cudaErrorInvalidValue;
+    if (p.use_ext) {
+        // VAE decoder GEMMs: CTA-pair kernel, plain store with the GemmExt epilogue / producer; N a multiple of the tile, or (bn 256)
+        // one ragged last-N tile a multiple of 32 wide
+        if (!p.pair || p.epi != EPI_STORE || p.bias != nullptr || p.vt.ptr != nullptr) return cudaErrorInvalidValue;
+        if (p.ext.kpt > 0 && p.K != 9 * p.ext.kpt * GEMM_BK) return cudaErrorInvalidValue;
+        if (p.bn == 128 && p.N % 128 == 0)
+            return launch_gemm2<128, EPI_STORE, true>(p.tmA, p.tmB, p.C, nullptr, 0, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream, p.ext);
+        if (p.bn == 256 && (p.N % 256) % 32 == 0)
+            return launch_gemm2<256, EPI_STORE, true>(p.tmA, p.tmB, p.C, nullptr, 0, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream, p.ext);
+        return cudaErrorInvalidValue;
+    }
     if (p.pair) {
         // ragged M is fine (zero-filled loads, masked stores); a ragged last-N tile (multiple of 32 wide) only for plain stores
         if (p.N % p.bn != 0 && (p.epi != EPI_STORE || p.bn != 256 || (p.N % 256) % 32 != 0)) return cudaErrorInvalidValue;

@@ -37,6 +37,18 @@ struct GemmRowWin {
     const int* count;
     const int* offset;
 };
+// Optional extensions of the CTA-pair EPI_STORE GEMM for the VAE decoder (vae_decoder.cu).  The image stack lives in HBM as
+// [batch][hp][wp][C] bf16 with a one-pixel zero border, i.e. as a [batch * hp * wp, C] matrix: a 3x3 convolution with padding 1 is
+// then nine accumulating GEMMs whose A tiles are the same rows shifted by (dy * wp + dx) - the producer only offsets the TMA row
+// coordinate (rows before / after the matrix are zero-filled) and W is packed [Cout][tap][Cin].
+struct GemmExt {
+    int kpt;             // > 0: implicit 3x3 convolution, k-blocks per tap (= Cin / 64); 0: plain GEMM
+    int wp, hp;          // padded width / height; hp > 0: rows on the border of their image are stored as zero
+    const bf16* bias;    // optional [N]: bf16(acc + bias)
+    const bf16* resid;   // optional [M, ldr]: out = bf16(bf16(acc + bias) + resid)   (ResnetBlock2D / Attention residual)
+    int ldr;
+    float* out_f32;      // non-null: the fp32 accumulators go to out_f32[M, ldc] instead of C (attention scores)
+};
 struct GemmPlan {
     CUtensorMap tmA;  // A [M,K], box 128 x 64
     CUtensorMap tmB;  // W [N,K], box bn  x 64
@@ -51,6 +63,8 @@ struct GemmPlan {
     int num_sms;
     GemmVtOut vt;   // zero-initialised by make_gemm_plan
     GemmRowWin rows;
+    int use_ext;    // 1: ext applies (pair kernel, EPI_STORE; bn 256 or 128)
+    GemmExt ext;
 };
 cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream);
 // builds the maps of a plan (A: [M,K] ld=lda; W: [N,K] ld=K)

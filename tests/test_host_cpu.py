@@ -32,6 +32,12 @@ def test_cabi_loads_and_exports_header_symbols():
     assert tdeclared == set(_lib.TEXT_SIGNATURES), tdeclared ^ set(_lib.TEXT_SIGNATURES)
     for name in tdeclared:
         assert hasattr(lib, name), name
+    # and so does the VAE-decode end
+    vheader = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ndit_vae.h")).read(), flags=re.S)
+    vdeclared = set(re.findall(r"\b(nvae_[a-z_0-9]+)\s*\(", vheader))
+    assert vdeclared == set(_lib.VAE_SIGNATURES), vdeclared ^ set(_lib.VAE_SIGNATURES)
+    for name in vdeclared:
+        assert hasattr(lib, name), name
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
