@@ -279,8 +279,13 @@ struct Gemm2Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+// EXT (VAE decoder): a second set of four epilogue warps (the 3x3 convolutions with 128 output channels have a main loop of only
+// 18 k-blocks per tile, and their epilogue also reads the residual): warps 2-5 take the first half of the tile's columns,
+// warps 6-9 the second half, each on the TMEM lane quadrant (warp & 3) it may access.
+template <bool EXT> struct Gemm2Threads { static constexpr int N = EXT ? 320 : GEMM_THREADS; static constexpr int EPI_WARPS = EXT ? 8 : 4; };
+
 template <int BN, int EPI, bool EXT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Threads<EXT>::N, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      bf16* __restrict__ C, const int* __restrict__ w_row_off, int w_row_mul, int M, int N, int K, int ldc,
                      const GemmVtOut vt, const GemmRowWin rows, const GemmExt ext) {
@@ -332,7 +337,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 8);
+            mbar_init(tempty_bar(s), 2 * Gemm2Threads<EXT>::EPI_WARPS);
         }
         fence_mbar_init();
     }
@@ -438,12 +443,20 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const int y = rr / ext.wp, x = rr - y * ext.wp;
                     on_border = y == 0 || y == ext.hp - 1 || x == 0 || x == ext.wp - 1;
                 }
+                constexpr int CHUNKS = (BN / 32) / (EXT ? 2 : 1);
+                const int c_first = EXT ? ((warp - 2) >> 2) * CHUNKS : 0;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = c_first; c < c_first + CHUNKS; ++c) {
                     const int col0 = n_blk * BN + c * 32;
                     if (col0 >= N) break;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    uint4 rq4[4];
+                    if (EXT && ext.resid != nullptr && lrow < Meff) {      // residual tile in flight while the accumulators arrive
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (col0 + j * 8 < N) rq4[j] = *reinterpret_cast<const uint4*>(ext.resid + static_cast<size_t>(row) * ext.ldr + col0 + j * 8);
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -472,8 +485,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                     }
                                 }
                                 if (ext.resid != nullptr && lrow < Meff) {
-                                    const uint4 rq = *reinterpret_cast<const uint4*>(ext.resid + static_cast<size_t>(row) * ext.ldr + col0 + j * 8);
-                                    const uint32_t r4[4] = {rq.x, rq.y, rq.z, rq.w};
+                                    const uint32_t r4[4] = {rq4[j].x, rq4[j].y, rq4[j].z, rq4[j].w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         const float2 rf = unpack_bf16(r4[e]);
@@ -550,7 +562,7 @@ static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    return launch_k(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt, rows, ext);
+    return launch_k(kern, dim3(2 * pairs), dim3(Gemm2Threads<EXT>::N), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt, rows, ext);
 }
 
 // ---------------------------------------------------------------------------- host side

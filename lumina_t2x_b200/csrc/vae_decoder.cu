@@ -65,6 +65,16 @@ __global__ void vae_pack_conv_kernel(bf16* __restrict__ dst, const void* __restr
         dst[i] = src_f32 ? __float2bfloat16_rn(static_cast<const float*>(src)[si]) : static_cast<const bf16*>(src)[si];
     }
 }
+// dst[(t * cin + i) * cout + o] = bf16(src[(o * cin + i) * taps + t])    (conv_in: [K][Cout], consecutive threads read consecutive channels)
+__global__ void vae_pack_conv_t_kernel(bf16* __restrict__ dst, const void* __restrict__ src, int src_f32, int cout, int cin, int taps) {
+    const size_t total = static_cast<size_t>(cout) * cin * taps;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t o = i % cout, r = i / cout;
+        const size_t ci = r % cin, t = r / cin;
+        const size_t si = (o * cin + ci) * taps + t;
+        dst[i] = src_f32 ? __float2bfloat16_rn(static_cast<const float*>(src)[si]) : static_cast<const bf16*>(src)[si];
+    }
+}
 __global__ void vae_copy_vec_kernel(void* __restrict__ dst, int dst_f32, const void* __restrict__ src, int src_f32, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -102,15 +112,16 @@ __global__ void vae_conv_in_kernel(const bf16* __restrict__ z, const bf16* __res
         pq[t] = v;
     }
     __syncthreads();
-    const int K = 9 * Cz;
+    const int K = 9 * Cz;           // w is [K][Cout]
     for (int o0 = threadIdx.x * 8; o0 < Cout; o0 += blockDim.x * 8) {
         float acc[8];
+        ld8(bias + o0, acc);
+        for (int k = 0; k < K; ++k) {
+            float wv[8];
+            ld8(w + static_cast<size_t>(k) * Cout + o0, wv);
+            const float a = pq[k];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const bf16* wr = w + static_cast<size_t>(o0 + e) * K;
-            float a = 0.f;
-            for (int k = 0; k < K; ++k) a += pq[k] * __bfloat162float(wr[k]);
-            acc[e] = a + __bfloat162float(bias[o0 + e]);
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(a, wv[e], acc[e]);
         }
         st8(orow + o0, acc);
     }
@@ -126,14 +137,22 @@ __global__ void __launch_bounds__(256) vae_gn_stats_kernel(const bf16* __restric
     const int p0 = chunk * GN_PPC, p1 = min(P, p0 + GN_PPC);
     const bf16* xb = x + static_cast<size_t>(b) * P * C + c8 * 8;
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-    for (int p = p0 + pl; p < p1; p += ppb) {
-        float v[8];
-        ld8(xb + static_cast<size_t>(p) * C, v);
-        s0 += (v[0] + v[1]) + (v[2] + v[3]);
-        q0 += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
-        s1 += (v[4] + v[5]) + (v[6] + v[7]);
-        q1 += (v[4] * v[4] + v[5] * v[5]) + (v[6] * v[6] + v[7] * v[7]);
+    auto add = [&](const uint4& u) {
+        const float2 a = unpack_bf16(u.x), bq = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        s0 += (a.x + a.y) + (bq.x + bq.y);
+        q0 += (a.x * a.x + a.y * a.y) + (bq.x * bq.x + bq.y * bq.y);
+        s1 += (c.x + c.y) + (d.x + d.y);
+        q1 += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+    };
+    int p = p0 + pl;
+    for (; p + 3 * ppb < p1; p += 4 * ppb) {          // four independent 16-byte loads in flight per thread
+        const uint4 u0 = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * C);
+        const uint4 u1 = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + ppb) * C);
+        const uint4 u2 = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + 2 * ppb) * C);
+        const uint4 u3 = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + 3 * ppb) * C);
+        add(u0); add(u1); add(u2); add(u3);
     }
+    for (; p < p1; p += ppb) add(*reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * C));
     sm[threadIdx.x] = make_float4(s0, q0, s1, q1);
     __syncthreads();
     if (threadIdx.x < tpp) {
@@ -145,66 +164,87 @@ __global__ void __launch_bounds__(256) vae_gn_stats_kernel(const bf16* __restric
         partial[(static_cast<size_t>(b) * chunks + chunk) * tpp + threadIdx.x] = a;
     }
 }
-// pass 1b: (mean, rstd) per (image, group); 8 threads per group, double accumulation over the chunk partials
-__global__ void __launch_bounds__(256) vae_gn_finalize_kernel(const float4* __restrict__ partial, float2* __restrict__ stats, int C, int chunks,
-                                                              int G, double inv_count, float eps) {
-    const int b = blockIdx.x, g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+// pass 1b: one block per (group, image): double accumulation over the chunk partials, then the per-channel affine of the group
+//   ab[b][c] = (rstd * gamma[c], beta[c] - mean * rstd * gamma[c])
+__global__ void __launch_bounds__(256) vae_gn_finalize_kernel(const float4* __restrict__ partial, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float2* __restrict__ ab, int C, int chunks, int G,
+                                                              double inv_count, float eps) {
+    __shared__ double rs[8], rq[8];
+    __shared__ float2 st;
+    const int g = blockIdx.x, b = blockIdx.y;
     const int tpp = C >> 3, cpg = C / G, hv0 = g * cpg / 4, nhv = cpg / 4;
     double s = 0.0, q = 0.0;
-    if (g < G) {
-        for (int chunk = sub; chunk < chunks; chunk += 8) {
-            const float4* row = partial + (static_cast<size_t>(b) * chunks + chunk) * tpp;
-            for (int i = 0; i < nhv; ++i) {
-                const int hv = hv0 + i;
-                const float4 t = row[hv >> 1];
-                if (hv & 1) { s += t.z; q += t.w; } else { s += t.x; q += t.y; }
-            }
+    for (int chunk = threadIdx.x; chunk < chunks; chunk += 256) {
+        const float4* row = partial + (static_cast<size_t>(b) * chunks + chunk) * tpp;
+        for (int i = 0; i < nhv; ++i) {
+            const int hv = hv0 + i;
+            const float4 t = row[hv >> 1];
+            if (hv & 1) { s += t.z; q += t.w; } else { s += t.x; q += t.y; }
         }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         q += __shfl_xor_sync(0xffffffffu, q, o);
     }
-    if (g < G && sub == 0) {
-        const double mean = s * inv_count;
-        double var = q * inv_count - mean * mean;
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int i = 0; i < 8; ++i) { ts += rs[i]; tq += rq[i]; }
+        const double mean = ts * inv_count;
+        double var = tq * inv_count - mean * mean;
         if (var < 0.0) var = 0.0;
-        stats[b * G + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
-    }
-}
-// pass 2: y = bf16(act((x - mean) * rstd * gamma + beta)), act = SiLU or identity, zeros on the border
-__global__ void __launch_bounds__(256) vae_gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ stats,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           bf16* __restrict__ y, int P, int C, int G, int Hp, int Wp, int silu) {
-    __shared__ float2 ab[512];
-    const int b = blockIdx.y, cpg = C / G;
-    for (int c = threadIdx.x; c < C; c += 256) {
-        const float2 st = stats[b * G + c / cpg];
-        const float a = st.y * gamma[c];
-        ab[c] = make_float2(a, beta[c] - st.x * a);
+        st = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
     }
     __syncthreads();
-    const int tpp = C >> 3;
-    const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    const int p = static_cast<int>(idx / tpp), c8 = static_cast<int>(idx - static_cast<long long>(p) * tpp);
-    if (p >= P) return;
-    const int py = p / Wp, px = p - py * Wp;
-    const size_t off = (static_cast<size_t>(b) * P + p) * C + c8 * 8;
-    float v[8];
-    if (py == 0 || py == Hp - 1 || px == 0 || px == Wp - 1) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    } else {
-        ld8(x + off, v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float2 t = ab[c8 * 8 + e];
-            const float n = fmaf(v[e], t.x, t.y);
-            v[e] = silu ? n / (1.0f + __expf(-n)) : n;
-        }
+    if (threadIdx.x < cpg) {
+        const int c = g * cpg + threadIdx.x;
+        const float a = st.y * gamma[c];
+        ab[static_cast<size_t>(b) * C + c] = make_float2(a, beta[c] - st.x * a);
     }
-    st8(y + off, v);
+}
+// pass 2: y = bf16(act(x * a[c] + b[c])), act = SiLU or identity, zeros on the border; 8 consecutive 16-byte vectors per thread
+constexpr int GN_VPT = 8;
+__global__ void __launch_bounds__(256) vae_gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ ab_g, bf16* __restrict__ y, int P,
+                                                           int C, int Hp, int Wp, int silu) {
+    __shared__ float2 ab[512];
+    const int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += 256) ab[c] = ab_g[static_cast<size_t>(b) * C + c];
+    __syncthreads();
+    const int tpp = C >> 3;
+    const long long total = static_cast<long long>(P) * tpp;
+    const long long base = static_cast<long long>(blockIdx.x) * (256 * GN_VPT) + threadIdx.x;
+    const bf16* xb = x + static_cast<size_t>(b) * P * C;
+    bf16* yb = y + static_cast<size_t>(b) * P * C;
+    uint4 u[GN_VPT];
+#pragma unroll
+    for (int i = 0; i < GN_VPT; ++i) {
+        const long long idx = base + i * 256;
+        u[i] = idx < total ? *reinterpret_cast<const uint4*>(xb + idx * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < GN_VPT; ++i) {
+        const long long idx = base + i * 256;
+        if (idx >= total) break;
+        const int p = static_cast<int>(idx / tpp), c8 = static_cast<int>(idx - static_cast<long long>(p) * tpp);
+        const int py = p / Wp, px = p - py * Wp;
+        float v[8];
+        if (py == 0 || py == Hp - 1 || px == 0 || px == Wp - 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        } else {
+            const float2 a = unpack_bf16(u[i].x), bq = unpack_bf16(u[i].y), c = unpack_bf16(u[i].z), d = unpack_bf16(u[i].w);
+            v[0] = a.x; v[1] = a.y; v[2] = bq.x; v[3] = bq.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float2 t = ab[c8 * 8 + e];
+                const float n = fmaf(v[e], t.x, t.y);
+                v[e] = silu ? n / (1.0f + __expf(-n)) : n;
+            }
+        }
+        st8(yb + idx * 8, v);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- Upsample2D (nearest, x2)
@@ -297,43 +337,90 @@ __global__ void vae_colmask_kernel(uint8_t* __restrict__ m, int Hp, int Wp, int 
 }
 
 // ---------------------------------------------------------------------------------------------- conv_out
-// Decoder.forward tail: conv_out(silu(conv_norm_out(x))) (3x3, C -> Co <= 4, padding 1) on the normalised padded buffer; output NCHW.
-// One thread per output pixel, 128 consecutive pixels of one image row per block; weights in shared memory as [tap][c] float4
-// (one 16-byte broadcast load feeds the Co accumulators of a channel).
+// Decoder.forward tail: conv_out(silu(conv_norm_out(x))) (3x3, C -> CO <= 4, padding 1) on the normalised padded buffer; output NCHW.
+// CUDA cores (N = 3 is no tensor-core shape).  A half-warp owns 8 consecutive output pixels of a row: its 16 lanes split the
+// channels (lane l: channels 8l..8l+7 of every 128, one coalesced 256-byte read per pixel), each lane keeps 8 x CO partial sums,
+// one 16-byte shared-memory weight read ([tap][e][C/8] float4, conflict free) feeds 8 x CO FMAs, and the partial sums meet in a
+// butterfly at the end.  Each block walks CONV_OUT_ROWS image rows so the weight staging is amortised.
+constexpr int CONV_OUT_ROWS = 8;
+template <int CO>
 __global__ void __launch_bounds__(128) vae_conv_out_kernel(const bf16* __restrict__ xn, const bf16* __restrict__ w, const bf16* __restrict__ bias,
                                                            bf16* __restrict__ out, int Hh, int Ww, int C, int Co) {
-    extern __shared__ float4 wsm[];     // [9 * C]
+    extern __shared__ float4 wsm[];     // [9][8][C / 8]
+    const int tpp = C >> 3;
     for (int i = threadIdx.x; i < 9 * C; i += 128) {
+        const int tap = i / C, c = i - tap * C;
         float t[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int o = 0; o < Co; ++o) t[o] = __bfloat162float(w[static_cast<size_t>(o) * 9 * C + i]);
-        wsm[i] = make_float4(t[0], t[1], t[2], t[3]);
+        for (int o = 0; o < Co; ++o) t[o] = __bfloat162float(w[(static_cast<size_t>(o) * 9 + tap) * C + c]);
+        wsm[(tap * 8 + (c & 7)) * tpp + (c >> 3)] = make_float4(t[0], t[1], t[2], t[3]);
     }
     __syncthreads();
-    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x >= Ww) return;
+    const int hw = threadIdx.x >> 4, l = threadIdx.x & 15, b = blockIdx.z;
+    const int xq = blockIdx.x * 64 + hw * 8;
+    const bool live = xq < Ww;                     // Ww % 8 == 0
+    const int x0 = live ? xq : Ww - 8;
     const int Wp = Ww + 2, Hp = Hh + 2;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-        const bf16* src = xn + ((static_cast<size_t>(b) * Hp + y + tap / 3) * Wp + x + tap % 3) * C;
-        const float4* wt = wsm + tap * C;
-        for (int c = 0; c < C; c += 8) {
-            float v[8];
-            ld8(src + c, v);
+    float bo[CO];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float4 ww = wt[c + e];
-                a0 = fmaf(v[e], ww.x, a0); a1 = fmaf(v[e], ww.y, a1); a2 = fmaf(v[e], ww.z, a2); a3 = fmaf(v[e], ww.w, a3);
+    for (int o = 0; o < CO; ++o) bo[o] = o < Co ? __bfloat162float(bias[o]) : 0.f;
+    for (int yy = 0; yy < CONV_OUT_ROWS; ++yy) {
+        const int y = blockIdx.y * CONV_OUT_ROWS + yy;
+        if (y >= Hh) break;
+        float acc[8][CO];
+#pragma unroll
+        for (int px = 0; px < 8; ++px)
+#pragma unroll
+            for (int o = 0; o < CO; ++o) acc[px][o] = 0.f;
+        for (int c8 = l; c8 < tpp; c8 += 16) {
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+                const bf16* src = xn + ((static_cast<size_t>(b) * Hp + y + r) * Wp + x0) * C + c8 * 8;
+                float v[10][8];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) ld8(src + static_cast<size_t>(j) * C, v[j]);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float4 ww = wsm[((r * 3 + dx) * 8 + e) * tpp + c8];
+                        const float wq[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+                        for (int px = 0; px < 8; ++px)
+#pragma unroll
+                            for (int o = 0; o < CO; ++o) acc[px][o] = fmaf(v[px + dx][e], wq[o], acc[px][o]);
+                    }
+                }
             }
         }
+#pragma unroll
+        for (int px = 0; px < 8; ++px)
+#pragma unroll
+            for (int o = 0; o < CO; ++o) {
+                float a = acc[px][o];
+                a += __shfl_xor_sync(0xffffffffu, a, 8);
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                acc[px][o] = a + bo[o];
+            }
+        if (live && l < Co) {
+            float r8[8];
+#pragma unroll
+            for (int px = 0; px < 8; ++px) {
+                float t = acc[px][0];
+#pragma unroll
+                for (int o = 1; o < CO; ++o) t = l == o ? acc[px][o] : t;
+                r8[px] = t;
+            }
+            st8(out + ((static_cast<size_t>(b) * Co + l) * Hh + y) * Ww + x0, r8);
+        }
     }
-    const float acc[4] = {a0, a1, a2, a3};
-    for (int o = 0; o < Co; ++o)
-        out[((static_cast<size_t>(b) * Co + o) * Hh + y) * Ww + x] = __float2bfloat16_rn(acc[o] + __bfloat162float(bias[o]));
 }
 
 // ---------------------------------------------------------------------------------------------- engine
 struct Slot {
     int kind;          // 0: conv / linear weight -> bf16 [cout][taps][cin]; 1: bias -> bf16 [n]; 2: GroupNorm vector -> f32 [n]
+    bool transposed = false;   // kind 0 packed [taps][cin][cout] instead (conv_in)
     int cout, cin, taps;
     void* ptr;
     bool loaded;
@@ -366,7 +453,7 @@ struct nvae_engine {
     float* S = nullptr;
     uint8_t* colmask = nullptr;
     float4* partial = nullptr;
-    float2* stats = nullptr;
+    float2* ab = nullptr;
     int Tpad = 0, chunk = 0;
     std::vector<GemmPlan> plans;
     size_t plan_i = 0;
@@ -399,7 +486,9 @@ int add_slot(nvae_engine* h, const std::string& key, int kind, int cout, int cin
     cudaError_t e = cudaMalloc(&p, n * (kind == 2 ? 4 : 2) + 256);
     if (e != cudaSuccess) return h->fail(NDIT_ERR_NOMEM, "cudaMalloc(%s): %s", key.c_str(), cudaGetErrorString(e));
     h->w_allocs.push_back(p);
-    h->slots[key] = Slot{kind, cout, cin, taps, p, false};
+    Slot sl;
+    sl.kind = kind; sl.cout = cout; sl.cin = cin; sl.taps = taps; sl.ptr = p; sl.loaded = false;
+    h->slots[key] = sl;
     return 0;
 }
 int add_conv(nvae_engine* h, const std::string& pre, int cin, int cout, int taps, Conv* c) {
@@ -478,10 +567,11 @@ int vae_gn(nvae_engine* h, cudaStream_t s, const Geo& g, const Norm& n, const bf
     vae_gn_stats_kernel<<<dim3(chunks, g.B), 256, 0, s>>>(in, h->partial, g.P, n.c, chunks);
     VCK(cudaGetLastError());
     const double inv_count = 1.0 / (static_cast<double>(g.H) * g.W * (n.c / h->G));
-    vae_gn_finalize_kernel<<<g.B, 256, 0, s>>>(h->partial, h->stats, n.c, chunks, h->G, inv_count, GN_EPS);
+    vae_gn_finalize_kernel<<<dim3(h->G, g.B), 256, 0, s>>>(h->partial, n.g, n.b, h->ab, n.c, chunks, h->G, inv_count, GN_EPS);
     VCK(cudaGetLastError());
     const long long vecs = static_cast<long long>(g.P) * (n.c / 8);
-    vae_gn_apply_kernel<<<dim3(static_cast<unsigned>((vecs + 255) / 256), g.B), 256, 0, s>>>(in, h->stats, n.g, n.b, out, g.P, n.c, h->G, g.Hp, g.Wp, silu);
+    vae_gn_apply_kernel<<<dim3(static_cast<unsigned>((vecs + 256 * GN_VPT - 1) / (256 * GN_VPT)), g.B), 256, 0, s>>>(in, h->ab, out, g.P, n.c, g.Hp,
+                                                                                                                g.Wp, silu);
     VCK(cudaGetLastError());
     return 0;
 }
@@ -578,8 +668,10 @@ int vae_walk(nvae_engine* h, cudaStream_t s, const bf16* z, bf16* out, int B, in
     if (!e) e = vae_gn(h, s, g, h->norm_out, h->X, h->Nn, 1);
     if (!e && !h->building) {
         const int C = h->ch[3];
-        vae_conv_out_kernel<<<dim3((g.W + 127) / 128, g.H, B), 128, 9 * C * sizeof(float4), s>>>(h->Nn, h->conv_out.w, h->conv_out.b, out, g.H, g.W, C,
-                                                                                                 h->cfg.out_channels);
+        const dim3 grid((g.W + 63) / 64, (g.H + CONV_OUT_ROWS - 1) / CONV_OUT_ROWS, B);
+        const size_t sm = 9 * static_cast<size_t>(C) * sizeof(float4);
+        if (h->cfg.out_channels == 3) vae_conv_out_kernel<3><<<grid, 128, sm, s>>>(h->Nn, h->conv_out.w, h->conv_out.b, out, g.H, g.W, C, 3);
+        else vae_conv_out_kernel<4><<<grid, 128, sm, s>>>(h->Nn, h->conv_out.w, h->conv_out.b, out, g.H, g.W, C, h->cfg.out_channels);
         cudaError_t ce = cudaGetLastError();
         if (ce != cudaSuccess) e = h->fail(NDIT_ERR_CUDA, "conv_out: %s", cudaGetErrorString(ce));
     }
@@ -615,8 +707,11 @@ int prepare(nvae_engine* h, int B, int lh, int lw, cudaStream_t s) {
     }
     const int C0 = h->ch[0], T = (lh + 2) * (lw + 2);
     h->Tpad = (T + 63) / 64 * 64;
-    long long chunk = (64ll << 20) / (static_cast<long long>(h->Tpad) * 4) / 256 * 256;
-    if (chunk < 256) chunk = 256;
+    // query rows per pass of the mid-block attention: the P V product has only C / 256 column tiles, so a pass needs about
+    // 256 * (SM pairs) / (C / 256) rows to occupy every SM pair; the image is split evenly into passes of at most that many rows
+    const int want = 256 * ((h->num_sms / 2 + C0 / 256 - 1) / (C0 / 256));
+    const int passes = (T + want - 1) / want;
+    long long chunk = ((T + passes - 1) / passes + 255) / 256 * 256;
     if (chunk > T) chunk = T;
     h->chunk = static_cast<int>(chunk);
     int e = 0;
@@ -635,7 +730,7 @@ int prepare(nvae_engine* h, int B, int lh, int lw, cudaStream_t s) {
     e = e ? e : ws_alloc(h, &h->colmask, static_cast<size_t>(h->Tpad));
     const size_t chunks = (max_p + GN_PPC - 1) / GN_PPC;
     e = e ? e : ws_alloc(h, &h->partial, static_cast<size_t>(B) * chunks * 64);
-    e = e ? e : ws_alloc(h, &h->stats, static_cast<size_t>(B) * h->G);
+    e = e ? e : ws_alloc(h, &h->ab, static_cast<size_t>(B) * 512);
     if (e) { free_ws(h); return e; }
     vae_colmask_kernel<<<(h->Tpad + 255) / 256, 256, 0, s>>>(h->colmask, lh + 2, lw + 2, h->Tpad);
     VCK(cudaGetLastError());
@@ -671,6 +766,7 @@ extern "C" int nvae_create(const nvae_config* c, nvae_handle* out) {
     int e = 0;
     e = e ? e : add_conv(h, "post_quant_conv", Cz, Cz, 1, &h->pq);
     e = e ? e : add_conv(h, "decoder.conv_in", Cz, C0, 9, &h->conv_in);
+    if (!e) h->slots["decoder.conv_in.weight"].transposed = true;
     e = e ? e : add_res(h, "decoder.mid_block.resnets.0", C0, C0, &h->mid_res[0]);
     e = e ? e : add_res(h, "decoder.mid_block.resnets.1", C0, C0, &h->mid_res[1]);
     e = e ? e : add_norm(h, "decoder.mid_block.attentions.0.group_norm", C0, &h->mid_attn.gn);
@@ -696,7 +792,10 @@ extern "C" int nvae_create(const nvae_config* c, nvae_handle* out) {
     e = e ? e : add_conv(h, "decoder.conv_out", h->ch[3], c->out_channels, 9, &h->conv_out);
     if (e) { snprintf(g_vae_err, sizeof(g_vae_err), "%s", h->err); nvae_destroy(h); return e; }
     const int osm = 9 * h->ch[3] * static_cast<int>(sizeof(float4));
-    if (osm > 48 * 1024) cudaFuncSetAttribute(vae_conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, osm);
+    if (osm > 48 * 1024) {
+        cudaFuncSetAttribute(vae_conv_out_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, osm);
+        cudaFuncSetAttribute(vae_conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, osm);
+    }
     *out = h;
     return NDIT_OK;
 }
@@ -736,7 +835,8 @@ extern "C" int nvae_set_weight(nvae_handle h, const char* key, const void* src, 
         if (!ok) return h->fail(NDIT_ERR_INVALID, "%s: shape mismatch (want [%d, %d, %d, %d])", key, sl.cout, sl.cin, side, side);
         const size_t total = static_cast<size_t>(sl.cout) * sl.cin * sl.taps;
         const int grid = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
-        vae_pack_conv_kernel<<<grid, 256, 0, s>>>(static_cast<bf16*>(sl.ptr), src, dtype == NDIT_F32, sl.cout, sl.cin, sl.taps);
+        if (sl.transposed) vae_pack_conv_t_kernel<<<grid, 256, 0, s>>>(static_cast<bf16*>(sl.ptr), src, dtype == NDIT_F32, sl.cout, sl.cin, sl.taps);
+        else vae_pack_conv_kernel<<<grid, 256, 0, s>>>(static_cast<bf16*>(sl.ptr), src, dtype == NDIT_F32, sl.cout, sl.cin, sl.taps);
     } else {
         if (ndim != 1 || shape[0] != sl.cout) return h->fail(NDIT_ERR_INVALID, "%s: shape mismatch (want [%d])", key, sl.cout);
         vae_copy_vec_kernel<<<(sl.cout + 255) / 256, 256, 0, s>>>(sl.ptr, sl.kind == 2, src, dtype == NDIT_F32, sl.cout);
