@@ -27,7 +27,7 @@ typedef struct nvae_engine* nvae_handle;
 typedef struct nvae_config {
     int32_t latent_channels;         /* 4 (<= 16) */
     int32_t out_channels;            /* 3 (<= 4) */
-    int32_t block_out_channels[4];   /* encoder order, as in the config; each a multiple of 128, at most 512 */
+    int32_t block_out_channels[4];   /* encoder order, as in the config; each 128, 256 or 512 */
     int32_t layers_per_block;        /* 2: every up block has layers_per_block + 1 resnets */
     int32_t norm_num_groups;         /* 32 */
 } nvae_config;

@@ -38,7 +38,7 @@ using namespace ndit;
 
 namespace {
 
-constexpr int GN_PPC = 512;        // pixels per block of the statistics pass
+constexpr int GN_PPC = 512;        // pixels per block of the statistics pass (at most)
 constexpr float GN_EPS = 1e-6f;    // Decoder / ResnetBlock2D / Attention all build their GroupNorm with eps = 1e-6
 
 __device__ __forceinline__ void ld8(const bf16* p, float* f) {
@@ -129,12 +129,13 @@ __global__ void vae_conv_in_kernel(const bf16* __restrict__ z, const bf16* __res
 
 // ---------------------------------------------------------------------------------------------- GroupNorm
 // pass 1: per (image, chunk of pixels, 4-channel slice) partial sum / sum of squares (border pixels are zero and add nothing)
-__global__ void __launch_bounds__(256) vae_gn_stats_kernel(const bf16* __restrict__ x, float4* __restrict__ partial, int P, int C, int chunks) {
+__global__ void __launch_bounds__(256) vae_gn_stats_kernel(const bf16* __restrict__ x, float4* __restrict__ partial, int P, int C, int chunks,
+                                                            int ppc) {
     __shared__ float4 sm[256];
     const int tpp = C >> 3, ppb = 256 / tpp;
     const int c8 = threadIdx.x % tpp, pl = threadIdx.x / tpp;
     const int b = blockIdx.y, chunk = blockIdx.x;
-    const int p0 = chunk * GN_PPC, p1 = min(P, p0 + GN_PPC);
+    const int p0 = chunk * ppc, p1 = min(P, p0 + ppc);
     const bf16* xb = x + static_cast<size_t>(b) * P * C + c8 * 8;
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
     auto add = [&](const uint4& u) {
@@ -204,33 +205,41 @@ __global__ void __launch_bounds__(256) vae_gn_finalize_kernel(const float4* __re
         ab[static_cast<size_t>(b) * C + c] = make_float2(a, beta[c] - st.x * a);
     }
 }
-// pass 2: y = bf16(act(x * a[c] + b[c])), act = SiLU or identity, zeros on the border; 8 consecutive 16-byte vectors per thread
-constexpr int GN_VPT = 8;
-__global__ void __launch_bounds__(256) vae_gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ ab_g, bf16* __restrict__ y, int P,
-                                                           int C, int Hp, int Wp, int silu) {
-    __shared__ float2 ab[512];
+// pass 2: y = bf16(act(x * a[c] + b[c])), act = SiLU or identity, zeros on the border.  C / 8 divides the block size (C is 128,
+// 256 or 512), so a thread keeps the same 8 channels for all of its GN_VPT vectors: their affine lives in registers and consecutive
+// vectors of a thread are 256 / (C / 8) pixels apart.
+constexpr int GN_VPT = 4;
+__global__ void __launch_bounds__(256, 3) vae_gn_apply_kernel(const bf16* __restrict__ x, const float2* __restrict__ ab_g, bf16* __restrict__ y,
+                                                              int P, int C, int Hp, int Wp, int silu) {
     const int b = blockIdx.y;
-    for (int c = threadIdx.x; c < C; c += 256) ab[c] = ab_g[static_cast<size_t>(b) * C + c];
-    __syncthreads();
-    const int tpp = C >> 3;
-    const long long total = static_cast<long long>(P) * tpp;
-    const long long base = static_cast<long long>(blockIdx.x) * (256 * GN_VPT) + threadIdx.x;
-    const bf16* xb = x + static_cast<size_t>(b) * P * C;
-    bf16* yb = y + static_cast<size_t>(b) * P * C;
+    const unsigned tpp = C >> 3, ppi = 256u / tpp;                    // pixels covered by one pass of the block
+    const unsigned c8 = threadIdx.x % tpp;
+    const unsigned p0 = blockIdx.x * (ppi * GN_VPT) + threadIdx.x / tpp;
+    float2 ab[8];
+    {
+        const float4* src = reinterpret_cast<const float4*>(ab_g + static_cast<size_t>(b) * C + c8 * 8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float4 t = src[e];
+            ab[2 * e] = make_float2(t.x, t.y);
+            ab[2 * e + 1] = make_float2(t.z, t.w);
+        }
+    }
+    const bf16* xb = x + static_cast<size_t>(b) * P * C + c8 * 8;
+    bf16* yb = y + static_cast<size_t>(b) * P * C + c8 * 8;
     uint4 u[GN_VPT];
 #pragma unroll
     for (int i = 0; i < GN_VPT; ++i) {
-        const long long idx = base + i * 256;
-        u[i] = idx < total ? *reinterpret_cast<const uint4*>(xb + idx * 8) : make_uint4(0, 0, 0, 0);
+        const unsigned p = p0 + i * ppi;
+        u[i] = p < static_cast<unsigned>(P) ? *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * C) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < GN_VPT; ++i) {
-        const long long idx = base + i * 256;
-        if (idx >= total) break;
-        const int p = static_cast<int>(idx / tpp), c8 = static_cast<int>(idx - static_cast<long long>(p) * tpp);
-        const int py = p / Wp, px = p - py * Wp;
+        const unsigned p = p0 + i * ppi;
+        if (p >= static_cast<unsigned>(P)) break;
+        const unsigned py = p / static_cast<unsigned>(Wp), px = p - py * static_cast<unsigned>(Wp);
         float v[8];
-        if (py == 0 || py == Hp - 1 || px == 0 || px == Wp - 1) {
+        if (py == 0 || py == static_cast<unsigned>(Hp - 1) || px == 0 || px == static_cast<unsigned>(Wp - 1)) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
         } else {
@@ -238,12 +247,11 @@ __global__ void __launch_bounds__(256) vae_gn_apply_kernel(const bf16* __restric
             v[0] = a.x; v[1] = a.y; v[2] = bq.x; v[3] = bq.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float2 t = ab[c8 * 8 + e];
-                const float n = fmaf(v[e], t.x, t.y);
-                v[e] = silu ? n / (1.0f + __expf(-n)) : n;
+                const float n = fmaf(v[e], ab[e].x, ab[e].y);
+                v[e] = silu ? __fdividef(n, 1.0f + __expf(-n)) : n;
             }
         }
-        st8(yb + idx * 8, v);
+        st8(yb + static_cast<size_t>(p) * C, v);
     }
 }
 
@@ -563,15 +571,17 @@ int vae_conv(nvae_engine* h, cudaStream_t s, const Geo& g, const Conv& c, const 
 
 int vae_gn(nvae_engine* h, cudaStream_t s, const Geo& g, const Norm& n, const bf16* in, bf16* out, int silu) {
     if (h->building) return 0;
-    const int chunks = (g.P + GN_PPC - 1) / GN_PPC;
-    vae_gn_stats_kernel<<<dim3(chunks, g.B), 256, 0, s>>>(in, h->partial, g.P, n.c, chunks);
+    // pixels per block of the statistics pass: GN_PPC for the large stages, fewer when that would leave SMs idle (>= ~4 blocks per SM)
+    int ppc = GN_PPC;
+    while (ppc > 32 && (g.P + ppc - 1) / ppc < 4 * h->num_sms) ppc >>= 1;      // independent of the batch: one image decodes the same alone or in a batch
+    const int chunks = (g.P + ppc - 1) / ppc;
+    vae_gn_stats_kernel<<<dim3(chunks, g.B), 256, 0, s>>>(in, h->partial, g.P, n.c, chunks, ppc);
     VCK(cudaGetLastError());
     const double inv_count = 1.0 / (static_cast<double>(g.H) * g.W * (n.c / h->G));
     vae_gn_finalize_kernel<<<dim3(h->G, g.B), 256, 0, s>>>(h->partial, n.g, n.b, h->ab, n.c, chunks, h->G, inv_count, GN_EPS);
     VCK(cudaGetLastError());
-    const long long vecs = static_cast<long long>(g.P) * (n.c / 8);
-    vae_gn_apply_kernel<<<dim3(static_cast<unsigned>((vecs + 256 * GN_VPT - 1) / (256 * GN_VPT)), g.B), 256, 0, s>>>(in, h->ab, out, g.P, n.c, g.Hp,
-                                                                                                                g.Wp, silu);
+    const int ppb = (256 / (n.c / 8)) * GN_VPT;          // pixels per block
+    vae_gn_apply_kernel<<<dim3((g.P + ppb - 1) / ppb, g.B), 256, 0, s>>>(in, h->ab, out, g.P, n.c, g.Hp, g.Wp, silu);
     VCK(cudaGetLastError());
     return 0;
 }
@@ -728,7 +738,8 @@ int prepare(nvae_engine* h, int B, int lh, int lw, cudaStream_t s) {
     e = e ? e : ws_alloc(h, &h->S, static_cast<size_t>(h->chunk) * h->Tpad);
     e = e ? e : ws_alloc(h, &h->Pm, static_cast<size_t>(h->chunk) * h->Tpad);
     e = e ? e : ws_alloc(h, &h->colmask, static_cast<size_t>(h->Tpad));
-    const size_t chunks = (max_p + GN_PPC - 1) / GN_PPC;
+    // most blocks any statistics pass launches per image (see vae_gn: at most GN_PPC pixels per block, halved while SMs would idle)
+    const size_t chunks = std::max<size_t>((max_p + GN_PPC - 1) / GN_PPC, 8 * static_cast<size_t>(h->num_sms) + 2);
     e = e ? e : ws_alloc(h, &h->partial, static_cast<size_t>(B) * chunks * 64);
     e = e ? e : ws_alloc(h, &h->ab, static_cast<size_t>(B) * 512);
     if (e) { free_ws(h); return e; }
@@ -751,7 +762,7 @@ extern "C" int nvae_create(const nvae_config* c, nvae_handle* out) {
     if (c->norm_num_groups != 32) return bad("norm_num_groups must be 32");
     if (c->layers_per_block < 1 || c->layers_per_block > 8) return bad("layers_per_block 1..8");
     for (int i = 0; i < 4; ++i)
-        if (c->block_out_channels[i] < 128 || c->block_out_channels[i] > 512 || c->block_out_channels[i] % 128) return bad("block_out_channels: multiples of 128 up to 512");
+        if (c->block_out_channels[i] != 128 && c->block_out_channels[i] != 256 && c->block_out_channels[i] != 512) return bad("block_out_channels: 128, 256 or 512");
     if (c->block_out_channels[3] < 256) return bad("the mid block needs at least 256 channels");
     int dev = 0;
     cudaDeviceProp prop;
