@@ -268,13 +268,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // operand-read traffic per flop is halved against the single-CTA kernel; the leader CTA issues one
 // tcgen05.mma (M=256) that drives both tensor cores, each accumulating its 128 rows in its own TMEM.
 // Used when M % 256 == 0 (the four block GEMMs at full size).
-template <int BN_>
+// SHARE (3x3 convolution only): a stage holds the A rows of ONE (dy, k-block) with a one-row halo on either side (136 rows: 17 swizzle
+// atoms) and the W tiles of the three taps (dy, dx = -1, 0, +1); the three dx taps read the same A bytes through descriptors whose
+// start address is advanced by dx rows (128 B; base offset 0, see the MMA warp), so A crosses L2 -> shared memory three times per tile, not nine.
+constexpr int GEMM_SHARE_ROWS = 136;
+template <int BN_, bool SHARE = false>
 struct Gemm2Cfg {
     static constexpr int BN = BN_;                           // 256, or 192 when N is a multiple of 192 only (fused q|k|v)
-    static constexpr int A_BYTES = 128 * GEMM_BK * 2;        // this CTA's A rows
-    static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the W tile
+    static constexpr int A_BYTES = (SHARE ? GEMM_SHARE_ROWS : 128) * GEMM_BK * 2;        // this CTA's A rows
+    static constexpr int B_ONE = (BN / 2) * GEMM_BK * 2;     // this CTA's half of one W tile
+    static constexpr int B_BYTES = (SHARE ? 3 : 1) * B_ONE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB / 28 KB
-    static constexpr int STAGES = BN_ == 128 ? 8 : 6;
+    static constexpr int STAGES = SHARE ? (BN_ == 128 ? 5 : 3) : (BN_ == 128 ? 8 : 6);
     static constexpr int TMEM_COLS = 512;                    // accumulator stages at columns 0 and 256
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
@@ -284,12 +289,12 @@ struct Gemm2Cfg {
 // warps 6-9 the second half, each on the TMEM lane quadrant (warp & 3) it may access.
 template <bool EXT> struct Gemm2Threads { static constexpr int N = EXT ? 320 : GEMM_THREADS; static constexpr int EPI_WARPS = EXT ? 8 : 4; };
 
-template <int BN, int EPI, bool EXT>
+template <int BN, int EPI, bool EXT, bool SHARE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Threads<EXT>::N, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      bf16* __restrict__ C, const int* __restrict__ w_row_off, int w_row_mul, int M, int N, int K, int ldc,
                      const GemmVtOut vt, const GemmRowWin rows, const GemmExt ext) {
-    using Cfg = Gemm2Cfg<BN>;
+    using Cfg = Gemm2Cfg<BN, SHARE>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -308,7 +313,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int m_tiles = (M + 255) / 256;      // ragged last tile: TMA zero-fills the rows >= M, stores are masked
     const int n_tiles = (N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
-    const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    const int num_kb = SHARE ? 3 * ext.kpt : (K + GEMM_BK - 1) / GEMM_BK;     // pipeline stages per tile
     const int n_full = N / BN;
     const int full_tiles = m_tiles * n_full;
     const int n_rem = N - n_full * BN;        // width of the ragged last-N tile (0: none); a multiple of 32
@@ -374,13 +379,21 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land on this barrier
                     int a_col = kb * GEMM_BK, a_row = row0 + m_blk * 256 + static_cast<int>(rank) * 128;
-                    if (EXT && ext.kpt > 0) {       // implicit 3x3 convolution: tap (dy, dx) reads the rows shifted by dy * wp + dx
-                        const int tap = kb / ext.kpt;
-                        a_col = (kb - tap * ext.kpt) * GEMM_BK;
-                        a_row += (tap / 3 - 1) * ext.wp + (tap % 3 - 1);
+                    if (SHARE) {                    // stage = (dy, k-block): A rows with a one-row halo, W tiles of the three dx taps
+                        const int dy = kb / ext.kpt, kc = kb - dy * ext.kpt;
+                        tma_load_2d_pair(sa, &tmA, full_bar(stage), kc * GEMM_BK, a_row + (dy - 1) * ext.wp - 1);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+                            tma_load_2d_pair(sa + Cfg::A_BYTES + dx * Cfg::B_ONE, &tmB, full_bar(stage), ((dy * 3 + dx) * ext.kpt + kc) * GEMM_BK, w0);
+                    } else {
+                        if (EXT && ext.kpt > 0) {   // implicit 3x3 convolution: tap (dy, dx) reads the rows shifted by dy * wp + dx
+                            const int tap = kb / ext.kpt;
+                            a_col = (kb - tap * ext.kpt) * GEMM_BK;
+                            a_row += (tap / 3 - 1) * ext.wp + (tap % 3 - 1);
+                        }
+                        tma_load_2d_pair(sa, &tmA, full_bar(stage), a_col, a_row);
+                        tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, w0);
                     }
-                    tma_load_2d_pair(sa, &tmA, full_bar(stage), a_col, a_row);
-                    tma_load_2d_pair(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, w0);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -407,10 +420,23 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint64_t da = make_smem_desc_kmajor(sa, 1024, UMMA_SW128);
-                        const uint64_t db = make_smem_desc_kmajor(sa + Cfg::A_BYTES, 1024, UMMA_SW128);
+                        if (SHARE) {
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int dx = 0; dx < 3; ++dx) {
+                                // rows dx .. dx + 127 of the haloed tile: start address + dx * 128 B.  MEASURED on B200: the 128B swizzle
+                                // of the operand fetch follows the absolute shared-memory address (bits 7-9 select the XOR phase), exactly
+                                // like the TMA write did, so the descriptor's base-offset field stays 0 (setting it to dx gives garbage).
+                                const uint64_t da = make_smem_desc_kmajor(sa + dx * 128, 1024, UMMA_SW128);
+                                const uint64_t db = make_smem_desc_kmajor(sa + Cfg::A_BYTES + dx * Cfg::B_ONE, 1024, UMMA_SW128);
+#pragma unroll
+                                for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | dx | k) != 0);
+                            }
+                        } else {
+                            const uint64_t da = make_smem_desc_kmajor(sa, 1024, UMMA_SW128);
+                            const uint64_t db = make_smem_desc_kmajor(sa + Cfg::A_BYTES, 1024, UMMA_SW128);
+#pragma unroll
+                            for (int k = 0; k < GEMM_BK / 16; ++k) umma_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
                         umma_commit_pair(empty_bar(stage));
                         if (kb == num_kb - 1) umma_commit_pair(tfull_bar(as));
                     }
@@ -547,22 +573,23 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-template <int BN, int EPI, bool EXT = false>
+template <int BN, int EPI, bool EXT = false, bool SHARE = false>
 static cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* C, const int* w_row_off, int w_row_mul, int M, int N,
                                 int K, int ldc, int num_sms, const GemmVtOut& vt, const GemmRowWin& rows, cudaStream_t stream,
                                 const GemmExt& ext = GemmExt{}) {
-    auto kern = gemm2_bf16_tn_kernel<BN, EPI, EXT>;
+    auto kern = gemm2_bf16_tn_kernel<BN, EPI, EXT, SHARE>;
+    using Cfg2 = Gemm2Cfg<BN, SHARE>;
     static PerDeviceFlag flags;
     bool& configured = flags.here();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = ((M + 255) / 256) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (pairs > tiles) pairs = tiles;
-    return launch_k(kern, dim3(2 * pairs), dim3(Gemm2Threads<EXT>::N), Gemm2Cfg<BN>::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt, rows, ext);
+    return launch_k(kern, dim3(2 * pairs), dim3(Gemm2Threads<EXT>::N), Cfg2::SMEM_BYTES, stream, tmA, tmB, C, w_row_off, w_row_mul, M, N, K, ldc, vt, rows, ext);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -595,6 +622,12 @@ cudaError_t gemm_bf16_tn(const GemmPlan& p, cudaStream_t stream) {
         // one ragged last-N tile a multiple of 32 wide
         if (!p.pair || p.epi != EPI_STORE || p.bias != nullptr || p.vt.ptr != nullptr) return cudaErrorInvalidValue;
         if (p.ext.kpt > 0 && p.K != 9 * p.ext.kpt * GEMM_BK) return cudaErrorInvalidValue;
+        if (p.ext.share) {
+            if (p.ext.kpt <= 0 || p.N % p.bn != 0) return cudaErrorInvalidValue;
+            if (p.bn == 128) return launch_gemm2<128, EPI_STORE, true, true>(p.tmA, p.tmB, p.C, nullptr, 0, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream, p.ext);
+            if (p.bn == 256) return launch_gemm2<256, EPI_STORE, true, true>(p.tmA, p.tmB, p.C, nullptr, 0, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream, p.ext);
+            return cudaErrorInvalidValue;
+        }
         if (p.bn == 128 && p.N % 128 == 0)
             return launch_gemm2<128, EPI_STORE, true>(p.tmA, p.tmB, p.C, nullptr, 0, p.M, p.N, p.K, p.ldc, p.num_sms, p.vt, p.rows, stream, p.ext);
         if (p.bn == 256 && (p.N % 256) % 32 == 0)

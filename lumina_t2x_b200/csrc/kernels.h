@@ -43,6 +43,8 @@ struct GemmRowWin {
 // coordinate (rows before / after the matrix are zero-filled) and W is packed [Cout][tap][Cin].
 struct GemmExt {
     int kpt;             // > 0: implicit 3x3 convolution, k-blocks per tap (= Cin / 64); 0: plain GEMM
+    int share;           // 1 (with kpt > 0): one (128 + 8)-row A tile per (dy, k-block) serves the three dx taps (A map box = 136 rows):
+                         // A crosses L2 -> shared memory 3 times per tile instead of 9
     int wp, hp;          // padded width / height; hp > 0: rows on the border of their image are stored as zero
     const bf16* bias;    // optional [N]: bf16(acc + bias)
     const bf16* resid;   // optional [M, ldr]: out = bf16(bf16(acc + bias) + resid)   (ResnetBlock2D / Attention residual)
