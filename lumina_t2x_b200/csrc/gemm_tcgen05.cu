@@ -375,7 +375,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int w0 = w_off + n_blk * BN + static_cast<int>(rank) * ((n_blk < n_full ? BN : n_rem) / 2);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
-                if (lane == 0) {
+                if (EXT ? elect_one_sync() : lane == 0) {
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // both CTAs' bytes land on this barrier
                     int a_col = kb * GEMM_BK, a_row = row0 + m_blk * 256 + static_cast<int>(rank) * 128;
@@ -418,7 +418,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    if (lane == 0) {
+                    // EXT: one elected lane (elect.sync) - the MMAs then issue back to back; under `lane == 0` ptxas wraps every tcgen05
+                    // instruction in an ELECT loop of ~45 issue cycles, which a 64-cycle N = 128 MMA cannot hide
+                    if (EXT ? elect_one_sync() : lane == 0) {
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         if (SHARE) {
 #pragma unroll
