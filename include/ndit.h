@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NDIT_ABI_VERSION 4
+#define NDIT_ABI_VERSION 5
 
 typedef struct ndit_engine* ndit_handle;
 
@@ -113,6 +113,19 @@ int ndit_load_packed(ndit_handle h, const char* path);
  * cap_feats_dev: bf16 [batch, T, cap_feat_dim]; cap_mask_dev: uint8 [batch, T] (non-zero = valid). */
 int ndit_set_caption(ndit_handle h, const void* cap_feats_dev, const uint8_t* cap_mask_dev, int32_t batch, int32_t T,
                      void* stream);
+
+/* --- region-masked captions of the compositional model: the cap_feats / cap_mask / global_cap_feats / global_cap_mask / h_split_num /
+ * w_split_num kwargs of lumina_next_compositional_generation/models/model.py:902-953 (NextDiT.forward_with_cfg) -> :852-899 (forward).
+ * cap_feats_dev: bf16 [n_caps, T, cap_feat_dim] = the region captions followed by the negative (unconditional) caption (demo.py:211-223),
+ * cap_mask_dev: uint8 [n_caps, T]; global_cap_feats_dev bf16 [1, global_T, cap_feat_dim] / global_cap_mask_dev uint8 [1, global_T]: the
+ * caption the adaLN conditioning pools over for BOTH rows (:866-870).  The latent's token grid is cut into h_split x w_split rectangles
+ * of (H // h_split // 2) x (W // w_split // 2) tokens; rectangle (i, j) belongs to caption (i + 1) * (j + 1) - 1 (:879) and its tokens
+ * cross-attend to that caption only (Attention.forward :421-446: per-caption masked SDPA, nan_to_num, sum over the cond captions); every
+ * token of the unconditional row attends to the last caption.  Drives ndit_forward_cfg / ndit_sample with batch = 2 (one cond / uncond
+ * pair) until the next ndit_set_caption.  Grows the caption buffers when n_caps exceeds what the workspace holds.  head_dim 72. */
+int ndit_set_caption_regions(ndit_handle h, const void* cap_feats_dev, const uint8_t* cap_mask_dev, int32_t n_caps, int32_t T,
+                             const void* global_cap_feats_dev, const uint8_t* global_cap_mask_dev, int32_t global_T, int32_t h_split,
+                             int32_t w_split, void* stream);
 
 /* --- class-conditional model: the `y` argument of DiT_Llama.forward_with_cfg (models.py:946): labels_dev int64 [batch]
  * (second half = the null class num_classes for CFG).  Replaces ndit_set_caption for num_classes > 0. */

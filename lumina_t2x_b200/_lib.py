@@ -45,6 +45,7 @@ SIGNATURES = {
     "ndit_save_packed": (C.c_int, [_vp, C.c_char_p]),
     "ndit_load_packed": (C.c_int, [_vp, C.c_char_p]),
     "ndit_set_caption": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "ndit_set_caption_regions": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "ndit_set_labels": (C.c_int, [_vp, _vp, _i32, _vp]),
     "ndit_forward_cfg": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),
     "ndit_forward": (C.c_int, [_vp, _vp, C.POINTER(_f32), _i32, _i32, _i32, C.POINTER(NditStepParams), _vp, _vp]),
@@ -121,7 +122,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ndit_abi_version() != 4:
+    if lib.ndit_abi_version() != 5:
         raise RuntimeError("libndit_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -125,14 +125,20 @@ __device__ long long g_at_timing[2][64][8];
 #define AT_STAMP(k)
 #endif
 
-template <int HD>
+// REGION (compositional generation, lumina_next_compositional_generation/models/model.py:421-446, 872-887): the caption segment holds
+// n_cond region captions followed by the unconditional one.  Batch row 0 (cond) attends, per query token, to the ONE caption whose region
+// contains the token (region_id = (h_split + 1) * (w_split + 1) - 1 of its rectangle, :879; the reference sums the per-caption SDPA
+// outputs, of which at most one is non-zero for a token, every other caption being fully masked -> NaN -> nan_to_num -> 0); batch row 1
+// (uncond) attends to the last caption from every token (region_mask[-1] = 1, :885).  All captions of a batch row run as ONE softmax
+// segment over the concatenated keys with a per-row mask, which is the same thing because exactly one caption survives the mask.
+template <int HD, bool REGION>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmQ16,
                        const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
                        const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmKy64,
                        const __grid_constant__ CUtensorMap tmKy16, const __grid_constant__ CUtensorMap tmVyt,
                        const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh, bf16* __restrict__ out,
-                       int N, int T, int H, int Hkv, float sl2_self, float sl2_cross, const int* __restrict__ kv_len) {
+                       int N, int T, int H, int Hkv, float sl2_self, float sl2_cross, const int* __restrict__ kv_len, const AttnRegion reg) {
     using Dm = AttnDims<HD>;
     constexpr int HDP = Dm::HDP;
     extern __shared__ uint8_t smem_raw[];
@@ -159,7 +165,11 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
     // rows are computed like any other and dropped by the caller).  Read before pdl_wait: written by a host copy, not a kernel.
     const int Nv = kv_len != nullptr ? kv_len[b] : N;
     const int n_self = (Nv + AT_BKV - 1) / AT_BKV;
-    const int n_cross = (T + AT_BKV - 1) / AT_BKV;      // 0 for the class-conditional model
+    const int n_tb = (T + AT_BKV - 1) / AT_BKV;          // kv blocks per caption; 0 for the class-conditional model
+    // REGION: captions [cap0, cap0 + n_caps) belong to this batch row (cond: the region captions, uncond: the last one)
+    const int cap0 = REGION ? (b == 0 ? 0 : reg.n_cond) : b;
+    const int n_caps = REGION ? (b == 0 ? reg.n_cond : 1) : 1;
+    const int n_cross = n_tb * n_caps;
     const int n_total = n_self + n_cross;
 
     if (warp == 0 && lane == 0) {
@@ -228,13 +238,15 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                         tma_load_3d(vd, &tmVt, v_full(s), kv0, 0, b * Hkv + g);
                         tma_load_3d(vd + Dm::VHALF_BYTES, &tmVt, v_full(s), kv0 + 64, 0, b * Hkv + g);
                     } else {
-                        const int kv0 = (jj - n_self) * AT_BKV;
-                        tma_load_3d(kd, &tmKy64, k_full(s), 0, g, b * T + kv0);
+                        const int jc = jj - n_self;
+                        const int cap = REGION ? cap0 + jc / n_tb : b;                  // caption row of this block
+                        const int kv0 = (REGION ? jc % n_tb : jc) * AT_BKV;
+                        tma_load_3d(kd, &tmKy64, k_full(s), 0, g, cap * T + kv0);
 #pragma unroll
                         for (int c = 0; c < Dm::N16; ++c)
-                            tma_load_3d(kd + AT_Q64_BYTES + c * AT_Q16_BYTES, &tmKy16, k_full(s), 64 + 16 * c, g, b * T + kv0);
-                        tma_load_3d(vd, &tmVyt, v_full(s), kv0, 0, b * Hkv + g);
-                        tma_load_3d(vd + Dm::VHALF_BYTES, &tmVyt, v_full(s), kv0 + 64, 0, b * Hkv + g);
+                            tma_load_3d(kd + AT_Q64_BYTES + c * AT_Q16_BYTES, &tmKy16, k_full(s), 64 + 16 * c, g, cap * T + kv0);
+                        tma_load_3d(vd, &tmVyt, v_full(s), kv0, 0, cap * Hkv + g);
+                        tma_load_3d(vd + Dm::VHALF_BYTES, &tmVyt, v_full(s), kv0 + 64, 0, cap * Hkv + g);
                     }
                 }
                 __syncwarp();
@@ -352,13 +364,26 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
 #pragma unroll
         for (int i = 0; i < HD / 2; ++i) o_self[i] = 0u;
         float m_ref = -INFINITY;
+        // REGION: the one caption row this query token attends to (-1: none - a token outside every rectangle, or whose region id
+        // is not a cond caption: the reference then adds nan_to_num(NaN) = 0)
+        int my_cap = b;
+        if constexpr (REGION) {
+            if (b == 0) {
+                const int hs = (qrow / reg.Wp) / reg.hp, ws = (qrow % reg.Wp) / reg.wp;
+                const int rid = (hs + 1) * (ws + 1) - 1;
+                my_cap = (hs < reg.hs && ws < reg.ws && rid < reg.n_cond) ? rid : -1;
+            } else {
+                my_cap = reg.n_cond;
+            }
+        }
 
         // O_x[:, 0:HD] / rowsum (column HD) -> packed bf16.  combine: dst = bf16(dst + bf16(gt * bf16(value)))
         auto read_o = [&](uint32_t* dst, bool combine, float gt) {
             uint32_t l8[8];
             tmem_ld_32x32b_x8(to + HD, l8);       // HD is a multiple of 8
             tmem_ld_wait();
-            const float inv = 1.0f / __uint_as_float(l8[0]);
+            float inv = 1.0f / __uint_as_float(l8[0]);
+            if constexpr (REGION) { if (__uint_as_float(l8[0]) == 0.f) inv = 0.f; }   // no valid key: nan_to_num(softmax of all -inf) = 0
 #pragma unroll
             for (int c = 0; c < HD / 8; ++c) {
                 uint32_t v[8];
@@ -400,12 +425,15 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                     vw[c] = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
                 }
             } else {
-                const int t0 = (jj - n_self) * AT_BKV;
+                const int jc = jj - n_self;
+                const int cap = REGION ? cap0 + jc / n_tb : b;
+                const int t0 = (REGION ? jc % n_tb : jc) * AT_BKV;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int t = t0 + c * 32 + lane;
-                    const bool ok = (t < T) && (ymask[b * T + t] != 0);
+                    const bool ok = (t < T) && (ymask[cap * T + t] != 0);
                     vw[c] = __ballot_sync(0xffffffffu, ok);
+                    if constexpr (REGION) { if (cap != my_cap) vw[c] = 0u; }     // per row: another region's caption
                 }
             }
             const bool all_valid = (vw[0] & vw[1] & vw[2] & vw[3]) == 0xffffffffu;
@@ -447,13 +475,16 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                 }
             }
             const float m_new = fmaxf(m_ref, mb);
-            if (first) {
+            // REGION, caption segment: a row may meet its first valid key in any block of the segment (its caption need not be the
+            // first one); until then m_ref stays -inf ("unseen"), O_x of the row is all zeros and needs no rescale
+            const bool unseen = REGION && cross && m_ref == -INFINITY;
+            if (first && !(REGION && cross)) {
                 m_ref = (m_new == -INFINITY) ? 0.f : m_new;
             } else {
                 // lazy rescale (warp-uniform decision because tcgen05.ld/st are warp-collective)
-                const bool need = (m_new - m_ref) * sl2 > AT_RESCALE_LOG2;
-                if (__any_sync(0xffffffffu, need)) {
-                    const float alpha = ex2_approx((m_ref - m_new) * sl2);   // scales O and the row sum (column HD)
+                const bool need = !unseen && (m_new - m_ref) * sl2 > AT_RESCALE_LOG2;
+                if (!first && __any_sync(0xffffffffu, need)) {
+                    const float alpha = unseen ? 1.0f : ex2_approx((m_ref - m_new) * sl2);   // scales O and the row sum (column HD)
                     mbar_wait(o_full(x), (jj - 1) & 1);
                     tc_fence_after();
 #pragma unroll
@@ -468,8 +499,9 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_c
                     tmem_st_wait();
                     m_ref = m_new;
                 }
+                if (unseen) m_ref = m_new;      // still -inf if this block held no valid key for the row either
             }
-            const float moff = m_ref * sl2;
+            const float moff = (REGION && m_ref == -INFINITY) ? 0.f : m_ref * sl2;
             AT_STAMP(3);
             if (jj == 0 && x == 0) {
                 __syncwarp();
@@ -527,9 +559,9 @@ extern "C" int ndit_debug_attn_timing(long long* out) {   // [2][64][8] clock64 
 }
 #endif
 
-template <int HD>
+template <int HD, bool REGION>
 static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
-    auto kern = attention_fused_kernel<HD>;
+    auto kern = attention_fused_kernel<HD, REGION>;
     static PerDeviceFlag flags;
     bool& configured = flags.here();
     if (!configured) {
@@ -541,14 +573,21 @@ static cudaError_t launch_attention(const AttnPlan& p, cudaStream_t stream) {
     const dim3 grid((p.N + 2 * AT_BQ - 1) / (2 * AT_BQ), p.H, p.B);
     return launch_k(kern, grid, dim3(AT_THREADS), AttnDims<HD>::SMEM_BYTES, stream, p.tmQ64, p.tmQ16, p.tmK64, p.tmK16, p.tmVt, p.tmKy64, p.tmKy16, p.tmVyt, p.ymask,
                                                       p.gate_tanh, p.out, p.N, p.T, p.H, p.Hkv, p.scale_self * log2e,
-                                                      p.scale_cross * log2e, p.kv_len);
+                                                      p.scale_cross * log2e, p.kv_len, p.region);
 }
 
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
     if (p.T < 0 || p.N <= 0) return cudaErrorInvalidValue;
-    if (p.hd == 72) return launch_attention<72>(p, stream);
-    if (p.hd == 48) return launch_attention<48>(p, stream);
-    if (p.hd == 96) return launch_attention<96>(p, stream);
+    if (p.region.n_cond > 0) {
+        // region-masked cross-attention of the compositional model: one cond / uncond pair, text-conditioned Next-DiT (head_dim 72)
+        const AttnRegion& r = p.region;
+        if (p.B != 2 || p.T <= 0 || p.hd != 72 || p.kv_len != nullptr || r.Wp <= 0 || r.hp <= 0 || r.wp <= 0 || r.hs <= 0 || r.ws <= 0)
+            return cudaErrorInvalidValue;
+        return launch_attention<72, true>(p, stream);
+    }
+    if (p.hd == 72) return launch_attention<72, false>(p, stream);
+    if (p.hd == 48) return launch_attention<48, false>(p, stream);
+    if (p.hd == 96) return launch_attention<96, false>(p, stream);
     return cudaErrorInvalidValue;
 }
 
@@ -558,9 +597,20 @@ cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream) {
 __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, const bf16* __restrict__ kvy, int ld_kvy,
                                      const uint8_t* __restrict__ ymask, const float* __restrict__ gate_tanh,
                                      bf16* __restrict__ out, int N, int T, int H, int Hkv, int hd, float scale_self,
-                                     float scale_cross, const int* __restrict__ kv_len) {
+                                     float scale_cross, const int* __restrict__ kv_len, const AttnRegion reg) {
     extern __shared__ float sh[];            // scores [max(N,T)] + q [hd] + red[32]
     const int n = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    // caption row of this query token: its own batch row, or (region mode, see attention_fused_kernel) the caption of its region
+    int cap = b;
+    if (reg.n_cond > 0) {
+        if (b == 0) {
+            const int hs = (n / reg.Wp) / reg.hp, ws = (n % reg.Wp) / reg.wp;
+            const int rid = (hs + 1) * (ws + 1) - 1;
+            cap = (hs < reg.hs && ws < reg.ws && rid < reg.n_cond) ? rid : -1;
+        } else {
+            cap = reg.n_cond;
+        }
+    }
     const int g = h / (H / Hkv);
     const int L = N > T ? N : T;
     float* sc = sh;
@@ -572,16 +622,16 @@ __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, c
     float result[2] = {0.f, 0.f};            // this thread owns output dims threadIdx.x (< hd) for both segments
     for (int seg = 0; seg < 2; ++seg) {
         const int len = seg == 0 ? (kv_len != nullptr ? kv_len[b] : N) : T;
-        if (len == 0) continue;              // no caption segment (uniform for the whole block)
+        if (len == 0 || (seg == 1 && cap < 0)) continue;   // no caption segment / no caption for this token (uniform for the whole block)
         const float scale = seg == 0 ? scale_self : scale_cross;
         float mx = -INFINITY;
         for (int k = threadIdx.x; k < len; k += blockDim.x) {
             const bf16* kp = seg == 0 ? qkv + (static_cast<size_t>(b) * N + k) * ld_qkv + H * hd + g * hd
-                                      : kvy + (static_cast<size_t>(b) * T + k) * ld_kvy + g * hd;
+                                      : kvy + (static_cast<size_t>(cap) * T + k) * ld_kvy + g * hd;
             float s = 0.f;
             for (int d = 0; d < hd; ++d) s += qv[d] * __bfloat162float(kp[d]);
             s *= scale;
-            if (seg == 1 && ymask[b * T + k] == 0) s = -INFINITY;
+            if (seg == 1 && ymask[cap * T + k] == 0) s = -INFINITY;
             sc[k] = s;
             mx = fmaxf(mx, s);
         }
@@ -608,10 +658,10 @@ __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, c
             float acc = 0.f;
             for (int k = 0; k < len; ++k) {
                 const bf16* vp = seg == 0 ? qkv + (static_cast<size_t>(b) * N + k) * ld_qkv + (H + Hkv) * hd + g * hd
-                                          : kvy + (static_cast<size_t>(b) * T + k) * ld_kvy + Hkv * hd + g * hd;
+                                          : kvy + (static_cast<size_t>(cap) * T + k) * ld_kvy + Hkv * hd + g * hd;
                 acc += sc[k] * __bfloat162float(vp[d]);
             }
-            result[seg] = bf16_round(acc / sum);
+            result[seg] = sum > 0.f ? bf16_round(acc / sum) : (reg.n_cond > 0 ? 0.f : bf16_round(acc / sum));   // region mode: nan_to_num
         }
         __syncthreads();
     }
@@ -623,8 +673,9 @@ __global__ void attention_ref_kernel(const bf16* __restrict__ qkv, int ld_qkv, c
 
 cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_kvy, const uint8_t* ymask,
                           const float* gate_tanh, bf16* out, int B, int N, int T, int H, int Hkv, int hd,
-                          float scale_self, float scale_cross, cudaStream_t stream, const int* kv_len) {
+                          float scale_self, float scale_cross, cudaStream_t stream, const int* kv_len, AttnRegion region) {
     if (hd > 128) return cudaErrorInvalidValue;
+    if (region.n_cond > 0 && (B != 2 || T <= 0 || region.Wp <= 0 || region.hp <= 0 || region.wp <= 0)) return cudaErrorInvalidValue;
     const int L = N > T ? N : T;
     const size_t sh = (L + hd + 32) * sizeof(float);
     static size_t configured_sz[64] = {};
@@ -637,7 +688,7 @@ cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_k
         configured = sh;
     }
     attention_ref_kernel<<<dim3(N, H, B), 128, sh, stream>>>(qkv, ld_qkv, kvy, ld_kvy, ymask, gate_tanh, out, N, T, H, Hkv,
-                                                           hd, scale_self, scale_cross, kv_len);
+                                                           hd, scale_self, scale_cross, kv_len, region);
     return cudaGetLastError();
 }
 

@@ -148,6 +148,10 @@ struct ndit_engine {
     int rope_next = 0;
     // caption state
     int cap_batch = 0, cap_T = 0;
+    int cap_rows = 0;                        // caption rows held in yhat / kvy / vyt (= cap_batch, or n_cond + 1 in region mode)
+    int cap_rows_req = 0, cap_rows_max = 0;  // caption-row capacity of the workspace: max(max_batch, what ndit_set_caption_regions asked for)
+    // region-masked captions of the compositional model (ndit_set_caption_regions): n_cond region captions + the unconditional one
+    int region_cond = 0, region_hs = 1, region_ws = 1;
     // plans
     int plan_M = 0, plan_B = 0, plan_N = 0, plan_T = 0;
     std::vector<GemmPlan> p_qkv, p_wo, p_w13, p_w2;
@@ -158,7 +162,7 @@ struct ndit_engine {
     // CUDA graphs of whole fixed-grid solves (ndit_sample): key = everything the captured launch sequence depends on
     struct SolveGraph {
         std::vector<float> grid;
-        int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0, vt_epi = 0, moe_grouped = 0;
+        int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, cap_rows = 0, region_cond = 0, region_hs = 0, region_ws = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0, vt_epi = 0, moe_grouped = 0;
         ndit_step_params sp;
         cudaGraphExec_t exec = nullptr;
         int64_t launches = 0;
@@ -258,10 +262,12 @@ static int alloc_workspace(ndit_engine* h) {
     h->Bmax = c.max_batch; h->Tmax = h->cls ? 0 : c.max_cap_len; h->Tpad_max = (h->Tmax + 7) / 8 * 8;
     h->Mmax = c.max_batch * c.max_tokens;
     const size_t M = h->Mmax, B = h->Bmax, T = h->Tmax;
+    h->cap_rows_max = h->cap_rows_req > h->Bmax ? h->cap_rows_req : h->Bmax;
+    const size_t Bc = h->cap_rows_max;       // caption rows (region mode may hold more captions than batch rows)
     WALLOC(X, M * D); WALLOC(u, M * D); WALLOC(qkv, M * h->Wq); WALLOC(attn, M * D); WALLOC(o, M * D); WALLOC(hbuf, M * F);
     WALLOC(vt, B * h->Hkv * h->vrows * ((size_t)c.max_tokens + 8));
-    WALLOC(yhat, L * B * T * C); WALLOC(kvy, L * B * T * 2 * KV); WALLOC(vyt, L * B * h->Hkv * h->vrows * h->Tpad_max);
-    WALLOC(ymask, B * T); WALLOC(pool, B * C); WALLOC(capemb, B * cd); WALLOC(tf, B * 256); WALLOC(trow, B + 8); WALLOC(kvlen, B + 8); WALLOC(h1, B * cd); WALLOC(sc, B * cd);
+    WALLOC(yhat, L * Bc * T * C); WALLOC(kvy, L * Bc * T * 2 * KV); WALLOC(vyt, L * Bc * h->Hkv * h->vrows * h->Tpad_max);
+    WALLOC(ymask, Bc * T); WALLOC(pool, B * C); WALLOC(capemb, B * cd); WALLOC(tf, B * 256); WALLOC(trow, B + 8); WALLOC(kvlen, B + 8); WALLOC(h1, B * cd); WALLOC(sc, B * cd);
     WALLOC(mod, B * (L * NCH * D + h->FD * D)); WALLOC(tok, M * h->O);
     if (S > 1) {
         int emax = c.moe_space_experts > 2 ? c.moe_space_experts : 2;
@@ -273,7 +279,7 @@ static int alloc_workspace(ndit_engine* h) {
         }
     }
     const size_t lat = B * c.in_channels * (size_t)c.max_tokens * 4;
-    WALLOC(vel, lat); WALLOC(ystate, lat); WALLOC(ymid, lat); WALLOC(kbuf[0], lat); WALLOC(kbuf[1], lat); WALLOC(kbuf[2], lat); WALLOC(stage_z, lat); WALLOC(stage_cap, B * T * C); WALLOC(stage_mask, B * T);
+    WALLOC(vel, lat); WALLOC(ystate, lat); WALLOC(ymid, lat); WALLOC(kbuf[0], lat); WALLOC(kbuf[1], lat); WALLOC(kbuf[2], lat); WALLOC(stage_z, lat); WALLOC(stage_cap, Bc * T * C); WALLOC(stage_mask, Bc * T);
     for (int i = 0; i < 2; ++i) {
         int r = dev_alloc(h, &h->rope[i].tab, (size_t)c.max_tokens * (h->hd / 2), true);
         h->rope[i].Hp = 0;
@@ -282,7 +288,8 @@ static int alloc_workspace(ndit_engine* h) {
     h->plan_M = h->plan_B = h->plan_N = h->plan_T = 0;
     h->attn_plans_valid = false;
     h->vt_ones_valid = false;
-    h->cap_batch = h->cap_T = 0;
+    h->cap_batch = h->cap_T = h->cap_rows = 0;
+    h->region_cond = 0; h->region_hs = h->region_ws = 1;
     for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     h->graphs.clear();
     h->traj_buf = nullptr; h->traj_cap_elems = 0;
@@ -785,20 +792,19 @@ extern "C" int ndit_load_packed(ndit_handle h, const char* path) {
 
 // ------------------------------------------------------------------------------------ caption
 
-extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* mask, int32_t batch, int32_t T, void* stream) {
-    if (!h || !cap || !mask) return NDIT_ERR_INVALID;
-    if (h->cls) return h->fail(NDIT_ERR_STATE, "ndit_set_caption: this engine is class-conditional (use ndit_set_labels)");
-    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
-    if (batch < 1 || batch > h->Bmax || T < 1 || T > h->Tmax) return h->fail(NDIT_ERR_INVALID, "caption batch/T out of range (%d,%d)", batch, T);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+// Caption-side work shared by ndit_set_caption and ndit_set_caption_regions: `rows` caption rows [rows, T, C] -> per layer
+// attention_y_norm, wk_y | wv_y, ky_norm, V^T with its all-ones row.  pool_cap / pool_mask [pool_rows, pool_T]: what the adaLN
+// conditioning pools over (model.py:847-850) - the caption rows themselves, or the global caption of the compositional model.
+static int set_caption_impl(ndit_engine* h, const bf16* capb, const uint8_t* mask, int rows, int T, const bf16* pool_cap,
+                            const uint8_t* pool_mask_u8, int pool_rows, int pool_T, cudaStream_t s) {
     const size_t C = h->C, KV = (size_t)h->Hkv * h->hd, L = h->L;
-    const int M = batch * T;
+    const int M = rows * T;
     const int Tpad = (T + 7) / 8 * 8;
     mask_to_u8_kernel<<<(M + 255) / 256, 256, 0, s>>>(h->ymask, mask, M);
     CKL(cudaGetLastError());
-    const bf16* capb = static_cast<const bf16*>(cap);
-    CKL(cond_prepare(0.f, nullptr, capb, h->ymask, h->capln_w, h->capln_b, h->tf, h->pool, batch, T, (int)C, 1, s));
-    CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, nullptr, batch, h->cd, (int)C, 0, POST_NONE, 0, 0, 0, s));
+    CKL(cond_prepare(0.f, nullptr, pool_cap ? pool_cap : capb, pool_cap ? pool_mask_u8 : h->ymask, h->capln_w, h->capln_b, h->tf, h->pool,
+                     pool_rows, pool_T, (int)C, 1, s));
+    CKL(gemv_rows(h->pool, h->Wcap, h->bcap, nullptr, h->capemb, nullptr, pool_rows, h->cd, (int)C, 0, POST_NONE, 0, 0, 0, s));
     CKL(rms_rows_layers(capb, h->yn, h->yhat, M, (int)C, (int)L, h->cfg.norm_eps, s));
     const size_t ys = (size_t)M * C, ks = (size_t)M * 2 * KV;
     for (size_t l = 0; l < L; ++l) {
@@ -809,13 +815,67 @@ extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* m
         CKL(gemm_bf16_tn(p, s));
     }
     CKL(ln_rows(h->kvy, (int)(2 * KV), ks, h->kyn_w, h->kyn_b, KV, M, (int)KV, (int)L, s));
-    const size_t vs = (size_t)batch * h->Hkv * h->vrows * Tpad;
+    const size_t vs = (size_t)rows * h->Hkv * h->vrows * Tpad;
     CK(cudaMemsetAsync(h->vyt, 0, L * vs * sizeof(bf16), s));
-    CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, batch, T, h->Hkv, h->hd, h->vrows, (int)L, s));
-    CKL(fill_ones_row(h->vyt, Tpad, vs, batch * h->Hkv, Tpad, h->hd, h->vrows, (int)L, s));
-    if (batch != h->cap_batch || T != h->cap_T) h->attn_plans_valid = false;
+    CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, rows, T, h->Hkv, h->hd, h->vrows, (int)L, s));
+    CKL(fill_ones_row(h->vyt, Tpad, vs, rows * h->Hkv, Tpad, h->hd, h->vrows, (int)L, s));
+    return NDIT_OK;
+}
+
+extern "C" int ndit_set_caption(ndit_handle h, const void* cap, const uint8_t* mask, int32_t batch, int32_t T, void* stream) {
+    if (!h || !cap || !mask) return NDIT_ERR_INVALID;
+    if (h->cls) return h->fail(NDIT_ERR_STATE, "ndit_set_caption: this engine is class-conditional (use ndit_set_labels)");
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    if (batch < 1 || batch > h->Bmax || T < 1 || T > h->Tmax) return h->fail(NDIT_ERR_INVALID, "caption batch/T out of range (%d,%d)", batch, T);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int e = set_caption_impl(h, static_cast<const bf16*>(cap), mask, batch, T, nullptr, nullptr, batch, T, s)) return e;
+    if (batch != h->cap_batch || batch != h->cap_rows || T != h->cap_T || h->region_cond != 0) h->attn_plans_valid = false;
     h->cap_batch = batch;
+    h->cap_rows = batch;
     h->cap_T = T;
+    h->region_cond = 0; h->region_hs = h->region_ws = 1;
+    return NDIT_OK;
+}
+
+extern "C" int ndit_set_caption_regions(ndit_handle h, const void* cap, const uint8_t* mask, int32_t n_caps, int32_t T,
+                                        const void* global_cap, const uint8_t* global_mask, int32_t global_T, int32_t h_split,
+                                        int32_t w_split, void* stream) {
+    if (!h || !cap || !mask || !global_cap || !global_mask) return NDIT_ERR_INVALID;
+    if (h->cls || h->flag) return h->fail(NDIT_ERR_STATE, "ndit_set_caption_regions: text-conditioned Next-DiT only");
+    if (!h->finalized) return h->fail(NDIT_ERR_STATE, "weights not finalized");
+    if (h->hd != 72) return h->fail(NDIT_ERR_INVALID, "region-masked cross-attention is built for head_dim 72 (got %d)", h->hd);
+    if (n_caps < 2 || n_caps > 64) return h->fail(NDIT_ERR_INVALID, "need 1..63 region captions + the unconditional one (got %d rows)", n_caps);
+    if (T < 1 || T > h->Tmax || global_T < 1 || global_T > h->Tmax) return h->fail(NDIT_ERR_INVALID, "caption length out of range (%d, %d; max %d)", T, global_T, h->Tmax);
+    if (h_split < 1 || w_split < 1) return h->fail(NDIT_ERR_INVALID, "h_split / w_split must be >= 1");
+    // model.py:879-883 indexes region_mask[region_id] with region_id up to h_split * w_split - 1: beyond the caption rows it raises
+    if (h_split * w_split - 1 >= n_caps) return h->fail(NDIT_ERR_INVALID, "region id %d >= %d caption rows (the reference raises IndexError)", h_split * w_split - 1, n_caps);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n_caps > h->cap_rows_max) {            // grow the caption buffers (weights stay; like ndit_reserve)
+        CK(cudaDeviceSynchronize());
+        const int old_req = h->cap_rows_req;
+        free_workspace(h);
+        h->cap_rows_req = n_caps;
+        if (int r = alloc_workspace(h)) {
+            free_workspace(h);
+            h->cap_rows_req = old_req;
+            char msg[512];
+            snprintf(msg, sizeof(msg), "%s", h->err);
+            if (alloc_workspace(h)) return h->fail(NDIT_ERR_NOMEM, "ndit_set_caption_regions: could not restore the workspace after: %s", msg);
+            return h->fail(r, "ndit_set_caption_regions(%d caption rows): %s", n_caps, msg);
+        }
+    }
+    // adaLN conditioning: the pooled GLOBAL caption, one row broadcast to cond and uncond (model.py:866-870: cap_emb [1, D])
+    mask_to_u8_kernel<<<(global_T + 255) / 256, 256, 0, s>>>(h->stage_mask, global_mask, global_T);
+    CKL(cudaGetLastError());
+    if (int e = set_caption_impl(h, static_cast<const bf16*>(cap), mask, n_caps, T, static_cast<const bf16*>(global_cap), h->stage_mask, 1,
+                                 global_T, s))
+        return e;
+    CK(cudaMemcpyAsync(h->capemb + h->cd, h->capemb, sizeof(float) * h->cd, cudaMemcpyDeviceToDevice, s));
+    h->attn_plans_valid = false;
+    h->cap_batch = 2;
+    h->cap_rows = n_caps;
+    h->cap_T = T;
+    h->region_cond = n_caps - 1; h->region_hs = h_split; h->region_ws = w_split;
     return NDIT_OK;
 }
 
@@ -828,6 +888,7 @@ extern "C" int ndit_set_labels(ndit_handle h, const int64_t* labels, int32_t bat
     CKL(gather_label_rows(h->Yemb, reinterpret_cast<const long long*>(labels), h->capemb, batch, h->cfg.num_classes + 1, h->cd, s));
     if (batch != h->cap_batch) h->attn_plans_valid = false;
     h->cap_batch = batch;
+    h->cap_rows = batch;
     h->cap_T = 0;
     return NDIT_OK;
 }
@@ -838,7 +899,8 @@ extern "C" int ndit_set_labels(ndit_handle h, const int64_t* labels, int32_t bat
 // (head_dim, head, token); the 64-wide box covers elements [0,64) (head_dim 48: 48..63 are out-of-bounds zeros), the
 // 16-wide box elements [64,80) of head_dim 72.  V^T buffers are [group][vrows][tokens].
 static int build_attn_maps(AttnPlan* a, const bf16* qkv, int Wq, const bf16* vt, const bf16* kvy, const bf16* vyt, int B, int N,
-                           int T, int H, int Hkv, int hd, int bkv = 128) {
+                           int T, int H, int Hkv, int hd, int bkv = 128, int cap_rows = 0) {
+    const uint64_t Bc = cap_rows > 0 ? cap_rows : B;     // caption rows (region mode: more captions than batch rows)
     const int vrows = attn_vrows(hd), KV = Hkv * hd, Tpad = (T + 7) / 8 * 8, Npad = (N + 7) / 8 * 8;
     const uint64_t rs = (uint64_t)Wq * 2, M = (uint64_t)B * N;
     int e = 0;
@@ -850,9 +912,9 @@ static int build_attn_maps(AttnPlan* a, const bf16* qkv, int Wq, const bf16* vt,
         e |= make_tmap_3d(&a->tmK16, qkv + (size_t)H * hd, hd, Hkv, M, hd * 2, rs, 16, 1, bkv, 32);
     }
     if (T > 0) {
-        e |= make_tmap_3d(&a->tmKy64, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, bkv, 128);
-        if (hd > 64) e |= make_tmap_3d(&a->tmKy16, kvy, hd, Hkv, (uint64_t)B * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, bkv, 32);
-        e |= make_tmap_3d(&a->tmVyt, vyt, Tpad, vrows, (uint64_t)B * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * vrows * 2, 64, vrows, 1, 128);
+        e |= make_tmap_3d(&a->tmKy64, kvy, hd, Hkv, Bc * T, hd * 2, (uint64_t)2 * KV * 2, 64, 1, bkv, 128);
+        if (hd > 64) e |= make_tmap_3d(&a->tmKy16, kvy, hd, Hkv, Bc * T, hd * 2, (uint64_t)2 * KV * 2, 16, 1, bkv, 32);
+        e |= make_tmap_3d(&a->tmVyt, vyt, Tpad, vrows, Bc * Hkv, (uint64_t)Tpad * 2, (uint64_t)Tpad * vrows * 2, 64, vrows, 1, 128);
     }
     a->B = B; a->N = N; a->T = T; a->H = H; a->Hkv = Hkv; a->hd = hd; a->bkv = bkv;
     return e;
@@ -929,10 +991,12 @@ static int ensure_plans(ndit_engine* h, int batch, int N) {
         for (size_t l = 0; l < L; ++l) {
             AttnPlan& a = h->p_attn[l];
             memset(&a, 0, sizeof(a));
-            const bf16* kvy = h->kvy + l * (size_t)batch * T * 2 * KV;
-            const bf16* vyt = h->vyt + l * (size_t)batch * h->Hkv * h->vrows * Tpad;
+            const size_t crows = h->cls ? (size_t)batch : (size_t)h->cap_rows;
+            const bf16* kvy = h->kvy + l * crows * T * 2 * KV;
+            const bf16* vyt = h->vyt + l * crows * h->Hkv * h->vrows * Tpad;
+            const bool gen3 = attn_gen(h->attn_tp) == 3 && h->region_cond == 0;     // region-masked captions: first-generation kernel
             if (build_attn_maps(&a, h->qkv, (int)Wq, h->vt, kvy, vyt, batch, N, T, h->H, h->Hkv, h->hd,
-                                attn_gen(h->attn_tp) == 3 ? attention_hr_bkv(h->hd) : 128))
+                                gen3 ? attention_hr_bkv(h->hd) : 128, (int)crows))
                 return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
             a.ymask = h->ymask;
             a.gate_tanh = h->gate_tanh + l * h->H;
@@ -986,6 +1050,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
     if (!plain && (batch < 2 || (batch & 1) || batch > h->Bmax)) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
     if (plain && (batch < 1 || batch > h->Bmax)) return h->fail(NDIT_ERR_INVALID, "batch must be in 1..%d", h->Bmax);
+    if (h->region_cond > 0 && (plain || batch != 2))
+        return h->fail(NDIT_ERR_INVALID, "region-masked captions (ndit_set_caption_regions) drive forward_with_cfg of one cond / uncond pair");
     if (plain) {
         t = t_rows[0];
         bool uniform = true;
@@ -1061,6 +1127,12 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
         scale_self = (float)sqrt(1.0 / (double)hd);
     }
     const float scale_cross = (float)(1.0 / sqrt((double)hd));
+    // region rectangles of the compositional model: H // h_split // patch_size x W // w_split // patch_size tokens (model.py:875)
+    AttnRegion region{0, 0, 0, 0, 0, 0};
+    if (h->region_cond > 0) {
+        region = AttnRegion{h->region_cond, Wp, Hp / h->region_hs, Wp / h->region_ws, h->region_hs, h->region_ws};
+        if (region.hp < 1 || region.wp < 1) return h->fail(NDIT_ERR_INVALID, "%d x %d regions do not fit a %d x %d token grid", h->region_hs, h->region_ws, Hp, Wp);
+    }
 
     if (list != nullptr) {
         for (int i = 0; i < batch; ++i) {
@@ -1101,9 +1173,9 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
         PROF(KC_ROWWISE, ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
                        h->kn_b + (size_t)l * h->Hkv * hd, rope, M, rope_rows_per_batch, h->H, h->Hkv, hd, s));
         if (h->attn_ref) {
-            PROF(KC_ATTN, attention_ref(h->qkv, h->Wq, h->kvy + (size_t)l * batch * h->cap_T * 2 * h->Hkv * hd, 2 * h->Hkv * hd, h->ymask,
+            PROF(KC_ATTN, attention_ref(h->qkv, h->Wq, h->kvy + (size_t)l * h->cap_rows * h->cap_T * 2 * h->Hkv * hd, 2 * h->Hkv * hd, h->ymask,
                               h->gate_tanh + (size_t)l * h->H, h->attn, batch, N, h->cap_T, h->H, h->Hkv, hd, scale_self,
-                              scale_cross, s, list != nullptr ? h->kvlen : nullptr));
+                              scale_cross, s, list != nullptr ? h->kvlen : nullptr, region));
         } else {
             if (!vt_fused)
                 PROF(KC_ROWWISE, transpose_v(h->qkv, h->Wq, (h->H + h->Hkv) * hd, 0, h->vt, Npad, 0, batch, N, h->Hkv, hd, h->vrows, 1, s));
@@ -1111,7 +1183,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
             a.scale_self = scale_self;
             a.scale_cross = scale_cross;
             a.kv_len = list != nullptr ? h->kvlen : nullptr;
-            PROF(KC_ATTN, attn_gen(h->attn_tp) == 3 ? attention_fused_hr(a, s) : attention_fused(a, s));
+            a.region = region;
+            PROF(KC_ATTN, (attn_gen(h->attn_tp) == 3 && region.n_cond == 0) ? attention_fused_hr(a, s) : attention_fused(a, s));
         }
         PROF(KC_GEMM_WO, gemm_bf16_tn(h->p_wo[l], s));
         PROF(KC_ROWWISE, resid_rms_mod(h->X, h->o, h->flag ? nullptr : h->an2 + (size_t)l * D, ml + (size_t)o_g1 * D, h->fn1 + (size_t)l * D,
@@ -1284,6 +1357,7 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
     ndit_engine::SolveGraph* hit = nullptr;
     for (auto& g : h->graphs) {
         if (g.batch == batch && g.height == height && g.width == width && g.method == method && g.cap_T == h->cap_T &&
+            g.cap_rows == h->cap_rows && g.region_cond == h->region_cond && g.region_hs == h->region_hs && g.region_ws == h->region_ws &&
             g.with_traj == (int)with_traj && g.attn_ref == h->attn_ref && g.attn_tp == h->attn_tp && g.pdl == h->pdl && g.vt_epi == h->vt_epi && g.moe_grouped == h->moe_grouped &&
             (int)g.grid.size() == n_grid && !memcmp(g.grid.data(), grid, n_grid * sizeof(float)) && !memcmp(&g.sp, sp, sizeof(*sp))) {
             hit = &g;
@@ -1297,6 +1371,7 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
         if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
         slot->grid.assign(grid, grid + n_grid);
         slot->batch = batch; slot->height = height; slot->width = width; slot->method = method; slot->cap_T = h->cap_T;
+        slot->cap_rows = h->cap_rows; slot->region_cond = h->region_cond; slot->region_hs = h->region_hs; slot->region_ws = h->region_ws;
         slot->with_traj = with_traj; slot->attn_ref = h->attn_ref; slot->attn_tp = h->attn_tp; slot->pdl = h->pdl; slot->vt_epi = h->vt_epi; slot->moe_grouped = h->moe_grouped; slot->sp = *sp;
         slot->launches = 0;
         slot->last_use = ++h->graph_clock;

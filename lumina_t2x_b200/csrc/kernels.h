@@ -75,6 +75,13 @@ int make_gemm_plan(GemmPlan* p, const bf16* A, int lda, const bf16* W, bf16* C, 
                    int num_sms, int allow_pair = 1, int w_total_rows = 0);
 
 // ---------------------------------------------------------------- attention (attention_tcgen05.cu)
+// Region-masked caption cross-attention of the compositional model (lumina_next_compositional_generation/models/model.py:421-446,
+// 872-887): the caption buffers hold n_cond region captions followed by the unconditional one; the latent's token grid (Wp tokens per
+// row) is cut into hs x ws rectangles of hp x wp tokens and rectangle (i, j) belongs to caption (i + 1) * (j + 1) - 1.  n_cond == 0: off.
+struct AttnRegion {
+    int n_cond;
+    int Wp, hp, wp, hs, ws;
+};
 struct AttnPlan {
     CUtensorMap tmQ64, tmQ16;    // q  : dims (hd, H,   B*N) on the qkv buffer, boxes (64,1,128) / (16,1,128)
     CUtensorMap tmK64, tmK16;    // k  : dims (hd, Hkv, B*N)
@@ -89,6 +96,7 @@ struct AttnPlan {
     int B, N, T, H, Hkv, hd;     // T = 0: no caption segment (class-conditional model); hd = 72, 48 or 96
     float scale_self, scale_cross;
     int bkv;                     // kv rows per K box: 128 (attention_fused) or attention_hr_bkv(hd) (attention_fused_hr)
+    AttnRegion region;           // n_cond > 0: region-masked captions (attention_fused and attention_ref only; B = 2)
 };
 // first-generation kernel: one softmax thread per row, P through shared memory (attention_tcgen05.cu)
 cudaError_t attention_fused(const AttnPlan& p, cudaStream_t stream);
@@ -99,7 +107,8 @@ cudaError_t attention_fused_hr(const AttnPlan& p, cudaStream_t stream);
 // slow CUDA-core reference of the same op (debug / NDIT_ATTN=ref); same inputs in plain layouts
 cudaError_t attention_ref(const bf16* qkv, int ld_qkv, const bf16* kvy, int ld_kvy, const uint8_t* ymask,
                           const float* gate_tanh, bf16* out, int B, int N, int T, int H, int Hkv, int hd,
-                          float scale_self, float scale_cross, cudaStream_t stream, const int* kv_len = nullptr);
+                          float scale_self, float scale_cross, cudaStream_t stream, const int* kv_len = nullptr,
+                          AttnRegion region = AttnRegion{0, 0, 0, 0, 0, 0});
 
 // ---------------------------------------------------------------- row-wise kernels (rowwise.cu)
 // X[token, :] = bf16(patch(x[b % n]) . Wx^T + bx)

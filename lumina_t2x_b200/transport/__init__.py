@@ -21,6 +21,7 @@ import torch as th
 from ..models.dit_llama import DiT_Llama
 from ..models.lumina_t2i import DiT_Llama as FlagDiT
 from ..models.nextdit import NextDiT
+from ..models.compositional import NextDiT as CompositionalNextDiT
 
 __all__ = ["create_transport", "Sampler", "Transport", "ModelType", "PathType", "WeightType", "ODE"]
 
@@ -99,6 +100,9 @@ def _time_grid(t0, t1, num_steps, time_shifting_factor):
 _ENGINE_KW = {
     NextDiT: (("cap_feats", "cap_mask", "cfg_scale", "scale_factor", "scale_watershed", "base_seqlen", "proportional_attn"),
               ("cap_feats", "cap_mask", "cfg_scale")),
+    CompositionalNextDiT: (("cap_feats", "cap_mask", "cfg_scale", "scale_factor", "scale_watershed", "base_seqlen", "proportional_attn",
+                            "global_cap_feats", "global_cap_mask", "h_split_num", "w_split_num"),
+                           ("cap_feats", "cap_mask", "cfg_scale", "global_cap_feats", "global_cap_mask")),
     DiT_Llama: (("y", "cfg_scale", "rope_scaling_factor", "ntk_factor"), ("y", "cfg_scale")),
     FlagDiT: (("cap_feats", "cap_mask", "cfg_scale", "rope_scaling_factor", "ntk_factor", "base_seqlen", "proportional_attn"),
               ("cap_feats", "cap_mask", "cfg_scale")),

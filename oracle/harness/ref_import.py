@@ -174,6 +174,21 @@ def import_reference_full_model():
     return mod
 
 
+def import_reference_compositional_model():
+    """Unmodified ``lumina_next_compositional_generation/models/model.py`` (region-masked cross-attention), fairscale replaced by the
+    world-size-1 stub above."""
+    install_shims()
+    _install_fairscale_stub()
+    pkg = types.ModuleType("ref_lumina_next_compositional_models")
+    pkg.__path__ = [REF_ROOT + "/lumina_next_compositional_generation/models"]
+    sys.modules["ref_lumina_next_compositional_models"] = pkg
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("ref_lumina_next_compositional_models.model")
+    return mod
+
+
 def import_reference_full_transport():
     """Unmodified ``lumina_next_t2i/transport`` package (create_transport, Sampler with sample_ode AND sample_sde)."""
     import importlib.util

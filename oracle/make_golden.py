@@ -274,8 +274,8 @@ def make_signatures() -> None:
     """Constructor / forward_with_cfg signatures and factory names of the four reference model packages (drop-in surface)."""
     import inspect
     import json
-    from oracle.harness.ref_import import import_reference_flag_dit, import_reference_moe
-    mods = {"next_t2i_mini": import_reference_mini()[0].nextdit, "imagenet": import_reference_imagenet(), "lumina_t2i": import_reference_flag_dit(),
+    from oracle.harness.ref_import import import_reference_compositional_model, import_reference_flag_dit, import_reference_moe
+    mods = {"compositional": import_reference_compositional_model(), "next_t2i_mini": import_reference_mini()[0].nextdit, "imagenet": import_reference_imagenet(), "lumina_t2i": import_reference_flag_dit(),
             "moe_time": import_reference_moe("models"), "moe_space": import_reference_moe("models1"), "moe_both": import_reference_moe("models2")}
 
     def sig(fn):
@@ -438,8 +438,57 @@ def make_gemma() -> None:
     torch.save(dict(cfg=cfg.__dict__, weight_seed=0, transformers=transformers.__version__, cases=cases), os.path.join(OUT, "gemma_tiny.pt"))
 
 
+COMPOSITIONAL_CASES = {
+    # name: latent hw, region captions, split, caption length, t, kwargs
+    "comp_2x2": dict(hw=(32, 32), n_regions=4, hs=2, ws=2, T=16, t=0.35,
+                     kw=dict(cfg_scale=3.0, scale_factor=1.0, scale_watershed=1.0, base_seqlen=64, proportional_attn=True)),
+    # 1 x 3 split of a non-square latent whose width is not divisible by 3 (rightmost token column has no region -> zeros), NTK branch
+    "comp_1x3": dict(hw=(16, 40), n_regions=3, hs=1, ws=3, T=24, t=0.7,
+                     kw=dict(cfg_scale=2.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=32, proportional_attn=True)),
+    # single region = plain text-to-image through the compositional code path, linear-interpolation RoPE branch
+    "comp_1x1": dict(hw=(24, 16), n_regions=1, hs=1, ws=1, T=16, t=0.1,
+                     kw=dict(cfg_scale=4.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=None, proportional_attn=False)),
+}
+
+
+def make_compositional() -> None:
+    """Region-masked cross-attention: the UNMODIFIED ``lumina_next_compositional_generation/models/model.py`` in fp32 on CPU (its
+    fp32 SDPA branch does not repeat kv heads, model.py:407-417, so n_kv_heads = n_heads), pinned against ``oracle/compositional_oracle.py``.
+    2 x 2 regions exercise the reference's region_id formula ((i + 1) * (j + 1) - 1: rectangles (0, 1) and (1, 0) share caption 1,
+    caption 2 owns nothing, rectangle (1, 1) -> caption 3)."""
+    import dataclasses
+    from oracle import compositional_oracle as CO
+    from oracle.harness.ref_import import import_reference_compositional_model
+    ref = import_reference_compositional_model()
+    torch.set_grad_enabled(False)
+    cfg = dataclasses.replace(O.config_tiny(n_layers=2), n_kv_heads=O.config_tiny().n_heads)
+    W = O.synthetic_weights(cfg, seed=0, dtype=torch.bfloat16)
+    m = ref.NextDiT(patch_size=2, in_channels=4, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads,
+                    qk_norm=True, cap_feat_dim=cfg.cap_feat_dim)
+    m.load_state_dict({k: v.clone() for k, v in W.items()}, strict=True)
+    m = m.eval().float()
+    for name, c in COMPOSITIONAL_CASES.items():
+        z, cap, mask, gcap, gmask = CO.synthetic_inputs(cfg, c["hw"], c["n_regions"], c["T"], seed=21)
+        t = torch.full((2,), c["t"])
+        kw = dict(c["kw"], global_cap_feats=gcap.float(), global_cap_mask=gmask, h_split_num=c["hs"], w_split_num=c["ws"])
+        out = m.forward_with_cfg(z.float(), t, cap.float(), mask, **kw)
+        assert torch.isfinite(out).all()
+        o = CO.forward_with_cfg(cfg, W, z.float(), t, cap.float(), mask, precision="fp32", **kw)
+        o16 = CO.forward_with_cfg(cfg, W, z.float(), t, cap.float(), mask, precision="bf16", **kw)
+        fx = dict(case=name, cfg=dict(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, cap_feat_dim=cfg.cap_feat_dim),
+                  hw=c["hw"], n_regions=c["n_regions"], hs=c["hs"], ws=c["ws"], T=c["T"], t=c["t"], kw=c["kw"], weight_seed=0, input_seed=21,
+                  out_fp32=out.clone())
+        torch.save(fx, os.path.join(OUT, f"{name}.pt"))
+        print(name, tuple(out.shape), "absmax", out.abs().max().item(), "oracle fp32 rel", ((o - out).abs().max() / out.abs().max()).item(),
+              "oracle bf16 vs ref fp32", ((o16 - out).abs().max() / out.abs().max()).item())
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "gemma":
+    if len(sys.argv) > 1 and sys.argv[1] == "compositional":
+        make_compositional()
+    elif len(sys.argv) > 1 and sys.argv[1] == "signatures":
+        make_signatures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "gemma":
         make_gemma()
     elif len(sys.argv) > 1 and sys.argv[1] == "imagenet_plain_forward":
         make_imagenet_plain_forward()

@@ -43,6 +43,10 @@ FILES = [
     "lumina_next_t2i/transport/path.py",
     "lumina_next_t2i/transport/transport.py",
     "lumina_next_t2i/transport/utils.py",
+    # compositional generation: region-masked caption cross-attention
+    "lumina_next_compositional_generation/models/__init__.py",
+    "lumina_next_compositional_generation/models/components.py",
+    "lumina_next_compositional_generation/models/model.py",
     # class-conditional Next-DiT (config 1), MoE variants (config 5), Flag-DiT (config 4)
     "Next-DiT-ImageNet/models/models.py",
     "Next-DiT-MoE/models/models.py",

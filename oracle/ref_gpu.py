@@ -43,6 +43,9 @@ def build_reference(state_dict, *, dim, n_layers, n_heads, n_kv_heads, cap_feat_
     if flavour == "mini":
         mod = ref_import.import_reference_mini()[0].nextdit
         extra = dict(use_flash_attn=use_flash_attn)
+    elif flavour == "compositional":     # lumina_next_compositional_generation/models/model.py (region-masked cross-attention)
+        mod = ref_import.import_reference_compositional_model()
+        extra = {}
     else:
         mod = ref_import.import_reference_full_model()
         extra = {}

@@ -25,7 +25,7 @@ def test_cabi_loads_and_exports_header_symbols():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ndit_abi_version() == 4
+    assert lib.ndit_abi_version() == 5
     # the caption-encoder end has its own header
     theader = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ndit_text.h")).read(), flags=re.S)
     tdeclared = set(re.findall(r"\b(ntxt_[a-z_0-9]+)\s*\(", theader))
@@ -154,9 +154,9 @@ def test_model_mirrors_keep_the_reference_signatures():
     import inspect
     import json
     from lumina_t2x_b200 import models
-    from lumina_t2x_b200.models import dit_llama, lumina_t2i, moe
+    from lumina_t2x_b200.models import compositional, dit_llama, lumina_t2i, moe
     table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "signatures.json")))
-    mirrors = {"next_t2i_mini": (models.NextDiT, models), "imagenet": (dit_llama.DiT_Llama, models), "lumina_t2i": (lumina_t2i.DiT_Llama, lumina_t2i),
+    mirrors = {"compositional": (compositional.NextDiT, compositional), "next_t2i_mini": (models.NextDiT, models), "imagenet": (dit_llama.DiT_Llama, models), "lumina_t2i": (lumina_t2i.DiT_Llama, lumina_t2i),
                "moe_time": (dit_llama.DiT_Llama, moe), "moe_space": (dit_llama.DiT_Llama, moe), "moe_both": (dit_llama.DiT_Llama, moe)}
     for name, ref in table.items():
         cls, pkg = mirrors[name]
