@@ -44,7 +44,7 @@ typedef struct ndit_config {
     int32_t n_heads;        /* 32   */
     int32_t n_kv_heads;     /* 8 (GQA) or n_heads */
     int32_t cap_feat_dim;   /* 2048 */
-    int32_t in_channels;    /* 4    */
+    int32_t in_channels;    /* 4 (sdxl VAE latents; 16 = sd3 VAE, lumina_next_t2i/train.py:323); even, 2..16 */
     int32_t patch_size;     /* 2    */
     int32_t multiple_of;    /* 256  */
     int32_t learn_sigma;    /* 1    */
@@ -69,6 +69,12 @@ typedef struct ndit_config {
                                  * time MoE then space MoE, 6-chunk adaLN :451-506,760-808.  (0, 0): dense FFN.  Expert
                                  * outputs are accumulated in expert-index order in bf16, like the reference's
                                  * ``results[idx] += w * expert(x[idx])``; top-k ties go to the lower expert index. */
+    int32_t ffn_dim;        /* 0: FeedForward's hidden width is derived as in model.py:470-473 without ffn_dim_multiplier,
+                             * multiple_of * ceil(int(2 * 4 * dim / 3) / multiple_of).  > 0: the hidden width itself (the host computes
+                             * int(ffn_dim_multiplier * int(2 * 4 * dim / 3)) rounded up to multiple_of in Python's arithmetic, :471-473);
+                             * a multiple of 128. */
+    int32_t no_qk_norm;     /* != 0: the qk_norm=False architecture (model.py:219-220: q_norm = k_norm = ky_norm = Identity): no
+                             * q/k LayerNorm before the rotary embedding, no LayerNorm on the caption keys, no *_norm keys in the state dict */
 } ndit_config;
 
 /* Per-call arguments of NextDiT.forward_with_cfg (model.py:866-913) that are not tensors. */

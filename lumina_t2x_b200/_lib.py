@@ -18,7 +18,8 @@ class NditConfig(C.Structure):
                 ("multiple_of", C.c_int32), ("learn_sigma", C.c_int32), ("norm_eps", C.c_float),
                 ("max_tokens", C.c_int32), ("max_cap_len", C.c_int32), ("max_batch", C.c_int32),
                 ("num_classes", C.c_int32), ("flag_dit", C.c_int32),
-                ("moe_time_experts", C.c_int32), ("moe_space_experts", C.c_int32)]
+                ("moe_time_experts", C.c_int32), ("moe_space_experts", C.c_int32),
+                ("ffn_dim", C.c_int32), ("no_qk_norm", C.c_int32)]
 
 
 class NditStepParams(C.Structure):

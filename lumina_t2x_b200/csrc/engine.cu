@@ -333,12 +333,13 @@ static int create_impl(ndit_engine* h) {
     h->hd = c.dim / c.n_heads; h->C = h->cls ? 0 : c.cap_feat_dim; h->cd = c.dim < 1024 ? c.dim : 1024;
     if (h->hd != 72 && h->hd != 48 && h->hd != 96) return h->fail(NDIT_ERR_INVALID, "head_dim must be 72, 48 or 96 (got %d)", h->hd);
     h->vrows = attn_vrows(h->hd);
-    if (c.patch_size != 2 || c.in_channels != 4) return h->fail(NDIT_ERR_INVALID, "patch_size 2 / in_channels 4 only");
+    if (c.patch_size != 2 || c.in_channels < 2 || c.in_channels > 16 || (c.in_channels & 1))
+        return h->fail(NDIT_ERR_INVALID, "patch_size 2 and an even in_channels in 2..16 only (got %d, %d)", c.patch_size, c.in_channels);
     if (h->H % h->Hkv != 0) return h->fail(NDIT_ERR_INVALID, "n_heads %% n_kv_heads != 0");
     if (c.max_batch < 2 || c.max_batch > 4 || (c.max_batch & 1)) return h->fail(NDIT_ERR_INVALID, "max_batch must be 2 or 4");
     if (h->C % 8 != 0 || h->D % 64 != 0) return h->fail(NDIT_ERR_INVALID, "dims must be multiples of 8/64");
     int hidden = static_cast<int>(2 * (4 * c.dim) / 3);                 // model.py:441-503 FeedForward
-    h->F = c.multiple_of * ((hidden + c.multiple_of - 1) / c.multiple_of);
+    h->F = c.ffn_dim > 0 ? c.ffn_dim : c.multiple_of * ((hidden + c.multiple_of - 1) / c.multiple_of);
     if (h->F % 128 != 0) return h->fail(NDIT_ERR_INVALID, "ffn dim must be a multiple of 128");
     const int out_ch = c.learn_sigma ? 2 * c.in_channels : c.in_channels;
     h->O = c.patch_size * c.patch_size * out_ch;
@@ -350,7 +351,7 @@ static int create_impl(ndit_engine* h) {
     if (cc_major != 10) return h->fail(NDIT_ERR_INVALID, "needs an sm_100 device (compute capability %d.x found)", cc_major);
 
     const size_t D = h->D, L = h->L, F = h->F, C = h->C, cd = h->cd, KV = (size_t)h->Hkv * h->hd;
-    ALLOC(Wx, D * 16); ALLOC(bx, D); ALLOC(Wt0, cd * 256); ALLOC(bt0, cd); ALLOC(Wt2, cd * cd); ALLOC(bt2, cd);
+    ALLOC(Wx, D * 4 * c.in_channels); ALLOC(bx, D); ALLOC(Wt0, cd * 256); ALLOC(bt0, cd); ALLOC(Wt2, cd * cd); ALLOC(bt2, cd);
     ALLOC(capln_w, C); ALLOC(capln_b, C); ALLOC(Wcap, cd * C); ALLOC(bcap, cd);
     const size_t NCH = h->NCH;
     ALLOC(Wada, (L * NCH * D + h->FD * D) * cd); ALLOC(bada, L * NCH * D + h->FD * D);
@@ -492,7 +493,7 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
     }
     if (!h->cls) { VEC("pad_token", h->pad_token, D) }
     if (h->flag) { VEC("eol_token", h->eol_token, D) }
-    MAT("x_embedder.weight", h->Wx, D, 16) VEC("x_embedder.bias", h->bx, D)
+    MAT("x_embedder.weight", h->Wx, D, (size_t)4 * h->cfg.in_channels) VEC("x_embedder.bias", h->bx, D)
     MAT("t_embedder.mlp.0.weight", h->Wt0, cd, 256) VEC("t_embedder.mlp.0.bias", h->bt0, cd)
     MAT("t_embedder.mlp.2.weight", h->Wt2, cd, cd) VEC("t_embedder.mlp.2.bias", h->bt2, cd)
     if (!h->cls) {
@@ -512,6 +513,8 @@ extern "C" int ndit_set_weight(ndit_handle h, const char* key, const void* src, 
     if (sscanf(key, "layers.%d.%n", &li, &pos) >= 1 && pos > 0 && li >= 0 && li < h->L) {
         const char* sub = key + pos;
         const size_t l = li;
+        if (h->cfg.no_qk_norm && (!strncmp(sub, "attention.q_norm.", 17) || !strncmp(sub, "attention.k_norm.", 17) || !strncmp(sub, "attention.ky_norm.", 18)))
+            return h->fail(NDIT_ERR_INVALID, "unexpected state-dict key for a qk_norm=False model: %s", key);
         // FFN sub-blocks: "<name>.w{1,2,3}.weight" (dense) or "<name>.experts.<j>.w{1,2,3}.weight" + "<name>.gate.weight" (MoE)
         for (int f = 0; f < h->NF; ++f) {
             const size_t nl = strlen(h->ffn_name[f]);
@@ -651,7 +654,7 @@ static void expected_keys(const ndit_engine* h, std::vector<std::string>* out) {
                               "attention.ky_norm.bias", "attention_norm.weight", "ffn_norm.weight", "attention_y_norm.weight"};
     for (int l = 0; l < h->L; ++l) {
         const std::string pre = "layers." + std::to_string(l) + ".";
-        for (const char* k : per) out->push_back(pre + k);
+        for (const char* k : per) if (!(h->cfg.no_qk_norm && strstr(k, "_norm."))) out->push_back(pre + k);
         for (int f = 0; f < h->NF; ++f) {
             const std::string fp = pre + h->ffn_name[f] + ".";
             const int E = h->ffn_E[f];
@@ -663,8 +666,8 @@ static void expected_keys(const ndit_engine* h, std::vector<std::string>* out) {
             if (h->cls) out->push_back(pre + h->ffn_norm_name[f] + ".weight");
         }
         if (h->cls) for (const char* k : per_cls) out->push_back(pre + k);
-        else if (h->flag) for (const char* k : per_flag) out->push_back(pre + k);
-        else for (const char* k : per_t2i) out->push_back(pre + k);
+        else if (h->flag) { for (const char* k : per_flag) if (!(h->cfg.no_qk_norm && strstr(k, "ky_norm."))) out->push_back(pre + k); }
+        else { for (const char* k : per_t2i) if (!(h->cfg.no_qk_norm && strstr(k, "ky_norm."))) out->push_back(pre + k); }
     }
 }
 
@@ -814,7 +817,7 @@ static int set_caption_impl(ndit_engine* h, const bf16* capb, const uint8_t* mas
             return h->fail(NDIT_ERR_CUDA, "%s", tmap_last_error());
         CKL(gemm_bf16_tn(p, s));
     }
-    CKL(ln_rows(h->kvy, (int)(2 * KV), ks, h->kyn_w, h->kyn_b, KV, M, (int)KV, (int)L, s));
+    if (!h->cfg.no_qk_norm) CKL(ln_rows(h->kvy, (int)(2 * KV), ks, h->kyn_w, h->kyn_b, KV, M, (int)KV, (int)L, s));
     const size_t vs = (size_t)rows * h->Hkv * h->vrows * Tpad;
     CK(cudaMemsetAsync(h->vyt, 0, L * vs * sizeof(bf16), s));
     CKL(transpose_v(h->kvy, (int)(2 * KV), (int)KV, ks, h->vyt, Tpad, vs, rows, T, h->Hkv, h->hd, h->vrows, (int)L, s));
@@ -1170,6 +1173,9 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
         const bool vt_fused = h->vt_epi && !h->attn_ref;
         h->p_qkv[l].vt = vt_fused ? GemmVtOut{h->vt, (h->H + h->Hkv) * hd, hd, h->Hkv, h->vrows, Npad, N} : GemmVtOut{};
         PROF(KC_GEMM_QKV, gemm_bf16_tn(h->p_qkv[l], s));
+        if (h->cfg.no_qk_norm)      // qk_norm=False: q_norm / k_norm are Identity (model.py:219), only the rotary embedding remains
+            PROF(KC_ROWWISE, rope_qk(h->qkv, h->Wq, rope, M, rope_rows_per_batch, h->H, h->Hkv, hd, s));
+        else
         PROF(KC_ROWWISE, ln_rope_qk(h->qkv, h->Wq, h->qn_w + (size_t)l * D, h->qn_b + (size_t)l * D, h->kn_w + (size_t)l * h->Hkv * hd,
                        h->kn_b + (size_t)l * h->Hkv * hd, rope, M, rope_rows_per_batch, h->H, h->Hkv, hd, s));
         if (h->attn_ref) {

@@ -141,6 +141,8 @@ cudaError_t rope_table(float2* tab, int Hp, int Wp, int hd, float theta, float l
 // in place on qkv [M, ld]: q = bf16(rope(LN(q))), k = bf16(rope(LN(k)))
 cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const bf16* kw, const bf16* kb,
                        const float2* rope, int M, int N_tokens, int H, int Hkv, int hd, cudaStream_t s);
+// qk_norm=False: rotary embedding only, in place on the q|k columns of qkv [M, ld]
+cudaError_t rope_qk(bf16* qkv, int ld, const float2* rope, int M, int N_tokens, int H, int Hkv, int hd, cudaStream_t s);
 // in place LayerNorm(width) + affine on rows of a [M, ld] matrix (no rope), layer-batched via blockIdx.y
 cudaError_t ln_rows(bf16* x, int ld, size_t layer_stride_x, const bf16* w, const bf16* b, size_t layer_stride_w,
                     int M, int width, int layers, cudaStream_t s);

@@ -922,6 +922,36 @@ cudaError_t ln_rope_qk(bf16* qkv, int ld, const bf16* qw, const bf16* qb, const 
     return cudaGetLastError();
 }
 
+// qk_norm=False (model.py:219-220: q_norm = k_norm = Identity): only the rotary embedding, q|k <- bf16(rope(float(q|k))), in place.
+// One thread per 8-element vector of the contiguous q|k run of a token (nqk vectors per row).
+__global__ void __launch_bounds__(256)
+rope_qk_kernel(bf16* __restrict__ qkv, int ld, const float2* __restrict__ rope, int M, int N_tokens, int nq, int nqk, int hd) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<size_t>(M) * nqk) return;
+    const int row = static_cast<int>(idx / nqk), v = static_cast<int>(idx % nqk);
+    const int vv = v < nq ? v : v - nq;                  // vector index inside its segment (q or k); hd % 8 == 0
+    bf16* p = qkv + static_cast<size_t>(row) * ld + v * 8;
+    const float2* rp = rope + static_cast<size_t>(row % N_tokens) * (hd >> 1) + (((vv * 8) % hd) >> 1);
+    float x[8], r[8];
+    load8(p, x);
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) {
+        const float2 cs = rp[pr];
+        r[2 * pr] = x[2 * pr] * cs.x - x[2 * pr + 1] * cs.y;
+        r[2 * pr + 1] = x[2 * pr] * cs.y + x[2 * pr + 1] * cs.x;
+    }
+    store8(p, r);
+}
+
+cudaError_t rope_qk(bf16* qkv, int ld, const float2* rope, int M, int N_tokens, int H, int Hkv, int hd, cudaStream_t s) {
+    if (hd % 8 != 0 || ld % 8 != 0) return cudaErrorInvalidValue;
+    const int nq = H * hd / 8, nqk = (H + Hkv) * hd / 8;
+    const size_t total = static_cast<size_t>(M) * nqk;
+    return launch_k(rope_qk_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, qkv, ld, rope, M, N_tokens, nq, nqk, hd);
+}
+
 // LayerNorm(width)+affine in place on rows (ky_norm, model.py:421), batched over layers.
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_rows_kernel(bf16* __restrict__ x, int ld, size_t lsx, const bf16* __restrict__ w, const bf16* __restrict__ b,

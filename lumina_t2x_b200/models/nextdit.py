@@ -305,14 +305,17 @@ class NextDiT(EngineModule):
 
     # ------------------------------------------------------------------ engine plumbing
     def _check_supported(self) -> None:
-        if not self.qk_norm:
-            raise NotImplementedError("the B200 engine implements the qk_norm=True architecture (Lumina-Next-T2I)")
-        if self._ffn_dim_multiplier is not None:
-            raise NotImplementedError("ffn_dim_multiplier is not supported by the B200 engine")
+        if self.ffn_dim % 128 != 0:
+            raise NotImplementedError(f"the B200 engine needs a FeedForward width that is a multiple of 128 (got {self.ffn_dim})")
+        if self.in_channels % 2 != 0 or not 2 <= self.in_channels <= 16:
+            raise NotImplementedError(f"the B200 engine runs an even in_channels in 2..16 (got {self.in_channels})")
 
     def _ndit_config(self):
+        # ffn_dim: the hidden width as Python computed it in __init__ (model.py:470-473, incl. ffn_dim_multiplier);
+        # no_qk_norm: qk_norm=False -> q_norm / k_norm / ky_norm are nn.Identity (model.py:219-220)
         return _lib.NditConfig(self.dim, self.n_layers, self.n_heads, self.n_kv_heads, self.cap_feat_dim, self.in_channels,
-                               self.patch_size, self.multiple_of, int(self.learn_sigma), float(self.norm_eps), *self._limits, 0)
+                               self.patch_size, self.multiple_of, int(self.learn_sigma), float(self.norm_eps), *self._limits, 0, 0, 0, 0,
+                               int(self.ffn_dim), 0 if self.qk_norm else 1)
 
     def _set_caption(self, lib, h, cap_feats: torch.Tensor, cap_mask: torch.Tensor, stream):
         key = self._tensor_key(cap_feats, cap_mask)

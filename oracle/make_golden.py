@@ -438,6 +438,48 @@ def make_gemma() -> None:
     torch.save(dict(cfg=cfg.__dict__, weight_seed=0, transformers=transformers.__version__, cases=cases), os.path.join(OUT, "gemma_tiny.pt"))
 
 
+VARIANT_CASES = {
+    # ctor variants of the same NextDiT (models/nextdit.py:607-690): name -> (config overrides, call)
+    "variant_noqknorm": dict(cfg=dict(qk_norm=False), hw=(16, 24), T=24, ul=8, t=0.6,
+                             kw=dict(cfg_scale=4.0, scale_factor=2.0, scale_watershed=0.3, base_seqlen=16, proportional_attn=True)),
+    # sd3-VAE latents (in_channels 16, lumina_next_t2i/train.py:323) with a custom FeedForward width (ffn_dim_multiplier 1.3:
+    # int(1.3 * 1536) = 1996 -> 2048 instead of 1536)
+    "variant_c16_ffn13": dict(cfg=dict(in_channels=16, ffn_dim_multiplier=1.3), hw=(16, 16), T=16, ul=8, t=0.25,
+                              kw=dict(cfg_scale=2.0, scale_factor=1.0, scale_watershed=1.0, base_seqlen=64, proportional_attn=True)),
+}
+
+
+def make_variants() -> None:
+    """qk_norm=False, in_channels=16 and ffn_dim_multiplier through the unmodified mini reference (fp32 and CPU-autocast bf16)."""
+    import dataclasses
+    models, _ = import_reference_mini()
+    torch.set_grad_enabled(False)
+    for name, c in VARIANT_CASES.items():
+        cfg = dataclasses.replace(O.config_tiny(n_layers=2), **c["cfg"])
+        W = O.synthetic_weights(cfg, seed=0, dtype=torch.bfloat16)
+        outs = {}
+        for dt in (torch.float32, torch.bfloat16):
+            m = models.nextdit.NextDiT(patch_size=cfg.patch_size, in_channels=cfg.in_channels, dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                                       n_kv_heads=cfg.n_kv_heads, ffn_dim_multiplier=cfg.ffn_dim_multiplier, qk_norm=cfg.qk_norm,
+                                       cap_feat_dim=cfg.cap_feat_dim, use_flash_attn=False)
+            m.load_state_dict({k: v.clone() for k, v in W.items()}, strict=True)       # pins the key set (no *_norm keys without qk_norm)
+            m = m.eval().to(dt)
+            z, cap, mask = O.synthetic_inputs(cfg, c["hw"], c["T"], c["ul"], seed=1)
+            t = torch.full((2,), c["t"])
+            if dt == torch.float32:
+                outs[dt] = m.forward_with_cfg(z.float(), t, cap.float(), mask, **c["kw"])
+            else:
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    outs[dt] = m.forward_with_cfg(z, t, cap, mask, **c["kw"])
+        o = O.forward_with_cfg(cfg, W, z.float(), t, cap.float(), mask, precision="fp32", **c["kw"])
+        out32, out16 = outs[torch.float32], outs[torch.bfloat16]
+        fx = dict(case=name, cfg_overrides=c["cfg"], hw=c["hw"], T=c["T"], ul=c["ul"], t=c["t"], kw=c["kw"], weight_seed=0, input_seed=1,
+                  out_fp32=out32.clone(), out_autocast_cpu_bf16=out16.float().to(torch.bfloat16))
+        torch.save(fx, os.path.join(OUT, f"{name}.pt"))
+        print(name, tuple(out32.shape), "absmax", out32.abs().max().item(), "oracle fp32 rel", ((o - out32).abs().max() / out32.abs().max()).item(),
+              "ref bf16 vs fp32", ((out16.float() - out32).abs().max() / out32.abs().max()).item())
+
+
 COMPOSITIONAL_CASES = {
     # name: latent hw, region captions, split, caption length, t, kwargs
     "comp_2x2": dict(hw=(32, 32), n_regions=4, hs=2, ws=2, T=16, t=0.35,
@@ -488,6 +530,8 @@ if __name__ == "__main__":
         make_compositional()
     elif len(sys.argv) > 1 and sys.argv[1] == "signatures":
         make_signatures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants":
+        make_variants()
     elif len(sys.argv) > 1 and sys.argv[1] == "gemma":
         make_gemma()
     elif len(sys.argv) > 1 and sys.argv[1] == "imagenet_plain_forward":

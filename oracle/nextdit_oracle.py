@@ -67,6 +67,8 @@ class NextDiTConfig:
     multiple_of: int = 256
     norm_eps: float = 1e-5
     learn_sigma: bool = True
+    qk_norm: bool = True                            # False: q_norm / k_norm / ky_norm are nn.Identity (models/nextdit.py:166-175)
+    ffn_dim_multiplier: Optional[float] = None      # models/nextdit.py:422-424
 
     @property
     def head_dim(self) -> int:
@@ -76,6 +78,8 @@ class NextDiTConfig:
     def ffn_dim(self) -> int:
         # models/nextdit.py:421-425
         h = int(2 * (4 * self.dim) / 3)
+        if self.ffn_dim_multiplier is not None:
+            h = int(self.ffn_dim_multiplier * h)
         return self.multiple_of * ((h + self.multiple_of - 1) // self.multiple_of)
 
     @property
@@ -189,8 +193,9 @@ def attention(p: _Prec, cfg: NextDiTConfig, W: Dict[str, Tensor], pre: str, x: T
     xk = p.linear(x, W[pre + "wk.weight"])
     xv = p.linear(x, W[pre + "wv.weight"])
     # LayerNorm over ALL heads jointly, fp32 output under autocast (:330-331)
-    xq = F.layer_norm(xq, (H * hd,), W[pre + "q_norm.weight"].float(), W[pre + "q_norm.bias"].float(), 1e-5)
-    xk = F.layer_norm(xk, (Hkv * hd,), W[pre + "k_norm.weight"].float(), W[pre + "k_norm.bias"].float(), 1e-5)
+    if cfg.qk_norm:
+        xq = F.layer_norm(xq, (H * hd,), W[pre + "q_norm.weight"].float(), W[pre + "q_norm.bias"].float(), 1e-5)
+        xk = F.layer_norm(xk, (Hkv * hd,), W[pre + "k_norm.weight"].float(), W[pre + "k_norm.bias"].float(), 1e-5)
     xq = p.r(apply_rope(xq.view(B, N, H, hd), ang))           # rope fp32 then .to(dtype) (:337-340)
     xk = p.r(apply_rope(xk.view(B, N, Hkv, hd), ang))
     xv = xv.view(B, N, Hkv, hd)
@@ -201,7 +206,8 @@ def attention(p: _Prec, cfg: NextDiTConfig, W: Dict[str, Tensor], pre: str, x: T
     out = _sdpa(p, q, k, v, softmax_scale, None)               # x_mask is all ones for tensor input
     # gated cross-attention to the caption tokens, reusing the RoPE'd q (:381-394)
     yk = p.linear(y, W[pre + "wk_y.weight"])
-    yk = F.layer_norm(yk, (Hkv * hd,), W[pre + "ky_norm.weight"].float(), W[pre + "ky_norm.bias"].float(), 1e-5)
+    if cfg.qk_norm:
+        yk = F.layer_norm(yk, (Hkv * hd,), W[pre + "ky_norm.weight"].float(), W[pre + "ky_norm.bias"].float(), 1e-5)
     yk = p.r(yk).view(B, -1, Hkv, hd).repeat_interleave(rep, dim=2).permute(0, 2, 1, 3)
     yv = p.linear(y, W[pre + "wv_y.weight"]).view(B, -1, Hkv, hd).repeat_interleave(rep, dim=2).permute(0, 2, 1, 3)
     out_y = _sdpa(p, q, yk, yv, 1.0 / math.sqrt(hd), y_mask)
@@ -491,7 +497,7 @@ def state_dict_shapes(cfg: NextDiTConfig) -> Dict[str, tuple]:
         s[a + "wk_y.weight"] = (Hkv * hd, C)
         s[a + "wv_y.weight"] = (Hkv * hd, C)
         s[a + "wo.weight"] = (D, D)
-        for n, w in (("q_norm", D), ("k_norm", Hkv * hd), ("ky_norm", Hkv * hd)):
+        for n, w in (("q_norm", D), ("k_norm", Hkv * hd), ("ky_norm", Hkv * hd)) if cfg.qk_norm else ():
             s[a + n + ".weight"] = (w,)
             s[a + n + ".bias"] = (w,)
         f = f"layers.{i}.feed_forward."

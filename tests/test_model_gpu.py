@@ -63,6 +63,39 @@ def test_forward_with_cfg_vs_golden_and_oracle(tiny, path, attn):
     assert torch.equal(out[0, :3], out[1, :3])
 
 
+@pytest.mark.parametrize("name", ["variant_noqknorm", "variant_c16_ffn13"])
+def test_ctor_variants_vs_reference_fixture(name):
+    """qk_norm=False (rope-only q/k kernel, no ky LayerNorm, no *_norm keys), in_channels=16 (sd3 VAE latents: 64-wide patches, 128
+    output features) and ffn_dim_multiplier=1.3 (FeedForward width 2048 instead of 1536), against fixtures from the unmodified
+    reference; forward_with_cfg and a fused 4-point Euler solve == the generic loop."""
+    import dataclasses
+    from lumina_t2x_b200 import models, transport
+    fx = torch.load(os.path.join(GOLD, f"{name}.pt"), map_location="cpu", weights_only=False)
+    cfg = dataclasses.replace(O.config_tiny(n_layers=2), **fx["cfg_overrides"])
+    W = O.synthetic_weights(cfg, seed=fx["weight_seed"])
+    m = models.NextDiT(dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=cfg.qk_norm,
+                       in_channels=cfg.in_channels, ffn_dim_multiplier=cfg.ffn_dim_multiplier, cap_feat_dim=cfg.cap_feat_dim,
+                       max_tokens=256, max_cap_len=32)
+    m.load_state_dict(W, strict=True)
+    m = m.eval().to("cuda", dtype=torch.bfloat16)
+    z, cap, mask = O.synthetic_inputs(cfg, tuple(fx["hw"]), fx["T"], fx["ul"], seed=fx["input_seed"])
+    t = torch.full((2,), fx["t"])
+    out = m.forward_with_cfg(z.cuda(), t.cuda(), cap.cuda(), mask.cuda(), **fx["kw"]).float().cpu()
+    orc = O.forward_with_cfg(cfg, W, z, t, cap, mask, precision="bf16", **fx["kw"])
+    ref32 = fx["out_fp32"]
+    floor = _rel(fx["out_autocast_cpu_bf16"], ref32)
+    assert out.shape == ref32.shape and torch.isfinite(out).all()
+    assert _rel(out, orc) < 2e-2, (_rel(out, orc), floor)
+    assert _rel(out, ref32) < 1.5 * floor + 2e-3, (_rel(out, ref32), floor)
+    tr = transport.create_transport("Linear", "velocity", None, None, None)
+    fn = transport.Sampler(tr).sample_ode(sampling_method="euler", num_steps=4, atol=1e-6, rtol=1e-3, reverse=False, time_shifting_factor=1.0)
+    traj = fn(z.cuda(), m.forward_with_cfg, cap_feats=cap.cuda(), cap_mask=mask.cuda(), **fx["kw"])
+    traj2 = transport._fixed_grid_torch(
+        lambda tt, xx: m.forward_with_cfg(xx, torch.ones(2, device="cuda") * tt, cap.cuda(), mask.cuda(), **fx["kw"]),
+        z.cuda(), transport._time_grid(0, 1, 4, 1.0).cuda(), "euler")
+    assert torch.equal(traj, traj2)
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fwd_*.pt"))), ids=os.path.basename)
 def test_per_block_residual_taps_vs_reference(tiny, path):
     """Residual stream after every TransformerBlock (engine debug tap) against the per-block outputs the fixture recorded from the
