@@ -127,8 +127,8 @@ int ndit_set_caption(ndit_handle h, const void* cap_feats_dev, const uint8_t* ca
  * caption the adaLN conditioning pools over for BOTH rows (:866-870).  The latent's token grid is cut into h_split x w_split rectangles
  * of (H // h_split // 2) x (W // w_split // 2) tokens; rectangle (i, j) belongs to caption (i + 1) * (j + 1) - 1 (:879) and its tokens
  * cross-attend to that caption only (Attention.forward :421-446: per-caption masked SDPA, nan_to_num, sum over the cond captions); every
- * token of the unconditional row attends to the last caption.  Drives ndit_forward_cfg / ndit_sample with batch = 2 (one cond / uncond
- * pair) until the next ndit_set_caption.  Grows the caption buffers when n_caps exceeds what the workspace holds.  head_dim 72. */
+ * token of the unconditional row attends to the last caption.  Drives ndit_forward_cfg / ndit_sample / ndit_sample_sde (and ndit_forward:
+ * the guidance-free forward :852-899, row 0 = cond, row 1 = uncond) with batch = 2 (one cond / uncond pair) until the next ndit_set_caption.  Grows the caption buffers when n_caps exceeds what the workspace holds.  head_dim 72. */
 int ndit_set_caption_regions(ndit_handle h, const void* cap_feats_dev, const uint8_t* cap_mask_dev, int32_t n_caps, int32_t T,
                              const void* global_cap_feats_dev, const uint8_t* global_cap_mask_dev, int32_t global_T, int32_t h_split,
                              int32_t w_split, void* stream);

@@ -1053,8 +1053,8 @@ static int forward_impl(ndit_engine* h, const bf16* x, float t, int batch, int H
     if (batch != h->cap_batch) return h->fail(NDIT_ERR_STATE, "caption not set for batch %d (have %d)", batch, h->cap_batch);
     if (!plain && (batch < 2 || (batch & 1) || batch > h->Bmax)) return h->fail(NDIT_ERR_INVALID, "batch must be even and <= %d", h->Bmax);
     if (plain && (batch < 1 || batch > h->Bmax)) return h->fail(NDIT_ERR_INVALID, "batch must be in 1..%d", h->Bmax);
-    if (h->region_cond > 0 && (plain || batch != 2))
-        return h->fail(NDIT_ERR_INVALID, "region-masked captions (ndit_set_caption_regions) drive forward_with_cfg of one cond / uncond pair");
+    if (h->region_cond > 0 && (list != nullptr || batch != 2))
+        return h->fail(NDIT_ERR_INVALID, "region-masked captions (ndit_set_caption_regions) drive one cond / uncond pair of rows (batch 2, tensor input)");
     if (plain) {
         t = t_rows[0];
         bool uniform = true;

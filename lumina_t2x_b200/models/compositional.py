@@ -58,9 +58,33 @@ class NextDiT(_BaseNextDiT):
             # the reference dereferences global_cap_mask unconditionally (model.py:866)
             raise AttributeError("global_cap_feats / global_cap_mask are required by the compositional NextDiT (model.py:866)")
 
+    @torch.no_grad()
     def forward(self, x, t, cap_feats, cap_mask, global_cap_feats=None, global_cap_mask=None, h_split_num=1, w_split_num=1):
-        raise NotImplementedError("the B200 engine runs the compositional model through forward_with_cfg (one cond / uncond pair, as demo.py "
-                                  "calls it); the guidance-free forward of model.py:852 is not built")
+        """model.py:852-899 (inference): x [2, C, H, W] - row 0 attends to the region captions, row 1 to the last caption (:421-446 pairs the
+        FIRST row with every caption but the last and the LAST row with the last one, so the reference itself only makes sense for a pair);
+        t [2]; returns the first C output channels [2, C, H, W], no guidance.  Uses the RoPE table / attention scaling the module holds."""
+        self._need_globals(global_cap_feats, global_cap_mask)
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[0] != 2:
+            raise ValueError("the compositional forward takes a pair of rows: x [2, C, H, W]")
+        self._check_inputs(x, cap_feats, cap_mask, global_cap_feats, global_cap_mask)
+        lib, h = self._engine(x.device)
+        lin, ntk = getattr(self, "_freqs_state", (1.0, float(self.scale_factor)))
+        prop, base = getattr(self, "_attn_state", (False, None))
+        sp = _lib.NditStepParams(0.0, lin, 1.0, int(prop), int(base) if base is not None else 0, ntk)
+        tv = (t.detach().float().reshape(-1).tolist() if isinstance(t, torch.Tensor) else [float(t)] * 2)
+        if len(tv) == 1:
+            tv = tv * 2
+        if len(tv) != 2:
+            raise ValueError(f"t has {len(tv)} entries for a batch of 2")
+        xb = x.detach().to(torch.bfloat16).contiguous()
+        out = torch.empty_like(xb)
+        with torch.cuda.device(x.device):
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            self._ensure_capacity(lib, h, self._tokens_for(x.shape[2], x.shape[3]), max(cap_feats.shape[1], global_cap_feats.shape[1]), 2)
+            self._set_caption_regions(lib, h, cap_feats, cap_mask, global_cap_feats, global_cap_mask, h_split_num, w_split_num, stream)
+            ta = (C.c_float * 2)(*tv)
+            _lib.check(lib.ndit_forward(h, C.c_void_p(xb.data_ptr()), ta, 2, x.shape[2], x.shape[3], C.byref(sp), C.c_void_p(out.data_ptr()), stream), h)
+        return out.to(x.dtype)
 
     @torch.no_grad()
     def forward_with_cfg(self, x, t, cap_feats, cap_mask, cfg_scale, scale_factor=1.0, scale_watershed=1.0, base_seqlen: Optional[int] = None,

@@ -116,6 +116,47 @@ def test_gqa_long_captions_ragged_tokens(attn):
     assert _rel(out, orc) < 3e-2, _rel(out, orc)
 
 
+def test_plain_forward_pair(tiny_mha):
+    """NextDiT.forward of the compositional model (model.py:852-899): a pair of DIFFERENT rows with different timesteps, row 0 on the region
+    captions, row 1 on the last caption, no guidance; on a fresh module (default RoPE table, no proportional attention)."""
+    cfg, W, _ = tiny_mha
+    m = _build(cfg, W, max_tokens=256, max_cap_len=16)
+    z, cap, mask, gcap, gmask = CO.synthetic_inputs(cfg, (24, 32), 4, 16, seed=17)
+    x = torch.randn(2, cfg.in_channels, 24, 32, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    t = torch.tensor([0.3, 0.8])
+    out = m(x.cuda(), t.cuda(), cap.cuda(), mask.cuda(), global_cap_feats=gcap.cuda(), global_cap_mask=gmask.cuda(), h_split_num=2,
+            w_split_num=2).float().cpu()
+    orc = CO.forward(cfg, W, x, t, cap, mask, gcap, gmask, 2, 2, precision="bf16")
+    ref = CO.forward(cfg, W, x.float(), t, cap.float(), mask, gcap.float(), gmask, 2, 2, precision="fp32")
+    assert out.shape == x.shape and torch.isfinite(out).all()
+    assert _rel(out, orc) < 3e-2, _rel(out, orc)
+    assert _rel(out, ref) < 1.5 * _rel(orc, ref) + 2e-3, (_rel(out, ref), _rel(orc, ref))
+
+
+@pytest.mark.parametrize("method", ["Euler", "Heun"])
+def test_sde_loop_in_engine_equals_host_loop(tiny_mha, method):
+    """transport.Sampler.sample_sde with the compositional kwargs: the in-engine stochastic loop (ndit_sample_sde over region-masked
+    captions) gives the bits of the mirror's host loop around the same forward_with_cfg."""
+    from lumina_t2x_b200 import transport
+    cfg, W, m = tiny_mha
+    z, cap, mask, gcap, gmask = CO.synthetic_inputs(cfg, (32, 32), 4, 16, seed=19)
+    kw = dict(cap_feats=cap.cuda(), cap_mask=mask.cuda(), cfg_scale=2.0, scale_factor=1.0, scale_watershed=1.0, base_seqlen=64,
+              proportional_attn=True, global_cap_feats=gcap.cuda(), global_cap_mask=gmask.cuda(), h_split_num=2, w_split_num=2)
+    tr = transport.create_transport("Linear", "velocity", None, None, None)
+    fn = transport.Sampler(tr).sample_sde(sampling_method=method, diffusion_form="sigma", diffusion_norm=1.0, last_step="Mean",
+                                          last_step_size=0.04, num_steps=5)
+    zb = z.cuda().to(torch.bfloat16)
+    torch.manual_seed(7)
+    n0 = m.launch_count()
+    fused = fn(zb, m.forward_with_cfg, **kw)
+    n1 = m.launch_count()
+    torch.manual_seed(7)
+    host = fn(zb, lambda x, t, **k: m.forward_with_cfg(x, t, **k), **kw)
+    assert len(fused) == len(host) == 5 and n1 > n0
+    for i, (a, b) in enumerate(zip(fused, host)):
+        assert torch.equal(a, b), (method, i, (a.float() - b.float()).abs().max().item())
+
+
 @pytest.mark.parametrize("method", ["euler", "midpoint"])
 def test_sampler_fused_solve_equals_generic_loop(tiny_mha, method):
     """transport.Sampler.sample_ode with the compositional kwargs (demo.py:185-250): the in-engine solve (graph replay on the second
@@ -174,15 +215,27 @@ def test_against_the_real_reference_on_the_gpu():
             return ref.forward_with_cfg(z.to(dtype), t, cap.to(dtype), mask, **k2).float()
 
     out16 = run(torch.bfloat16)
+    # the same bf16 run with PyTorch's math SDPA backend for the masked caption cross-attention (flash_attn_varlen_func of the self-attention
+    # is unaffected): separates bf16 rounding noise from what the fused SDPA backends do with fully masked (token, caption) rows
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    with sdpa_kernel(SDPBackend.MATH):
+        out16_math = run(torch.bfloat16)
     out32 = run(torch.float32)
-    floor, mine, cross = _rel(out16, out32), _rel(eng, out32), _rel(eng, out16)
-    print("COMPOSITIONAL_REFERENCE_PARITY", dict(ref_bf16_vs_fp32=floor, engine_vs_fp32=mine, engine_vs_ref_bf16=cross))
+    floor, floor_math, mine, cross = _rel(out16, out32), _rel(out16_math, out32), _rel(eng, out32), _rel(eng, out16_math)
+    rec = dict(test="compositional_mha_4layers_2x2", ref_bf16_vs_fp32=floor, ref_bf16_math_sdpa_vs_fp32=floor_math, engine_vs_fp32=mine,
+               engine_vs_ref_bf16_math_sdpa=cross, torch=torch.__version__)
+    print("COMPOSITIONAL_REFERENCE_PARITY", rec)
     try:
         import json
-        os.makedirs(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out"), exist_ok=True)
-        with open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "reference_parity.jsonl"), "a") as f:
-            f.write(json.dumps(dict(test="compositional_mha_4layers_2x2", ref_bf16_vs_fp32=floor, engine_vs_fp32=mine, engine_vs_ref_bf16=cross)) + "\n")
+        out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "reference_parity.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
     except OSError:
         pass
     assert torch.isfinite(eng).all()
-    assert mine <= 1.5 * floor + 2e-3, (mine, floor)
+    # Measured on torch 2.11: the reference's default autocast path is 0.67 (relative L-inf) away from its own fp32 output on this
+    # input - far outside bf16 noise (1.6e-2 for the plain model at the same size, profiles/r02_reference_parity_full_size.jsonl) -
+    # while the engine is 2.0e-2 from the fp32 truth.  So the bar is the tighter of the two bf16 runs, and an absolute cap.
+    best = min(floor, floor_math)
+    assert mine <= max(1.5 * best + 5e-3, 2.5e-2), (mine, floor, floor_math)

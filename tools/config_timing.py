@@ -76,6 +76,19 @@ def main():
                                                 base_seqlen=64 * 64 + 64 * 2, ntk_factor=1.0)
                 fl = flops(2, 4160, 3072, 32, 32, 96, 8192, 32, T=128)
                 name = "config4: Flag-DiT DiT_Llama_5B_patch2 1024x1024"
+            elif c == 6:
+                # compositional generation at the config-2 shape: 4 region captions (2 x 2 split) + the negative one, T = 128
+                from lumina_t2x_b200.models import compositional
+                m = randomize(compositional.NextDiT_2B_GQA_patch2(qk_norm=True, cap_feat_dim=2048, max_tokens=4096, max_cap_len=128))
+                z = torch.randn(2, 4, 128, 128, device="cuda", generator=g).bfloat16()
+                cap = torch.randn(5, 128, 2048, device="cuda", generator=g).bfloat16()
+                mask = torch.ones(5, 128, dtype=torch.int64, device="cuda")
+                gcap = torch.randn(1, 128, 2048, device="cuda", generator=g).bfloat16()
+                gmask = torch.ones(1, 128, dtype=torch.int64, device="cuda")
+                fn = lambda: m.forward_with_cfg(z, torch.full((2,), 0.5, device="cuda"), cap, mask, 4.0, base_seqlen=4096,  # noqa: E731
+                                                proportional_attn=True, global_cap_feats=gcap, global_cap_mask=gmask, h_split_num=2, w_split_num=2)
+                fl = flops(2, 4096, 2304, 32, 8, 72, 6144, 24, T=128)     # algorithmic: one caption per token
+                name = "compositional: NextDiT_2B_GQA_patch2 1024x1024, 2x2 regions (5 caption rows)"
             else:
                 m = randomize(moe.DiT_Llama_600M_patch2_Both(input_size=64, num_classes=1000, qk_norm=True))
                 z = torch.randn(2, 4, 64, 64, device="cuda", generator=g).bfloat16()
@@ -91,6 +104,13 @@ def main():
         rec = {"config": name, "ms_per_forward": round(ms, 3), "kernel_launches_per_forward": per,
                "algorithmic_tflop": round((fl[0] + fl[1]) / 1e12, 3),
                "tflops": round((fl[0] + fl[1]) / 1e9 / ms, 1), "params_B": round(m.parameter_count() / 1e9, 3)}
+        if c == 6:
+            # the same engine with plain captions (one per row): what the region-masked caption segment costs on top
+            from lumina_t2x_b200.models.nextdit import NextDiT as _Base
+            pfn = lambda: _Base.forward_with_cfg(m, z, torch.full((2,), 0.5, device="cuda"), cap[:2], mask[:2], 4.0, base_seqlen=4096,  # noqa: E731
+                                                 proportional_attn=True)
+            pfn()
+            rec["ms_per_forward_plain_captions_same_engine"] = round(timed(pfn), 3)
         if c in (1, 5):
             # whole 30-point Euler solve through transport.Sampler (29 model calls): direct launches vs the captured CUDA graph
             from lumina_t2x_b200 import transport
