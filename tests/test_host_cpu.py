@@ -285,3 +285,53 @@ def test_checkpoint_tooling_safetensors_and_convert(tmp_path):
     assert all(torch.equal(sd2[k], sd[k]) for k in sd)
     with pytest.raises(ValueError):
         checkpoint.convert(str(tmp_path / "x.bin"), str(tmp_path))
+
+
+def test_compositional_mirror_host_logic():
+    """models.compositional: same parameter inventory as the plain NextDiT (the reference class differs only in forward code), the
+    sampler routes its bound forward_with_cfg to the in-engine solve with exactly the reference's keyword set (signatures.json), the
+    reference's own failure modes are kept (missing global caption, region id beyond the caption rows), and there is no CPU path."""
+    import inspect
+    import json
+    from lumina_t2x_b200 import models, transport
+    from lumina_t2x_b200.models import compositional
+    from oracle import nextdit_oracle as O
+    cfg = O.config_tiny(2)
+    kw = dict(dim=cfg.dim, n_layers=2, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=True, cap_feat_dim=cfg.cap_feat_dim)
+    m = compositional.NextDiT(**kw)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == O.state_dict_shapes(cfg)
+    assert isinstance(m, models.NextDiT) and transport._engine_of(m.forward_with_cfg) is m
+    allowed, required = transport._ENGINE_KW[compositional.NextDiT]
+    table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "signatures.json")))
+    ref_kw = [p for p, _ in table["compositional"]["forward_with_cfg"]][3:]          # after self, x, t
+    assert list(allowed) == ref_kw and set(required) <= set(allowed)
+    assert [p for p in inspect.signature(m.forward).parameters] == ["x", "t", "cap_feats", "cap_mask", "global_cap_feats", "global_cap_mask",
+                                                                  "h_split_num", "w_split_num"]
+    x, t = torch.zeros(2, 4, 16, 16), torch.zeros(2)
+    cap, mask = torch.zeros(3, 8, cfg.cap_feat_dim), torch.ones(3, 8)
+    with pytest.raises(AttributeError):        # the reference dereferences global_cap_mask unconditionally (model.py:866)
+        m.forward_with_cfg(x, t, cap, mask, 2.0)
+    with pytest.raises(ValueError):            # one cond / uncond pair
+        m.forward_with_cfg(torch.zeros(4, 4, 16, 16), t, cap, mask, 2.0, global_cap_feats=cap[:1], global_cap_mask=mask[:1])
+    with pytest.raises(RuntimeError):          # CPU tensors: no fallback
+        m.forward_with_cfg(x, t, cap, mask, 2.0, global_cap_feats=cap[:1], global_cap_mask=mask[:1])
+    with pytest.raises(NotImplementedError):   # head_dim 48: the region kernel is instantiated for head_dim 72
+        compositional.NextDiT(dim=384, n_layers=1, n_heads=8, qk_norm=True, cap_feat_dim=64)._check_supported()
+
+
+def test_nextdit_ctor_variants_host_logic():
+    """qk_norm=False drops the *_norm keys, ffn_dim_multiplier follows model.py:470-473 in Python arithmetic, in_channels sizes the
+    embedder / final layer; the engine config carries them (ffn_dim, no_qk_norm)."""
+    import dataclasses
+    from lumina_t2x_b200 import models
+    from oracle import nextdit_oracle as O
+    for over in (dict(qk_norm=False), dict(in_channels=16, ffn_dim_multiplier=1.3), dict(ffn_dim_multiplier=0.5)):
+        cfg = dataclasses.replace(O.config_tiny(2), **over)
+        m = models.NextDiT(dim=cfg.dim, n_layers=2, n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, qk_norm=cfg.qk_norm, in_channels=cfg.in_channels,
+                           ffn_dim_multiplier=cfg.ffn_dim_multiplier, cap_feat_dim=cfg.cap_feat_dim)
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == O.state_dict_shapes(cfg), over
+        c = m._ndit_config()
+        assert c.ffn_dim == cfg.ffn_dim and c.no_qk_norm == (0 if cfg.qk_norm else 1) and c.in_channels == cfg.in_channels
+        m._check_supported()
+    with pytest.raises(NotImplementedError):
+        models.NextDiT(dim=576, n_layers=1, n_heads=8, qk_norm=True, cap_feat_dim=64, in_channels=3)._check_supported()
