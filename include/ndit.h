@@ -195,7 +195,9 @@ int ndit_sample_host(ndit_handle h, const void* z_host, const void* cap_feats_ho
                      int32_t method, const ndit_step_params* sp, void* final_host, void* stream);
 
 /* --- instrumentation */
-int64_t ndit_launch_count(ndit_handle h);          /* kernels launched by this handle so far */
+int64_t ndit_launch_count(ndit_handle h);          /* kernels launched by this handle so far (a graph replay counts the launches it contains) */
+int64_t ndit_graph_replay_count(ndit_handle h);    /* ndit_sample calls that ran as ONE CUDA-graph launch: a solve is recorded the second time
+                                                    * it is requested with the same shape / grid / parameters and replayed from then on */
 int ndit_set_option(ndit_handle h, const char* name, int32_t value);
 /* options: "attn_ref" = 1: CUDA-core debug attention kernel; "attn_tp" = 1: experimental attention kernel with P in tensor
  * memory (head_dim 72); "pdl" = 1: programmatic dependent launch for the hot-loop kernels (process-wide); "profile" = 1:

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ndit_sample_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _i32, _i32,
                                    C.POINTER(NditStepParams), _vp, _vp]),
     "ndit_launch_count": (_i64, [_vp]),
+    "ndit_graph_replay_count": (_i64, [_vp]),
     "ndit_set_option": (C.c_int, [_vp, C.c_char_p, _i32]),
     "ndit_profile_read": (C.c_int, [_vp, C.POINTER(_f32), C.POINTER(_i64), _i32]),
     "ndit_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

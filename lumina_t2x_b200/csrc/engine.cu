@@ -165,6 +165,7 @@ struct ndit_engine {
         int batch = 0, height = 0, width = 0, method = 0, cap_T = 0, cap_rows = 0, region_cond = 0, region_hs = 0, region_ws = 0, with_traj = 0, attn_ref = 0, attn_tp = 0, pdl = 0, vt_epi = 0, moe_grouped = 0;
         ndit_step_params sp;
         cudaGraphExec_t exec = nullptr;
+        bool capture_failed = false;         // this solve could not be captured: run it directly from now on
         int64_t launches = 0;
         uint64_t last_use = 0;
         RopeSlot rope_after[2];              // what a replay leaves in the two RoPE table slots
@@ -173,6 +174,8 @@ struct ndit_engine {
     std::vector<SolveGraph> graphs;
     uint64_t graph_clock = 0;
     int use_graph = 1;                       // option "graph" / NDIT_GRAPH: replay a captured graph for repeated solves
+    cudaStream_t capture_stream = nullptr;   // capture happens here when the caller's stream is the legacy default stream (not capturable)
+    int64_t graph_replays = 0;               // solves that ran as one graph launch (ndit_graph_replay_count)
     bf16* traj_buf = nullptr;                // internal trajectory buffer of graph-captured solves [traj_cap][count]
     size_t traj_cap_elems = 0;
 
@@ -404,6 +407,7 @@ extern "C" int ndit_destroy(ndit_handle h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->rope_rows) cudaFree(h->rope_rows);
     if (h->tap_buf) cudaFree(h->tap_buf);
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     free_workspace(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
@@ -435,6 +439,7 @@ extern "C" int ndit_reserve(ndit_handle h, int32_t max_tokens, int32_t max_cap_l
 
 extern "C" int64_t ndit_parameter_count(ndit_handle h) { return h ? h->n_params : 0; }
 extern "C" int64_t ndit_launch_count(ndit_handle h) { return h ? h->launches : 0; }
+extern "C" int64_t ndit_graph_replay_count(ndit_handle h) { return h ? h->graph_replays : 0; }
 
 extern "C" int ndit_set_option(ndit_handle h, const char* name, int32_t value) {
     if (!h || !name) return NDIT_ERR_INVALID;
@@ -1380,9 +1385,11 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
         slot->cap_rows = h->cap_rows; slot->region_cond = h->region_cond; slot->region_hs = h->region_hs; slot->region_ws = h->region_ws;
         slot->with_traj = with_traj; slot->attn_ref = h->attn_ref; slot->attn_tp = h->attn_tp; slot->pdl = h->pdl; slot->vt_epi = h->vt_epi; slot->moe_grouped = h->moe_grouped; slot->sp = *sp;
         slot->launches = 0;
+        slot->capture_failed = false;
         slot->last_use = ++h->graph_clock;
         return 0;
     }
+    if (hit->capture_failed) return 0;
     if (!hit->exec) {
         const int eol = h->flag ? 1 : 0;
         if (int e = ensure_plans(h, batch, (height / 2) * (width / 2 + eol))) return e;
@@ -1391,29 +1398,47 @@ static int sample_graph(ndit_engine* h, int batch, int height, int width, const 
         // shapes may run between two replays
         h->vt_ones_valid = false;
         for (auto& r : h->rope) r.Hp = 0;
-        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+        // The legacy default stream (what PyTorch hands over unless the caller switched streams) and the per-thread default stream cannot
+        // be captured (cudaStreamBeginCapture fails with cudaErrorStreamCaptureUnsupported): record the launch sequence on an engine-owned
+        // non-blocking stream instead - nothing executes during capture - and launch the instantiated graph on the caller's stream.
+        cudaStream_t cs = s;
+        if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) {
+            if (!h->capture_stream && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError();
+                h->capture_stream = nullptr;
+                hit->capture_failed = true;
+                return 0;
+            }
+            cs = h->capture_stream;
+        }
+        auto give_up = [&]() {               // nothing recorded during a failed capture has run: the caller runs the solve directly
+            cudaGetLastError();
+            h->vt_ones_valid = false;
+            for (auto& r : h->rope) r.Hp = 0;
+            hit->capture_failed = true;
+            return 0;
+        };
+        if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) return give_up();
         const int64_t l0 = h->launches;
-        const int rc = sample_body(h, batch, height, width, grid, n_grid, method, sp, with_traj ? h->traj_buf : nullptr, s);
-        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const int rc = sample_body(h, batch, height, width, grid, n_grid, method, sp, with_traj ? h->traj_buf : nullptr, cs);
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         const int64_t captured = h->launches - l0;
         h->launches = l0;
         if (rc != NDIT_OK || ce != cudaSuccess || graph == nullptr) {
             if (graph) cudaGraphDestroy(graph);
-            cudaGetLastError();
-            h->vt_ones_valid = false;      // nothing recorded during a failed capture has run
-            for (auto& r : h->rope) r.Hp = 0;
-            return rc != NDIT_OK ? rc : 0;
+            return give_up();                // a genuine error (not a capture restriction) shows up again in the direct run
         }
         cudaGraphExec_t exec = nullptr;
         const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (ie != cudaSuccess) { cudaGetLastError(); h->vt_ones_valid = false; for (auto& r : h->rope) r.Hp = 0; return 0; }
+        if (ie != cudaSuccess) return give_up();
         hit->exec = exec; hit->launches = captured;
         hit->rope_after[0] = h->rope[0]; hit->rope_after[1] = h->rope[1]; hit->rope_next_after = h->rope_next;
     }
     hit->last_use = ++h->graph_clock;
     if (cudaGraphLaunch(hit->exec, s) != cudaSuccess) return h->fail(NDIT_ERR_CUDA, "cudaGraphLaunch of the captured solve failed");
     h->launches += hit->launches;
+    h->graph_replays += 1;
     h->rope[0] = hit->rope_after[0]; h->rope[1] = hit->rope_after[1]; h->rope_next = hit->rope_next_after;
     h->vt_ones_valid = (h->plan_B == batch && h->plan_N == (height / 2) * (width / 2 + (h->flag ? 1 : 0)));
     return 1;

@@ -227,6 +227,10 @@ class EngineModule(nn.Module):
     def launch_count(self) -> int:
         return int(_lib.load().ndit_launch_count(self._handle)) if self._handle is not None else 0
 
+    def graph_replay_count(self) -> int:
+        """Fixed-grid solves that ran as one CUDA-graph launch (ndit_graph_replay_count)."""
+        return int(_lib.load().ndit_graph_replay_count(self._handle)) if self._handle is not None else 0
+
     def set_option(self, name: str, value: int) -> None:
         lib, h = self._engine(next(self.parameters()).device)
         _lib.check(lib.ndit_set_option(h, name.encode(), int(value)), h)

@@ -110,6 +110,7 @@ def test_graph_replay_equals_direct_launches_and_survives_other_shapes():
     refB = fn(zB, m.forward_with_cfg, cap_feats=capB, cap_mask=maskB, **kw)
     m.set_option("graph", 1)
     launches = []
+    r0 = m.graph_replay_count()
     for i in range(3):            # 1st: direct (registers the solve), 2nd: capture + launch, 3rd: replay
         n0 = m.launch_count()
         a = fn(zA, m.forward_with_cfg, cap_feats=capA, cap_mask=maskA, **kw)
@@ -118,6 +119,9 @@ def test_graph_replay_equals_direct_launches_and_survives_other_shapes():
         b = fn(zB, m.forward_with_cfg, cap_feats=capB, cap_mask=maskB, **kw)     # another shape in between
         assert torch.equal(b, refB), i
     assert launches[0] > 0 and launches[2] >= launches[0] - 8        # replays are counted with the launches they contain
+    # the graphs really ran: both shapes were captured on the 2nd pass and replayed on the 3rd (PyTorch's current stream is the legacy
+    # default stream, which cannot be captured - the engine records on its own stream and launches the graph on the caller's)
+    assert m.graph_replay_count() - r0 == 4, m.graph_replay_count() - r0
     # a forward_with_cfg of yet another shape right after a replay (V^T layout / RoPE slots are shared state)
     zC, capC, maskC = (v.cuda() for v in O.synthetic_inputs(cfg, (24, 24), 16, 8, seed=6))
     t = torch.full((2,), 0.7, device="cuda")

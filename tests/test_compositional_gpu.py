@@ -169,8 +169,10 @@ def test_sampler_fused_solve_equals_generic_loop(tiny_mha, method):
     tr = transport.create_transport("Linear", "velocity", None, None, None)
     fn = transport.Sampler(tr).sample_ode(sampling_method=method, num_steps=5, atol=1e-6, rtol=1e-3, reverse=False, time_shifting_factor=4.0)
     zc = z.cuda()
+    r0 = m.graph_replay_count()
     fused = fn(zc, m.forward_with_cfg, **kw)
-    fused2 = fn(zc, m.forward_with_cfg, **kw)                   # second solve: CUDA-graph replay
+    fused2 = fn(zc, m.forward_with_cfg, **kw)                   # second solve: captured and launched as one CUDA graph
+    assert m.graph_replay_count() == r0 + 1
     generic = transport._fixed_grid_torch(lambda tt, xx: m.forward_with_cfg(xx, torch.ones(2, device="cuda") * tt, **kw), zc,
                                           transport._time_grid(0, 1, 5, 4.0).cuda(), method)
     assert fused.shape == (5,) + tuple(z.shape) and torch.isfinite(fused).all()

@@ -121,7 +121,9 @@ def main():
                 m.set_option("graph", gopt)
                 solve = lambda: sfn(z, m.forward_with_cfg, y=y, cfg_scale=4.0)[-1]  # noqa: E731
                 outs[gopt] = solve()
+                r0 = m.graph_replay_count()
                 rec["ms_per_model_call_in_solve_graph%d" % gopt] = round(timed(solve, warm=2, iters=5) / 29, 3)
+                rec["graph_replays_graph%d" % gopt] = m.graph_replay_count() - r0
             rec["graph_equals_direct"] = bool(torch.equal(outs[0], outs[1]))
         print(json.dumps(rec), flush=True)
         del m
