@@ -396,6 +396,7 @@ def run_engine(args, rank, local_rank, world):
     barrier()
     clocks.start()
     l0 = lib.ndit_launch_count(h)
+    g0 = lib.ndit_graph_replay_count(h)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -407,6 +408,7 @@ def run_engine(args, rank, local_rank, world):
     my_ms = e0.elapsed_time(e1)
     ms = max_over_ranks(my_ms)
     launches = int(lib.ndit_launch_count(h) - l0)
+    graph_replays = int(lib.ndit_graph_replay_count(h) - g0)
     clk = clocks.stop()
     assert torch.isfinite(final_dev.float()).all(), "non-finite latents"
     per_rank = None
@@ -464,6 +466,7 @@ def run_engine(args, rank, local_rank, world):
         "e2e": {"value": world * args.steps / e2e_s, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "ndit_sample_host (C ABI, pinned host buffers, H2D + D2H inside the timed region)"},
         "gpu_launches": launches,
+        "cuda_graph_replays": graph_replays,     # timed solves that ran as one graph launch (their kernels are counted in gpu_launches)
         "algorithmic_tflop_per_latent": total_tf,
         "tflops_whole_path": total_tf * lat_per_s / world,
         "frac_of_bf16_peak_whole_path": total_tf * lat_per_s / world / pk["bf16"],
