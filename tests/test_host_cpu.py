@@ -335,3 +335,36 @@ def test_nextdit_ctor_variants_host_logic():
         m._check_supported()
     with pytest.raises(NotImplementedError):
         models.NextDiT(dim=576, n_layers=1, n_heads=8, qk_norm=True, cap_feat_dim=64, in_channels=3)._check_supported()
+
+
+def test_region_assignment_formula_of_the_kernel_matches_the_reference_mask():
+    """attention_fused_kernel<72, REGION> / attention_ref_kernel pick ONE caption per query token with integer arithmetic
+    (attention_tcgen05.cu: hs = (row / Wp) / hp, ws = (row % Wp) / wp, id = (hs + 1) * (ws + 1) - 1, valid iff hs < h_split, ws < w_split,
+    id < n_cond; hp = Hp / h_split, wp = Wp / w_split as set up in engine.cu).  Restated here and checked against the boolean region
+    mask of the oracle (= model.py:872-887, pinned by the comp_*.pt fixtures) over many grids: for every cond caption row r and token n,
+    mask[r, n] == (caption_of(n) == r); at most one caption per token; the last row is all ones."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from oracle import compositional_oracle as CO
+
+    def caption_of(n, Hp, Wp, hs, ws, n_cond):
+        hp, wp = Hp // hs, Wp // ws
+        i, j = (n // Wp) // hp, (n % Wp) // wp
+        rid = (i + 1) * (j + 1) - 1
+        return rid if (i < hs and j < ws and rid < n_cond) else -1
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(1, 24), st.integers(1, 24), st.integers(1, 4), st.integers(1, 4), st.integers(0, 3))
+    def check(Hp, Wp, hs, ws, extra):
+        if hs > Hp or ws > Wp:
+            return                                        # the engine rejects regions that do not fit the token grid
+        n_caps = hs * ws + extra                          # the smallest the reference accepts is h_split * w_split rows (region id < rows)
+        n_cond = n_caps - 1
+        mask = CO.region_mask(n_caps, Hp, Wp, hs, ws)
+        assert mask[-1].all()
+        owner = torch.tensor([caption_of(n, Hp, Wp, hs, ws, n_cond) for n in range(Hp * Wp)])
+        for r in range(n_cond):
+            assert torch.equal(mask[r], owner == r), (Hp, Wp, hs, ws, n_caps, r)
+        assert (mask[:-1].sum(0) <= 1).all()
+
+    check()
