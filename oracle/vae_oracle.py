@@ -5,9 +5,14 @@ What the reference runs on the finished latent (lumina_next_t2i/sample.py:117-12
     vae = AutoencoderKL.from_pretrained("stabilityai/sdxl-vae" | "stabilityai/sd-vae-ft-{mse,ema}", torch_dtype=torch.float32).cuda()
     samples = vae.decode(samples / factor).sample
 
-PARITY UNPINNED.  The algorithm lives in a third-party dependency, Hugging Face ``diffusers`` (``requirements.txt`` lists it
-unpinned), which is absent from /root/reference AND from this image, so no fixture could be recorded from it.  This file restates
-the published implementation (diffusers 0.2x; file names relative to ``src/diffusers/models``):
+PARITY UNPINNED AGAINST DIFFUSERS.  The algorithm lives in a third-party dependency, Hugging Face ``diffusers`` (``requirements.txt``
+lists it unpinned), which is absent from /root/reference AND from this image, so no fixture could be recorded from it.  What IS pinned:
+the arithmetic of every building block (ResnetBlock, 1-head attention block, nearest-2x upsample + conv, GroupNorm eps, swish, mid block)
+against the independent implementation of the same LDM / taming-transformers decoder blocks that ships with transformers
+(models/janus/modeling_janus.py), assembled in diffusers' order with this oracle's weights
+(tests/test_oracle_vs_golden.py::test_vae_oracle_blocks_against_an_independent_ldm_decoder_implementation, 1e-5, tiny and sdxl
+architectures); the assembly order, the state-dict key names and the published parameter count remain a restatement of diffusers'
+published code.  This file restates that implementation (diffusers 0.2x; file names relative to ``src/diffusers/models``):
 
     AutoencoderKL.decode / _decode     autoencoders/autoencoder_kl.py   z = post_quant_conv(z); dec = decoder(z); DecoderOutput(sample=dec)
     Decoder.forward                    autoencoders/vae.py              conv_in -> mid_block -> up_blocks -> conv_norm_out -> SiLU -> conv_out
